@@ -1,0 +1,83 @@
+"""Reader/writer for the '.gacase' text test-case format shared by oracle/ref_driver.cpp,
+oracle/ga_oracle.cpp, the tests and bench.py (format documented in oracle/ref_driver.cpp)."""
+
+
+class Case:
+    def __init__(self, nodes=None, edges=None, reads=None, b=10, B=0, gfa_overlap=None):
+        self.nodes = nodes or []     # [(id, sequence)]
+        self.edges = edges or []     # [(from, from_start, to, to_end)]
+        self.reads = reads or []     # [(name, sequence, [(node, pos, reverse)])]
+        self.b = b
+        self.B = B
+        self.gfa_overlap = gfa_overlap  # None => vg semantics
+
+
+def write_case(case, path):
+    with open(path, "w") as f:
+        if case.gfa_overlap is None:
+            f.write("G vg\n")
+        else:
+            f.write("G gfa %d\n" % case.gfa_overlap)
+        for nid, seq in case.nodes:
+            f.write("N %d %s\n" % (nid, seq))
+        for a, fs, b, te in case.edges:
+            f.write("E %d %d %d %d\n" % (a, int(fs), b, int(te)))
+        f.write("P %d %d\n" % (case.b, case.B))
+        for name, seq, seeds in case.reads:
+            f.write("R %s %s %d\n" % (name, seq, len(seeds)))
+            for node, pos, rev in seeds:
+                f.write("S %d %d %d\n" % (node, pos, int(rev)))
+
+
+def read_case(path):
+    c = Case()
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while i < len(lines):
+        p = lines[i].split()
+        i += 1
+        if not p:
+            continue
+        if p[0] == "G":
+            c.gfa_overlap = int(p[2]) if p[1] == "gfa" else None
+        elif p[0] == "N":
+            c.nodes.append((int(p[1]), p[2]))
+        elif p[0] == "E":
+            c.edges.append((int(p[1]), bool(int(p[2])), int(p[3]), bool(int(p[4]))))
+        elif p[0] == "P":
+            c.b, c.B = int(p[1]), int(p[2])
+        elif p[0] == "R":
+            n = int(p[3])
+            seeds = []
+            for _ in range(n):
+                q = lines[i].split()
+                i += 1
+                seeds.append((int(q[1]), int(q[2]), bool(int(q[3]))))
+            c.reads.append((p[1], p[2], seeds))
+    return c
+
+
+def parse_ref_output(text):
+    """Parse the stdout of oracle/_ref/ref_align (and ga_oracle, same format) into dicts."""
+    reads = []
+    timing = None
+    cur = None
+    for line in text.split("\n"):
+        if line.startswith("READ "):
+            p = line.split()
+            cur = {"name": p[1], "mappings": [], "trace": []}
+            for kv in p[2:]:
+                k, v = kv.split("=")
+                cur[k] = int(v, 16) if k == "th" else int(v)
+            reads.append(cur)
+        elif line.startswith("M "):
+            cur["mappings"].append(tuple(int(x) for x in line.split()[1:]))
+        elif line.startswith("T "):
+            cur["trace"].append(tuple(int(x) for x in line.split()[1:]))
+        elif line.startswith("TIME "):
+            timing = {}
+            for kv in line.split()[1:]:
+                k, v = kv.split("=")
+                timing[k] = float(v)
+    return reads, timing
