@@ -1,0 +1,1031 @@
+// Per-stream banded bit-parallel DP + traceback: the device-side algorithm.
+//
+// One GPU thread owns one DP stream (one direction of one read/seed pair); the 32 streams of a warp run the
+// slice loop in lock step so that their column history can be interleaved lane-by-lane (coalesced 8-byte
+// stores) and so that __reduce_*_sync can size the shared slab.  All arithmetic is integer/bitwise except the
+// 2-state correctness HMM, which only adds/compares host-precomputed doubles (no FMA contraction possible).
+//
+// What is reproduced (reference = /root/reference):
+//   band selection            projectForwardFromMinScore                    GraphAligner.h:1110-1159
+//   row -1 scores + flags     forceComponentZeroRow                         GraphAligner.h:1903-1995
+//   word step                 getNextSlice (Myers VP/VN)                    GraphAligner.h:1349-1427
+//   node fill / in-edge merge calculateNode, getNodeStartSlice, sources     GraphAligner.h:1270-1347,1457-1573
+//   column min-merge          WordSlice::mergeTwoSlices (values only)       WordSlice.h:361-421
+//   slice driver / stop rule  getSqrtSlices, removeWronglyAlignedEnd        GraphAligner.h:2554-2856
+//   correctness HMM           AlignmentCorrectnessEstimationState::NextState AlignmentCorrectnessEstimation.cpp:71-89
+//   traceback + tie-breaks    getTraceFromTable*, pickBacktracePredecessor  GraphAligner.h:493-591,894-1021
+// What is deliberately different: no confirmedRows bookkeeping (acyclic band components are final after one
+// topological pass; cyclic components are iterated to the unique min-plus fix point), no sqrt checkpointing
+// (the full VP/VN history stays in HBM, so traceback never recomputes), no graph-sized scratch.
+#ifndef GA_CORE_CUH
+#define GA_CORE_CUH
+#include <stdint.h>
+#include "ga_types.h"
+
+#ifdef __CUDACC__
+#define GA_DEV __device__ __forceinline__
+#define GA_DEV_NOINLINE __device__ __noinline__
+#define GA_POPC(x) __popcll(x)
+#define GA_CTZ(x) (__ffsll((long long)(x)) - 1)
+#define GA_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
+#define GA_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define GA_DEV inline
+#define GA_DEV_NOINLINE inline
+#define GA_POPC(x) __builtin_popcountll(x)
+#define GA_CTZ(x) __builtin_ctzll(x)
+#define GA_WARP_MAX(x) (x)
+#define GA_WARP_ANY(x) (x)
+#endif
+
+#define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
+#define GA_HDR_WORDS 6u         // slabOff, ncols, nodeOff, nNodes, minScore, flags
+#define GA_HN_WORDS 3u          // node, colStart, nodeMin
+
+struct GaHmmTables
+{
+	double correctMul[65];
+	double falseMul[65];
+	double c2c, c2f, f2c, f2f;
+	double startCorrect, startFalse;
+};
+
+// per-lane memory; every pointer is already offset by the lane, element i lives at p[i * LANES]
+struct GaLaneMem
+{
+	uint32_t* tiny[2];
+	uint32_t* hash[2];
+	uint64_t* heap;
+	uint32_t* indeg;
+	uint32_t* order;
+	uint32_t* hdr;
+	uint32_t* histNode;
+	uint64_t* colVP;
+	uint64_t* colVN;
+	int32_t* colSBS;
+	uint32_t* moves;
+	uint32_t* pathNodes;
+};
+
+struct GaCol
+{
+	uint64_t VP, VN;
+	int32_t sbs, scoreEnd;
+};
+
+// tiny = frozen end state of a column, cf. reference TinySlice (NodeSlice.h:26-31):
+// bit0 VP63, bit1 VN63, bit2 scoreBeforeExists of the column, bits 3.. scoreEnd
+GA_DEV uint32_t ga_tiny_pack(const GaCol& c, bool sbE)
+{
+	return ((uint32_t)c.scoreEnd << 3) | (sbE ? 4u : 0u) | (uint32_t)((c.VN >> 62) & 2) | (uint32_t)(c.VP >> 63);
+}
+GA_DEV int32_t ga_tiny_score(uint32_t t) { return (int32_t)(t >> 3); }
+// value of row 62 of the frozen column = scoreEnd - VP63 + VN63 (GraphAligner.h:1368)
+GA_DEV int32_t ga_tiny_row62(uint32_t t) { return (int32_t)(t >> 3) - (int32_t)(t & 1) + (int32_t)((t >> 1) & 1); }
+
+GA_DEV uint32_t ga_base(const ga_graph_view& g, uint64_t w)
+{
+	return (g.seq2[w >> 4] >> ((uint32_t)(w & 15) * 2)) & 3u;
+}
+
+// Myers word step without the confirmedRows bookkeeping (GraphAligner.h:1349-1399).
+GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftInside, bool diagInside, bool previousEq, int32_t upleftRow62)
+{
+	GaCol r;
+	if (!leftSbE || !diagInside) Eq &= ~(uint64_t)1;
+	int32_t sbs = L.sbs + 1;
+	if (upleftInside)
+	{
+		int32_t d = upleftRow62 + (previousEq ? 0 : 1);
+		if (d < sbs) sbs = d;
+	}
+	int32_t hin = sbs - L.sbs;
+	uint64_t Xv = Eq | L.VN;
+	if (hin < 0) Eq |= 1;
+	uint64_t Xh = (((Eq & L.VP) + L.VP) ^ L.VP) | Eq;
+	uint64_t Ph = L.VN | ~(Xh | L.VP);
+	uint64_t Mh = L.VP & Xh;
+	r.scoreEnd = L.scoreEnd + (int32_t)(Ph >> 63) - (int32_t)(Mh >> 63);
+	Ph <<= 1;
+	Mh <<= 1;
+	if (hin < 0) Mh |= 1; else if (hin > 0) Ph |= 1;
+	r.VP = Mh | ~(Xv | Ph);
+	r.VN = Ph & Xv;
+	r.sbs = sbs;
+	return r;
+}
+
+// column := min(column, vertical ramp from `top`) where top < column.sbs (GraphAligner.h:1504-1509,1541-1546
+// with WordSlice.h:361-421).  The ramp is the steepest column there is, so the minimum differs from the
+// computed column only by "paying back" D = sbs - top deficits at the first non-VP rows.
+GA_DEV void ga_vertical_merge(GaCol& c, int32_t top)
+{
+	while (c.sbs > top)
+	{
+		uint64_t m = ~c.VP;
+		if (m == 0)
+		{
+			c.scoreEnd -= 1;
+		}
+		else
+		{
+			uint64_t b = m & (0 - m);
+			if (c.VN & b) c.VN ^= b; else c.VP |= b;
+		}
+		c.sbs -= 1;
+	}
+}
+
+// exact element-wise minimum of two columns (values of WordSlice::mergeTwoSlices, WordSlice.h:361-421).
+// A 1-Lipschitz column has a unique (sbs,VP,VN) form, so any exact minimum is bit-identical to the reference's.
+GA_DEV_NOINLINE GaCol ga_merge_cols(const GaCol& A, const GaCol& B)
+{
+	GaCol r;
+	r.sbs = A.sbs < B.sbs ? A.sbs : B.sbs;
+	r.scoreEnd = A.scoreEnd < B.scoreEnd ? A.scoreEnd : B.scoreEnd;
+	int32_t d = A.sbs - B.sbs;
+	uint64_t VP = 0, VN = 0;
+	for (int row = 0; row < 64; row++)
+	{
+		int32_t da = (int32_t)((A.VP >> row) & 1) - (int32_t)((A.VN >> row) & 1);
+		int32_t db = (int32_t)((B.VP >> row) & 1) - (int32_t)((B.VN >> row) & 1);
+		int32_t dn = d + da - db;
+		int32_t delta;
+		if (d <= 0) delta = (dn <= 0) ? da : da - dn;
+		else delta = (dn > 0) ? db : db + dn;
+		if (delta > 0) VP |= (uint64_t)1 << row;
+		else if (delta < 0) VN |= (uint64_t)1 << row;
+		d = dn;
+	}
+	r.VP = VP;
+	r.VN = VN;
+	return r;
+}
+
+GA_DEV int32_t ga_col_value(uint64_t VP, uint64_t VN, int32_t sbs, int row)
+{
+	uint64_t mask = (row >= 63) ? ~(uint64_t)0 : ~(~(uint64_t)0 << (row + 1));
+	return sbs + (int32_t)GA_POPC(VP & mask) - (int32_t)GA_POPC(VN & mask);
+}
+
+// ---- open-addressing node -> band-slot table, stamped per slice so it never needs clearing ----------------
+template <int LANES>
+GA_DEV int ga_hash_find(const uint32_t* table, uint32_t hashMask, uint32_t stamp, const uint32_t* histNode, uint32_t nodeOff, uint32_t node)
+{
+	uint32_t h = (node * 2654435761u) & hashMask;
+	while (true)
+	{
+		uint32_t e = table[(size_t)h * LANES];
+		if ((e >> 16) != stamp) return -1;
+		uint32_t slot = e & 0xffffu;
+		if (histNode[(size_t)((nodeOff + slot) * GA_HN_WORDS) * LANES] == node) return (int)slot;
+		h = (h + 1) & hashMask;
+	}
+}
+
+template <int LANES>
+GA_DEV void ga_hash_insert(uint32_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node, uint32_t slot)
+{
+	uint32_t h = (node * 2654435761u) & hashMask;
+	while ((table[(size_t)h * LANES] >> 16) == stamp) h = (h + 1) & hashMask;
+	table[(size_t)h * LANES] = (stamp << 16) | slot;
+}
+
+// ---- binary min-heap of (priority << 32 | node) --------------------------------------------------------------
+template <int LANES>
+GA_DEV void ga_heap_push(uint64_t* heap, uint32_t& n, uint64_t v)
+{
+	uint32_t i = n++;
+	while (i > 0)
+	{
+		uint32_t p = (i - 1) >> 1;
+		uint64_t pv = heap[(size_t)p * LANES];
+		if (pv <= v) break;
+		heap[(size_t)i * LANES] = pv;
+		i = p;
+	}
+	heap[(size_t)i * LANES] = v;
+}
+
+template <int LANES>
+GA_DEV uint64_t ga_heap_pop(uint64_t* heap, uint32_t& n)
+{
+	uint64_t top = heap[0];
+	uint64_t v = heap[(size_t)(--n) * LANES];
+	uint32_t i = 0;
+	while (true)
+	{
+		uint32_t c = 2 * i + 1;
+		if (c >= n) break;
+		uint64_t cv = heap[(size_t)c * LANES];
+		if (c + 1 < n)
+		{
+			uint64_t cv2 = heap[(size_t)(c + 1) * LANES];
+			if (cv2 < cv) { cv = cv2; c = c + 1; }
+		}
+		if (cv >= v) break;
+		heap[(size_t)i * LANES] = cv;
+		i = c;
+	}
+	if (n > 0) heap[(size_t)i * LANES] = v;
+	return top;
+}
+
+struct GaStreamState
+{
+	// stream constants
+	const uint8_t* seq;
+	uint32_t partLen;
+	uint32_t nslices;
+	uint32_t startNode;
+	// running state
+	int32_t status;
+	bool done;
+	int32_t prevMin;
+	double hmmC, hmmF;
+	uint32_t histNodeTop;
+	uint32_t slicesPushed;
+	uint64_t wordColumns;
+	uint32_t cyclicSlices;
+};
+
+// IUPAC match masks (bit0 A, bit1 C, bit2 G, bit3 T), GraphAligner.h:2039-2110; 0 = invalid character
+GA_DEV uint32_t ga_iupac_mask(uint8_t c)
+{
+	switch (c)
+	{
+		case 'A': case 'a': return 1;
+		case 'C': case 'c': return 2;
+		case 'G': case 'g': return 4;
+		case 'T': case 't': return 8;
+		case 'N': case 'n': return 15;
+		case 'R': case 'r': return 1 | 4;
+		case 'Y': case 'y': return 2 | 8;
+		case 'K': case 'k': return 4 | 8;
+		case 'M': case 'm': return 2 | 1;
+		case 'S': case 's': return 2 | 4;
+		case 'W': case 'w': return 1 | 8;
+		case 'B': case 'b': return 2 | 4 | 8;
+		case 'D': case 'd': return 1 | 4 | 8;
+		case 'H': case 'h': return 1 | 2 | 8;
+		case 'V': case 'v': return 1 | 2 | 4;
+		default: return 0;
+	}
+}
+
+// exact (case-sensitive, non-IUPAC) comparison used for the row above the slice, GraphAligner.h:1503,1540
+GA_DEV uint32_t ga_exact_code(uint8_t c)
+{
+	switch (c)
+	{
+		case 'A': return 0;
+		case 'C': return 1;
+		case 'G': return 2;
+		case 'T': return 3;
+		default: return 4;
+	}
+}
+
+#define GA_HDR(s, f) mem.hdr[(size_t)((s) * GA_HDR_WORDS + (f)) * LANES]
+#define GA_HN(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
+
+// ------------------------------------------------------------------------------------------------------------
+// Band selection for slice s from slice s-1 (GraphAligner.h:1110-1159).  Appends the band's node list to the
+// node history at nodeOff and fills hashCur.  Returns the number of band nodes; ncols/by reference.
+// ------------------------------------------------------------------------------------------------------------
+template <int LANES>
+GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int s, int bandwidth,
+	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, uint32_t* hashCur, uint32_t stampCur, uint32_t nodeOff, uint32_t& ncolsOut)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const int32_t expand = bandwidth + 64;
+	uint32_t nc = 0;
+	uint32_t ncols = 0;
+	uint32_t heapN = 0;
+	for (uint32_t i = 0; i < pNodes; i++)
+	{
+		int32_t nodeMin = (int32_t)GA_HN(pNodeOff + i, 2);
+		if (nodeMin > st.prevMin + bandwidth) continue;
+		uint32_t node = GA_HN(pNodeOff + i, 0);
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		if (nc >= caps.maxNodes || nodeOff + nc >= caps.histNodes) { st.status = nc >= caps.maxNodes ? GA_ERR_NODE_OVERFLOW : GA_ERR_HIST_OVERFLOW; return -1; }
+		GA_HN(nodeOff + nc, 0) = node;
+		GA_HN(nodeOff + nc, 1) = ncols;
+		ga_hash_insert<LANES>(hashCur, hashMask, stampCur, node, nc);
+		nc++;
+		ncols += len;
+		if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return -1; }
+		uint32_t pcs = GA_HN(pNodeOff + i, 1);
+		int32_t endscore = ga_tiny_score(tinyPrev[(size_t)(pcs + len - 1) * LANES]);
+		if (endscore > st.prevMin + expand) continue;
+		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		{
+			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
+			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(endscore - st.prevMin + 1) << 32) | g.outAdj[e]);
+		}
+	}
+	while (heapN > 0)
+	{
+		uint64_t top = mem.heap[0];
+		int32_t prio = (int32_t)(top >> 32);
+		if (prio > expand) break;
+		ga_heap_pop<LANES>(mem.heap, heapN);
+		uint32_t node = (uint32_t)top;
+		if (ga_hash_find<LANES>(hashCur, hashMask, stampCur, mem.histNode, nodeOff, node) >= 0) continue;
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		if (nc >= caps.maxNodes || nodeOff + nc >= caps.histNodes) { st.status = nc >= caps.maxNodes ? GA_ERR_NODE_OVERFLOW : GA_ERR_HIST_OVERFLOW; return -1; }
+		GA_HN(nodeOff + nc, 0) = node;
+		GA_HN(nodeOff + nc, 1) = ncols;
+		ga_hash_insert<LANES>(hashCur, hashMask, stampCur, node, nc);
+		nc++;
+		ncols += len;
+		if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return -1; }
+		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		{
+			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
+			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(prio + (int32_t)len) << 32) | g.outAdj[e]);
+		}
+	}
+	if (ncols > caps.maxCols) { st.status = GA_ERR_COL_OVERFLOW; return -1; }
+	ncolsOut = ncols;
+	return (int)nc;
+}
+
+struct GaSliceCtx
+{
+	int s;
+	uint32_t nodeOff, nNodes;     // this slice's node list in the node history
+	uint32_t pNodeOff, pNodes;    // previous slice's
+	uint32_t slabOff;             // this slice's first column in the warp slab
+	uint32_t* tinyCur;
+	const uint32_t* tinyPrev;
+	uint32_t* hashCur;
+	const uint32_t* hashPrev;
+	uint32_t stampCur, stampPrev;
+	uint64_t BA, BC, BG, BT;
+	uint32_t prevCharCode;        // exact code of sequence[j0-1], 4 = matches nothing
+	bool firstSlice;
+};
+
+// Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
+// forced = the node belongs to a cyclic block whose row -1 scores were already forced into colSBS
+// (ga_force_block); first = its columns hold no computed value yet.  Returns true if the node's columns changed.
+template <int LANES>
+GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, bool forced, bool first)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+	const uint64_t wStart = g.nodeStart[node];
+	const uint32_t len = (uint32_t)(g.nodeStart[node + 1] - wStart);
+	const int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
+	const bool inPrev = pslot >= 0;
+	const uint32_t pcs = inPrev ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
+
+	// ---- column 0 -------------------------------------------------------------------------------------------
+	uint32_t seqWord = g.seq2[wStart >> 4];
+	uint32_t base = (seqWord >> ((uint32_t)(wStart & 15) * 2)) & 3u;
+	uint64_t Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
+	bool previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
+	const uint32_t oldTiny0 = inPrev ? cx.tinyPrev[(size_t)pcs * LANES] : 0;
+
+	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
+	int32_t sbs0;
+	if (forced)
+	{
+		sbs0 = mem.colSBS[(size_t)(cx.slabOff + cs) * LANES];
+	}
+	else
+	{
+		sbs0 = inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff;
+		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+		{
+			uint32_t u = g.inAdj[e];
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
+			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
+			if (cu < 0 && pu < 0) continue;
+			uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
+			if (cu >= 0)
+			{
+				uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
+				int32_t v = mem.colSBS[(size_t)(cx.slabOff + ucs + ulen - 1) * LANES] + 1;
+				if (v < sbs0) sbs0 = v;
+			}
+			if (pu >= 0)
+			{
+				uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
+				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES]) + 1;
+				if (v < sbs0) sbs0 = v;
+			}
+		}
+	}
+	const bool sbE0 = inPrev && ga_tiny_score(oldTiny0) == sbs0;
+	bool anyIn = false;
+	GaCol c0;
+	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
+	for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+	{
+		uint32_t u = g.inAdj[e];
+		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
+		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
+		if (cu < 0 && pu < 0) continue;
+		uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
+		bool foundOneUp = pu >= 0;
+		int32_t upRow62 = 0;
+		uint32_t upTiny = 0;
+		if (foundOneUp)
+		{
+			uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
+			upTiny = cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES];
+			upRow62 = ga_tiny_row62(upTiny);
+		}
+		GaCol L;
+		bool LsbE;
+		uint64_t EqHere = Eq;
+		if (cu >= 0)
+		{
+			uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
+			size_t idx = (size_t)(cx.slabOff + ucs + ulen - 1) * LANES;
+			L.VP = mem.colVP[idx];
+			L.VN = mem.colVN[idx];
+			L.sbs = mem.colSBS[idx];
+			uint32_t t = cx.tinyCur[(size_t)(ucs + ulen - 1) * LANES];
+			L.scoreEnd = ga_tiny_score(t);
+			LsbE = (t & 4u) != 0;
+		}
+		else
+		{
+			// neighbour only in the previous band: synthetic source column from its end score (GraphAligner.h:1294-1301)
+			int32_t es = ga_tiny_score(upTiny);
+			L.VP = ~(uint64_t)0;
+			L.VN = 0;
+			L.sbs = es;
+			L.scoreEnd = es + 64;
+			LsbE = true;
+			EqHere &= 1;
+		}
+		GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, upRow62);
+		if (!anyIn) { c0 = cand; anyIn = true; }
+		else c0 = ga_merge_cols(c0, cand);
+	}
+	if (!anyIn)
+	{
+		// source node (GraphAligner.h:1317-1347,1475-1488); a band node always has a band predecessor or is kept
+		if (!inPrev) { st.status = GA_ERR_INTERNAL; return false; }
+		int32_t ps = ga_tiny_score(oldTiny0);
+		uint64_t mismatch = 1;
+		if (cx.firstSlice)
+		{
+			uint32_t m = ga_iupac_mask(st.seq[0]);
+			mismatch = ((m >> base) & 1u) ? 0 : 1;
+		}
+		c0.VP = (~(uint64_t)1) | mismatch;
+		c0.VN = 0;
+		c0.scoreEnd = ps + 63 + (int32_t)mismatch;
+		c0.sbs = ps;
+	}
+	else if (inPrev && c0.sbs > ga_tiny_score(oldTiny0))
+	{
+		ga_vertical_merge(c0, ga_tiny_score(oldTiny0));
+	}
+	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return false; }
+	{
+		size_t idx = (size_t)(cx.slabOff + cs) * LANES;
+		if (forced && !first && mem.colVP[idx] == c0.VP && mem.colVN[idx] == c0.VN) return false; // nothing upstream changed
+		mem.colVP[idx] = c0.VP;
+		mem.colVN[idx] = c0.VN;
+		mem.colSBS[idx] = c0.sbs;
+		cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
+	}
+
+	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
+	GaCol L = c0;
+	bool LsbE = sbE0;
+	uint32_t oldTinyLeft = oldTiny0;
+	for (uint32_t k = 1; k < len; k++)
+	{
+		uint64_t w = wStart + k;
+		if ((w & 15) == 0) seqWord = g.seq2[w >> 4];
+		base = (seqWord >> ((uint32_t)(w & 15) * 2)) & 3u;
+		Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
+		previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
+		uint32_t oldTiny = inPrev ? cx.tinyPrev[(size_t)(pcs + k) * LANES] : 0;
+		int32_t sbsF = L.sbs + 1;
+		if (inPrev && ga_tiny_score(oldTiny) < sbsF) sbsF = ga_tiny_score(oldTiny);
+		if (forced) sbsF = mem.colSBS[(size_t)(cx.slabOff + cs + k) * LANES];
+		bool sbE = inPrev && ga_tiny_score(oldTiny) == sbsF;
+		GaCol c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft));
+		if (inPrev && c.sbs > ga_tiny_score(oldTiny)) ga_vertical_merge(c, ga_tiny_score(oldTiny));
+		if (c.sbs != sbsF) { st.status = GA_ERR_INTERNAL; return false; }
+		size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
+		mem.colVP[idx] = c.VP;
+		mem.colVN[idx] = c.VN;
+		mem.colSBS[idx] = c.sbs;
+		cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
+		L = c;
+		LsbE = sbE;
+		oldTinyLeft = oldTiny;
+	}
+	return true;
+}
+
+// Row -1 scores for a cyclic block of band nodes (the slots listed in order[from..to)) by shortest paths over
+// the block (forceComponentZeroRow, GraphAligner.h:1903-1995), then reset every column to the all-ones ramp.
+// The nodes of the block are re-listed in order[] by increasing first-column score (a good sweep order).
+template <int LANES>
+GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const int32_t INF = 0x3fffffff;
+	uint32_t heapN = 0;
+	// indeg[slot] != 0 marks block membership at this point (Kahn left these nodes unresolved)
+	for (uint32_t q = from; q < to; q++)
+	{
+		uint32_t slot = mem.order[(size_t)q * LANES];
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
+		uint32_t pcs = pslot >= 0 ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
+		int32_t s0 = pslot >= 0 ? ga_tiny_score(cx.tinyPrev[(size_t)pcs * LANES]) : INF;
+		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+		{
+			uint32_t u = g.inAdj[e];
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
+			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
+			uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
+			if (cu >= 0 && mem.indeg[(size_t)cu * LANES] == 0)
+			{
+				uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
+				int32_t v = mem.colSBS[(size_t)(cx.slabOff + ucs + ulen - 1) * LANES] + 1;
+				if (v < s0) s0 = v;
+			}
+			if (pu >= 0)
+			{
+				uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
+				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES]) + 1;
+				if (v < s0) s0 = v;
+			}
+		}
+		int32_t v = s0;
+		for (uint32_t k = 0; k < len; k++)
+		{
+			if (k > 0 && v < INF)
+			{
+				v = v + 1;
+				if (pslot >= 0)
+				{
+					int32_t o = ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]);
+					if (o < v) v = o;
+				}
+			}
+			mem.colSBS[(size_t)(cx.slabOff + cs + k) * LANES] = v;
+		}
+		if (v < INF)
+		{
+			for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+			{
+				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+				if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
+				if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
+				ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(v + 1) << 32) | (uint32_t)cu);
+			}
+		}
+	}
+	while (heapN > 0)
+	{
+		uint64_t top = ga_heap_pop<LANES>(mem.heap, heapN);
+		int32_t score = (int32_t)(top >> 32);
+		uint32_t slot = (uint32_t)top;
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		bool endUpdated = true;
+		for (uint32_t k = 0; k < len; k++)
+		{
+			size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
+			if (mem.colSBS[idx] <= score) { endUpdated = false; break; }
+			mem.colSBS[idx] = score;
+			score++;
+		}
+		if (!endUpdated) continue;
+		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		{
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+			if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
+			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
+			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)score << 32) | (uint32_t)cu);
+		}
+	}
+	// reset columns to {VP = all ones, VN = 0, scoreEnd = sbs + 64, scoreBeforeExists} (GraphAligner.h:1981-1993)
+	for (uint32_t q = from; q < to; q++)
+	{
+		uint32_t slot = mem.order[(size_t)q * LANES];
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
+		uint32_t pcs = pslot >= 0 ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
+		for (uint32_t k = 0; k < len; k++)
+		{
+			size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
+			GaCol c;
+			c.VP = ~(uint64_t)0;
+			c.VN = 0;
+			c.sbs = mem.colSBS[idx];
+			if (c.sbs >= INF) { st.status = GA_ERR_INTERNAL; return; }
+			c.scoreEnd = c.sbs + 64;
+			bool sbE = pslot >= 0 && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
+			mem.colVP[idx] = c.VP;
+			mem.colVN[idx] = c.VN;
+			cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
+		}
+	}
+}
+
+// One slice for one stream, after band selection: topological pass (Kahn) over the acyclic part, fix-point
+// sweeps over what is left (cyclic components and everything downstream of them), slice minimum, HMM step.
+// Returns false when the stream stops (error or early stop).
+template <int LANES>
+GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, GaStreamState& st, GaSliceCtx& cx, uint32_t ncols)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const uint32_t nc = cx.nNodes;
+	// Peq words for the 64 read characters of this slice (GraphAligner.h:2338-2351)
+	{
+		const uint8_t* p = st.seq + (size_t)cx.s * 64;
+		uint64_t BA = 0, BC = 0, BG = 0, BT = 0;
+		for (int i = 0; i < 64; i++)
+		{
+			uint32_t m = ga_iupac_mask(p[i]);
+			BA |= (uint64_t)(m & 1u) << i;
+			BC |= (uint64_t)((m >> 1) & 1u) << i;
+			BG |= (uint64_t)((m >> 2) & 1u) << i;
+			BT |= (uint64_t)((m >> 3) & 1u) << i;
+		}
+		cx.BA = BA; cx.BC = BC; cx.BG = BG; cx.BT = BT;
+		cx.prevCharCode = cx.s > 0 ? ga_exact_code(p[-1]) : 4;
+		cx.firstSlice = cx.s == 0;
+	}
+	// in-degrees inside the band
+	uint32_t ready = 0;   // order[0..ready) = nodes whose predecessors are all evaluated (FIFO)
+	for (uint32_t slot = 0; slot < nc; slot++)
+	{
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		uint32_t d = 0;
+		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+		{
+			if (ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.inAdj[e]) >= 0) d++;
+		}
+		mem.indeg[(size_t)slot * LANES] = d;
+		if (d == 0) mem.order[(size_t)(ready++) * LANES] = slot;
+	}
+	uint32_t done = 0;
+	while (done < ready)
+	{
+		uint32_t slot = mem.order[(size_t)(done++) * LANES];
+		ga_calc_node<LANES>(g, caps, mem, st, cx, slot, false, true);
+		if (st.status != GA_OK) return false;
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		{
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+			if (cu < 0) continue;
+			uint32_t d = mem.indeg[(size_t)cu * LANES] - 1;
+			mem.indeg[(size_t)cu * LANES] = d;
+			if (d == 0) mem.order[(size_t)(ready++) * LANES] = (uint32_t)cu;
+		}
+	}
+	if (done < nc)
+	{
+		// cyclic remainder: indeg != 0 marks membership
+		st.cyclicSlices++;
+		uint32_t from = ready;
+		for (uint32_t slot = 0; slot < nc; slot++)
+		{
+			if (mem.indeg[(size_t)slot * LANES] != 0) mem.order[(size_t)(ready++) * LANES] = slot;
+		}
+		ga_force_block<LANES>(g, caps, mem, st, cx, from, ready);
+		if (st.status != GA_OK) return false;
+		bool first = true;
+		uint32_t sweeps = 0;
+		while (true)
+		{
+			bool changed = false;
+			for (uint32_t q = from; q < ready; q++)
+			{
+				bool c = ga_calc_node<LANES>(g, caps, mem, st, cx, mem.order[(size_t)q * LANES], true, first);
+				if (st.status != GA_OK) return false;
+				changed = changed || c;
+			}
+			if (!changed && !first) break;
+			first = false;
+			if (++sweeps > 64u * (ready - from) + 64u) { st.status = GA_ERR_CYCLE_ITER; return false; }
+		}
+	}
+	// slice minimum and per-node minimum (GraphAligner.h:2375,2410-2418; all rows are final here)
+	int32_t minScore = 0x7fffffff;
+	for (uint32_t slot = 0; slot < nc; slot++)
+	{
+		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		int32_t nodeMin = 0x7fffffff;
+		for (uint32_t k = 0; k < len; k++)
+		{
+			int32_t v = ga_tiny_score(cx.tinyCur[(size_t)(cs + k) * LANES]);
+			if (v < nodeMin) nodeMin = v;
+		}
+		GA_HN(cx.nodeOff + slot, 2) = (uint32_t)nodeMin;
+		if (nodeMin < minScore) minScore = nodeMin;
+	}
+	st.wordColumns += ncols;
+	// correctness HMM (AlignmentCorrectnessEstimation.cpp:71-89); doubles are only added and compared
+	int32_t m = minScore - st.prevMin;
+	if (m < 0 || m > 64) { st.status = GA_ERR_INTERNAL; return false; }
+	double cc = st.hmmC + hmm.c2c, fc = st.hmmF + hmm.f2c;
+	double cf = st.hmmC + hmm.c2f, ff = st.hmmF + hmm.f2f;
+	bool correctFromCorrect = cc >= fc;
+	bool falseFromCorrect = cf >= ff;
+	double nc2 = (cc > fc ? cc : fc) + hmm.correctMul[m];
+	double nf2 = (cf > ff ? cf : ff) + hmm.falseMul[m];
+	GA_HDR(cx.s, 4) = (uint32_t)minScore;
+	if (!correctFromCorrect) return false;   // GraphAligner.h:2640-2647: stop, slice not recorded
+	st.hmmC = nc2;
+	st.hmmF = nf2;
+	GA_HDR(cx.s, 5) = (nc2 > nf2 ? 1u : 0u) | (falseFromCorrect ? 2u : 0u);
+	st.prevMin = minScore;
+	st.slicesPushed = (uint32_t)cx.s + 1;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Traceback over the stored history (getTraceFromTable / pickBacktracePredecessor, GraphAligner.h:493-591,
+// 894-1021).  Emits 2-bit moves and the node crossed into at every node boundary, both in backward order.
+// ------------------------------------------------------------------------------------------------------------
+template <int LANES>
+struct GaSliceView
+{
+	uint32_t slabOff, nodeOff, nNodes;
+};
+
+template <int LANES>
+GA_DEV int ga_slice_find(const GaLaneMem& mem, uint32_t nodeOff, uint32_t nNodes, uint32_t node)
+{
+	for (uint32_t i = 0; i < nNodes; i++)
+	{
+		if (GA_HN(nodeOff + i, 0) == node) return (int)i;
+	}
+	return -1;
+}
+
+// value of (node, off) at `row` of slice s, or `maxv` when the node is not in that slice's band
+// (getValueOrMax, GraphAligner.h:2008-2017).  s == -1 is the initial slice: seed node = 0, else maxv.
+template <int LANES>
+GA_DEV int32_t ga_hist_value(const ga_graph_view& g, const GaLaneMem& mem, const GaStreamState& st, int s, uint32_t node, uint32_t off, int row, int32_t maxv)
+{
+	if (s < 0) return node == st.startNode ? 0 : maxv;
+	uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
+	int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
+	if (slot < 0) return maxv;
+	size_t idx = (size_t)(GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1) + off) * LANES;
+	return ga_col_value(mem.colVP[idx], mem.colVN[idx], mem.colSBS[idx], row);
+}
+
+template <int LANES>
+GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut)
+{
+	uint32_t nMoves = 0, nPath = 0;
+	uint32_t curWord = 0;
+	int64_t j = (int64_t)nSlices * 64 - 1;
+	const int32_t maxv = (int32_t)st.partLen;
+	while (true)
+	{
+		int s = (int)(j >> 6);
+		int row = (int)(j & 63);
+		int32_t here = ga_hist_value<LANES>(g, mem, st, s, node, off, row, maxv);
+		uint32_t move = 4;
+		uint32_t nnode = node, noff = off;
+		if (j == 0 && node == st.startNode && (here == 0 || here == 1))
+		{
+			move = GA_MOVE_END;
+		}
+		else
+		{
+			uint64_t w = g.nodeStart[node] + off;
+			bool match = ((ga_iupac_mask(st.seq[j]) >> ga_base(g, w)) & 1u) != 0;
+			if (off == 0)
+			{
+				for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1] && move == 4; e++)
+				{
+					uint32_t u = g.inAdj[e];
+					uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+					int32_t hs = ga_hist_value<LANES>(g, mem, st, s, u, uoff, row, maxv);
+					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; break; }
+					int32_t ds = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, u, uoff, row - 1, maxv);
+					if (ds == (match ? here : here - 1)) { move = GA_MOVE_D; nnode = u; noff = uoff; break; }
+				}
+			}
+			else
+			{
+				int32_t hs = ga_hist_value<LANES>(g, mem, st, s, node, off - 1, row, maxv);
+				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; }
+				else
+				{
+					int32_t ds = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, node, off - 1, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, node, off - 1, row - 1, maxv);
+					if (ds == (match ? here : here - 1)) { move = GA_MOVE_D; noff = off - 1; }
+				}
+			}
+			if (move == 4)
+			{
+				int32_t us = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, node, off, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, node, off, row - 1, maxv);
+				if (us == here - 1) move = GA_MOVE_V;
+			}
+			if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
+		}
+		if (nMoves >= caps.maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+		curWord |= move << ((nMoves & 15) * 2);
+		nMoves++;
+		if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
+		if (move == GA_MOVE_END) break;
+		if (move != GA_MOVE_V && off == 0)
+		{
+			if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+			mem.pathNodes[(size_t)nPath * LANES] = nnode;
+			nPath++;
+		}
+		if (move != GA_MOVE_H) j--;
+		node = nnode;
+		off = noff;
+		if (j < 0) { st.status = GA_ERR_TRACE; break; }
+	}
+	if (nMoves & 15) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
+	nMovesOut = nMoves;
+	nPathOut = nPath;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Whole stream: forward slices (lock step across the warp), end trimming, tie list, traceback.
+// `active` = this lane holds a stream.  warpColTop is the warp-uniform bump pointer into the column slab.
+// ------------------------------------------------------------------------------------------------------------
+template <int LANES>
+GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, bool active,
+	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, ga_stream_out* out)
+{
+	GaStreamState st;
+	st.status = GA_OK;
+	st.done = !active;
+	st.seq = active ? parts + in->seqOff : nullptr;
+	st.partLen = active ? in->partLen : 0;
+	st.nslices = st.partLen / 64;
+	st.startNode = active ? in->startNode : 0;
+	st.prevMin = 0;
+	st.hmmC = hmm.startCorrect;
+	st.hmmF = hmm.startFalse;
+	st.histNodeTop = 0;
+	st.slicesPushed = 0;
+	st.wordColumns = 0;
+	st.cyclicSlices = 0;
+	uint32_t slicesRun = 0;
+	if (active && st.nslices > caps.maxSlices) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; }
+	const uint32_t hashMask = caps.hashSize - 1;
+
+	// initial slice (getInitialSliceOnlyOneNode, GraphAligner.h:2945-2960): the seed node, every column 0.
+	// It lives at node-history entry 0 and in tiny table 0 / hash table 0 with stamp 1.
+	uint32_t pNodeOff = 0, pNodes = 0;
+	if (!st.done)
+	{
+		uint32_t len = (uint32_t)(g.nodeStart[st.startNode + 1] - g.nodeStart[st.startNode]);
+		if (len > caps.maxCols) { st.status = GA_ERR_COL_OVERFLOW; st.done = true; }
+		else
+		{
+			GA_HN(0, 0) = st.startNode;
+			GA_HN(0, 1) = 0;
+			GA_HN(0, 2) = 0;
+			ga_hash_insert<LANES>(mem.hash[0], hashMask, 1, st.startNode, 0);
+			for (uint32_t k = 0; k < len; k++) mem.tiny[0][(size_t)k * LANES] = 0;
+			pNodes = 1;
+			st.histNodeTop = 1;
+		}
+	}
+	uint64_t warpColTop = 0;
+	for (int s = 0; ; s++)
+	{
+		bool run = !st.done && (uint32_t)s < st.nslices;
+		if (!GA_WARP_ANY(run)) break;
+		// table (s+1)&1 holds slice s, table s&1 holds slice s-1
+		const int tc = (s + 1) & 1, tp = s & 1;
+		const uint32_t stampCur = (uint32_t)((s + 1) >> 1) + 1, stampPrev = (uint32_t)(s >> 1) + 1;
+		uint32_t ncols = 0;
+		int nc = 0;
+		uint32_t nodeOff = st.histNodeTop;
+		if (run)
+		{
+			// slice 0 always runs with rampBandwidth (rampUntil = 0, GraphAligner.h:2612)
+			int bandwidth = (s == 0) ? rampBandwidth : initialBandwidth;
+			nc = ga_select_band<LANES>(g, caps, mem, st, s, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tc], stampCur, nodeOff, ncols);
+			if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
+		}
+		uint32_t maxc = GA_WARP_MAX(ncols);
+		uint64_t slabOff = warpColTop;
+		warpColTop += maxc;
+		if (warpColTop > caps.warpCols)
+		{
+			if (run) { st.status = GA_ERR_COL_OVERFLOW; st.done = true; }
+			break;   // warp-uniform
+		}
+		if (run)
+		{
+			slicesRun++;
+			GaSliceCtx cx;
+			cx.s = s;
+			cx.nodeOff = nodeOff;
+			cx.nNodes = (uint32_t)nc;
+			cx.pNodeOff = pNodeOff;
+			cx.pNodes = pNodes;
+			cx.slabOff = (uint32_t)slabOff;
+			cx.tinyCur = mem.tiny[tc];
+			cx.tinyPrev = mem.tiny[tp];
+			cx.hashCur = mem.hash[tc];
+			cx.hashPrev = mem.hash[tp];
+			cx.stampCur = stampCur;
+			cx.stampPrev = stampPrev;
+			GA_HDR(s, 0) = (uint32_t)slabOff;
+			GA_HDR(s, 1) = ncols;
+			GA_HDR(s, 2) = nodeOff;
+			GA_HDR(s, 3) = (uint32_t)nc;
+			bool cont = ga_fill_slice<LANES>(g, caps, hmm, mem, st, cx, ncols);
+			if (!cont) st.done = true;
+			else
+			{
+				pNodeOff = nodeOff;
+				pNodes = (uint32_t)nc;
+				st.histNodeTop = nodeOff + (uint32_t)nc;
+			}
+		}
+	}
+	if (!active) return;
+	out->nSlicesRun = (int32_t)slicesRun;
+	out->wordColumns = st.wordColumns;
+	out->cyclicSlices = st.cyclicSlices;
+	out->nMoves = 0;
+	out->nPathNodes = 0;
+	out->nTies = 0;
+	out->nSlices = 0;
+	out->score = 0;
+	out->endNode = 0;
+	out->endOff = 0;
+	if (st.status != GA_OK) { out->status = st.status; return; }
+
+	// removeWronglyAlignedEnd (GraphAligner.h:2554-2569)
+	int n = (int)st.slicesPushed;
+	if (n > 0)
+	{
+		bool currentlyCorrect = (GA_HDR(n - 1, 5) & 1u) != 0;
+		while (!currentlyCorrect)
+		{
+			n--;
+			if (n == 0) break;
+			currentlyCorrect = (GA_HDR(n - 1, 5) & 2u) != 0;   // FalseFromCorrect of the new last slice, as the reference reads it
+		}
+	}
+	out->nSlices = n;
+	if (n == 0) { out->status = GA_EMPTY; return; }
+	// trace start: a minimum-score cell of the last retained slice (GraphAligner.h:918-932).  Every tied cell is
+	// reported; the chosen one is the last in this kernel's evaluation order (host re-decides on cross-node ties).
+	{
+		const int sl = n - 1;
+		const int32_t minScore = (int32_t)GA_HDR(sl, 4);
+		const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
+		uint32_t nTies = 0, endNode = 0, endOff = 0;
+		for (uint32_t slot = 0; slot < nNodes; slot++)
+		{
+			if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
+			uint32_t node = GA_HN(nodeOff + slot, 0);
+			uint32_t cs = GA_HN(nodeOff + slot, 1);
+			uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+			for (uint32_t k = 0; k < len; k++)
+			{
+				size_t idx = (size_t)(slabOff + cs + k) * LANES;
+				int32_t v = mem.colSBS[idx] + (int32_t)GA_POPC(mem.colVP[idx]) - (int32_t)GA_POPC(mem.colVN[idx]);
+				if (v != minScore) continue;
+				if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
+				nTies++;
+				endNode = node;
+				endOff = k;
+			}
+		}
+		if (nTies == 0) { out->status = GA_ERR_INTERNAL; return; }
+		out->nTies = nTies;
+		out->score = minScore;
+		out->endNode = endNode;
+		out->endOff = endOff;
+		uint32_t nMoves = 0, nPath = 0;
+		ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath);
+		out->nMoves = nMoves;
+		out->nPathNodes = nPath;
+	}
+	out->status = st.status;
+}
+
+#endif

@@ -1,0 +1,84 @@
+// Plain-old-data types shared by the host C++ layer and the CUDA kernels.
+// No torch / STL types here: these structs cross the extern "C" boundary (include/graphaligner_b200.h).
+#ifndef GA_TYPES_H
+#define GA_TYPES_H
+#include <stdint.h>
+
+// Device-resident view of the AlignmentGraph (reference AlignmentGraph.h:46-56), flattened:
+//   nodeStart   prefix offsets in bp over the concatenated digraph sequence, nNodes+1 entries
+//               (index 0 and nNodes-1 are the reference's 1-bp dummy nodes, AlignmentGraph.cpp:22-30,108-118)
+//   seq2        2-bit packed bases (A=0,C=1,G=2,T=3), 16 per 32-bit word, indexed by global bp
+//   inOff/inAdj, outOff/outAdj  CSR of in-/out-neighbours IN THE REFERENCE'S INSERTION ORDER
+//               (AlignmentGraph.cpp:104-105) - the traceback tie-break depends on it
+typedef struct ga_graph_view
+{
+	uint32_t nNodes;
+	const uint64_t* nodeStart;
+	const uint32_t* seq2;
+	const uint32_t* inOff;
+	const uint32_t* inAdj;
+	const uint32_t* outOff;
+	const uint32_t* outAdj;
+} ga_graph_view;
+
+// One DP stream = one direction of one (read, seed) pair: the padded read part aligned forward from a
+// start node (reference getSplitAlignment, GraphAligner.h:2969-3024).
+typedef struct ga_stream_in
+{
+	uint64_t seqOff;     // byte offset of the padded part in the parts buffer
+	uint32_t partLen;    // padded length (multiple of 64) = reference sequence.size()
+	uint32_t startNode;  // graph node index whose columns are all 0 in the initial slice
+} ga_stream_in;
+
+enum
+{
+	GA_OK = 0,
+	GA_EMPTY = 1,                // no slice survived removeWronglyAlignedEnd -> this direction failed
+	GA_ERR_NODE_OVERFLOW = 2,    // band had more nodes than maxNodes (host retries with larger caps)
+	GA_ERR_COL_OVERFLOW = 3,     // band had more columns than maxCols / column history exhausted
+	GA_ERR_QUEUE_OVERFLOW = 4,
+	GA_ERR_HIST_OVERFLOW = 5,    // node-list history exhausted
+	GA_ERR_ALT_METHOD = 6,       // band >= 200000 bp: reference switches to calculateSliceAlternate (not built)
+	GA_ERR_TRACE = 7,            // traceback found no predecessor (reference: assert(false); abort())
+	GA_ERR_TRACE_OVERFLOW = 8,
+	GA_ERR_INTERNAL = 9,
+	GA_ERR_CYCLE_ITER = 10       // cyclic component did not converge within the iteration cap
+};
+
+#define GA_MAX_TIES 8
+
+typedef struct ga_stream_out
+{
+	int32_t status;
+	int32_t nSlices;        // slices retained after removeWronglyAlignedEnd (= bandwidthPerSlice.size())
+	int32_t score;          // minScore of the last retained slice
+	int32_t nSlicesRun;     // forward slices evaluated (incl. the one that triggered the early stop)
+	uint64_t wordColumns;   // forward-pass word updates (SURVEY 8d "W")
+	uint32_t endNode;       // trace start cell: node index, offset in node (row = 64*nSlices-1)
+	uint32_t endOff;
+	uint32_t nMoves;        // number of 2-bit moves in the trace (backward order)
+	uint32_t nPathNodes;    // node indices crossed into, backward order
+	uint64_t traceOff;      // offset (in 32-bit words) of this stream's record in the trace arena
+	uint32_t nTies;         // cells of the last retained slice tied at the minimum (incl. the chosen one)
+	uint32_t cyclicSlices;  // slices whose band held a cyclic component
+	uint32_t tieNode[GA_MAX_TIES];
+	uint32_t tieOff[GA_MAX_TIES];
+} ga_stream_out;
+
+// moves (2 bits each, backward from the end cell)
+enum { GA_MOVE_H = 0, GA_MOVE_D = 1, GA_MOVE_V = 2, GA_MOVE_END = 3 };
+
+typedef struct ga_caps
+{
+	uint32_t maxNodes;      // band nodes per slice (per stream)
+	uint32_t maxCols;       // band columns per slice (per stream)
+	uint32_t hashSize;      // power of two, >= 2*maxNodes
+	uint32_t maxQueue;      // heap / ready-queue entries
+	uint32_t maxSlices;     // slice headers per stream
+	uint32_t histNodes;     // node-list history entries per stream
+	uint64_t warpCols;      // column-history capacity per warp, in columns (x lanes x 20 B)
+	uint32_t maxMoves;      // per-stream temporary trace capacity (moves)
+	uint32_t maxPathNodes;
+} ga_caps;
+
+#endif
