@@ -65,7 +65,13 @@ struct GaLaneMem
 	int32_t* colSBS;
 	uint32_t* moves;
 	uint32_t* pathNodes;
+	uint32_t* ubkt;     // unordered_map emulation: bucket -> "before" node
+	uint32_t* unext;    // unordered_map emulation: forward list links
+	uint32_t* uorder;   // iteration order of the previous slice's node map
 };
+
+#define GA_HDR(s, f) mem.hdr[(size_t)((s) * GA_HDR_WORDS + (f)) * LANES]
+#define GA_HN(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
 
 struct GaCol
 {
@@ -191,44 +197,136 @@ GA_DEV void ga_hash_insert(uint32_t* table, uint32_t hashMask, uint32_t stamp, u
 	table[(size_t)h * LANES] = (stamp << 16) | slot;
 }
 
-// ---- binary min-heap of (priority << 32 | node) --------------------------------------------------------------
+// ---- std::priority_queue<NodeWithPriority, vector, greater<>> as libstdc++ implements it ----------------------
+// Entries are (priority << 32 | node) but ONLY the priority is compared (GraphAligner.h:1094-1108), and the
+// sift order follows std::__push_heap / std::__adjust_heap step by step: the pop order among equal priorities
+// decides the band's node order, which decides which of several tied minimum cells the traceback starts from.
+template <int LANES>
+GA_DEV void ga_heap_sift_up(uint64_t* heap, uint32_t hole, uint32_t top, uint64_t v)
+{
+	while (hole > top)
+	{
+		uint32_t parent = (hole - 1) >> 1;
+		uint64_t pv = heap[(size_t)parent * LANES];
+		if (!((uint32_t)(pv >> 32) > (uint32_t)(v >> 32))) break;
+		heap[(size_t)hole * LANES] = pv;
+		hole = parent;
+	}
+	heap[(size_t)hole * LANES] = v;
+}
+
 template <int LANES>
 GA_DEV void ga_heap_push(uint64_t* heap, uint32_t& n, uint64_t v)
 {
-	uint32_t i = n++;
-	while (i > 0)
-	{
-		uint32_t p = (i - 1) >> 1;
-		uint64_t pv = heap[(size_t)p * LANES];
-		if (pv <= v) break;
-		heap[(size_t)i * LANES] = pv;
-		i = p;
-	}
-	heap[(size_t)i * LANES] = v;
+	ga_heap_sift_up<LANES>(heap, n, 0, v);
+	n++;
 }
 
 template <int LANES>
 GA_DEV uint64_t ga_heap_pop(uint64_t* heap, uint32_t& n)
 {
 	uint64_t top = heap[0];
-	uint64_t v = heap[(size_t)(--n) * LANES];
-	uint32_t i = 0;
-	while (true)
+	uint32_t len = --n;            // elements that stay in the heap
+	if (len == 0) return top;
+	uint64_t v = heap[(size_t)len * LANES];
+	uint32_t hole = 0;
+	uint32_t child = 0;
+	while (child < (len - 1) / 2)
 	{
-		uint32_t c = 2 * i + 1;
-		if (c >= n) break;
-		uint64_t cv = heap[(size_t)c * LANES];
-		if (c + 1 < n)
-		{
-			uint64_t cv2 = heap[(size_t)(c + 1) * LANES];
-			if (cv2 < cv) { cv = cv2; c = c + 1; }
-		}
-		if (cv >= v) break;
-		heap[(size_t)i * LANES] = cv;
-		i = c;
+		child = 2 * (child + 1);
+		uint64_t r = heap[(size_t)child * LANES];
+		uint64_t l = heap[(size_t)(child - 1) * LANES];
+		if ((uint32_t)(r >> 32) > (uint32_t)(l >> 32)) { child--; r = l; }
+		heap[(size_t)hole * LANES] = r;
+		hole = child;
 	}
-	if (n > 0) heap[(size_t)i * LANES] = v;
+	if ((len & 1) == 0 && child == (len - 2) / 2)
+	{
+		child = 2 * (child + 1);
+		heap[(size_t)hole * LANES] = heap[(size_t)(child - 1) * LANES];
+		hole = child - 1;
+	}
+	ga_heap_sift_up<LANES>(heap, hole, 0, v);
 	return top;
+}
+
+// ---- iteration order of a libstdc++ std::unordered_map<size_t,...> filled key by key ---------------------------
+// The reference walks the previous slice's node map (NodeSlice.h:730-733 fills it in band order,
+// GraphAligner.h:1117 iterates it); the walk order is a pure function of the insertion order and of the
+// library's bucket-count schedule, which the host probes from a real std::unordered_map at start-up.
+struct GaUmapSchedule
+{
+	uint32_t n;
+	uint32_t threshold[48];   // inserting the threshold[i]-th element (1-based) rehashes to buckets[i] first
+	uint32_t buckets[48];
+};
+
+#define GA_UB_EMPTY 0xffffffffu
+#define GA_UB_BEGIN 0xfffffffeu
+#define GA_UNIL 0xffffffffu
+
+// keys: GA_HN(keyOff + i, 0), i in [0,n).  Writes the element indices in iteration order to mem.uorder.
+template <int LANES>
+GA_DEV void ga_umap_order(const GaUmapSchedule& sch, const GaLaneMem& mem, uint32_t keyOff, uint32_t n)
+{
+	uint32_t bktCount = 1;
+	uint32_t head = GA_UNIL;
+	uint32_t si = 0;
+	mem.ubkt[0] = GA_UB_EMPTY;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		if (si < sch.n && i + 1 == sch.threshold[si])
+		{
+			// _M_rehash_aux(n, true_type): relink every node, walking the old list front to back
+			uint32_t nb = sch.buckets[si++];
+			for (uint32_t b = 0; b < nb; b++) mem.ubkt[(size_t)b * LANES] = GA_UB_EMPTY;
+			uint32_t p = head;
+			head = GA_UNIL;
+			uint32_t bbeginBkt = 0;
+			while (p != GA_UNIL)
+			{
+				uint32_t nxt = mem.unext[(size_t)p * LANES];
+				uint32_t b = GA_HN(keyOff + p, 0) % nb;
+				uint32_t before = mem.ubkt[(size_t)b * LANES];
+				if (before == GA_UB_EMPTY)
+				{
+					mem.unext[(size_t)p * LANES] = head;
+					bool hadNext = head != GA_UNIL;
+					head = p;
+					mem.ubkt[(size_t)b * LANES] = GA_UB_BEGIN;
+					if (hadNext) mem.ubkt[(size_t)bbeginBkt * LANES] = p;
+					bbeginBkt = b;
+				}
+				else
+				{
+					uint32_t after = before == GA_UB_BEGIN ? head : mem.unext[(size_t)before * LANES];
+					mem.unext[(size_t)p * LANES] = after;
+					if (before == GA_UB_BEGIN) head = p; else mem.unext[(size_t)before * LANES] = p;
+				}
+				p = nxt;
+			}
+			bktCount = nb;
+		}
+		// _M_insert_bucket_begin
+		uint32_t key = GA_HN(keyOff + i, 0);
+		uint32_t b = key % bktCount;
+		uint32_t before = mem.ubkt[(size_t)b * LANES];
+		if (before != GA_UB_EMPTY)
+		{
+			uint32_t after = before == GA_UB_BEGIN ? head : mem.unext[(size_t)before * LANES];
+			mem.unext[(size_t)i * LANES] = after;
+			if (before == GA_UB_BEGIN) head = i; else mem.unext[(size_t)before * LANES] = i;
+		}
+		else
+		{
+			mem.unext[(size_t)i * LANES] = head;
+			if (head != GA_UNIL) mem.ubkt[(size_t)(GA_HN(keyOff + head, 0) % bktCount) * LANES] = i;
+			head = i;
+			mem.ubkt[(size_t)b * LANES] = GA_UB_BEGIN;
+		}
+	}
+	uint32_t k = 0;
+	for (uint32_t p = head; p != GA_UNIL; p = mem.unext[(size_t)p * LANES]) mem.uorder[(size_t)(k++) * LANES] = p;
 }
 
 struct GaStreamState
@@ -286,15 +384,13 @@ GA_DEV uint32_t ga_exact_code(uint8_t c)
 	}
 }
 
-#define GA_HDR(s, f) mem.hdr[(size_t)((s) * GA_HDR_WORDS + (f)) * LANES]
-#define GA_HN(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
 
 // ------------------------------------------------------------------------------------------------------------
 // Band selection for slice s from slice s-1 (GraphAligner.h:1110-1159).  Appends the band's node list to the
 // node history at nodeOff and fills hashCur.  Returns the number of band nodes; ncols/by reference.
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES>
-GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int s, int bandwidth,
+GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaUmapSchedule& sch, const GaLaneMem& mem, GaStreamState& st, int s, int bandwidth,
 	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, uint32_t* hashCur, uint32_t stampCur, uint32_t nodeOff, uint32_t& ncolsOut)
 {
 	const uint32_t hashMask = caps.hashSize - 1;
@@ -302,8 +398,11 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaL
 	uint32_t nc = 0;
 	uint32_t ncols = 0;
 	uint32_t heapN = 0;
-	for (uint32_t i = 0; i < pNodes; i++)
+	// the reference walks the previous slice's unordered_map (GraphAligner.h:1117)
+	ga_umap_order<LANES>(sch, mem, pNodeOff, pNodes);
+	for (uint32_t it = 0; it < pNodes; it++)
 	{
+		const uint32_t i = mem.uorder[(size_t)it * LANES];
 		int32_t nodeMin = (int32_t)GA_HN(pNodeOff + i, 2);
 		if (nodeMin > st.prevMin + bandwidth) continue;
 		uint32_t node = GA_HN(pNodeOff + i, 0);
@@ -841,8 +940,13 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				int32_t us = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, node, off, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, node, off, row - 1, maxv);
 				if (us == here - 1) move = GA_MOVE_V;
 			}
+#ifdef GA_HOST_DEBUG
+			if (move == 4) fprintf(stderr, "trace fail at node %u off %u j %ld here %d startNode %u inDeg %u\n", node, off, (long)j, here, st.startNode, g.inOff[node + 1] - g.inOff[node]);
+#endif
 			if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
 		}
+		// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
+		if (j == 0 && move != GA_MOVE_H) move = GA_MOVE_END;
 		if (nMoves >= caps.maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
 		curWord |= move << ((nMoves & 15) * 2);
 		nMoves++;
@@ -864,12 +968,90 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	nPathOut = nPath;
 }
 
+// Iterative Tarjan over the band of slice sl in the reference's visiting order (band order, outNeighbors order,
+// GraphAligner.h:1759-1856).  Returns the band slot of the first emitted node whose minimum equals minScore; for
+// a multi-node component the reference's work-list order decides instead, so there the choice is approximate.
+// Scratch: indeg = DFS index (0 = unvisited), order = low link, uorder = Tarjan stack, unext = call stack slots,
+// ubkt = call stack edge cursors, tiny[0] bit = on-stack flags are kept in the top bit of indeg.
+template <int LANES>
+GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, int sl, int32_t minScore)
+{
+	const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3);
+	if (nNodes == 1) return 0;
+	const uint32_t ONSTACK = 0x80000000u;
+	for (uint32_t i = 0; i < nNodes; i++) mem.indeg[(size_t)i * LANES] = 0;
+	uint32_t counter = 0;
+	uint32_t tstack = 0;
+	for (uint32_t root = 0; root < nNodes; root++)
+	{
+		if (mem.indeg[(size_t)root * LANES] != 0) continue;
+		uint32_t depth = 0;
+		mem.unext[0] = root;
+		mem.ubkt[0] = g.outOff[GA_HN(nodeOff + root, 0)];
+		counter++;
+		mem.indeg[(size_t)root * LANES] = counter | ONSTACK;
+		mem.order[(size_t)root * LANES] = counter;
+		mem.uorder[(size_t)(tstack++) * LANES] = root;
+		while (true)
+		{
+			uint32_t slot = mem.unext[(size_t)depth * LANES];
+			uint32_t node = GA_HN(nodeOff + slot, 0);
+			uint32_t e = mem.ubkt[(size_t)depth * LANES];
+			if (e < g.outOff[node + 1])
+			{
+				mem.ubkt[(size_t)depth * LANES] = e + 1;
+				int nb = ga_slice_find<LANES>(mem, nodeOff, nNodes, g.outAdj[e]);
+				if (nb < 0) continue;
+				uint32_t mark = mem.indeg[(size_t)nb * LANES];
+				if (mark == 0)
+				{
+					depth++;
+					mem.unext[(size_t)depth * LANES] = (uint32_t)nb;
+					mem.ubkt[(size_t)depth * LANES] = g.outOff[GA_HN(nodeOff + nb, 0)];
+					counter++;
+					mem.indeg[(size_t)nb * LANES] = counter | ONSTACK;
+					mem.order[(size_t)nb * LANES] = counter;
+					mem.uorder[(size_t)(tstack++) * LANES] = (uint32_t)nb;
+				}
+				else if (mark & ONSTACK)
+				{
+					uint32_t idx = mark & ~ONSTACK;
+					if (idx < mem.order[(size_t)slot * LANES]) mem.order[(size_t)slot * LANES] = idx;
+				}
+				continue;
+			}
+			// all neighbours done
+			uint32_t low = mem.order[(size_t)slot * LANES];
+			if (low == (mem.indeg[(size_t)slot * LANES] & ~ONSTACK))
+			{
+				// emit the component: stack entries down to slot, last pushed first
+				int found = -1;
+				while (true)
+				{
+					uint32_t back = mem.uorder[(size_t)(--tstack) * LANES];
+					mem.indeg[(size_t)back * LANES] &= ~ONSTACK;
+					// within a component the reference evaluates via a LIFO work-list; the root is popped first,
+					// so the earliest-listed member is the best guess for "evaluated last"
+					if (found < 0 && (int32_t)GA_HN(nodeOff + back, 2) == minScore) found = (int)back;
+					if (back == slot) break;
+				}
+				if (found >= 0) return found;
+			}
+			if (depth == 0) break;
+			depth--;
+			uint32_t parent = mem.unext[(size_t)depth * LANES];
+			if (low < mem.order[(size_t)parent * LANES]) mem.order[(size_t)parent * LANES] = low;
+		}
+	}
+	return -1;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Whole stream: forward slices (lock step across the warp), end trimming, tie list, traceback.
 // `active` = this lane holds a stream.  warpColTop is the warp-uniform bump pointer into the column slab.
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES>
-GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, bool active,
+GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaUmapSchedule& sch, const GaLaneMem& mem, bool active,
 	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, ga_stream_out* out)
 {
 	GaStreamState st;
@@ -923,7 +1105,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		{
 			// slice 0 always runs with rampBandwidth (rampUntil = 0, GraphAligner.h:2612)
 			int bandwidth = (s == 0) ? rampBandwidth : initialBandwidth;
-			nc = ga_select_band<LANES>(g, caps, mem, st, s, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tc], stampCur, nodeOff, ncols);
+			nc = ga_select_band<LANES>(g, caps, sch, mem, st, s, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tc], stampCur, nodeOff, ncols);
 			if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 		}
 		uint32_t maxc = GA_WARP_MAX(ncols);
@@ -991,13 +1173,14 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	}
 	out->nSlices = n;
 	if (n == 0) { out->status = GA_EMPTY; return; }
-	// trace start: a minimum-score cell of the last retained slice (GraphAligner.h:918-932).  Every tied cell is
-	// reported; the chosen one is the last in this kernel's evaluation order (host re-decides on cross-node ties).
+	// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
+	// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
+	// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
 	{
 		const int sl = n - 1;
 		const int32_t minScore = (int32_t)GA_HDR(sl, 4);
 		const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
-		uint32_t nTies = 0, endNode = 0, endOff = 0;
+		uint32_t nTies = 0;
 		for (uint32_t slot = 0; slot < nNodes; slot++)
 		{
 			if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
@@ -1011,11 +1194,22 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 				if (v != minScore) continue;
 				if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
 				nTies++;
-				endNode = node;
-				endOff = k;
 			}
 		}
 		if (nTies == 0) { out->status = GA_ERR_INTERNAL; return; }
+		int endSlot = ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore);
+		if (endSlot < 0) { out->status = GA_ERR_INTERNAL; return; }
+		uint32_t endNode = GA_HN(nodeOff + endSlot, 0), endOff = 0;
+		{
+			uint32_t cs = GA_HN(nodeOff + endSlot, 1);
+			uint32_t len = (uint32_t)(g.nodeStart[endNode + 1] - g.nodeStart[endNode]);
+			for (uint32_t k = 0; k < len; k++)
+			{
+				size_t idx = (size_t)(slabOff + cs + k) * LANES;
+				int32_t v = mem.colSBS[idx] + (int32_t)GA_POPC(mem.colVP[idx]) - (int32_t)GA_POPC(mem.colVN[idx]);
+				if (v == minScore) endOff = k;
+			}
+		}
 		out->nTies = nTies;
 		out->score = minScore;
 		out->endNode = endNode;

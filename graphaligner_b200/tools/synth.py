@@ -125,7 +125,7 @@ def make_graph(seed, backbone_len, chop=32, snp_every=0, bubble_every=0, indel_f
             next_bub += bubble_every
             plain(min(chop, max(1, backbone_len - pos)))
         elif next_inv is not None and pos >= next_inv:
-            n1 = g.add_node(_randseq(rng, int(rng.integers(8, chop + 1))))
+            n1 = g.add_node(_randseq(rng, int(rng.integers(min(8, chop), chop + 1))))
             connect(exits, [(n1, 0), (n1, 1)])
             exits = [(n1, 0), (n1, 1)]
             pos += len(g.seq[n1])
