@@ -1,0 +1,268 @@
+"""ctypes binding of include/graphaligner_b200.h.  The shared library is the product; this module only
+marshals numpy buffers into the C structs.  There is no fallback: importing works without a GPU (so the
+symbol table can be checked), creating an Aligner without one raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgraphaligner_b200.so")
+
+
+class GaBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_size_t), ("sequences", C.c_void_p), ("seq_offsets", C.c_void_p), ("names", C.c_void_p),
+                ("name_offsets", C.c_void_p), ("seed_offsets", C.c_void_p), ("seed_node", C.c_void_p), ("seed_pos", C.c_void_p),
+                ("seed_reverse", C.c_void_p), ("initial_bandwidth", C.c_int32), ("ramp_bandwidth", C.c_int32)]
+
+
+READ_RESULT = np.dtype([("failed", "<i4"), ("score", "<i4"), ("alignment_start", "<u8"), ("alignment_end", "<u8"),
+                        ("query_position", "<i4"), ("flags", "<u4"), ("mapping_offset", "<u8"), ("n_mappings", "<u8"),
+                        ("trace_offset", "<u8"), ("n_trace", "<u8"), ("word_columns", "<u8")])
+MAPPING = np.dtype([("node_id", "<i8"), ("offset", "<i8"), ("rank", "<i8"), ("is_reverse", "<i4"), ("from_length", "<i4"),
+                    ("to_length", "<i4"), ("reserved", "<u4"), ("read_start", "<u8")])
+TRACE_ITEM = np.dtype([("node_id", "<i4"), ("offset", "<u4"), ("readpos", "<u8"), ("reverse", "u1"), ("type", "u1"),
+                       ("graph_char", "S1"), ("read_char", "S1"), ("reserved", "<u4")])
+
+
+class GaStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("streams", "word_columns", "retries", "h2d_bytes", "d2h_bytes", "launches", "graph_bytes")]
+
+
+EXPORTS = ["ga_create", "ga_destroy", "ga_last_error", "ga_global_error", "ga_graph_new", "ga_graph_add_node", "ga_graph_add_edge",
+           "ga_graph_set_dbg_overlap", "ga_graph_finalize", "ga_graph_from_bigraph", "ga_graph_load_vg", "ga_graph_load_gfa",
+           "ga_graph_free", "ga_graph_node_count", "ga_graph_size_bp", "ga_graph_edge_count", "ga_graph_upload", "ga_align_batch",
+           "ga_stage_batch", "ga_run_staged", "ga_sync", "ga_finish_staged", "ga_staged_free", "ga_cuda_stream", "ga_results_count",
+           "ga_results_reads", "ga_results_mappings", "ga_results_trace", "ga_results_free", "ga_results_trace_hash", "ga_get_stats",
+           "ga_reset_stats"]
+
+_lib = None
+
+
+def load_library():
+    """Load libgraphaligner_b200.so; raises if it has not been built (python -m graphaligner_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libgraphaligner_b200.so is missing: run `python graphaligner_b200/build.py` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int32, C.c_uint64
+    sig = {
+        "ga_create": (vp, [C.c_int]), "ga_destroy": (None, [vp]), "ga_last_error": (C.c_char_p, [vp]), "ga_global_error": (C.c_char_p, []),
+        "ga_graph_new": (vp, []), "ga_graph_add_node": (C.c_int, [vp, i32, C.c_char_p, sz, C.c_int]), "ga_graph_add_edge": (C.c_int, [vp, i32, i32]),
+        "ga_graph_set_dbg_overlap": (C.c_int, [vp, i32]), "ga_graph_finalize": (C.c_int, [vp]),
+        "ga_graph_from_bigraph": (vp, [sz, vp, vp, vp, sz, vp, vp, vp, vp, i32]), "ga_graph_load_vg": (vp, [C.c_char_p]),
+        "ga_graph_load_gfa": (vp, [C.c_char_p]), "ga_graph_free": (None, [vp]), "ga_graph_node_count": (sz, [vp]), "ga_graph_size_bp": (sz, [vp]),
+        "ga_graph_edge_count": (sz, [vp]), "ga_graph_upload": (C.c_int, [vp, vp]), "ga_align_batch": (vp, [vp, C.POINTER(GaBatch)]),
+        "ga_stage_batch": (vp, [vp, C.POINTER(GaBatch)]), "ga_run_staged": (C.c_int, [vp, vp]), "ga_sync": (C.c_int, [vp]),
+        "ga_finish_staged": (vp, [vp, vp]), "ga_staged_free": (None, [vp, vp]), "ga_cuda_stream": (vp, [vp]), "ga_results_count": (sz, [vp]),
+        "ga_results_reads": (vp, [vp]), "ga_results_mappings": (vp, [vp]), "ga_results_trace": (vp, [vp]), "ga_results_free": (None, [vp]),
+        "ga_results_trace_hash": (u64, [vp, sz]), "ga_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_reset_stats": (C.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Graph:
+    """Host graph (the reference's AlignmentGraph) built through the C ABI."""
+
+    def __init__(self, handle):
+        self._lib = load_library()
+        if not handle:
+            raise RuntimeError("graph construction failed: " + self._lib.ga_global_error().decode())
+        self.handle = handle
+
+    @classmethod
+    def from_bigraph(cls, nodes, edges, gfa_overlap=None):
+        lib = load_library()
+        ids = np.array([n[0] for n in nodes], dtype=np.int64)
+        seqs = "".join(n[1] for n in nodes).encode()
+        offs = np.zeros(len(nodes) + 1, dtype=np.uint64)
+        np.cumsum([len(n[1]) for n in nodes], out=offs[1:])
+        seqbuf = np.frombuffer(seqs, dtype=np.uint8) if seqs else np.zeros(1, dtype=np.uint8)
+        fr = np.array([e[0] for e in edges], dtype=np.int64)
+        fs = np.array([1 if e[1] else 0 for e in edges], dtype=np.uint8)
+        to = np.array([e[2] for e in edges], dtype=np.int64)
+        te = np.array([1 if e[3] else 0 for e in edges], dtype=np.uint8)
+        h = lib.ga_graph_from_bigraph(len(nodes), _ptr(ids), _ptr(seqbuf), _ptr(offs), len(edges), _ptr(fr), _ptr(fs), _ptr(to), _ptr(te),
+                                      -1 if gfa_overlap is None else int(gfa_overlap))
+        return cls(h)
+
+    @classmethod
+    def from_case(cls, case):
+        return cls.from_bigraph(case.nodes, case.edges, case.gfa_overlap)
+
+    @classmethod
+    def load(cls, path):
+        lib = load_library()
+        if path.endswith(".vg"):
+            return cls(lib.ga_graph_load_vg(path.encode()))
+        if path.endswith(".gfa"):
+            return cls(lib.ga_graph_load_gfa(path.encode()))
+        raise ValueError("Unknown graph type (%s)" % path)
+
+    def node_count(self):
+        return self._lib.ga_graph_node_count(self.handle)
+
+    def size_bp(self):
+        return self._lib.ga_graph_size_bp(self.handle)
+
+    def edge_count(self):
+        return self._lib.ga_graph_edge_count(self.handle)
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self._lib.ga_graph_free(self.handle)
+            self.handle = None
+
+
+class PackedReads:
+    """Reads + seeds marshalled into the flat arrays of ga_batch (kept alive with the struct)."""
+
+    def __init__(self, reads, b, B=0):
+        # reads: [(name, sequence, [(node, pos, reverse)])]
+        self.n = len(reads)
+        self.total_bp = sum(len(r[1]) for r in reads)
+        seq = "".join(r[1] for r in reads).encode()
+        self.seq = np.frombuffer(seq, dtype=np.uint8).copy() if seq else np.zeros(1, dtype=np.uint8)
+        self.seq_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum([len(r[1]) for r in reads], out=self.seq_off[1:])
+        names = "".join(r[0] for r in reads).encode()
+        self.names = np.frombuffer(names, dtype=np.uint8).copy() if names else np.zeros(1, dtype=np.uint8)
+        self.name_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum([len(r[0]) for r in reads], out=self.name_off[1:])
+        self.seed_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum([len(r[2]) for r in reads], out=self.seed_off[1:])
+        seeds = [s for r in reads for s in r[2]]
+        self.seed_node = np.array([s[0] for s in seeds] or [0], dtype=np.int32)
+        self.seed_pos = np.array([s[1] for s in seeds] or [0], dtype=np.uint64)
+        self.seed_rev = np.array([1 if s[2] else 0 for s in seeds] or [0], dtype=np.uint8)
+        self.struct = GaBatch(self.n, _ptr(self.seq), _ptr(self.seq_off), _ptr(self.names), _ptr(self.name_off), _ptr(self.seed_off),
+                              _ptr(self.seed_node), _ptr(self.seed_pos), _ptr(self.seed_rev), int(b), int(B))
+
+
+class Results:
+    def __init__(self, lib, handle, names):
+        self._lib = lib
+        self.handle = handle
+        n = lib.ga_results_count(handle)
+        self.reads = self._view(lib.ga_results_reads(handle), READ_RESULT, n)
+        nm = int(self.reads["n_mappings"].sum())
+        nt = int(self.reads["n_trace"].sum())
+        self.mappings = self._view(lib.ga_results_mappings(handle), MAPPING, nm)
+        self.trace = self._view(lib.ga_results_trace(handle), TRACE_ITEM, nt)
+        self.names = names
+
+    @staticmethod
+    def _view(ptr, dtype, n):
+        if n == 0 or not ptr:
+            return np.zeros(0, dtype=dtype)
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n)
+
+    def trace_hash(self, i):
+        return int(self._lib.ga_results_trace_hash(self.handle, i))
+
+    def as_dicts(self, with_trace=False):
+        """Same shape as gacase.parse_ref_output, for differential tests against the oracle."""
+        out = []
+        for i in range(len(self.reads)):
+            r = self.reads[i]
+            failed = int(r["failed"])
+            d = {"name": self.names[i] if self.names else str(i), "failed": failed, "asserted": 0,
+                 "score": 0 if failed else int(r["score"]), "start": 0 if failed else int(r["alignment_start"]),
+                 "end": 0 if failed else int(r["alignment_end"]), "qpos": 0 if failed else int(r["query_position"]),
+                 "nmap": 0 if failed else int(r["n_mappings"]), "ntrace": 0 if failed else int(r["n_trace"]),
+                 "th": 0 if failed else self.trace_hash(i), "flags": int(r["flags"]), "mappings": [], "trace": []}
+            if not failed:
+                m = self.mappings[int(r["mapping_offset"]):int(r["mapping_offset"]) + int(r["n_mappings"])]
+                d["mappings"] = [(int(x["node_id"]), int(x["is_reverse"]), int(x["offset"]), int(x["from_length"]), int(x["to_length"])) for x in m]
+                if with_trace:
+                    t = self.trace[int(r["trace_offset"]):int(r["trace_offset"]) + int(r["n_trace"])]
+                    d["trace"] = [(int(x["node_id"]), int(x["offset"]), int(x["reverse"]), int(x["readpos"]), int(x["type"])) for x in t]
+            out.append(d)
+        return out
+
+    def free(self):
+        if self.handle:
+            self.reads = self.mappings = self.trace = None
+            self._lib.ga_results_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.free()
+
+
+class Aligner:
+    """One GPU context with a replicated graph: the batched form of the reference's AlignOneWay."""
+
+    def __init__(self, graph, device=0):
+        self._lib = load_library()
+        self.ctx = self._lib.ga_create(int(device))
+        if not self.ctx:
+            raise RuntimeError("ga_create failed: " + self._lib.ga_global_error().decode())
+        self.graph = graph
+        if self._lib.ga_graph_upload(self.ctx, graph.handle) != 0:
+            raise RuntimeError("ga_graph_upload failed: " + self.last_error())
+
+    def last_error(self):
+        return self._lib.ga_last_error(self.ctx).decode()
+
+    def align(self, reads, b=10, B=0):
+        packed = reads if isinstance(reads, PackedReads) else PackedReads(reads, b, B)
+        h = self._lib.ga_align_batch(self.ctx, C.byref(packed.struct))
+        if not h:
+            raise RuntimeError("ga_align_batch failed: " + self.last_error())
+        names = None if isinstance(reads, PackedReads) else [r[0] for r in reads]
+        return Results(self._lib, h, names)
+
+    def stage(self, packed):
+        h = self._lib.ga_stage_batch(self.ctx, C.byref(packed.struct))
+        if not h:
+            raise RuntimeError("ga_stage_batch failed: " + self.last_error())
+        return h
+
+    def run(self, staged):
+        if self._lib.ga_run_staged(self.ctx, staged) != 0:
+            raise RuntimeError("ga_run_staged failed: " + self.last_error())
+
+    def sync(self):
+        if self._lib.ga_sync(self.ctx) != 0:
+            raise RuntimeError("ga_sync failed: " + self.last_error())
+
+    def finish(self, staged, names=None):
+        h = self._lib.ga_finish_staged(self.ctx, staged)
+        if not h:
+            raise RuntimeError("ga_finish_staged failed: " + self.last_error())
+        return Results(self._lib, h, names)
+
+    def free_staged(self, staged):
+        self._lib.ga_staged_free(self.ctx, staged)
+
+    def cuda_stream(self):
+        return self._lib.ga_cuda_stream(self.ctx)
+
+    def stats(self):
+        s = GaStats()
+        self._lib.ga_get_stats(self.ctx, C.byref(s))
+        return {n: int(getattr(s, n)) for n, _ in GaStats._fields_}
+
+    def reset_stats(self):
+        self._lib.ga_reset_stats(self.ctx)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self._lib.ga_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        self.close()

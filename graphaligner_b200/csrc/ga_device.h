@@ -1,0 +1,39 @@
+// Device context: one per GPU.  Owns the replicated graph, constant tables, a stream and grow-only scratch.
+#ifndef GA_DEVICE_H
+#define GA_DEVICE_H
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "alignment_graph.h"
+#include "ga_host.h"
+#include "ga_types.h"
+
+namespace ga
+{
+
+// A batch whose inputs already live in HBM (parts + stream descriptors + per-warp layout): the timed region of
+// the "inputs resident" benchmark is RunStaged alone.
+struct StagedBatch;
+
+DeviceCtx* CreateDevice(int device);
+void DestroyDevice(DeviceCtx* ctx);
+const std::string& LastError(DeviceCtx* ctx);
+void SetError(DeviceCtx* ctx, const std::string& msg);
+// copies the finalized graph's flat arrays to the device (replica per GPU)
+void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph);
+size_t GraphBytesOnDevice(DeviceCtx* ctx);
+
+// plans the per-warp memory layout and copies parts + stream descriptors to the device.  `parts` must outlive the batch.
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+// launches the alignment kernel(s) on the context's stream (asynchronous); returns number of launches
+int RunStaged(DeviceCtx* ctx, StagedBatch* batch);
+// waits, copies results back, re-runs streams that overflowed their scratch with larger capacities
+void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats);
+void FreeStaged(DeviceCtx* ctx, StagedBatch* batch);
+void* DeviceStream(DeviceCtx* ctx);   // cudaStream_t
+void SyncDevice(DeviceCtx* ctx);
+
+}
+
+#endif

@@ -297,6 +297,7 @@ AlignmentResult traceToAlignment(const AlignmentGraph& graph, const std::string&
 		e.from_length = (int32_t)(btNodeEnd.off - btNodeStart.off + 1);
 		e.to_length = (int32_t)(btNodeEnd.j - btBeforeNode.j);
 		e.sequence = sequence.substr(btNodeStart.j, btNodeEnd.j - btBeforeNode.j);
+		e.read_start = btNodeStart.j;
 		r.alignment.path.mapping.back().edit.push_back(e);
 		oldNode = trace[pos].node;
 		btBeforeNode = btNodeEnd;
@@ -313,6 +314,7 @@ AlignmentResult traceToAlignment(const AlignmentGraph& graph, const std::string&
 	e.from_length = (int32_t)(btNodeEnd.off - btNodeStart.off);
 	e.to_length = (int32_t)(btNodeEnd.j - btBeforeNode.j);
 	e.sequence = sequence.substr(btNodeStart.j, btNodeEnd.j - btBeforeNode.j);
+	e.read_start = btNodeStart.j;
 	r.alignment.path.mapping.back().edit.push_back(e);
 	r.alignmentFailed = false;
 	return r;

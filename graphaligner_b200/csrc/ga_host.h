@@ -24,6 +24,7 @@ struct Edit
 	int32_t from_length = 0;
 	int32_t to_length = 0;
 	std::string sequence;
+	size_t read_start = 0;   // not a vg field: sequence == read.substr(read_start, to_length)
 };
 struct Mapping
 {

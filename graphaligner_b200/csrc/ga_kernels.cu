@@ -1,0 +1,516 @@
+// CUDA translation unit: the alignment kernel (one thread per DP stream, one warp per 32 streams) and the
+// device context that feeds it.  sm_100a only; there is no CPU fallback - every entry point fails loudly when
+// no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "ga_core.cuh"
+#include "ga_device.h"
+
+namespace ga
+{
+
+#define GA_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } } while (0)
+
+static const int LANES = 32;
+
+struct WarpDesc
+{
+	uint64_t colBase;      // first column of this warp's slab (units: columns, x LANES elements)
+	uint64_t hdrBase;      // element offsets into the pooled arrays (already x LANES)
+	uint64_t hnBase;
+	uint64_t movesBase;
+	uint64_t pathBase;
+	uint64_t warpCols;
+	uint32_t maxSlices;
+	uint32_t histNodes;
+	uint32_t maxMoves;
+	uint32_t maxPathNodes;
+};
+
+struct ScratchPtrs
+{
+	uint32_t* tiny;     // [warp][2][maxCols][LANES]
+	uint32_t* hash;     // [warp][2][hashSize][LANES]
+	uint64_t* heap;     // [warp][maxQueue][LANES]
+	uint32_t* nodeTmp;  // [warp][4][maxNodes][LANES]  indeg, order, unext, uorder
+	uint32_t* ubkt;     // [warp][ubktSize][LANES]
+	uint32_t* hdr;
+	uint32_t* histNode;
+	uint64_t* colVP;
+	uint64_t* colVN;
+	int32_t* colSBS;
+	uint32_t* moves;
+	uint32_t* pathNodes;
+	uint32_t ubktSize;
+};
+
+__constant__ GaHmmTables c_hmm;
+__constant__ GaUmapSchedule c_sched;
+
+__global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
+	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth,
+	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t warp = tid >> 5;
+	const uint32_t lane = tid & 31;
+	if (warp * 32 >= nStreams) return;   // whole warp out of range (warp-uniform)
+	const bool active = tid < nStreams;
+	const WarpDesc wd = warpDescs[warp];
+	ga_caps wc = caps;
+	wc.maxSlices = wd.maxSlices;
+	wc.histNodes = wd.histNodes;
+	wc.warpCols = wd.warpCols;
+	wc.maxMoves = wd.maxMoves;
+	wc.maxPathNodes = wd.maxPathNodes;
+	GaLaneMem mem;
+	{
+		size_t w = warp;
+		mem.tiny[0] = sp.tiny + (w * 2 + 0) * caps.maxCols * LANES + lane;
+		mem.tiny[1] = sp.tiny + (w * 2 + 1) * caps.maxCols * LANES + lane;
+		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * LANES + lane;
+		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * LANES + lane;
+		mem.heap = sp.heap + w * caps.maxQueue * LANES + lane;
+		mem.indeg = sp.nodeTmp + (w * 4 + 0) * caps.maxNodes * LANES + lane;
+		mem.order = sp.nodeTmp + (w * 4 + 1) * caps.maxNodes * LANES + lane;
+		mem.unext = sp.nodeTmp + (w * 4 + 2) * caps.maxNodes * LANES + lane;
+		mem.uorder = sp.nodeTmp + (w * 4 + 3) * caps.maxNodes * LANES + lane;
+		mem.ubkt = sp.ubkt + w * sp.ubktSize * LANES + lane;
+		mem.hdr = sp.hdr + wd.hdrBase + lane;
+		mem.histNode = sp.histNode + wd.hnBase + lane;
+		mem.colVP = sp.colVP + wd.colBase * LANES + lane;
+		mem.colVN = sp.colVN + wd.colBase * LANES + lane;
+		mem.colSBS = sp.colSBS + wd.colBase * LANES + lane;
+		mem.moves = sp.moves + wd.movesBase + lane;
+		mem.pathNodes = sp.pathNodes + wd.pathBase + lane;
+	}
+	ga_stream_out* out = active ? outs + tid : nullptr;
+	ga_run_stream<LANES>(g, wc, c_hmm, c_sched, mem, active, active ? streams + tid : nullptr, parts, initialBandwidth, rampBandwidth, out);
+	if (!active) return;
+	// compact this stream's trace record into the arena
+	uint32_t moveWords = (out->nMoves + 15) / 16;
+	uint32_t words = moveWords + out->nPathNodes;
+	unsigned long long off = atomicAdd(arenaTop, (unsigned long long)words);
+	out->traceOff = off;
+	if (off + words > arenaCap)
+	{
+		if (out->status == GA_OK) out->status = GA_ERR_TRACE_OVERFLOW;
+		return;
+	}
+	for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * LANES];
+	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * LANES];
+}
+
+// ---- device buffer pool -----------------------------------------------------------------------------------------
+struct Buffer
+{
+	void* ptr = nullptr;
+	size_t cap = 0;
+	void ensure(size_t bytes)
+	{
+		if (bytes <= cap) return;
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		GA_CUDA(cudaMalloc(&ptr, want));
+		cap = want;
+	}
+	void release()
+	{
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+	}
+};
+
+struct DeviceCtx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string lastError;
+	// graph
+	Buffer gNodeStart, gSeq, gInOff, gInAdj, gOutOff, gOutAdj;
+	ga_graph_view view;
+	size_t graphBytes = 0;
+	bool hasGraph = false;
+	// batch buffers
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bVP, bVN, bSBS, bMoves, bPath, bArena, bArenaTop;
+	GaUmapSchedule sched;
+	// pinned staging
+	void* pinnedOut = nullptr;
+	size_t pinnedOutCap = 0;
+};
+
+struct StagedBatch
+{
+	std::vector<ga_stream_in> sorted;      // streams in launch order (longest first)
+	std::vector<uint32_t> perm;            // launch index -> caller's index
+	ga_caps caps;
+	ScratchPtrs sp;
+	int b = 0, B = 0;
+	uint64_t arenaCap = 0;
+	size_t nWarps = 0;
+	int launches = 0;
+	// host copy of the inputs, kept for retries
+	const std::vector<uint8_t>* hostParts = nullptr;
+	int capScale = 1;
+};
+
+static GaHmmTables makeHmmTables()
+{
+	// Same expressions, same association, same libm as the reference (AlignmentCorrectnessEstimation.cpp:6-26,51-59,
+	// 81-85); the device only adds and compares these doubles.
+	GaHmmTables t;
+	const double correctMismatch = log(0.2);
+	const double correctMatch = log(1.0 - 0.2);
+	const double falseMismatch = log(0.5);
+	const double falseMatch = log(1.0 - 0.5);
+	std::vector<double> logFactorials;
+	logFactorials.push_back(0);
+	for (int i = 1; i <= 64; i++) logFactorials.push_back(logFactorials.back() + log(i));
+	for (int m = 0; m <= 64; m++)
+	{
+		double chooseresult = logFactorials[64] - logFactorials[m] - logFactorials[64 - m];
+		t.correctMul[m] = chooseresult + m * correctMismatch + (64 - m) * correctMatch;
+		t.falseMul[m] = chooseresult + m * falseMismatch + (64 - m) * falseMatch;
+	}
+	t.f2c = log(0.00001);
+	t.f2f = log(1.0 - 0.00001);
+	t.c2f = log(0.000000000000001);
+	t.c2c = log(1.0 - 0.000000000000001);
+	t.startCorrect = log(0.8);
+	t.startFalse = log(0.2);
+	return t;
+}
+
+static GaUmapSchedule probeUmapSchedule(size_t maxElems)
+{
+	// bucket-count growth of the very std::unordered_map the reference uses for a slice's node map
+	GaUmapSchedule sch;
+	sch.n = 0;
+	std::unordered_map<size_t, int> probe;
+	size_t last = probe.bucket_count();
+	for (size_t k = 1; k <= maxElems && sch.n < 48; k++)
+	{
+		probe[k] = 0;
+		if (probe.bucket_count() != last)
+		{
+			last = probe.bucket_count();
+			sch.threshold[sch.n] = (uint32_t)k;
+			sch.buckets[sch.n] = (uint32_t)last;
+			sch.n++;
+		}
+	}
+	return sch;
+}
+
+DeviceCtx* CreateDevice(int device)
+{
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) throw std::runtime_error(std::string("graphaligner_b200: no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU path");
+	if (device < 0 || device >= count) throw std::runtime_error("graphaligner_b200: device index out of range");
+	GA_CUDA(cudaSetDevice(device));
+	DeviceCtx* ctx = new DeviceCtx();
+	ctx->device = device;
+	GA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	GaHmmTables hmm = makeHmmTables();
+	GA_CUDA(cudaMemcpyToSymbol(c_hmm, &hmm, sizeof(hmm)));
+	ctx->sched = probeUmapSchedule(70000);
+	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
+	return ctx;
+}
+
+void DestroyDevice(DeviceCtx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bVP, &ctx->bVN, &ctx->bSBS, &ctx->bMoves, &ctx->bPath, &ctx->bArena, &ctx->bArenaTop };
+	for (Buffer* b : all) b->release();
+	if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const std::string& LastError(DeviceCtx* ctx) { return ctx->lastError; }
+void SetError(DeviceCtx* ctx, const std::string& msg) { ctx->lastError = msg; }
+void* DeviceStream(DeviceCtx* ctx) { return (void*)ctx->stream; }
+void SyncDevice(DeviceCtx* ctx)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+size_t GraphBytesOnDevice(DeviceCtx* ctx) { return ctx->graphBytes; }
+
+template <typename T>
+static const T* uploadVec(DeviceCtx* ctx, Buffer& buf, const std::vector<T>& v)
+{
+	buf.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+	GA_CUDA(cudaMemcpyAsync(buf.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->graphBytes += v.size() * sizeof(T);
+	return (const T*)buf.ptr;
+}
+
+void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
+{
+	if (!graph.Finalized()) throw std::logic_error("UploadGraph: graph not finalized");
+	GA_CUDA(cudaSetDevice(ctx->device));
+	ctx->graphBytes = 0;
+	ctx->view.nNodes = (uint32_t)graph.NodeSize();
+	ctx->view.nodeStart = uploadVec(ctx, ctx->gNodeStart, graph.NodeStarts());
+	ctx->view.seq2 = uploadVec(ctx, ctx->gSeq, graph.Seq2());
+	ctx->view.inOff = uploadVec(ctx, ctx->gInOff, graph.InOff());
+	ctx->view.inAdj = uploadVec(ctx, ctx->gInAdj, graph.InAdj());
+	ctx->view.outOff = uploadVec(ctx, ctx->gOutOff, graph.OutOff());
+	ctx->view.outAdj = uploadVec(ctx, ctx->gOutAdj, graph.OutAdj());
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->hasGraph = true;
+}
+
+static uint32_t nextPow2(uint32_t v)
+{
+	uint32_t p = 1;
+	while (p < v) p <<= 1;
+	return p;
+}
+
+static ga_caps defaultCaps(int b, int B, int scale)
+{
+	int bw = std::max(b, B);
+	ga_caps c;
+	memset(&c, 0, sizeof(c));
+	// a band holds the kept nodes (scores within bw of the minimum) plus everything within bw+64 bp downstream
+	uint32_t cols = (uint32_t)(4 * (bw + 64) + 256);
+	c.maxCols = std::max<uint32_t>(1024, cols * 2) * scale;
+	c.maxNodes = std::min<uint32_t>(60000, std::max<uint32_t>(128, c.maxCols / 8) * scale);
+	c.hashSize = nextPow2(c.maxNodes * 2);
+	c.maxQueue = c.maxNodes * 8;
+	return c;
+}
+
+StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth, BatchStats* stats)
+{
+	if (!ctx->hasGraph) throw std::logic_error("StageStreams: no graph uploaded to this device");
+	GA_CUDA(cudaSetDevice(ctx->device));
+	StagedBatch* sb = new StagedBatch();
+	sb->b = initialBandwidth;
+	sb->B = rampBandwidth;
+	sb->hostParts = &parts;
+	const size_t n = streams.size();
+	// longest streams first: the 32 streams of a warp iterate as long as the longest of them
+	sb->perm.resize(n);
+	std::iota(sb->perm.begin(), sb->perm.end(), 0u);
+	std::stable_sort(sb->perm.begin(), sb->perm.end(), [&](uint32_t a, uint32_t b2) { return streams[a].partLen > streams[b2].partLen; });
+	sb->sorted.resize(n);
+	for (size_t i = 0; i < n; i++) sb->sorted[i] = streams[sb->perm[i]];
+	return sb;
+}
+
+static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
+{
+	const size_t n = sb->sorted.size();
+	const int scale = sb->capScale;
+	sb->caps = defaultCaps(sb->b, sb->B, scale);
+	ga_caps& caps = sb->caps;
+	const size_t nWarps = (n + 31) / 32;
+	sb->nWarps = nWarps;
+	const int bw = std::max(sb->b, sb->B);
+	const uint64_t colsGuess = (uint64_t)(3 * (bw + 64) + 96) * scale;
+	const uint64_t nodesGuess = (colsGuess / 6 + 16);
+	std::vector<WarpDesc> wds(nWarps);
+	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0;
+	sb->arenaCap = 0;
+	for (size_t w = 0; w < nWarps; w++)
+	{
+		uint32_t maxLen = 0;
+		for (size_t i = w * 32; i < std::min(n, w * 32 + 32); i++)
+		{
+			maxLen = std::max(maxLen, sb->sorted[i].partLen);
+			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + (uint64_t)sb->sorted[i].partLen * 2 + 64;
+		}
+		uint32_t nslices = maxLen / 64;
+		WarpDesc& d = wds[w];
+		d.maxSlices = nslices;
+		d.histNodes = (uint32_t)std::min<uint64_t>(0xfffffff0u, (uint64_t)nslices * nodesGuess + caps.maxNodes + 8);
+		d.warpCols = (uint64_t)nslices * colsGuess + caps.maxCols;
+		d.maxMoves = maxLen * 3 + 256;
+		d.maxPathNodes = maxLen * 2 + 256;
+		d.colBase = colTop;
+		colTop += d.warpCols;
+		d.hdrBase = hdrTop;
+		hdrTop += (uint64_t)d.maxSlices * GA_HDR_WORDS * LANES;
+		d.hnBase = hnTop;
+		hnTop += (uint64_t)d.histNodes * GA_HN_WORDS * LANES;
+		d.movesBase = movesTop;
+		movesTop += (uint64_t)(d.maxMoves / 16 + 1) * LANES;
+		d.pathBase = pathTop;
+		pathTop += (uint64_t)d.maxPathNodes * LANES;
+	}
+	uint32_t ubktSize = 13;
+	for (uint32_t i = 0; i < ctx->sched.n; i++)
+	{
+		ubktSize = ctx->sched.buckets[i];
+		if (ctx->sched.buckets[i] >= caps.maxNodes) break;
+	}
+	ubktSize = std::max(ubktSize, caps.maxNodes);
+	ctx->bParts.ensure(sb->hostParts->size() + 64);
+	ctx->bIn.ensure(n * sizeof(ga_stream_in));
+	ctx->bOut.ensure(n * sizeof(ga_stream_out));
+	ctx->bWd.ensure(nWarps * sizeof(WarpDesc));
+	ctx->bTiny.ensure(nWarps * 2 * caps.maxCols * LANES * sizeof(uint32_t));
+	ctx->bHash.ensure(nWarps * 2 * (size_t)caps.hashSize * LANES * sizeof(uint32_t));
+	ctx->bHeap.ensure(nWarps * (size_t)caps.maxQueue * LANES * sizeof(uint64_t));
+	ctx->bNodeTmp.ensure(nWarps * 4 * (size_t)caps.maxNodes * LANES * sizeof(uint32_t));
+	ctx->bUbkt.ensure(nWarps * (size_t)ubktSize * LANES * sizeof(uint32_t));
+	ctx->bHdr.ensure(hdrTop * sizeof(uint32_t));
+	ctx->bHn.ensure(hnTop * sizeof(uint32_t));
+	ctx->bVP.ensure(colTop * LANES * sizeof(uint64_t));
+	ctx->bVN.ensure(colTop * LANES * sizeof(uint64_t));
+	ctx->bSBS.ensure(colTop * LANES * sizeof(int32_t));
+	ctx->bMoves.ensure(movesTop * sizeof(uint32_t));
+	ctx->bPath.ensure(pathTop * sizeof(uint32_t));
+	ctx->bArena.ensure(sb->arenaCap * sizeof(uint32_t));
+	ctx->bArenaTop.ensure(sizeof(unsigned long long));
+	sb->sp.tiny = (uint32_t*)ctx->bTiny.ptr;
+	sb->sp.hash = (uint32_t*)ctx->bHash.ptr;
+	sb->sp.heap = (uint64_t*)ctx->bHeap.ptr;
+	sb->sp.nodeTmp = (uint32_t*)ctx->bNodeTmp.ptr;
+	sb->sp.ubkt = (uint32_t*)ctx->bUbkt.ptr;
+	sb->sp.ubktSize = ubktSize;
+	sb->sp.hdr = (uint32_t*)ctx->bHdr.ptr;
+	sb->sp.histNode = (uint32_t*)ctx->bHn.ptr;
+	sb->sp.colVP = (uint64_t*)ctx->bVP.ptr;
+	sb->sp.colVN = (uint64_t*)ctx->bVN.ptr;
+	sb->sp.colSBS = (int32_t*)ctx->bSBS.ptr;
+	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
+	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
+	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts->data(), sb->hostParts->size(), cudaMemcpyHostToDevice, ctx->stream));
+	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
+	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));   // wds is a local
+	if (stats) stats->h2dBytes += sb->hostParts->size() + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc);
+}
+
+int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	const size_t n = sb->sorted.size();
+	if (n == 0) return 0;
+	// the node -> slot tables rely on stamps; clear what an earlier batch left behind
+	GA_CUDA(cudaMemsetAsync(ctx->bHash.ptr, 0, sb->nWarps * 2 * (size_t)sb->caps.hashSize * LANES * sizeof(uint32_t), ctx->stream));
+	GA_CUDA(cudaMemsetAsync(ctx->bArenaTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
+	const int threads = 64;
+	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
+	ga_align_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
+		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+	GA_CUDA(cudaGetLastError());
+	sb->launches++;
+	return 1;
+}
+
+static bool isOverflow(int32_t status)
+{
+	return status == GA_ERR_NODE_OVERFLOW || status == GA_ERR_COL_OVERFLOW || status == GA_ERR_QUEUE_OVERFLOW || status == GA_ERR_HIST_OVERFLOW || status == GA_ERR_TRACE_OVERFLOW;
+}
+
+void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	const size_t n = sb->sorted.size();
+	outs.assign(n, ga_stream_out());
+	arena.clear();
+	if (n == 0) return;
+	std::vector<ga_stream_out> sortedOuts(n);
+	unsigned long long top = 0;
+	GA_CUDA(cudaMemcpyAsync(sortedOuts.data(), ctx->bOut.ptr, n * sizeof(ga_stream_out), cudaMemcpyDeviceToHost, ctx->stream));
+	GA_CUDA(cudaMemcpyAsync(&top, ctx->bArenaTop.ptr, sizeof(top), cudaMemcpyDeviceToHost, ctx->stream));
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (top > sb->arenaCap) top = sb->arenaCap;
+	arena.resize(top);
+	if (top) GA_CUDA(cudaMemcpyAsync(arena.data(), ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (stats)
+	{
+		stats->d2hBytes += n * sizeof(ga_stream_out) + top * sizeof(uint32_t) + sizeof(top);
+		stats->launches += sb->launches;
+	}
+	for (size_t i = 0; i < n; i++) outs[sb->perm[i]] = sortedOuts[i];
+	// streams that ran out of scratch are re-run with larger capacities (never on the CPU)
+	std::vector<uint32_t> again;
+	for (size_t i = 0; i < n; i++)
+	{
+		if (isOverflow(outs[i].status)) again.push_back((uint32_t)i);
+	}
+	if (!again.empty() && sb->capScale < 64)
+	{
+		std::vector<ga_stream_in> sub;
+		for (uint32_t i : again)
+		{
+			// find the original descriptor: perm maps sorted -> original, so invert lazily
+			sub.push_back(ga_stream_in());
+		}
+		std::vector<uint32_t> inv(n);
+		for (size_t i = 0; i < n; i++) inv[sb->perm[i]] = (uint32_t)i;
+		for (size_t k = 0; k < again.size(); k++) sub[k] = sb->sorted[inv[again[k]]];
+		StagedBatch* retry = StageStreams(ctx, sub, *sb->hostParts, sb->b, sb->B, stats);
+		retry->capScale = sb->capScale * 4;
+		layoutAndUpload(ctx, retry, stats);
+		RunStaged(ctx, retry);
+		std::vector<ga_stream_out> subOuts;
+		std::vector<uint32_t> subArena;
+		FinishStaged(ctx, retry, subOuts, subArena, stats);
+		delete retry;
+		if (stats) stats->retries += again.size();
+		uint64_t base = arena.size();
+		arena.insert(arena.end(), subArena.begin(), subArena.end());
+		for (size_t k = 0; k < again.size(); k++)
+		{
+			outs[again[k]] = subOuts[k];
+			outs[again[k]].traceOff += base;
+		}
+	}
+}
+
+void FreeStaged(DeviceCtx* ctx, StagedBatch* sb)
+{
+	(void)ctx;
+	delete sb;
+}
+
+// exposed for ga_device users: layout + upload happen at stage time
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int b, int B, BatchStats* stats)
+{
+	StagedBatch* sb = StageStreams(ctx, streams, parts, b, B, stats);
+	layoutAndUpload(ctx, sb, stats);
+	return sb;
+}
+
+void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth,
+	std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats)
+{
+	StagedBatch* sb = StageAndUpload(ctx, streams, parts, initialBandwidth, rampBandwidth, stats);
+	try
+	{
+		RunStaged(ctx, sb);
+		FinishStaged(ctx, sb, outs, arena, stats);
+	}
+	catch (...)
+	{
+		delete sb;
+		throw;
+	}
+	delete sb;
+}
+
+}

@@ -1,0 +1,79 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the reference's outputs.
+Bar: bit-exact scores, alignment ranges, mappings and full trace (FNV fingerprint of every trace item)."""
+import os
+
+import pytest
+
+from graphaligner_b200.tools import gacase, synth
+from helpers import GOLDEN, REF_ALIGN, assert_same, load_expected, run_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from graphaligner_b200 import api as a
+    a.load_library()
+    return a
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fixture(api, golden_dir, name):
+    case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
+    expected = load_expected(os.path.join(golden_dir, name + ".expected"))
+    graph = api.Graph.from_case(case)
+    aligner = api.Aligner(graph)
+    res = aligner.align(case.reads, case.b, case.B)
+    assert_same(res.as_dicts(), expected, name)
+    res.free()
+    aligner.close()
+
+
+def test_smallexample_known_answer(api, golden_dir):
+    # the reference's only shipped fixture (test/smallexample): NDEBUG build -> score 25, node 6738+ offset 0,
+    # one edit 41/65, alignmentEnd 128, 65 trace items
+    case = gacase.read_case(os.path.join(golden_dir, "smallexample.gacase"))
+    aligner = api.Aligner(api.Graph.from_case(case))
+    d = aligner.align(case.reads, 10, 0).as_dicts()[0]
+    assert (d["failed"], d["score"], d["start"], d["end"], d["ntrace"]) == (0, 25, 0, 128, 65)
+    assert d["mappings"] == [(6738 * 2, 0, 0, 41, 65)]
+    aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,kw,nreads,rl,b", [
+    (101, dict(chop=32, snp_every=1000), 64, 5000, 10),
+    (102, dict(chop=32, bubble_every=100, inversion_every=3000), 64, 4000, 10),
+    (103, dict(chop=16, bubble_every=50, indel_frac=0.5), 48, 2000, 35),
+    (104, dict(chop=32, bubble_every=100, tangle_every=8000, tangle_levels=8), 32, 3000, 20),
+])
+def test_against_reference_run_here(api, tmp_path, seed, kw, nreads, rl, b):
+    # seeded inputs, the reference itself run on the box's CPU as the checker
+    g = synth.make_graph(seed, 60000, **kw)
+    case = synth.make_case(seed, g, nreads, rl, b=b, seed_offsets=(0, rl // 2), decoys=1)
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    assert_same(res.as_dicts(), expected, "seed %d" % seed)
+    aligner.close()
+
+
+def test_empty_and_degenerate_inputs(api, golden_dir):
+    case = gacase.read_case(os.path.join(golden_dir, "dag_snp.gacase"))
+    aligner = api.Aligner(api.Graph.from_case(case))
+    # empty batch
+    assert len(aligner.align([], 10, 0).as_dicts()) == 0
+    name, seq, seeds = case.reads[0]
+    reads = [
+        ("noseeds", seq, []),                                   # "has no seed hits" -> failed
+        ("badnode", seq, [(999999, 0, False)]),                  # unknown node: reference throws out_of_range
+        ("badpos", seq, [(seeds[0][0], len(seq) + 5, False)]),   # seed beyond the read
+        ("badchar", seq[:50] + "X" + seq[51:], seeds),           # the reference aborts on 'X'
+        ("ok", seq, seeds),
+    ]
+    d = aligner.align(reads, 10, 0).as_dicts()
+    assert [x["failed"] for x in d] == [1, 1, 1, 1, 0]
+    assert d[1]["flags"] & 2 and d[2]["flags"] & 2 and d[3]["flags"] & 4
+    aligner.close()
