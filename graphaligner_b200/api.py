@@ -34,7 +34,7 @@ EXPORTS = ["ga_create", "ga_destroy", "ga_last_error", "ga_global_error", "ga_gr
            "ga_graph_free", "ga_graph_node_count", "ga_graph_size_bp", "ga_graph_edge_count", "ga_graph_upload", "ga_align_batch",
            "ga_stage_batch", "ga_run_staged", "ga_sync", "ga_finish_staged", "ga_staged_free", "ga_cuda_stream", "ga_results_count",
            "ga_results_reads", "ga_results_mappings", "ga_results_trace", "ga_results_free", "ga_results_trace_hash", "ga_get_stats",
-           "ga_reset_stats"]
+           "ga_reset_stats", "ga_measure_int32_peak"]
 
 _lib = None
 
@@ -58,7 +58,7 @@ def load_library():
         "ga_stage_batch": (vp, [vp, C.POINTER(GaBatch)]), "ga_run_staged": (C.c_int, [vp, vp]), "ga_sync": (C.c_int, [vp]),
         "ga_finish_staged": (vp, [vp, vp]), "ga_staged_free": (None, [vp, vp]), "ga_cuda_stream": (vp, [vp]), "ga_results_count": (sz, [vp]),
         "ga_results_reads": (vp, [vp]), "ga_results_mappings": (vp, [vp]), "ga_results_trace": (vp, [vp]), "ga_results_free": (None, [vp]),
-        "ga_results_trace_hash": (u64, [vp, sz]), "ga_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_reset_stats": (C.c_int, [vp]),
+        "ga_results_trace_hash": (u64, [vp, sz]), "ga_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_reset_stats": (C.c_int, [vp]), "ga_measure_int32_peak": (C.c_double, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -255,6 +255,9 @@ class Aligner:
         s = GaStats()
         self._lib.ga_get_stats(self.ctx, C.byref(s))
         return {n: int(getattr(s, n)) for n, _ in GaStats._fields_}
+
+    def int32_peak(self):
+        return float(self._lib.ga_measure_int32_peak(self.ctx))
 
     def reset_stats(self):
         self._lib.ga_reset_stats(self.ctx)

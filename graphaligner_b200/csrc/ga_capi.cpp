@@ -349,6 +349,13 @@ int ga_get_stats(const ga_ctx* ctx, ga_stats* out)
 	return 0;
 }
 
+double ga_measure_int32_peak(ga_ctx* ctx)
+{
+	double v = 0;
+	guarded(ctx, [&]() { v = ga::MeasureInt32Peak(ctx->dev); });
+	return v;
+}
+
 int ga_reset_stats(ga_ctx* ctx)
 {
 	ctx->stats = ga::BatchStats();

@@ -23,6 +23,8 @@ void SetError(DeviceCtx* ctx, const std::string& msg);
 // copies the finalized graph's flat arrays to the device (replica per GPU)
 void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph);
 size_t GraphBytesOnDevice(DeviceCtx* ctx);
+// INT32 lane-ops per second of a dependency-free LOP3/IADD3 kernel on this device (roofline denominator)
+double MeasureInt32Peak(DeviceCtx* ctx);
 
 // plans the per-warp memory layout and copies parts + stream descriptors to the device.  `parts` must outlive the batch.
 StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth, BatchStats* stats);

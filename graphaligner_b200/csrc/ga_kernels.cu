@@ -109,6 +109,25 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * LANES];
 }
 
+// INT32 roofline probe: 8 independent dependency chains per thread of alternating LOP3 / IADD3, no memory traffic.
+// Its rate is the denominator of the integer-ALU roofline fraction.
+__global__ void ga_int32_peak_kernel(uint32_t* sink, int iters)
+{
+	uint32_t a0 = threadIdx.x, a1 = blockIdx.x, a2 = 0x9e3779b9u, a3 = 0x7f4a7c15u, a4 = 1, a5 = 2, a6 = 3, a7 = 4;
+	uint32_t k = threadIdx.x * 2654435761u + 1;
+#pragma unroll 1
+	for (int i = 0; i < iters; i++)
+	{
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+		{
+			a0 = (a0 ^ k) & (a0 | 0x55555555u); a1 = a1 + k + 3; a2 = (a2 ^ k) & (a2 | 0x33333333u); a3 = a3 + k + 5;
+			a4 = (a4 ^ k) & (a4 | 0x0f0f0f0fu); a5 = a5 + k + 7; a6 = (a6 ^ k) & (a6 | 0x00ff00ffu); a7 = a7 + k + 9;
+		}
+	}
+	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) sink[0] = a0;
+}
+
 // ---- device buffer pool -----------------------------------------------------------------------------------------
 struct Buffer
 {
@@ -251,6 +270,35 @@ void SyncDevice(DeviceCtx* ctx)
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 size_t GraphBytesOnDevice(DeviceCtx* ctx) { return ctx->graphBytes; }
+
+double MeasureInt32Peak(DeviceCtx* ctx)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	cudaDeviceProp prop;
+	GA_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+	ctx->bArenaTop.ensure(64);
+	const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 16;
+	cudaEvent_t e0, e1;
+	GA_CUDA(cudaEventCreate(&e0));
+	GA_CUDA(cudaEventCreate(&e1));
+	double best = 0;
+	for (int rep = 0; rep < 5; rep++)
+	{
+		GA_CUDA(cudaEventRecord(e0, ctx->stream));
+		ga_int32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->bArenaTop.ptr, iters);
+		GA_CUDA(cudaEventRecord(e1, ctx->stream));
+		GA_CUDA(cudaEventSynchronize(e1));
+		float ms = 0;
+		GA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		// 8 unrolled rounds x 8 chains; a LOP3 chain step is 1 instruction, an IADD3 chain step is 1 instruction
+		double ops = (double)blocks * threads * iters * 8.0 * 8.0;
+		double rate = ops / (ms * 1e-3);
+		if (rep > 0 && rate > best) best = rate;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return best;
+}
 
 template <typename T>
 static const T* uploadVec(DeviceCtx* ctx, Buffer& buf, const std::vector<T>& v)

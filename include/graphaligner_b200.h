@@ -144,6 +144,9 @@ typedef struct ga_stats
 } ga_stats;
 int ga_get_stats(const ga_ctx* ctx, ga_stats* out);   /* cumulative since ga_create / ga_reset_stats */
 int ga_reset_stats(ga_ctx* ctx);
+/* measured INT32 lane-operations per second of a dependency-free LOP3/IADD3 kernel on this GPU: the denominator of
+ * the integer-ALU roofline fraction.  Returns 0 on failure. */
+double ga_measure_int32_peak(ga_ctx* ctx);
 
 #ifdef __cplusplus
 }
