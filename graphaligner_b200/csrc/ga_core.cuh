@@ -1052,7 +1052,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES>
 GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaUmapSchedule& sch, const GaLaneMem& mem, bool active,
-	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, ga_stream_out* out)
+	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* out)
 {
 	GaStreamState st;
 	st.status = GA_OK;
@@ -1215,7 +1215,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		out->endNode = endNode;
 		out->endOff = endOff;
 		uint32_t nMoves = 0, nPath = 0;
-		ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath);
+		if (!(debugFlags & 1u)) ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath);
 		out->nMoves = nMoves;
 		out->nPathNodes = nPath;
 	}

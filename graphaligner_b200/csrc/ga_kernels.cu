@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -56,7 +57,7 @@ __constant__ GaHmmTables c_hmm;
 __constant__ GaUmapSchedule c_sched;
 
 __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
-	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth,
+	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
 	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 		mem.pathNodes = sp.pathNodes + wd.pathBase + lane;
 	}
 	ga_stream_out* out = active ? outs + tid : nullptr;
-	ga_run_stream<LANES>(g, wc, c_hmm, c_sched, mem, active, active ? streams + tid : nullptr, parts, initialBandwidth, rampBandwidth, out);
+	ga_run_stream<LANES>(g, wc, c_hmm, c_sched, mem, active, active ? streams + tid : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
 	if (!active) return;
 	// compact this stream's trace record into the arena
 	uint32_t moveWords = (out->nMoves + 15) / 16;
@@ -164,6 +165,7 @@ struct DeviceCtx
 	// batch buffers
 	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bVP, bVN, bSBS, bMoves, bPath, bArena, bArenaTop;
 	GaUmapSchedule sched;
+	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	// pinned staging
 	void* pinnedOut = nullptr;
 	size_t pinnedOutCap = 0;
@@ -245,6 +247,7 @@ DeviceCtx* CreateDevice(int device)
 	GaHmmTables hmm = makeHmmTables();
 	GA_CUDA(cudaMemcpyToSymbol(c_hmm, &hmm, sizeof(hmm)));
 	ctx->sched = probeUmapSchedule(70000);
+	if (const char* f = getenv("GA_DEBUG_FLAGS")) ctx->debugFlags = (uint32_t)atoi(f);
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
 	return ctx;
 }
@@ -460,7 +463,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	const int threads = 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
 	ga_align_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
+		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
 		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 	GA_CUDA(cudaGetLastError());
 	sb->launches++;
