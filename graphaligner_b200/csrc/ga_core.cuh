@@ -1,8 +1,9 @@
 // Per-stream banded bit-parallel DP + traceback: the device-side algorithm.
 //
-// One GPU thread owns one DP stream (one direction of one read/seed pair); the 32 streams of a warp run the
-// slice loop in lock step so that their column history can be interleaved lane-by-lane (coalesced 8-byte
-// stores) and so that __reduce_*_sync can size the shared slab.  All arithmetic is integer/bitwise except the
+// One GPU thread owns one DP stream (one direction of one read/seed pair); the LANES (<= 32) streams of a warp
+// run the slice loop in lock step so that their column history can be interleaved lane-by-lane (coalesced
+// 16-byte stores) and so that __reduce_*_sync can size the shared slab.  LANES is chosen per batch: 32 when
+// there are enough streams to fill the GPU, fewer when the batch is small and per-stream latency decides.  All arithmetic is integer/bitwise except the
 // 2-state correctness HMM, which only adds/compares host-precomputed doubles (no FMA contraction possible).
 //
 // What is reproduced (reference = /root/reference):
@@ -40,7 +41,7 @@
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
 #define GA_HDR_WORDS 6u         // slabOff, ncols, nodeOff, nNodes, minScore, flags
-#define GA_HN_WORDS 3u          // node, colStart, nodeMin
+#define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
 
 struct GaHmmTables
 {
@@ -50,34 +51,88 @@ struct GaHmmTables
 	double startCorrect, startFalse;
 };
 
+#ifndef __CUDACC__
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+
 // per-lane memory; every pointer is already offset by the lane, element i lives at p[i * LANES]
 struct GaLaneMem
 {
-	uint32_t* tiny[2];
-	uint32_t* hash[2];
+	uint32_t* tiny[2];   // frozen end state per band column, current / previous slice
+	uint64_t* hash[2];   // node -> band slot, (node << 32 | stamp << 16 | slot)
 	uint64_t* heap;
 	uint32_t* indeg;
 	uint32_t* order;
+	uint32_t* nWlo;      // per band node of the current slice: nodeStart (low / high word) and its first column
+	uint32_t* nWhi;      //   in the previous slice's tiny array (0xffffffff = not in the previous band)
+	uint32_t* nPcs;
 	uint32_t* hdr;
 	uint32_t* histNode;
-	uint64_t* colVP;
-	uint64_t* colVN;
-	int32_t* colSBS;
+	uint4* col;          // column history, two 16-byte halves per column: {VP, VN} and {sbs, scoreEnd, -, -}
 	uint32_t* moves;
 	uint32_t* pathNodes;
-	uint32_t* ubkt;     // unordered_map emulation: bucket -> "before" node
-	uint32_t* unext;    // unordered_map emulation: forward list links
-	uint32_t* uorder;   // iteration order of the previous slice's node map
+	uint32_t* ubkt;      // unordered_map emulation: bucket -> "before" node
+	uint32_t* unext;     // unordered_map emulation: forward list links
+	uint32_t* uorder;    // iteration order of the previous slice's node map
+	const uint4* peq;    // this stream's match masks, two 16-byte halves per slice: {A, C} and {G, T} (not interleaved)
 };
 
 #define GA_HDR(s, f) mem.hdr[(size_t)((s) * GA_HDR_WORDS + (f)) * LANES]
 #define GA_HN(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
+#define GA_NOT_IN_PREV 0xffffffffu
 
 struct GaCol
 {
 	uint64_t VP, VN;
 	int32_t sbs, scoreEnd;
 };
+
+template <int LANES>
+GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c)
+{
+	uint4 a, b;
+	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
+	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
+	mem.col[(size_t)(col * 2) * LANES] = a;
+	mem.col[(size_t)(col * 2 + 1) * LANES] = b;
+}
+
+template <int LANES>
+GA_DEV GaCol ga_col_load(const GaLaneMem& mem, uint32_t col)
+{
+	uint4 a = mem.col[(size_t)(col * 2) * LANES];
+	uint4 b = mem.col[(size_t)(col * 2 + 1) * LANES];
+	GaCol c;
+	c.VP = (uint64_t)a.x | ((uint64_t)a.y << 32);
+	c.VN = (uint64_t)a.z | ((uint64_t)a.w << 32);
+	c.sbs = (int32_t)b.x;
+	c.scoreEnd = (int32_t)b.y;
+	return c;
+}
+
+template <int LANES>
+GA_DEV int32_t ga_col_load_sbs(const GaLaneMem& mem, uint32_t col)
+{
+	return (int32_t)mem.col[(size_t)(col * 2 + 1) * LANES].x;
+}
+
+template <int LANES>
+GA_DEV void ga_col_store_sbs(const GaLaneMem& mem, uint32_t col, int32_t sbs)
+{
+	uint4 b;
+	b.x = (uint32_t)sbs; b.y = 0; b.z = 0; b.w = 0;
+	mem.col[(size_t)(col * 2 + 1) * LANES] = b;
+}
+
+template <int LANES>
+GA_DEV void ga_col_prefetch(const GaLaneMem& mem, uint32_t col)
+{
+#ifdef __CUDACC__
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * 2) * LANES));
+#else
+	(void)mem; (void)col;
+#endif
+}
 
 // tiny = frozen end state of a column, cf. reference TinySlice (NodeSlice.h:26-31):
 // bit0 VP63, bit1 VN63, bit2 scoreBeforeExists of the column, bits 3.. scoreEnd
@@ -176,25 +231,24 @@ GA_DEV int32_t ga_col_value(uint64_t VP, uint64_t VN, int32_t sbs, int row)
 
 // ---- open-addressing node -> band-slot table, stamped per slice so it never needs clearing ----------------
 template <int LANES>
-GA_DEV int ga_hash_find(const uint32_t* table, uint32_t hashMask, uint32_t stamp, const uint32_t* histNode, uint32_t nodeOff, uint32_t node)
+GA_DEV int ga_hash_find(const uint64_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node)
 {
 	uint32_t h = (node * 2654435761u) & hashMask;
 	while (true)
 	{
-		uint32_t e = table[(size_t)h * LANES];
-		if ((e >> 16) != stamp) return -1;
-		uint32_t slot = e & 0xffffu;
-		if (histNode[(size_t)((nodeOff + slot) * GA_HN_WORDS) * LANES] == node) return (int)slot;
+		uint64_t e = table[(size_t)h * LANES];
+		if (((uint32_t)(e >> 16) & 0xffffu) != stamp) return -1;
+		if ((uint32_t)(e >> 32) == node) return (int)(e & 0xffffu);
 		h = (h + 1) & hashMask;
 	}
 }
 
 template <int LANES>
-GA_DEV void ga_hash_insert(uint32_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node, uint32_t slot)
+GA_DEV void ga_hash_insert(uint64_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node, uint32_t slot)
 {
 	uint32_t h = (node * 2654435761u) & hashMask;
-	while ((table[(size_t)h * LANES] >> 16) == stamp) h = (h + 1) & hashMask;
-	table[(size_t)h * LANES] = (stamp << 16) | slot;
+	while (((uint32_t)(table[(size_t)h * LANES] >> 16) & 0xffffu) == stamp) h = (h + 1) & hashMask;
+	table[(size_t)h * LANES] = ((uint64_t)node << 32) | ((uint64_t)stamp << 16) | slot;
 }
 
 // ---- std::priority_queue<NodeWithPriority, vector, greater<>> as libstdc++ implements it ----------------------
@@ -387,11 +441,31 @@ GA_DEV uint32_t ga_exact_code(uint8_t c)
 
 // ------------------------------------------------------------------------------------------------------------
 // Band selection for slice s from slice s-1 (GraphAligner.h:1110-1159).  Appends the band's node list to the
-// node history at nodeOff and fills hashCur.  Returns the number of band nodes; ncols/by reference.
+// node history at nodeOff (in the reference's band order), fills hashCur and the per-node scratch records.
+// Returns the number of band nodes.
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES>
-GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaUmapSchedule& sch, const GaLaneMem& mem, GaStreamState& st, int s, int bandwidth,
-	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, uint32_t* hashCur, uint32_t stampCur, uint32_t nodeOff, uint32_t& ncolsOut)
+GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, uint64_t* hashCur, uint32_t stampCur,
+	uint32_t nodeOff, uint32_t& nc, uint32_t& ncols, uint32_t node, uint64_t wStart, uint32_t len, uint32_t pcs)
+{
+	if (nc >= caps.maxNodes) { st.status = GA_ERR_NODE_OVERFLOW; return false; }
+	if (nodeOff + nc >= caps.histNodes) { st.status = GA_ERR_HIST_OVERFLOW; return false; }
+	GA_HN(nodeOff + nc, 0) = node;
+	GA_HN(nodeOff + nc, 1) = ncols;
+	GA_HN(nodeOff + nc, 3) = len;
+	mem.nWlo[(size_t)nc * LANES] = (uint32_t)wStart;
+	mem.nWhi[(size_t)nc * LANES] = (uint32_t)(wStart >> 32);
+	mem.nPcs[(size_t)nc * LANES] = pcs;
+	ga_hash_insert<LANES>(hashCur, caps.hashSize - 1, stampCur, node, nc);
+	nc++;
+	ncols += len;
+	if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return false; }
+	return true;
+}
+
+template <int LANES>
+GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaUmapSchedule& sch, const GaLaneMem& mem, GaStreamState& st, int bandwidth,
+	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, const uint64_t* hashPrev, uint32_t stampPrev, uint64_t* hashCur, uint32_t stampCur, uint32_t nodeOff, uint32_t& ncolsOut)
 {
 	const uint32_t hashMask = caps.hashSize - 1;
 	const int32_t expand = bandwidth + 64;
@@ -406,18 +480,12 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		int32_t nodeMin = (int32_t)GA_HN(pNodeOff + i, 2);
 		if (nodeMin > st.prevMin + bandwidth) continue;
 		uint32_t node = GA_HN(pNodeOff + i, 0);
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
-		if (nc >= caps.maxNodes || nodeOff + nc >= caps.histNodes) { st.status = nc >= caps.maxNodes ? GA_ERR_NODE_OVERFLOW : GA_ERR_HIST_OVERFLOW; return -1; }
-		GA_HN(nodeOff + nc, 0) = node;
-		GA_HN(nodeOff + nc, 1) = ncols;
-		ga_hash_insert<LANES>(hashCur, hashMask, stampCur, node, nc);
-		nc++;
-		ncols += len;
-		if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return -1; }
 		uint32_t pcs = GA_HN(pNodeOff + i, 1);
+		uint32_t len = GA_HN(pNodeOff + i, 3);
+		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, stampCur, nodeOff, nc, ncols, node, g.nodeStart[node], len, pcs)) return -1;
 		int32_t endscore = ga_tiny_score(tinyPrev[(size_t)(pcs + len - 1) * LANES]);
 		if (endscore > st.prevMin + expand) continue;
-		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(endscore - st.prevMin + 1) << 32) | g.outAdj[e]);
@@ -430,16 +498,14 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		if (prio > expand) break;
 		ga_heap_pop<LANES>(mem.heap, heapN);
 		uint32_t node = (uint32_t)top;
-		if (ga_hash_find<LANES>(hashCur, hashMask, stampCur, mem.histNode, nodeOff, node) >= 0) continue;
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
-		if (nc >= caps.maxNodes || nodeOff + nc >= caps.histNodes) { st.status = nc >= caps.maxNodes ? GA_ERR_NODE_OVERFLOW : GA_ERR_HIST_OVERFLOW; return -1; }
-		GA_HN(nodeOff + nc, 0) = node;
-		GA_HN(nodeOff + nc, 1) = ncols;
-		ga_hash_insert<LANES>(hashCur, hashMask, stampCur, node, nc);
-		nc++;
-		ncols += len;
-		if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return -1; }
-		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		if (ga_hash_find<LANES>(hashCur, hashMask, stampCur, node) >= 0) continue;
+		uint64_t wStart = g.nodeStart[node];
+		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - wStart);
+		// not kept, but it may still sit in the previous band (its minimum was outside the bandwidth)
+		int pslot = ga_hash_find<LANES>(hashPrev, hashMask, stampPrev, node);
+		uint32_t pcs = pslot >= 0 ? GA_HN(pNodeOff + pslot, 1) : GA_NOT_IN_PREV;
+		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, stampCur, nodeOff, nc, ncols, node, wStart, len, pcs)) return -1;
+		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(prio + (int32_t)len) << 32) | g.outAdj[e]);
@@ -458,16 +524,18 @@ struct GaSliceCtx
 	uint32_t slabOff;             // this slice's first column in the warp slab
 	uint32_t* tinyCur;
 	const uint32_t* tinyPrev;
-	uint32_t* hashCur;
-	const uint32_t* hashPrev;
+	uint64_t* hashCur;
+	const uint64_t* hashPrev;
 	uint32_t stampCur, stampPrev;
 	uint64_t BA, BC, BG, BT;
 	uint32_t prevCharCode;        // exact code of sequence[j0-1], 4 = matches nothing
 	bool firstSlice;
 };
 
+#define GA_MAX_CACHED_IN 6
+
 // Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
-// forced = the node belongs to a cyclic block whose row -1 scores were already forced into colSBS
+// forced = the node belongs to a cyclic block whose row -1 scores were already forced into the column records
 // (ga_force_block); first = its columns hold no computed value yet.  Returns true if the node's columns changed.
 template <int LANES>
 GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, bool forced, bool first)
@@ -475,11 +543,10 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-	const uint64_t wStart = g.nodeStart[node];
-	const uint32_t len = (uint32_t)(g.nodeStart[node + 1] - wStart);
-	const int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
-	const bool inPrev = pslot >= 0;
-	const uint32_t pcs = inPrev ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
+	const uint32_t len = GA_HN(cx.nodeOff + slot, 3);
+	const uint64_t wStart = (uint64_t)mem.nWlo[(size_t)slot * LANES] | ((uint64_t)mem.nWhi[(size_t)slot * LANES] << 32);
+	const uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
+	const bool inPrev = pcs != GA_NOT_IN_PREV;
 
 	// ---- column 0 -------------------------------------------------------------------------------------------
 	uint32_t seqWord = g.seq2[wStart >> 4];
@@ -487,87 +554,99 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	uint64_t Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
 	bool previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
 	const uint32_t oldTiny0 = inPrev ? cx.tinyPrev[(size_t)pcs * LANES] : 0;
+	uint32_t oldTinyNext = (inPrev && len > 1) ? cx.tinyPrev[(size_t)(pcs + 1) * LANES] : 0;
 
+	// in-neighbours that are in the current or the previous band: column index of their last column in the
+	// current slab / in the previous tiny array (0xffffffff = absent)
+	uint32_t inCur[GA_MAX_CACHED_IN], inPrevCol[GA_MAX_CACHED_IN];
+	uint32_t nIn = 0;
 	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
-	int32_t sbs0;
-	if (forced)
-	{
-		sbs0 = mem.colSBS[(size_t)(cx.slabOff + cs) * LANES];
-	}
-	else
-	{
-		sbs0 = inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff;
-		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
-		{
-			uint32_t u = g.inAdj[e];
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
-			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
-			if (cu < 0 && pu < 0) continue;
-			uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
-			if (cu >= 0)
-			{
-				uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
-				int32_t v = mem.colSBS[(size_t)(cx.slabOff + ucs + ulen - 1) * LANES] + 1;
-				if (v < sbs0) sbs0 = v;
-			}
-			if (pu >= 0)
-			{
-				uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
-				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES]) + 1;
-				if (v < sbs0) sbs0 = v;
-			}
-		}
-	}
-	const bool sbE0 = inPrev && ga_tiny_score(oldTiny0) == sbs0;
-	bool anyIn = false;
-	GaCol c0;
-	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
-	for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+	int32_t sbs0 = forced ? ga_col_load_sbs<LANES>(mem, cx.slabOff + cs) : (inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff);
+	const uint32_t eBegin = g.inOff[node], eEnd = g.inOff[node + 1];
+	for (uint32_t e = eBegin; e < eEnd; e++)
 	{
 		uint32_t u = g.inAdj[e];
-		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
-		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
+		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
+		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
 		if (cu < 0 && pu < 0) continue;
-		uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
-		bool foundOneUp = pu >= 0;
-		int32_t upRow62 = 0;
-		uint32_t upTiny = 0;
-		if (foundOneUp)
-		{
-			uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
-			upTiny = cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES];
-			upRow62 = ga_tiny_row62(upTiny);
-		}
-		GaCol L;
-		bool LsbE;
-		uint64_t EqHere = Eq;
+		uint32_t curCol = 0xffffffffu, prevCol = 0xffffffffu;
 		if (cu >= 0)
 		{
-			uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
-			size_t idx = (size_t)(cx.slabOff + ucs + ulen - 1) * LANES;
-			L.VP = mem.colVP[idx];
-			L.VN = mem.colVN[idx];
-			L.sbs = mem.colSBS[idx];
-			uint32_t t = cx.tinyCur[(size_t)(ucs + ulen - 1) * LANES];
-			L.scoreEnd = ga_tiny_score(t);
-			LsbE = (t & 4u) != 0;
+			curCol = GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1;
+			if (!forced)
+			{
+				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + curCol) + 1;
+				if (v < sbs0) sbs0 = v;
+			}
 		}
-		else
+		if (pu >= 0)
 		{
-			// neighbour only in the previous band: synthetic source column from its end score (GraphAligner.h:1294-1301)
-			int32_t es = ga_tiny_score(upTiny);
-			L.VP = ~(uint64_t)0;
-			L.VN = 0;
-			L.sbs = es;
-			L.scoreEnd = es + 64;
-			LsbE = true;
-			EqHere &= 1;
+			prevCol = GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1;
+			if (!forced)
+			{
+				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)prevCol * LANES]) + 1;
+				if (v < sbs0) sbs0 = v;
+			}
 		}
-		GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, upRow62);
-		if (!anyIn) { c0 = cand; anyIn = true; }
-		else c0 = ga_merge_cols(c0, cand);
+		if (nIn < GA_MAX_CACHED_IN) { inCur[nIn] = curCol; inPrevCol[nIn] = prevCol; }
+		nIn++;
 	}
-	if (!anyIn)
+	const bool sbE0 = inPrev && ga_tiny_score(oldTiny0) == sbs0;
+	GaCol c0;
+	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
+	if (nIn > 0)
+	{
+		uint32_t k = 0;
+		for (uint32_t e = eBegin; e < eEnd; e++)
+		{
+			uint32_t curCol, prevCol;
+			if (nIn <= GA_MAX_CACHED_IN)
+			{
+				if (k >= nIn) break;
+				curCol = inCur[k];
+				prevCol = inPrevCol[k];
+			}
+			else
+			{
+				// high in-degree: look the neighbour up again instead of caching
+				uint32_t u = g.inAdj[e];
+				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
+				int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+				if (cu < 0 && pu < 0) continue;
+				curCol = cu >= 0 ? GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1 : 0xffffffffu;
+				prevCol = pu >= 0 ? GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1 : 0xffffffffu;
+			}
+			bool foundOneUp = prevCol != 0xffffffffu;
+			uint32_t upTiny = foundOneUp ? cx.tinyPrev[(size_t)prevCol * LANES] : 0;
+			GaCol L;
+			bool LsbE;
+			uint64_t EqHere = Eq;
+			if (curCol != 0xffffffffu)
+			{
+				L = ga_col_load<LANES>(mem, cx.slabOff + curCol);
+				uint32_t t = cx.tinyCur[(size_t)curCol * LANES];
+				L.scoreEnd = ga_tiny_score(t);
+				LsbE = (t & 4u) != 0;
+			}
+			else
+			{
+				// neighbour only in the previous band: synthetic source column from its end score (GraphAligner.h:1294-1301)
+				int32_t es = ga_tiny_score(upTiny);
+				L.VP = ~(uint64_t)0;
+				L.VN = 0;
+				L.sbs = es;
+				L.scoreEnd = es + 64;
+				LsbE = true;
+				EqHere &= 1;
+			}
+			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny));
+			if (k == 0) c0 = cand;
+			else c0 = ga_merge_cols(c0, cand);
+			k++;
+		}
+		if (inPrev && c0.sbs > ga_tiny_score(oldTiny0)) ga_vertical_merge(c0, ga_tiny_score(oldTiny0));
+	}
+	else
 	{
 		// source node (GraphAligner.h:1317-1347,1475-1488); a band node always has a band predecessor or is kept
 		if (!inPrev) { st.status = GA_ERR_INTERNAL; return false; }
@@ -583,19 +662,14 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		c0.scoreEnd = ps + 63 + (int32_t)mismatch;
 		c0.sbs = ps;
 	}
-	else if (inPrev && c0.sbs > ga_tiny_score(oldTiny0))
-	{
-		ga_vertical_merge(c0, ga_tiny_score(oldTiny0));
-	}
 	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return false; }
+	if (forced && !first)
 	{
-		size_t idx = (size_t)(cx.slabOff + cs) * LANES;
-		if (forced && !first && mem.colVP[idx] == c0.VP && mem.colVN[idx] == c0.VN) return false; // nothing upstream changed
-		mem.colVP[idx] = c0.VP;
-		mem.colVN[idx] = c0.VN;
-		mem.colSBS[idx] = c0.sbs;
-		cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
+		GaCol old = ga_col_load<LANES>(mem, cx.slabOff + cs);
+		if (old.VP == c0.VP && old.VN == c0.VN) return false;   // nothing upstream changed
 	}
+	ga_col_store<LANES>(mem, cx.slabOff + cs, c0);
+	cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
 
 	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
 	GaCol L = c0;
@@ -608,18 +682,17 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		base = (seqWord >> ((uint32_t)(w & 15) * 2)) & 3u;
 		Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
 		previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
-		uint32_t oldTiny = inPrev ? cx.tinyPrev[(size_t)(pcs + k) * LANES] : 0;
+		const uint32_t oldTiny = oldTinyNext;
+		// software prefetch of the next column's previous-slice state (address known, value independent of this step)
+		oldTinyNext = (inPrev && k + 1 < len) ? cx.tinyPrev[(size_t)(pcs + k + 1) * LANES] : 0;
 		int32_t sbsF = L.sbs + 1;
 		if (inPrev && ga_tiny_score(oldTiny) < sbsF) sbsF = ga_tiny_score(oldTiny);
-		if (forced) sbsF = mem.colSBS[(size_t)(cx.slabOff + cs + k) * LANES];
+		if (forced) sbsF = ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + k);
 		bool sbE = inPrev && ga_tiny_score(oldTiny) == sbsF;
 		GaCol c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft));
 		if (inPrev && c.sbs > ga_tiny_score(oldTiny)) ga_vertical_merge(c, ga_tiny_score(oldTiny));
 		if (c.sbs != sbsF) { st.status = GA_ERR_INTERNAL; return false; }
-		size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
-		mem.colVP[idx] = c.VP;
-		mem.colVN[idx] = c.VN;
-		mem.colSBS[idx] = c.sbs;
+		ga_col_store<LANES>(mem, cx.slabOff + cs + k, c);
 		cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
 		L = c;
 		LsbE = sbE;
@@ -630,7 +703,6 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 
 // Row -1 scores for a cyclic block of band nodes (the slots listed in order[from..to)) by shortest paths over
 // the block (forceComponentZeroRow, GraphAligner.h:1903-1995), then reset every column to the all-ones ramp.
-// The nodes of the block are re-listed in order[] by increasing first-column score (a good sweep order).
 template <int LANES>
 GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to)
 {
@@ -643,26 +715,25 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		uint32_t slot = mem.order[(size_t)q * LANES];
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
-		int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
-		uint32_t pcs = pslot >= 0 ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
-		int32_t s0 = pslot >= 0 ? ga_tiny_score(cx.tinyPrev[(size_t)pcs * LANES]) : INF;
+		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
+		uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
+		bool inPrev = pcs != GA_NOT_IN_PREV;
+		int32_t s0 = inPrev ? ga_tiny_score(cx.tinyPrev[(size_t)pcs * LANES]) : INF;
 		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
 		{
 			uint32_t u = g.inAdj[e];
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, u);
-			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, u);
-			uint32_t ulen = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]);
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
+			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
 			if (cu >= 0 && mem.indeg[(size_t)cu * LANES] == 0)
 			{
-				uint32_t ucs = GA_HN(cx.nodeOff + cu, 1);
-				int32_t v = mem.colSBS[(size_t)(cx.slabOff + ucs + ulen - 1) * LANES] + 1;
+				uint32_t ucol = GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1;
+				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + ucol) + 1;
 				if (v < s0) s0 = v;
 			}
 			if (pu >= 0)
 			{
-				uint32_t upcs = GA_HN(cx.pNodeOff + pu, 1);
-				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)(upcs + ulen - 1) * LANES]) + 1;
+				uint32_t ucol = GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1;
+				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)ucol * LANES]) + 1;
 				if (v < s0) s0 = v;
 			}
 		}
@@ -672,19 +743,19 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			if (k > 0 && v < INF)
 			{
 				v = v + 1;
-				if (pslot >= 0)
+				if (inPrev)
 				{
 					int32_t o = ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]);
 					if (o < v) v = o;
 				}
 			}
-			mem.colSBS[(size_t)(cx.slabOff + cs + k) * LANES] = v;
+			ga_col_store_sbs<LANES>(mem, cx.slabOff + cs + k, v);
 		}
 		if (v < INF)
 		{
 			for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 			{
-				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
 				if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
 				if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 				ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(v + 1) << 32) | (uint32_t)cu);
@@ -698,19 +769,18 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		uint32_t slot = (uint32_t)top;
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
 		bool endUpdated = true;
 		for (uint32_t k = 0; k < len; k++)
 		{
-			size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
-			if (mem.colSBS[idx] <= score) { endUpdated = false; break; }
-			mem.colSBS[idx] = score;
+			if (ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + k) <= score) { endUpdated = false; break; }
+			ga_col_store_sbs<LANES>(mem, cx.slabOff + cs + k, score);
 			score++;
 		}
 		if (!endUpdated) continue;
 		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 		{
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
 			if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)score << 32) | (uint32_t)cu);
@@ -720,23 +790,20 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 	for (uint32_t q = from; q < to; q++)
 	{
 		uint32_t slot = mem.order[(size_t)q * LANES];
-		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
-		int pslot = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, mem.histNode, cx.pNodeOff, node);
-		uint32_t pcs = pslot >= 0 ? GA_HN(cx.pNodeOff + pslot, 1) : 0;
+		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
+		uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
+		bool inPrev = pcs != GA_NOT_IN_PREV;
 		for (uint32_t k = 0; k < len; k++)
 		{
-			size_t idx = (size_t)(cx.slabOff + cs + k) * LANES;
 			GaCol c;
 			c.VP = ~(uint64_t)0;
 			c.VN = 0;
-			c.sbs = mem.colSBS[idx];
+			c.sbs = ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + k);
 			if (c.sbs >= INF) { st.status = GA_ERR_INTERNAL; return; }
 			c.scoreEnd = c.sbs + 64;
-			bool sbE = pslot >= 0 && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
-			mem.colVP[idx] = c.VP;
-			mem.colVN[idx] = c.VN;
+			bool sbE = inPrev && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
+			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c);
 			cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
 		}
 	}
@@ -750,20 +817,14 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 {
 	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t nc = cx.nNodes;
-	// Peq words for the 64 read characters of this slice (GraphAligner.h:2338-2351)
+	// Peq words for the 64 read characters of this slice (GraphAligner.h:2338-2351), precomputed by ga_peq_kernel
 	{
-		const uint8_t* p = st.seq + (size_t)cx.s * 64;
-		uint64_t BA = 0, BC = 0, BG = 0, BT = 0;
-		for (int i = 0; i < 64; i++)
-		{
-			uint32_t m = ga_iupac_mask(p[i]);
-			BA |= (uint64_t)(m & 1u) << i;
-			BC |= (uint64_t)((m >> 1) & 1u) << i;
-			BG |= (uint64_t)((m >> 2) & 1u) << i;
-			BT |= (uint64_t)((m >> 3) & 1u) << i;
-		}
-		cx.BA = BA; cx.BC = BC; cx.BG = BG; cx.BT = BT;
-		cx.prevCharCode = cx.s > 0 ? ga_exact_code(p[-1]) : 4;
+		uint4 a = mem.peq[(size_t)cx.s * 2], b = mem.peq[(size_t)cx.s * 2 + 1];
+		cx.BA = (uint64_t)a.x | ((uint64_t)a.y << 32);
+		cx.BC = (uint64_t)a.z | ((uint64_t)a.w << 32);
+		cx.BG = (uint64_t)b.x | ((uint64_t)b.y << 32);
+		cx.BT = (uint64_t)b.z | ((uint64_t)b.w << 32);
+		cx.prevCharCode = cx.s > 0 ? ga_exact_code(st.seq[(size_t)cx.s * 64 - 1]) : 4;
 		cx.firstSlice = cx.s == 0;
 	}
 	// in-degrees inside the band
@@ -772,9 +833,9 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	{
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t d = 0;
-		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
+		for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 		{
-			if (ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.inAdj[e]) >= 0) d++;
+			if (ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.inAdj[e]) >= 0) d++;
 		}
 		mem.indeg[(size_t)slot * LANES] = d;
 		if (d == 0) mem.order[(size_t)(ready++) * LANES] = slot;
@@ -786,9 +847,9 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		ga_calc_node<LANES>(g, caps, mem, st, cx, slot, false, true);
 		if (st.status != GA_OK) return false;
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
-		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
+		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, mem.histNode, cx.nodeOff, g.outAdj[e]);
+			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
 			if (cu < 0) continue;
 			uint32_t d = mem.indeg[(size_t)cu * LANES] - 1;
 			mem.indeg[(size_t)cu * LANES] = d;
@@ -826,9 +887,8 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	int32_t minScore = 0x7fffffff;
 	for (uint32_t slot = 0; slot < nc; slot++)
 	{
-		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
 		int32_t nodeMin = 0x7fffffff;
 		for (uint32_t k = 0; k < len; k++)
 		{
@@ -861,13 +921,9 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 // ------------------------------------------------------------------------------------------------------------
 // Traceback over the stored history (getTraceFromTable / pickBacktracePredecessor, GraphAligner.h:493-591,
 // 894-1021).  Emits 2-bit moves and the node crossed into at every node boundary, both in backward order.
+// The walk keeps the current and the left column in registers and carries the current cell's score, so a step
+// inside a node costs one 32-byte column load (prefetched) instead of a chain of lookups.
 // ------------------------------------------------------------------------------------------------------------
-template <int LANES>
-struct GaSliceView
-{
-	uint32_t slabOff, nodeOff, nNodes;
-};
-
 template <int LANES>
 GA_DEV int ga_slice_find(const GaLaneMem& mem, uint32_t nodeOff, uint32_t nNodes, uint32_t node)
 {
@@ -881,14 +937,14 @@ GA_DEV int ga_slice_find(const GaLaneMem& mem, uint32_t nodeOff, uint32_t nNodes
 // value of (node, off) at `row` of slice s, or `maxv` when the node is not in that slice's band
 // (getValueOrMax, GraphAligner.h:2008-2017).  s == -1 is the initial slice: seed node = 0, else maxv.
 template <int LANES>
-GA_DEV int32_t ga_hist_value(const ga_graph_view& g, const GaLaneMem& mem, const GaStreamState& st, int s, uint32_t node, uint32_t off, int row, int32_t maxv)
+GA_DEV int32_t ga_hist_value(const GaLaneMem& mem, const GaStreamState& st, int s, uint32_t node, uint32_t off, int row, int32_t maxv)
 {
 	if (s < 0) return node == st.startNode ? 0 : maxv;
 	uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
 	int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
 	if (slot < 0) return maxv;
-	size_t idx = (size_t)(GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1) + off) * LANES;
-	return ga_col_value(mem.colVP[idx], mem.colVN[idx], mem.colSBS[idx], row);
+	GaCol c = ga_col_load<LANES>(mem, GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1) + off);
+	return ga_col_value(c.VP, c.VN, c.sbs, row);
 }
 
 template <int LANES>
@@ -896,53 +952,73 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 {
 	uint32_t nMoves = 0, nPath = 0;
 	uint32_t curWord = 0;
-	int64_t j = (int64_t)nSlices * 64 - 1;
+	int s = nSlices - 1;
+	int row = 63;
 	const int32_t maxv = (int32_t)st.partLen;
+	// per (slice, node) cache: index of the node's first column in the slab
+	uint32_t colBase = 0;
+	uint64_t wStart = 0;
+	bool reload = true;      // slice or node changed: re-resolve colBase and reload both columns
+	GaCol cur, left;
+	cur.VP = cur.VN = 0; cur.sbs = cur.scoreEnd = 0;
+	left = cur;
+	int32_t here = 0;
+	bool haveHere = false;
 	while (true)
 	{
-		int s = (int)(j >> 6);
-		int row = (int)(j & 63);
-		int32_t here = ga_hist_value<LANES>(g, mem, st, s, node, off, row, maxv);
+		if (reload)
+		{
+			uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
+			int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
+			if (slot < 0) { st.status = GA_ERR_TRACE; break; }
+			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
+			wStart = g.nodeStart[node];
+			cur = ga_col_load<LANES>(mem, colBase + off);
+			if (off > 0) left = ga_col_load<LANES>(mem, colBase + off - 1);
+			if (off > 1) ga_col_prefetch<LANES>(mem, colBase + off - 2);
+			if (off > 2) ga_col_prefetch<LANES>(mem, colBase + off - 3);
+			if (!haveHere) { here = ga_col_value(cur.VP, cur.VN, cur.sbs, row); haveHere = true; }
+			reload = false;
+		}
+		const int64_t j = (int64_t)s * 64 + row;
 		uint32_t move = 4;
 		uint32_t nnode = node, noff = off;
+		int32_t nhere = 0;
 		if (j == 0 && node == st.startNode && (here == 0 || here == 1))
 		{
 			move = GA_MOVE_END;
 		}
 		else
 		{
-			uint64_t w = g.nodeStart[node] + off;
-			bool match = ((ga_iupac_mask(st.seq[j]) >> ga_base(g, w)) & 1u) != 0;
+			bool match = ((ga_iupac_mask(st.seq[j]) >> ga_base(g, wStart + off)) & 1u) != 0;
+			int32_t diagWant = match ? here : here - 1;
 			if (off == 0)
 			{
-				for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1] && move == 4; e++)
+				for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 				{
 					uint32_t u = g.inAdj[e];
 					uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-					int32_t hs = ga_hist_value<LANES>(g, mem, st, s, u, uoff, row, maxv);
-					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; break; }
-					int32_t ds = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, u, uoff, row - 1, maxv);
-					if (ds == (match ? here : here - 1)) { move = GA_MOVE_D; nnode = u; noff = uoff; break; }
+					int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
+					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
+					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
+					if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
 				}
 			}
 			else
 			{
-				int32_t hs = ga_hist_value<LANES>(g, mem, st, s, node, off - 1, row, maxv);
-				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; }
+				int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
+				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
 				else
 				{
-					int32_t ds = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, node, off - 1, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, node, off - 1, row - 1, maxv);
-					if (ds == (match ? here : here - 1)) { move = GA_MOVE_D; noff = off - 1; }
+					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off - 1, 63, maxv) : ga_col_value(left.VP, left.VN, left.sbs, row - 1);
+					if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
 				}
 			}
 			if (move == 4)
 			{
-				int32_t us = row == 0 ? ga_hist_value<LANES>(g, mem, st, s - 1, node, off, 63, maxv) : ga_hist_value<LANES>(g, mem, st, s, node, off, row - 1, maxv);
-				if (us == here - 1) move = GA_MOVE_V;
+				int32_t us = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off, 63, maxv) : ga_col_value(cur.VP, cur.VN, cur.sbs, row - 1);
+				if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
 			}
-#ifdef GA_HOST_DEBUG
-			if (move == 4) fprintf(stderr, "trace fail at node %u off %u j %ld here %d startNode %u inDeg %u\n", node, off, (long)j, here, st.startNode, g.inOff[node + 1] - g.inOff[node]);
-#endif
 			if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
 		}
 		// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
@@ -952,16 +1028,30 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		nMoves++;
 		if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
 		if (move == GA_MOVE_END) break;
-		if (move != GA_MOVE_V && off == 0)
+		here = nhere;
+		if (move != GA_MOVE_V)
 		{
-			if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
-			mem.pathNodes[(size_t)nPath * LANES] = nnode;
-			nPath++;
+			if (off == 0)
+			{
+				if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+				mem.pathNodes[(size_t)nPath * LANES] = nnode;
+				nPath++;
+				reload = true;
+			}
+			else
+			{
+				cur = left;
+				if (noff > 0) left = ga_col_load<LANES>(mem, colBase + noff - 1);
+				if (noff > 2) ga_col_prefetch<LANES>(mem, colBase + noff - 3);
+			}
 		}
-		if (move != GA_MOVE_H) j--;
+		if (move != GA_MOVE_H)
+		{
+			row--;
+			if (row < 0) { row = 63; s--; reload = true; }
+		}
 		node = nnode;
 		off = noff;
-		if (j < 0) { st.status = GA_ERR_TRACE; break; }
 	}
 	if (nMoves & 15) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
 	nMovesOut = nMoves;
@@ -1046,6 +1136,21 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 	return -1;
 }
 
+// Match masks of 64 read characters: bit i of {A,C,G,T} word = characterMatch(read[i], base) with IUPAC codes
+// (GraphAligner.h:2338-2351).  Used by the Peq pre-pass kernel.
+GA_DEV void ga_peq_words(const uint8_t* p, uint64_t& BA, uint64_t& BC, uint64_t& BG, uint64_t& BT)
+{
+	BA = BC = BG = BT = 0;
+	for (int i = 0; i < 64; i++)
+	{
+		uint32_t m = ga_iupac_mask(p[i]);
+		BA |= (uint64_t)(m & 1u) << i;
+		BC |= (uint64_t)((m >> 1) & 1u) << i;
+		BG |= (uint64_t)((m >> 2) & 1u) << i;
+		BT |= (uint64_t)((m >> 3) & 1u) << i;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Whole stream: forward slices (lock step across the warp), end trimming, tie list, traceback.
 // `active` = this lane holds a stream.  warpColTop is the warp-uniform bump pointer into the column slab.
@@ -1084,6 +1189,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			GA_HN(0, 0) = st.startNode;
 			GA_HN(0, 1) = 0;
 			GA_HN(0, 2) = 0;
+			GA_HN(0, 3) = len;
 			ga_hash_insert<LANES>(mem.hash[0], hashMask, 1, st.startNode, 0);
 			for (uint32_t k = 0; k < len; k++) mem.tiny[0][(size_t)k * LANES] = 0;
 			pNodes = 1;
@@ -1105,7 +1211,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		{
 			// slice 0 always runs with rampBandwidth (rampUntil = 0, GraphAligner.h:2612)
 			int bandwidth = (s == 0) ? rampBandwidth : initialBandwidth;
-			nc = ga_select_band<LANES>(g, caps, sch, mem, st, s, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tc], stampCur, nodeOff, ncols);
+			nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], stampPrev, mem.hash[tc], stampCur, nodeOff, ncols);
 			if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 		}
 		uint32_t maxc = GA_WARP_MAX(ncols);
@@ -1186,11 +1292,11 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
 			uint32_t node = GA_HN(nodeOff + slot, 0);
 			uint32_t cs = GA_HN(nodeOff + slot, 1);
-			uint32_t len = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]);
+			uint32_t len = GA_HN(nodeOff + slot, 3);
 			for (uint32_t k = 0; k < len; k++)
 			{
-				size_t idx = (size_t)(slabOff + cs + k) * LANES;
-				int32_t v = mem.colSBS[idx] + (int32_t)GA_POPC(mem.colVP[idx]) - (int32_t)GA_POPC(mem.colVN[idx]);
+				GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+				int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
 				if (v != minScore) continue;
 				if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
 				nTies++;
@@ -1202,11 +1308,11 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		uint32_t endNode = GA_HN(nodeOff + endSlot, 0), endOff = 0;
 		{
 			uint32_t cs = GA_HN(nodeOff + endSlot, 1);
-			uint32_t len = (uint32_t)(g.nodeStart[endNode + 1] - g.nodeStart[endNode]);
+			uint32_t len = GA_HN(nodeOff + endSlot, 3);
 			for (uint32_t k = 0; k < len; k++)
 			{
-				size_t idx = (size_t)(slabOff + cs + k) * LANES;
-				int32_t v = mem.colSBS[idx] + (int32_t)GA_POPC(mem.colVP[idx]) - (int32_t)GA_POPC(mem.colVN[idx]);
+				GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+				int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
 				if (v == minScore) endOff = k;
 			}
 		}

@@ -20,7 +20,6 @@ namespace ga
 
 #define GA_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } } while (0)
 
-static const int LANES = 32;
 
 struct WarpDesc
 {
@@ -38,24 +37,44 @@ struct WarpDesc
 
 struct ScratchPtrs
 {
-	uint32_t* tiny;     // [warp][2][maxCols][LANES]
-	uint32_t* hash;     // [warp][2][hashSize][LANES]
-	uint64_t* heap;     // [warp][maxQueue][LANES]
-	uint32_t* nodeTmp;  // [warp][4][maxNodes][LANES]  indeg, order, unext, uorder
-	uint32_t* ubkt;     // [warp][ubktSize][LANES]
+	uint32_t* tiny;     // [warp][2][maxCols][S]
+	uint64_t* hash;     // [warp][2][hashSize][S]
+	uint64_t* heap;     // [warp][maxQueue][S]
+	uint32_t* nodeTmp;  // [warp][7][maxNodes][S]  indeg, order, unext, uorder, nWlo, nWhi, nPcs
+	uint32_t* ubkt;     // [warp][ubktSize][S]
 	uint32_t* hdr;
 	uint32_t* histNode;
-	uint64_t* colVP;
-	uint64_t* colVN;
-	int32_t* colSBS;
+	uint4* col;         // [warp slab][2][S]
 	uint32_t* moves;
 	uint32_t* pathNodes;
+	const uint4* peq;   // [stream][slice][2]
+	const uint64_t* peqOff;  // per stream: first uint4 of its masks
 	uint32_t ubktSize;
 };
 
 __constant__ GaHmmTables c_hmm;
 __constant__ GaUmapSchedule c_sched;
 
+// Match masks for every 64-row slice of every stream: one thread per (stream, slice), 64 bytes in, 32 bytes out.
+__global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq)
+{
+	const uint32_t stream = blockIdx.y;
+	if (stream >= nStreams) return;
+	const uint32_t nslices = streams[stream].partLen / 64;
+	const uint8_t* base = parts + streams[stream].seqOff;
+	for (uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x; sl < nslices; sl += gridDim.x * blockDim.x)
+	{
+		uint64_t A, C, G, T;
+		ga_peq_words(base + (size_t)sl * 64, A, C, G, T);
+		uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
+		dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
+		dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
+	}
+}
+
+// S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
+// less divergence; big batches run with S = 32 for full lane utilisation.
+template <int S>
 __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
 	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
 	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
@@ -63,8 +82,10 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t warp = tid >> 5;
 	const uint32_t lane = tid & 31;
-	if (warp * 32 >= nStreams) return;   // whole warp out of range (warp-uniform)
-	const bool active = tid < nStreams;
+	if ((uint64_t)warp * S >= nStreams) return;   // whole warp out of range (warp-uniform)
+	const uint32_t stream = warp * S + lane;
+	const bool active = lane < S && stream < nStreams;
+	const uint32_t ml = lane < S ? lane : 0;      // idle lanes alias lane 0's addresses but never touch memory
 	const WarpDesc wd = warpDescs[warp];
 	ga_caps wc = caps;
 	wc.maxSlices = wd.maxSlices;
@@ -75,26 +96,28 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	GaLaneMem mem;
 	{
 		size_t w = warp;
-		mem.tiny[0] = sp.tiny + (w * 2 + 0) * caps.maxCols * LANES + lane;
-		mem.tiny[1] = sp.tiny + (w * 2 + 1) * caps.maxCols * LANES + lane;
-		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * LANES + lane;
-		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * LANES + lane;
-		mem.heap = sp.heap + w * caps.maxQueue * LANES + lane;
-		mem.indeg = sp.nodeTmp + (w * 4 + 0) * caps.maxNodes * LANES + lane;
-		mem.order = sp.nodeTmp + (w * 4 + 1) * caps.maxNodes * LANES + lane;
-		mem.unext = sp.nodeTmp + (w * 4 + 2) * caps.maxNodes * LANES + lane;
-		mem.uorder = sp.nodeTmp + (w * 4 + 3) * caps.maxNodes * LANES + lane;
-		mem.ubkt = sp.ubkt + w * sp.ubktSize * LANES + lane;
-		mem.hdr = sp.hdr + wd.hdrBase + lane;
-		mem.histNode = sp.histNode + wd.hnBase + lane;
-		mem.colVP = sp.colVP + wd.colBase * LANES + lane;
-		mem.colVN = sp.colVN + wd.colBase * LANES + lane;
-		mem.colSBS = sp.colSBS + wd.colBase * LANES + lane;
-		mem.moves = sp.moves + wd.movesBase + lane;
-		mem.pathNodes = sp.pathNodes + wd.pathBase + lane;
+		mem.tiny[0] = sp.tiny + (w * 2 + 0) * caps.maxCols * S + ml;
+		mem.tiny[1] = sp.tiny + (w * 2 + 1) * caps.maxCols * S + ml;
+		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S + ml;
+		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S + ml;
+		mem.heap = sp.heap + w * caps.maxQueue * S + ml;
+		mem.indeg = sp.nodeTmp + (w * 7 + 0) * caps.maxNodes * S + ml;
+		mem.order = sp.nodeTmp + (w * 7 + 1) * caps.maxNodes * S + ml;
+		mem.unext = sp.nodeTmp + (w * 7 + 2) * caps.maxNodes * S + ml;
+		mem.uorder = sp.nodeTmp + (w * 7 + 3) * caps.maxNodes * S + ml;
+		mem.nWlo = sp.nodeTmp + (w * 7 + 4) * caps.maxNodes * S + ml;
+		mem.nWhi = sp.nodeTmp + (w * 7 + 5) * caps.maxNodes * S + ml;
+		mem.nPcs = sp.nodeTmp + (w * 7 + 6) * caps.maxNodes * S + ml;
+		mem.ubkt = sp.ubkt + w * sp.ubktSize * S + ml;
+		mem.hdr = sp.hdr + wd.hdrBase + ml;
+		mem.histNode = sp.histNode + wd.hnBase + ml;
+		mem.col = sp.col + wd.colBase * 2 * S + ml;
+		mem.moves = sp.moves + wd.movesBase + ml;
+		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
+		mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
 	}
-	ga_stream_out* out = active ? outs + tid : nullptr;
-	ga_run_stream<LANES>(g, wc, c_hmm, c_sched, mem, active, active ? streams + tid : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
+	ga_stream_out* out = active ? outs + stream : nullptr;
+	ga_run_stream<S>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
 	if (!active) return;
 	// compact this stream's trace record into the arena
 	uint32_t moveWords = (out->nMoves + 15) / 16;
@@ -106,8 +129,8 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 		if (out->status == GA_OK) out->status = GA_ERR_TRACE_OVERFLOW;
 		return;
 	}
-	for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * LANES];
-	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * LANES];
+	for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * S];
+	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * S];
 }
 
 // INT32 roofline probe: 8 independent dependency chains per thread of alternating LOP3 / IADD3, no memory traffic.
@@ -163,9 +186,11 @@ struct DeviceCtx
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bVP, bVN, bSBS, bMoves, bPath, bArena, bArenaTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bArena, bArenaTop;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
+	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
+	int smCount = 148;
 	// pinned staging
 	void* pinnedOut = nullptr;
 	size_t pinnedOutCap = 0;
@@ -184,6 +209,8 @@ struct StagedBatch
 	// host copy of the inputs, kept for retries
 	const std::vector<uint8_t>* hostParts = nullptr;
 	int capScale = 1;
+	int S = 32;            // streams per warp
+	size_t peqWords = 0;
 };
 
 static GaHmmTables makeHmmTables()
@@ -248,6 +275,12 @@ DeviceCtx* CreateDevice(int device)
 	GA_CUDA(cudaMemcpyToSymbol(c_hmm, &hmm, sizeof(hmm)));
 	ctx->sched = probeUmapSchedule(70000);
 	if (const char* f = getenv("GA_DEBUG_FLAGS")) ctx->debugFlags = (uint32_t)atoi(f);
+	if (const char* f = getenv("GA_STREAMS_PER_WARP")) ctx->forceS = atoi(f);
+	{
+		cudaDeviceProp prop;
+		GA_CUDA(cudaGetDeviceProperties(&prop, device));
+		ctx->smCount = prop.multiProcessorCount;
+	}
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
 	return ctx;
 }
@@ -257,7 +290,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bVP, &ctx->bVN, &ctx->bSBS, &ctx->bMoves, &ctx->bPath, &ctx->bArena, &ctx->bArenaTop };
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bArena, &ctx->bArenaTop };
 	for (Buffer* b : all) b->release();
 	if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -367,27 +400,42 @@ StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& strea
 	return sb;
 }
 
+static int pickStreamsPerWarp(DeviceCtx* ctx, size_t nStreams)
+{
+	// enough warps to give every SM sub-partition several to switch between; full warps once the batch is large
+	if (ctx->forceS > 0) return ctx->forceS;
+	const size_t wantWarps = (size_t)ctx->smCount * 16;
+	int S = 32;
+	while (S > 4 && (nStreams + S - 1) / S < wantWarps) S >>= 1;
+	return S;
+}
+
 static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 {
 	const size_t n = sb->sorted.size();
 	const int scale = sb->capScale;
 	sb->caps = defaultCaps(sb->b, sb->B, scale);
 	ga_caps& caps = sb->caps;
-	const size_t nWarps = (n + 31) / 32;
+	sb->S = pickStreamsPerWarp(ctx, n);
+	const size_t S = (size_t)sb->S;
+	const size_t nWarps = (n + S - 1) / S;
 	sb->nWarps = nWarps;
 	const int bw = std::max(sb->b, sb->B);
 	const uint64_t colsGuess = (uint64_t)(3 * (bw + 64) + 96) * scale;
 	const uint64_t nodesGuess = (colsGuess / 6 + 16);
 	std::vector<WarpDesc> wds(nWarps);
-	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0;
+	std::vector<uint64_t> peqOff(n);
+	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0, peqTop = 0;
 	sb->arenaCap = 0;
 	for (size_t w = 0; w < nWarps; w++)
 	{
 		uint32_t maxLen = 0;
-		for (size_t i = w * 32; i < std::min(n, w * 32 + 32); i++)
+		for (size_t i = w * S; i < std::min(n, w * S + S); i++)
 		{
 			maxLen = std::max(maxLen, sb->sorted[i].partLen);
 			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + (uint64_t)sb->sorted[i].partLen * 2 + 64;
+			peqOff[i] = peqTop;
+			peqTop += (uint64_t)(sb->sorted[i].partLen / 64) * 2;
 		}
 		uint32_t nslices = maxLen / 64;
 		WarpDesc& d = wds[w];
@@ -399,14 +447,15 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		d.colBase = colTop;
 		colTop += d.warpCols;
 		d.hdrBase = hdrTop;
-		hdrTop += (uint64_t)d.maxSlices * GA_HDR_WORDS * LANES;
+		hdrTop += (uint64_t)d.maxSlices * GA_HDR_WORDS * S;
 		d.hnBase = hnTop;
-		hnTop += (uint64_t)d.histNodes * GA_HN_WORDS * LANES;
+		hnTop += (uint64_t)d.histNodes * GA_HN_WORDS * S;
 		d.movesBase = movesTop;
-		movesTop += (uint64_t)(d.maxMoves / 16 + 1) * LANES;
+		movesTop += (uint64_t)(d.maxMoves / 16 + 1) * S;
 		d.pathBase = pathTop;
-		pathTop += (uint64_t)d.maxPathNodes * LANES;
+		pathTop += (uint64_t)d.maxPathNodes * S;
 	}
+	sb->peqWords = peqTop;
 	uint32_t ubktSize = 13;
 	for (uint32_t i = 0; i < ctx->sched.n; i++)
 	{
@@ -418,38 +467,50 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
 	ctx->bOut.ensure(n * sizeof(ga_stream_out));
 	ctx->bWd.ensure(nWarps * sizeof(WarpDesc));
-	ctx->bTiny.ensure(nWarps * 2 * caps.maxCols * LANES * sizeof(uint32_t));
-	ctx->bHash.ensure(nWarps * 2 * (size_t)caps.hashSize * LANES * sizeof(uint32_t));
-	ctx->bHeap.ensure(nWarps * (size_t)caps.maxQueue * LANES * sizeof(uint64_t));
-	ctx->bNodeTmp.ensure(nWarps * 4 * (size_t)caps.maxNodes * LANES * sizeof(uint32_t));
-	ctx->bUbkt.ensure(nWarps * (size_t)ubktSize * LANES * sizeof(uint32_t));
+	ctx->bTiny.ensure(nWarps * 2 * caps.maxCols * S * sizeof(uint32_t));
+	ctx->bHash.ensure(nWarps * 2 * (size_t)caps.hashSize * S * sizeof(uint64_t));
+	ctx->bHeap.ensure(nWarps * (size_t)caps.maxQueue * S * sizeof(uint64_t));
+	ctx->bNodeTmp.ensure(nWarps * 7 * (size_t)caps.maxNodes * S * sizeof(uint32_t));
+	ctx->bUbkt.ensure(nWarps * (size_t)ubktSize * S * sizeof(uint32_t));
 	ctx->bHdr.ensure(hdrTop * sizeof(uint32_t));
 	ctx->bHn.ensure(hnTop * sizeof(uint32_t));
-	ctx->bVP.ensure(colTop * LANES * sizeof(uint64_t));
-	ctx->bVN.ensure(colTop * LANES * sizeof(uint64_t));
-	ctx->bSBS.ensure(colTop * LANES * sizeof(int32_t));
+	ctx->bCol.ensure(colTop * 2 * S * sizeof(uint4));
+	ctx->bPeq.ensure(std::max<uint64_t>(peqTop, 1) * sizeof(uint4));
+	ctx->bPeqOff.ensure(n * sizeof(uint64_t));
 	ctx->bMoves.ensure(movesTop * sizeof(uint32_t));
 	ctx->bPath.ensure(pathTop * sizeof(uint32_t));
 	ctx->bArena.ensure(sb->arenaCap * sizeof(uint32_t));
 	ctx->bArenaTop.ensure(sizeof(unsigned long long));
 	sb->sp.tiny = (uint32_t*)ctx->bTiny.ptr;
-	sb->sp.hash = (uint32_t*)ctx->bHash.ptr;
+	sb->sp.hash = (uint64_t*)ctx->bHash.ptr;
 	sb->sp.heap = (uint64_t*)ctx->bHeap.ptr;
 	sb->sp.nodeTmp = (uint32_t*)ctx->bNodeTmp.ptr;
 	sb->sp.ubkt = (uint32_t*)ctx->bUbkt.ptr;
 	sb->sp.ubktSize = ubktSize;
 	sb->sp.hdr = (uint32_t*)ctx->bHdr.ptr;
 	sb->sp.histNode = (uint32_t*)ctx->bHn.ptr;
-	sb->sp.colVP = (uint64_t*)ctx->bVP.ptr;
-	sb->sp.colVN = (uint64_t*)ctx->bVN.ptr;
-	sb->sp.colSBS = (int32_t*)ctx->bSBS.ptr;
+	sb->sp.col = (uint4*)ctx->bCol.ptr;
+	sb->sp.peq = (const uint4*)ctx->bPeq.ptr;
+	sb->sp.peqOff = (const uint64_t*)ctx->bPeqOff.ptr;
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
 	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts->data(), sb->hostParts->size(), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));
-	GA_CUDA(cudaStreamSynchronize(ctx->stream));   // wds is a local
-	if (stats) stats->h2dBytes += sb->hostParts->size() + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc);
+	GA_CUDA(cudaMemcpyAsync(ctx->bPeqOff.ptr, peqOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));   // wds / peqOff are locals
+	if (stats) stats->h2dBytes += sb->hostParts->size() + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc) + n * sizeof(uint64_t);
+}
+
+template <int S>
+static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
+{
+	const size_t n = sb->sorted.size();
+	const int threads = 64;
+	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
+	ga_align_kernel<S><<<blocks, threads, 0, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
+		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 
 int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
@@ -458,16 +519,26 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	const size_t n = sb->sorted.size();
 	if (n == 0) return 0;
 	// the node -> slot tables rely on stamps; clear what an earlier batch left behind
-	GA_CUDA(cudaMemsetAsync(ctx->bHash.ptr, 0, sb->nWarps * 2 * (size_t)sb->caps.hashSize * LANES * sizeof(uint32_t), ctx->stream));
+	GA_CUDA(cudaMemsetAsync(ctx->bHash.ptr, 0, sb->nWarps * 2 * (size_t)sb->caps.hashSize * sb->S * sizeof(uint64_t), ctx->stream));
 	GA_CUDA(cudaMemsetAsync(ctx->bArenaTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
-	const int threads = 64;
-	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
-	ga_align_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
-		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+	{
+		dim3 grid(4, (unsigned)n);
+		ga_peq_kernel<<<grid, 64, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
+		GA_CUDA(cudaGetLastError());
+	}
+	switch (sb->S)
+	{
+		case 32: launchAlign<32>(ctx, sb); break;
+		case 16: launchAlign<16>(ctx, sb); break;
+		case 8: launchAlign<8>(ctx, sb); break;
+		case 4: launchAlign<4>(ctx, sb); break;
+		case 2: launchAlign<2>(ctx, sb); break;
+		case 1: launchAlign<1>(ctx, sb); break;
+		default: throw std::logic_error("unsupported streams-per-warp");
+	}
 	GA_CUDA(cudaGetLastError());
-	sb->launches++;
-	return 1;
+	sb->launches += 2;
+	return 2;
 }
 
 static bool isOverflow(int32_t status)
