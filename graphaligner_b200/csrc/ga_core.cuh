@@ -532,6 +532,63 @@ struct GaSliceCtx
 	bool firstSlice;
 };
 
+// Columns 1..len-1 of a node: the serial Myers chain (GraphAligner.h:1532-1570).  INPREV = the node is also in
+// the previous slice's band (then every column may be min-merged with the vertical ramp from the previous slice).
+// Returns the minimum scoreEnd over the node.
+template <int LANES, bool INPREV>
+GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, const GaSliceCtx& cx, uint64_t wStart, uint32_t len, uint32_t cs, uint32_t pcs,
+	uint32_t prevMask, bool forced, GaCol L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin)
+{
+	uint64_t w = wStart + 1;
+	uint32_t seqWord = g.seq2[w >> 4];
+	uint32_t shift = (uint32_t)(w & 15) * 2;
+	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * 2) * LANES;
+	uint32_t* tinyPtr = cx.tinyCur + (size_t)(cs + 1) * LANES;
+	const uint32_t* prevPtr = cx.tinyPrev + (size_t)(pcs + 2) * LANES;   // next column to prefetch
+	const uint32_t* seqPtr = g.seq2 + (w >> 4) + 1;
+	for (uint32_t k = 1; k < len; k++)
+	{
+		const uint32_t base = (seqWord >> shift) & 3u;
+		shift += 2;
+		if (shift == 32) { seqWord = *seqPtr++; shift = 0; }
+		const uint64_t lo = (base & 1u) ? cx.BC : cx.BA;
+		const uint64_t hi = (base & 1u) ? cx.BT : cx.BG;
+		const uint64_t Eq = (base & 2u) ? hi : lo;
+		const bool previousEq = ((prevMask >> base) & 1u) != 0;
+		GaCol c;
+		bool sbE = false;
+		if (INPREV)
+		{
+			const uint32_t oldTiny = oldTinyNext;
+			// software prefetch of the next column's previous-slice state (address known, value independent of this step)
+			if (k + 1 < len) oldTinyNext = *prevPtr;
+			prevPtr += LANES;
+			const int32_t oldScore = ga_tiny_score(oldTiny);
+			// forced row -1 score = min(left + 1, previous slice's end score); the flag says the latter attains it
+			sbE = forced ? (oldScore == (int32_t)colPtr[LANES].x) : (oldScore <= L.sbs + 1);
+			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft));
+			if (c.sbs > oldScore) ga_vertical_merge(c, oldScore);
+			oldTinyLeft = oldTiny;
+		}
+		else
+		{
+			c = ga_next_col(Eq, L, LsbE, false, LsbE, previousEq, 0);
+		}
+		uint4 ra, rb;
+		ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
+		rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = 0; rb.w = 0;
+		colPtr[0] = ra;
+		colPtr[LANES] = rb;
+		colPtr += 2 * LANES;
+		*tinyPtr = ga_tiny_pack(c, sbE);
+		tinyPtr += LANES;
+		if (c.scoreEnd < nodeMin) nodeMin = c.scoreEnd;
+		L = c;
+		LsbE = sbE;
+	}
+	return nodeMin;
+}
+
 #define GA_MAX_CACHED_IN 6
 
 // Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
@@ -662,7 +719,9 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		c0.scoreEnd = ps + 63 + (int32_t)mismatch;
 		c0.sbs = ps;
 	}
+#ifdef GA_HOST_DEBUG
 	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return false; }
+#endif
 	if (forced && !first)
 	{
 		GaCol old = ga_col_load<LANES>(mem, cx.slabOff + cs);
@@ -672,32 +731,16 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
 
 	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
-	GaCol L = c0;
-	bool LsbE = sbE0;
-	uint32_t oldTinyLeft = oldTiny0;
-	for (uint32_t k = 1; k < len; k++)
+	int32_t nodeMin = c0.scoreEnd;
+	if (len > 1)
 	{
-		uint64_t w = wStart + k;
-		if ((w & 15) == 0) seqWord = g.seq2[w >> 4];
-		base = (seqWord >> ((uint32_t)(w & 15) * 2)) & 3u;
-		Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
-		previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
-		const uint32_t oldTiny = oldTinyNext;
-		// software prefetch of the next column's previous-slice state (address known, value independent of this step)
-		oldTinyNext = (inPrev && k + 1 < len) ? cx.tinyPrev[(size_t)(pcs + k + 1) * LANES] : 0;
-		int32_t sbsF = L.sbs + 1;
-		if (inPrev && ga_tiny_score(oldTiny) < sbsF) sbsF = ga_tiny_score(oldTiny);
-		if (forced) sbsF = ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + k);
-		bool sbE = inPrev && ga_tiny_score(oldTiny) == sbsF;
-		GaCol c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft));
-		if (inPrev && c.sbs > ga_tiny_score(oldTiny)) ga_vertical_merge(c, ga_tiny_score(oldTiny));
-		if (c.sbs != sbsF) { st.status = GA_ERR_INTERNAL; return false; }
-		ga_col_store<LANES>(mem, cx.slabOff + cs + k, c);
-		cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
-		L = c;
-		LsbE = sbE;
-		oldTinyLeft = oldTiny;
+		// 4-bit set of graph bases that equal the read character just above the slice (exact compare,
+		// GraphAligner.h:1540); on the first slice the flag is "node is in the previous band" instead
+		const uint32_t prevMask = cx.firstSlice ? (inPrev ? 15u : 0u) : ((1u << cx.prevCharCode) & 15u);
+		if (inPrev) nodeMin = ga_node_columns<LANES, true>(g, mem, cx, wStart, len, cs, pcs, prevMask, forced, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
+		else nodeMin = ga_node_columns<LANES, false>(g, mem, cx, wStart, len, cs, pcs, prevMask, forced, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
 	}
+	GA_HN(cx.nodeOff + slot, 2) = (uint32_t)nodeMin;
 	return true;
 }
 
@@ -883,19 +926,11 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if (++sweeps > 64u * (ready - from) + 64u) { st.status = GA_ERR_CYCLE_ITER; return false; }
 		}
 	}
-	// slice minimum and per-node minimum (GraphAligner.h:2375,2410-2418; all rows are final here)
+	// slice minimum over the per-node minima ga_calc_node recorded (GraphAligner.h:2375,2410-2418; all rows are final)
 	int32_t minScore = 0x7fffffff;
 	for (uint32_t slot = 0; slot < nc; slot++)
 	{
-		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
-		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
-		int32_t nodeMin = 0x7fffffff;
-		for (uint32_t k = 0; k < len; k++)
-		{
-			int32_t v = ga_tiny_score(cx.tinyCur[(size_t)(cs + k) * LANES]);
-			if (v < nodeMin) nodeMin = v;
-		}
-		GA_HN(cx.nodeOff + slot, 2) = (uint32_t)nodeMin;
+		int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + slot, 2);
 		if (nodeMin < minScore) minScore = nodeMin;
 	}
 	st.wordColumns += ncols;
@@ -955,9 +990,9 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	int s = nSlices - 1;
 	int row = 63;
 	const int32_t maxv = (int32_t)st.partLen;
-	// per (slice, node) cache: index of the node's first column in the slab
-	uint32_t colBase = 0;
+	uint32_t colBase = 0;    // per (slice, node): index of the node's first column in the slab
 	uint64_t wStart = 0;
+	uint32_t seqWord = 0;    // 16 graph bases around the current column
 	bool reload = true;      // slice or node changed: re-resolve colBase and reload both columns
 	GaCol cur, left;
 	cur.VP = cur.VN = 0; cur.sbs = cur.scoreEnd = 0;
@@ -973,6 +1008,7 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			if (slot < 0) { st.status = GA_ERR_TRACE; break; }
 			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
 			wStart = g.nodeStart[node];
+			seqWord = g.seq2[(wStart + off) >> 4];
 			cur = ga_col_load<LANES>(mem, colBase + off);
 			if (off > 0) left = ga_col_load<LANES>(mem, colBase + off - 1);
 			if (off > 1) ga_col_prefetch<LANES>(mem, colBase + off - 2);
@@ -980,49 +1016,71 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			if (!haveHere) { here = ga_col_value(cur.VP, cur.VN, cur.sbs, row); haveHere = true; }
 			reload = false;
 		}
-		const int64_t j = (int64_t)s * 64 + row;
+		const uint64_t w = wStart + off;
 		uint32_t move = 4;
 		uint32_t nnode = node, noff = off;
 		int32_t nhere = 0;
-		if (j == 0 && node == st.startNode && (here == 0 || here == 1))
+		// read character vs graph base through the slice's precomputed match masks (same IUPAC table)
+		const uint32_t base = (seqWord >> ((uint32_t)(w & 15) * 2)) & 3u;
+		const uint4 pq = mem.peq[(size_t)s * 2 + (base >> 1)];
+		const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
+		const int32_t match = (int32_t)((eqWord >> row) & 1);
+		const int32_t diagWant = here - 1 + match;
+		if (off > 0 && row > 0)
 		{
-			move = GA_MOVE_END;
+			// fast path: strictly inside a node and inside a slice; the three candidates come from two register-held columns
+			const uint64_t maskRow = ~(uint64_t)0 >> (63 - row);
+			const int32_t hs = left.sbs + (int32_t)GA_POPC(left.VP & maskRow) - (int32_t)GA_POPC(left.VN & maskRow);
+			const int32_t ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
+			const int32_t us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+			if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
+			else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
+			else if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
 		}
 		else
 		{
-			bool match = ((ga_iupac_mask(st.seq[j]) >> ga_base(g, wStart + off)) & 1u) != 0;
-			int32_t diagWant = match ? here : here - 1;
-			if (off == 0)
+			const bool firstRow = s == 0 && row == 0;
+			if (firstRow && node == st.startNode && (here == 0 || here == 1))
 			{
-				for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
-				{
-					uint32_t u = g.inAdj[e];
-					uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-					int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
-					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
-					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
-					if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
-				}
+				move = GA_MOVE_END;
 			}
 			else
 			{
-				int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
-				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
+				if (off == 0)
+				{
+					for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
+					{
+						uint32_t u = g.inAdj[e];
+						uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+						int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
+						if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
+						int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
+						if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
+					}
+				}
 				else
 				{
-					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off - 1, 63, maxv) : ga_col_value(left.VP, left.VN, left.sbs, row - 1);
-					if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
+					int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
+					if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
+					else
+					{
+						int32_t ds = ga_hist_value<LANES>(mem, st, s - 1, node, off - 1, 63, maxv);   // row == 0 here
+						if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
+					}
 				}
+				if (move == 4)
+				{
+					int32_t us = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off, 63, maxv) : ga_col_value(cur.VP, cur.VN, cur.sbs, row - 1);
+					if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+				}
+				// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
+				if (firstRow && move != GA_MOVE_H && move != 4) move = GA_MOVE_END;
 			}
-			if (move == 4)
-			{
-				int32_t us = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off, 63, maxv) : ga_col_value(cur.VP, cur.VN, cur.sbs, row - 1);
-				if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
-			}
-			if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
 		}
-		// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
-		if (j == 0 && move != GA_MOVE_H) move = GA_MOVE_END;
+#ifdef GA_HOST_DEBUG
+		if (move == 4) fprintf(stderr, "trace fail at node %u off %u s %d row %d here %d\n", node, off, s, row, here);
+#endif
+		if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
 		if (nMoves >= caps.maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
 		curWord |= move << ((nMoves & 15) * 2);
 		nMoves++;
@@ -1043,6 +1101,7 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				cur = left;
 				if (noff > 0) left = ga_col_load<LANES>(mem, colBase + noff - 1);
 				if (noff > 2) ga_col_prefetch<LANES>(mem, colBase + noff - 3);
+				if (((wStart + noff) & 15) == 15) seqWord = g.seq2[(wStart + noff) >> 4];
 			}
 		}
 		if (move != GA_MOVE_H)
