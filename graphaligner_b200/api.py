@@ -18,7 +18,7 @@ class GaBatch(C.Structure):
 
 READ_RESULT = np.dtype([("failed", "<i4"), ("score", "<i4"), ("alignment_start", "<u8"), ("alignment_end", "<u8"),
                         ("query_position", "<i4"), ("flags", "<u4"), ("mapping_offset", "<u8"), ("n_mappings", "<u8"),
-                        ("trace_offset", "<u8"), ("n_trace", "<u8"), ("word_columns", "<u8")])
+                        ("reserved", "<u8"), ("n_trace", "<u8"), ("word_columns", "<u8")])
 MAPPING = np.dtype([("node_id", "<i8"), ("offset", "<i8"), ("rank", "<i8"), ("is_reverse", "<i4"), ("from_length", "<i4"),
                     ("to_length", "<i4"), ("reserved", "<u4"), ("read_start", "<u8")])
 TRACE_ITEM = np.dtype([("node_id", "<i4"), ("offset", "<u4"), ("readpos", "<u8"), ("reverse", "u1"), ("type", "u1"),
@@ -33,7 +33,7 @@ EXPORTS = ["ga_create", "ga_destroy", "ga_last_error", "ga_global_error", "ga_gr
            "ga_graph_set_dbg_overlap", "ga_graph_finalize", "ga_graph_from_bigraph", "ga_graph_load_vg", "ga_graph_load_gfa",
            "ga_graph_free", "ga_graph_node_count", "ga_graph_size_bp", "ga_graph_edge_count", "ga_graph_upload", "ga_align_batch",
            "ga_stage_batch", "ga_run_staged", "ga_sync", "ga_finish_staged", "ga_staged_free", "ga_cuda_stream", "ga_results_count",
-           "ga_results_reads", "ga_results_mappings", "ga_results_trace", "ga_results_free", "ga_results_trace_hash", "ga_get_stats",
+           "ga_results_reads", "ga_results_mappings", "ga_results_read_trace", "ga_results_free", "ga_results_trace_hash", "ga_get_stats",
            "ga_reset_stats", "ga_measure_int32_peak"]
 
 _lib = None
@@ -57,7 +57,7 @@ def load_library():
         "ga_graph_edge_count": (sz, [vp]), "ga_graph_upload": (C.c_int, [vp, vp]), "ga_align_batch": (vp, [vp, C.POINTER(GaBatch)]),
         "ga_stage_batch": (vp, [vp, C.POINTER(GaBatch)]), "ga_run_staged": (C.c_int, [vp, vp]), "ga_sync": (C.c_int, [vp]),
         "ga_finish_staged": (vp, [vp, vp]), "ga_staged_free": (None, [vp, vp]), "ga_cuda_stream": (vp, [vp]), "ga_results_count": (sz, [vp]),
-        "ga_results_reads": (vp, [vp]), "ga_results_mappings": (vp, [vp]), "ga_results_trace": (vp, [vp]), "ga_results_free": (None, [vp]),
+        "ga_results_reads": (vp, [vp]), "ga_results_mappings": (vp, [vp]), "ga_results_read_trace": (sz, [vp, sz, vp, sz]), "ga_results_free": (None, [vp]),
         "ga_results_trace_hash": (u64, [vp, sz]), "ga_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_reset_stats": (C.c_int, [vp]), "ga_measure_int32_peak": (C.c_double, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -151,16 +151,15 @@ class PackedReads:
 
 
 class Results:
-    def __init__(self, lib, handle, names):
+    def __init__(self, lib, handle, names, keepalive=None):
         self._lib = lib
         self.handle = handle
         n = lib.ga_results_count(handle)
         self.reads = self._view(lib.ga_results_reads(handle), READ_RESULT, n)
         nm = int(self.reads["n_mappings"].sum())
-        nt = int(self.reads["n_trace"].sum())
         self.mappings = self._view(lib.ga_results_mappings(handle), MAPPING, nm)
-        self.trace = self._view(lib.ga_results_trace(handle), TRACE_ITEM, nt)
         self.names = names
+        self.keepalive = keepalive   # the ga_batch buffers are referenced by the results (lazy trace items)
 
     @staticmethod
     def _view(ptr, dtype, n):
@@ -168,6 +167,13 @@ class Results:
             return np.zeros(0, dtype=dtype)
         buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype, count=n)
+
+    def read_trace(self, i):
+        """AlignmentResult::trace of read i (materialised on demand)."""
+        n = int(self.reads["n_trace"][i])
+        buf = np.zeros(max(n, 1), dtype=TRACE_ITEM)
+        got = self._lib.ga_results_read_trace(self.handle, i, buf.ctypes.data_as(C.c_void_p), n)
+        return buf[:min(n, got)]
 
     def trace_hash(self, i):
         return int(self._lib.ga_results_trace_hash(self.handle, i))
@@ -187,14 +193,14 @@ class Results:
                 m = self.mappings[int(r["mapping_offset"]):int(r["mapping_offset"]) + int(r["n_mappings"])]
                 d["mappings"] = [(int(x["node_id"]), int(x["is_reverse"]), int(x["offset"]), int(x["from_length"]), int(x["to_length"])) for x in m]
                 if with_trace:
-                    t = self.trace[int(r["trace_offset"]):int(r["trace_offset"]) + int(r["n_trace"])]
+                    t = self.read_trace(i)
                     d["trace"] = [(int(x["node_id"]), int(x["offset"]), int(x["reverse"]), int(x["readpos"]), int(x["type"])) for x in t]
             out.append(d)
         return out
 
     def free(self):
         if self.handle:
-            self.reads = self.mappings = self.trace = None
+            self.reads = self.mappings = None
             self._lib.ga_results_free(self.handle)
             self.handle = None
 
@@ -223,7 +229,7 @@ class Aligner:
         if not h:
             raise RuntimeError("ga_align_batch failed: " + self.last_error())
         names = None if isinstance(reads, PackedReads) else [r[0] for r in reads]
-        return Results(self._lib, h, names)
+        return Results(self._lib, h, names, keepalive=packed)
 
     def stage(self, packed):
         h = self._lib.ga_stage_batch(self.ctx, C.byref(packed.struct))
@@ -239,11 +245,11 @@ class Aligner:
         if self._lib.ga_sync(self.ctx) != 0:
             raise RuntimeError("ga_sync failed: " + self.last_error())
 
-    def finish(self, staged, names=None):
+    def finish(self, staged, names=None, keepalive=None):
         h = self._lib.ga_finish_staged(self.ctx, staged)
         if not h:
             raise RuntimeError("ga_finish_staged failed: " + self.last_error())
-        return Results(self._lib, h, names)
+        return Results(self._lib, h, names, keepalive=keepalive)
 
     def free_staged(self, staged):
         self._lib.ga_staged_free(self.ctx, staged)

@@ -29,14 +29,26 @@ struct ga_results
 {
 	std::vector<ga_read_result> reads;
 	std::vector<ga_mapping> mappings;
-	std::vector<ga_trace_item> trace;
+	// kept for the lazy trace items (ga_results_read_trace): what the device returned and what was decided per read
+	const AlignmentGraph* graph = nullptr;
+	std::vector<ga::ReadInput> inputs;
+	std::vector<ga_stream_in> streams;
+	std::vector<ga_stream_out> outs;
+	std::vector<uint32_t> arena;
+	struct Lazy
+	{
+		int64_t fwStream, bwStream;
+		size_t splitIndex;
+		bool fwShifted;
+		bool failed;
+		size_t nTraceItems;
+	};
+	std::vector<Lazy> lazy;
 };
 
 struct ga_staged
 {
-	std::vector<std::string> names;
-	std::vector<std::string> sequences;
-	std::vector<std::vector<ga::SeedHit>> seeds;
+	std::vector<ga::SeedHit> seeds;
 	std::vector<ga::ReadInput> reads;
 	std::unique_ptr<ga::BatchPlan> plan;
 	ga::StagedBatch* device = nullptr;
@@ -157,51 +169,61 @@ int ga_graph_upload(ga_ctx* ctx, const ga_graph* g)
 
 static void fillStaged(ga_staged* st, const ga_batch* batch)
 {
+	// nothing is copied: ReadInput points into the caller's buffers, which must stay valid until the results
+	// (and any lazily requested trace items) are no longer needed
 	const size_t n = batch->n_reads;
-	st->names.resize(n);
-	st->sequences.resize(n);
-	st->seeds.resize(n);
+	const uint64_t nSeeds = n ? batch->seed_offsets[n] : 0;
+	st->seeds.resize(nSeeds);
+	for (uint64_t k = 0; k < nSeeds; k++) st->seeds[k] = ga::SeedHit((int)batch->seed_node[k], (size_t)batch->seed_pos[k], batch->seed_reverse[k] != 0);
 	st->reads.resize(n);
 	for (size_t i = 0; i < n; i++)
 	{
-		st->sequences[i].assign(batch->sequences + batch->seq_offsets[i], batch->sequences + batch->seq_offsets[i + 1]);
-		if (batch->names && batch->name_offsets) st->names[i].assign(batch->names + batch->name_offsets[i], batch->names + batch->name_offsets[i + 1]);
-		for (uint64_t k = batch->seed_offsets[i]; k < batch->seed_offsets[i + 1]; k++)
+		ga::ReadInput& r = st->reads[i];
+		r.seq = batch->sequences + batch->seq_offsets[i];
+		r.seqLen = (size_t)(batch->seq_offsets[i + 1] - batch->seq_offsets[i]);
+		if (batch->names && batch->name_offsets)
 		{
-			st->seeds[i].emplace_back((int)batch->seed_node[k], (size_t)batch->seed_pos[k], batch->seed_reverse[k] != 0);
+			r.name = batch->names + batch->name_offsets[i];
+			r.nameLen = (size_t)(batch->name_offsets[i + 1] - batch->name_offsets[i]);
 		}
-		st->reads[i] = ga::ReadInput { &st->names[i], &st->sequences[i], &st->seeds[i] };
+		else
+		{
+			r.name = "";
+			r.nameLen = 0;
+		}
+		r.seeds = st->seeds.data() + batch->seed_offsets[i];
+		r.nSeeds = (size_t)(batch->seed_offsets[i + 1] - batch->seed_offsets[i]);
 	}
 	st->b = batch->initial_bandwidth;
 	st->B = batch->ramp_bandwidth;
 }
 
-static ga_results* packResults(const std::vector<ga::ReadInput>& reads, const std::vector<AlignmentResult>& results)
+static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as)
 {
-	ga_results* out = new ga_results();
-	out->reads.resize(results.size());
-	size_t nm = 0, nt = 0;
-	for (auto& r : results)
-	{
-		if (!r.alignmentFailed) { nm += r.alignment.path.mapping.size(); nt += r.trace.size(); }
-	}
-	out->mappings.reserve(nm);
-	out->trace.reserve(nt);
-	for (size_t i = 0; i < results.size(); i++)
-	{
-		const AlignmentResult& r = results[i];
+	const size_t n = as.size();
+	out->reads.resize(n);
+	out->lazy.resize(n);
+	std::vector<uint64_t> mapOff(n + 1, 0);
+	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].result.alignment.path.mapping.size());
+	out->mappings.resize(mapOff[n]);
+	ga::ParallelFor(n, [&](size_t i) {
+		const ga::ReadAssembly& a = as[i];
+		const AlignmentResult& r = a.result;
 		ga_read_result& o = out->reads[i];
 		memset(&o, 0, sizeof(o));
-		o.failed = r.alignmentFailed ? 1 : 0;
-		o.score = r.alignmentFailed ? std::numeric_limits<int32_t>::max() : r.alignment.score;
-		o.flags = r.flags;
-		o.word_columns = r.wordColumns;
-		o.mapping_offset = out->mappings.size();
-		o.trace_offset = out->trace.size();
-		if (r.alignmentFailed) continue;
+		o.failed = a.failed ? 1 : 0;
+		o.score = a.failed ? std::numeric_limits<int32_t>::max() : r.alignment.score;
+		o.flags = a.flags;
+		o.word_columns = a.wordColumns;
+		o.mapping_offset = mapOff[i];
+		out->lazy[i] = ga_results::Lazy { a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
+		if (a.failed) return;
 		o.alignment_start = r.alignmentStart;
 		o.alignment_end = r.alignmentEnd;
 		o.query_position = r.alignment.query_position;
+		o.n_mappings = r.alignment.path.mapping.size();
+		o.n_trace = a.nTraceItems;
+		ga_mapping* dst = out->mappings.data() + mapOff[i];
 		for (auto& m : r.alignment.path.mapping)
 		{
 			ga_mapping gm;
@@ -216,25 +238,9 @@ static ga_results* packResults(const std::vector<ga::ReadInput>& reads, const st
 				gm.to_length = m.edit[0].to_length;
 				gm.read_start = m.edit[0].read_start;
 			}
-			out->mappings.push_back(gm);
+			*dst++ = gm;
 		}
-		o.n_mappings = out->mappings.size() - o.mapping_offset;
-		for (auto& t : r.trace)
-		{
-			ga_trace_item gt;
-			memset(&gt, 0, sizeof(gt));
-			gt.node_id = t.nodeID;
-			gt.offset = (uint32_t)t.offset;
-			gt.readpos = t.readpos;
-			gt.reverse = t.reverse ? 1 : 0;
-			gt.type = (uint8_t)t.type;
-			gt.graph_char = t.graphChar;
-			gt.read_char = t.readChar;
-			out->trace.push_back(gt);
-		}
-		o.n_trace = out->trace.size() - o.trace_offset;
-	}
-	return out;
+	});
 }
 
 ga_staged* ga_stage_batch(ga_ctx* ctx, const ga_batch* batch)
@@ -266,27 +272,33 @@ int ga_sync(ga_ctx* ctx)
 
 ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 {
-	ga_results* res = nullptr;
+	ga_results* res = new ga_results();
 	int rc = guarded(ctx, [&]() {
-		std::vector<ga_stream_out> outs;
-		std::vector<uint32_t> arena;
-		ga::FinishStaged(ctx->dev, st->device, outs, arena, &ctx->stats);
-		std::vector<AlignmentResult> results(st->reads.size());
+		ga::FinishStaged(ctx->dev, st->device, res->outs, res->arena, &ctx->stats);
 		const AlignmentGraph& graph = ctx->graph->graph;
-		for (size_t i = 0; i < st->reads.size(); i++)
-		{
-			if (st->reads[i].seeds->empty()) continue;   // stays failed: "has no seed hits" (Aligner.cpp:131-138)
-			results[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, outs, arena);
-		}
-		for (size_t i = 0; i < results.size(); i++)
-		{
-			if (st->reads[i].seeds->empty()) results[i].alignment.score = std::numeric_limits<int32_t>::max();
-		}
+		const size_t n = st->reads.size();
+		std::vector<ga::ReadAssembly> as(n);
+		ga::ParallelFor(n, [&](size_t i) {
+			if (st->reads[i].nSeeds == 0)
+			{
+				as[i].result.alignment.score = std::numeric_limits<int32_t>::max();   // "has no seed hits" (Aligner.cpp:131-138)
+				return;
+			}
+			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, res->outs, res->arena, false);
+		});
 		ctx->stats.streams += st->plan->streams.size();
-		for (auto& o : outs) ctx->stats.wordColumns += o.wordColumns;
-		res = packResults(st->reads, results);
+		for (auto& o : res->outs) ctx->stats.wordColumns += o.wordColumns;
+		packResults(res, as);
+		res->graph = &graph;
+		res->inputs = st->reads;
+		res->streams = st->plan->streams;
 	});
-	return rc == 0 ? res : nullptr;
+	if (rc != 0)
+	{
+		delete res;
+		return nullptr;
+	}
+	return res;
 }
 
 void ga_staged_free(ga_ctx* ctx, ga_staged* st)
@@ -311,12 +323,55 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 size_t ga_results_count(const ga_results* r) { return r->reads.size(); }
 const ga_read_result* ga_results_reads(const ga_results* r) { return r->reads.data(); }
 const ga_mapping* ga_results_mappings(const ga_results* r) { return r->mappings.data(); }
-const ga_trace_item* ga_results_trace(const ga_results* r) { return r->trace.data(); }
 void ga_results_free(ga_results* r) { delete r; }
+
+static void materializeTrace(const ga_results* r, size_t i, std::vector<AlignmentResult::TraceItem>& items)
+{
+	const ga_results::Lazy& lz = r->lazy[i];
+	ga::ReadAssembly as;
+	as.failed = lz.failed;
+	as.fwStream = lz.fwStream;
+	as.bwStream = lz.bwStream;
+	as.splitIndex = lz.splitIndex;
+	as.fwShifted = lz.fwShifted;
+	as.nTraceItems = lz.nTraceItems;
+	ga::BuildTraceItems(*r->graph, r->inputs[i], as, r->streams, r->outs, r->arena, items);
+}
+
+size_t ga_results_read_trace(const ga_results* r, size_t i, ga_trace_item* buffer, size_t capacity)
+{
+	if (i >= r->reads.size() || r->lazy[i].failed) return 0;
+	if (buffer == nullptr || capacity < r->lazy[i].nTraceItems) return r->lazy[i].nTraceItems;
+	std::vector<AlignmentResult::TraceItem> items;
+	try
+	{
+		materializeTrace(r, i, items);
+	}
+	catch (...)
+	{
+		return 0;
+	}
+	for (size_t k = 0; k < items.size() && k < capacity; k++)
+	{
+		const AlignmentResult::TraceItem& t = items[k];
+		ga_trace_item gt;
+		memset(&gt, 0, sizeof(gt));
+		gt.node_id = t.nodeID;
+		gt.offset = (uint32_t)t.offset;
+		gt.readpos = t.readpos;
+		gt.reverse = t.reverse ? 1 : 0;
+		gt.type = (uint8_t)t.type;
+		gt.graph_char = t.graphChar;
+		gt.read_char = t.readChar;
+		buffer[k] = gt;
+	}
+	return items.size();
+}
 
 uint64_t ga_results_trace_hash(const ga_results* r, size_t i)
 {
 	uint64_t h = 14695981039346656037ull;
+	if (i >= r->reads.size() || r->lazy[i].failed) return h;
 	auto mix = [&h](uint64_t v) {
 		for (int b = 0; b < 8; b++)
 		{
@@ -324,15 +379,22 @@ uint64_t ga_results_trace_hash(const ga_results* r, size_t i)
 			h *= 1099511628211ull;
 		}
 	};
-	const ga_read_result& rr = r->reads[i];
-	for (uint64_t k = 0; k < rr.n_trace; k++)
+	std::vector<AlignmentResult::TraceItem> items;
+	try
 	{
-		const ga_trace_item& t = r->trace[rr.trace_offset + k];
-		mix((uint64_t)(int64_t)t.node_id);
+		materializeTrace(r, i, items);
+	}
+	catch (...)
+	{
+		return 0;
+	}
+	for (auto& t : items)
+	{
+		mix((uint64_t)(int64_t)t.nodeID);
 		mix(t.offset);
-		mix(t.reverse);
+		mix(t.reverse ? 1 : 0);
 		mix(t.readpos);
-		mix(t.type);
+		mix((uint64_t)t.type);
 	}
 	return h;
 }

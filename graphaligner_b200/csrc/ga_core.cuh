@@ -71,6 +71,7 @@ struct GaLaneMem
 	uint4* col;          // column history, two 16-byte halves per column: {VP, VN} and {sbs, scoreEnd, -, -}
 	uint32_t* moves;
 	uint32_t* pathNodes;
+	uint32_t* runs;      // GA_RUN_WORDS words per run
 	uint32_t* ubkt;      // unordered_map emulation: bucket -> "before" node
 	uint32_t* unext;     // unordered_map emulation: forward list links
 	uint32_t* uorder;    // iteration order of the previous slice's node map
@@ -390,6 +391,7 @@ struct GaStreamState
 	uint32_t partLen;
 	uint32_t nslices;
 	uint32_t startNode;
+	uint32_t trimRows;
 	// running state
 	int32_t status;
 	bool done;
@@ -590,6 +592,7 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 }
 
 #define GA_MAX_CACHED_IN 6
+#define GA_TRACE_PREFETCH 40u
 
 // Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
 // forced = the node belongs to a cyclic block whose row -1 scores were already forced into the column records
@@ -983,9 +986,12 @@ GA_DEV int32_t ga_hist_value(const GaLaneMem& mem, const GaStreamState& st, int 
 }
 
 template <int LANES>
-GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut)
+GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
 {
-	uint32_t nMoves = 0, nPath = 0;
+	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+	// current same-node run of the trimmed trace (walked backwards: 'last' is seen first)
+	bool runOpen = false;
+	uint32_t runNode = 0, runFirstOff = 0, runLastOff = 0, runFirstRow = 0, runLastRow = 0;
 	uint32_t curWord = 0;
 	int s = nSlices - 1;
 	int row = 63;
@@ -1011,10 +1017,30 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			seqWord = g.seq2[(wStart + off) >> 4];
 			cur = ga_col_load<LANES>(mem, colBase + off);
 			if (off > 0) left = ga_col_load<LANES>(mem, colBase + off - 1);
-			if (off > 1) ga_col_prefetch<LANES>(mem, colBase + off - 2);
-			if (off > 2) ga_col_prefetch<LANES>(mem, colBase + off - 3);
+			// the history is far larger than L2: start fetching the rest of this node's columns now, so that one
+			// HBM round trip is paid per node and slice instead of per step
+			for (uint32_t t = 2; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch<LANES>(mem, colBase + off - t);
 			if (!haveHere) { here = ga_col_value(cur.VP, cur.VN, cur.sbs, row); haveHere = true; }
 			reload = false;
+		}
+		// record the position we stand on (unless it lies in the trimmed tail)
+		{
+			const uint32_t j = (uint32_t)s * 64u + (uint32_t)row;
+			if (j < st.trimRows)
+			{
+				if (runOpen && runNode != node)
+				{
+					if (nRuns >= caps.maxRuns) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+					uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
+					r[0] = runNode; r[LANES] = runFirstOff; r[2 * LANES] = runLastOff; r[3 * LANES] = runFirstRow; r[4 * LANES] = runLastRow;
+					nRuns++;
+					runOpen = false;
+				}
+				if (!runOpen) { runOpen = true; runNode = node; runLastOff = off; runLastRow = j; }
+				runFirstOff = off;
+				runFirstRow = j;
+				nPos++;
+			}
 		}
 		const uint64_t w = wStart + off;
 		uint32_t move = 4;
@@ -1100,7 +1126,7 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			{
 				cur = left;
 				if (noff > 0) left = ga_col_load<LANES>(mem, colBase + noff - 1);
-				if (noff > 2) ga_col_prefetch<LANES>(mem, colBase + noff - 3);
+				if (noff >= GA_TRACE_PREFETCH) ga_col_prefetch<LANES>(mem, colBase + noff - GA_TRACE_PREFETCH);
 				if (((wStart + noff) & 15) == 15) seqWord = g.seq2[(wStart + noff) >> 4];
 			}
 		}
@@ -1113,8 +1139,20 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		off = noff;
 	}
 	if (nMoves & 15) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
+	if (runOpen && st.status == GA_OK)
+	{
+		if (nRuns >= caps.maxRuns) st.status = GA_ERR_TRACE_OVERFLOW;
+		else
+		{
+			uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
+			r[0] = runNode; r[LANES] = runFirstOff; r[2 * LANES] = runLastOff; r[3 * LANES] = runFirstRow; r[4 * LANES] = runLastRow;
+			nRuns++;
+		}
+	}
 	nMovesOut = nMoves;
 	nPathOut = nPath;
+	nRunsOut = nRuns;
+	nPosOut = nPos;
 }
 
 // Iterative Tarjan over the band of slice sl in the reference's visiting order (band order, outNeighbors order,
@@ -1225,6 +1263,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	st.partLen = active ? in->partLen : 0;
 	st.nslices = st.partLen / 64;
 	st.startNode = active ? in->startNode : 0;
+	st.trimRows = active ? in->trimRows : 0;
 	st.prevMin = 0;
 	st.hmmC = hmm.startCorrect;
 	st.hmmF = hmm.startFalse;
@@ -1317,6 +1356,8 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	out->cyclicSlices = st.cyclicSlices;
 	out->nMoves = 0;
 	out->nPathNodes = 0;
+	out->nRuns = 0;
+	out->nPositions = 0;
 	out->nTies = 0;
 	out->nSlices = 0;
 	out->score = 0;
@@ -1379,10 +1420,12 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		out->score = minScore;
 		out->endNode = endNode;
 		out->endOff = endOff;
-		uint32_t nMoves = 0, nPath = 0;
-		if (!(debugFlags & 1u)) ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath);
+		uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+		if (!(debugFlags & 1u)) ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath, nRuns, nPos);
 		out->nMoves = nMoves;
 		out->nPathNodes = nPath;
+		out->nRuns = nRuns;
+		out->nPositions = nPos;
 	}
 	out->status = st.status;
 }

@@ -1,8 +1,11 @@
 #include "ga_host.h"
 #include <algorithm>
-#include <chrono>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <thread>
 
 namespace ga
 {
@@ -11,7 +14,6 @@ static const uint32_t FLAG_STREAM_ERROR = 1;   // a stream hit a hard limit (see
 static const uint32_t FLAG_BAD_SEED = 2;       // seed node not in graph / position outside read
 static const uint32_t FLAG_BAD_CHAR = 4;       // read holds a character the reference aborts on
 static const uint32_t FLAG_CYCLIC = 8;         // some band held a cyclic component
-static const uint32_t FLAG_TIE = 16;           // final-slice minimum tied across nodes
 
 std::string ReverseComplement(const std::string& str)
 {
@@ -57,34 +59,103 @@ bool ValidReadChar(char c)
 	}
 }
 
-static void appendPart(std::vector<uint8_t>& parts, const std::string& part, ga_stream_in& in)
+unsigned HostThreads()
 {
-	// 'N' padding to a multiple of 64 rows (GraphAligner.h:2989-2998,3006-3016)
-	size_t padded = (part.size() + 63) / 64 * 64;
-	in.seqOff = parts.size();
-	in.partLen = (uint32_t)padded;
-	parts.insert(parts.end(), part.begin(), part.end());
-	parts.insert(parts.end(), padded - part.size(), (uint8_t)'N');
+	static unsigned n = []() {
+		if (const char* e = getenv("GA_HOST_THREADS"))
+		{
+			int v = atoi(e);
+			if (v > 0) return (unsigned)v;
+		}
+		unsigned h = std::thread::hardware_concurrency();
+		return h ? h : 1u;
+	}();
+	return n;
+}
+
+void ParallelFor(size_t n, const std::function<void(size_t)>& f)
+{
+	unsigned threads = (unsigned)std::min<size_t>(HostThreads(), n);
+	if (threads <= 1)
+	{
+		for (size_t i = 0; i < n; i++) f(i);
+		return;
+	}
+	std::atomic<size_t> next(0);
+	const size_t chunk = std::max<size_t>(1, n / (threads * 8));
+	std::vector<std::thread> pool;
+	std::exception_ptr error;
+	std::atomic<bool> failed(false);
+	auto work = [&]() {
+		try
+		{
+			while (!failed.load())
+			{
+				size_t begin = next.fetch_add(chunk);
+				if (begin >= n) break;
+				size_t end = std::min(n, begin + chunk);
+				for (size_t i = begin; i < end; i++) f(i);
+			}
+		}
+		catch (...)
+		{
+			if (!failed.exchange(true)) error = std::current_exception();
+		}
+	};
+	for (unsigned t = 0; t + 1 < threads; t++) pool.emplace_back(work);
+	work();
+	for (auto& t : pool) t.join();
+	if (error) std::rethrow_exception(error);
+}
+
+static char complementOf(char c)
+{
+	// one character of ReverseComplement above
+	switch (c)
+	{
+		case 'A': case 'a': return 'T';
+		case 'C': case 'c': return 'G';
+		case 'T': case 't': return 'A';
+		case 'G': case 'g': return 'C';
+		case 'N': case 'n': return 'N';
+		case 'U': case 'u': return 'A';
+		case 'R': case 'r': return 'Y';
+		case 'Y': case 'y': return 'R';
+		case 'K': case 'k': return 'M';
+		case 'M': case 'm': return 'K';
+		case 'S': case 's': return 'S';
+		case 'W': case 'w': return 'W';
+		case 'B': case 'b': return 'V';
+		case 'V': case 'v': return 'B';
+		case 'D': case 'd': return 'H';
+		case 'H': case 'h': return 'D';
+		default: return 'N';
+	}
 }
 
 BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads)
 {
-	firstSeedOfRead.reserve(reads.size() + 1);
-	size_t totalBytes = 0;
-	for (auto& r : reads) totalBytes += (r.sequence->size() + 128) * std::max<size_t>(1, r.seeds->size());
-	parts.reserve(totalBytes);
-	for (size_t ri = 0; ri < reads.size(); ri++)
+	const size_t n = reads.size();
+	badChar.assign(n, 0);
+	ParallelFor(n, [&](size_t i) {
+		const char* p = reads[i].seq;
+		for (size_t k = 0; k < reads[i].seqLen; k++)
+		{
+			if (!ValidReadChar(p[k])) { badChar[i] = 1; break; }
+		}
+	});
+	struct Job { uint32_t read; uint32_t backward; size_t pos; };
+	std::vector<Job> jobs;
+	firstSeedOfRead.reserve(n + 1);
+	size_t top = 0;
+	const size_t overlap = (size_t)graph.DBGOverlap;
+	for (size_t ri = 0; ri < n; ri++)
 	{
 		firstSeedOfRead.push_back((uint32_t)seeds.size());
-		const std::string& seq = *reads[ri].sequence;
-		bool badChar = false;
-		for (char c : seq)
+		const size_t len = reads[ri].seqLen;
+		for (size_t si = 0; si < reads[ri].nSeeds; si++)
 		{
-			if (!ValidReadChar(c)) { badChar = true; break; }
-		}
-		for (size_t si = 0; si < reads[ri].seeds->size(); si++)
-		{
-			const SeedHit& hit = (*reads[ri].seeds)[si];
+			const SeedHit& hit = reads[ri].seeds[si];
 			SeedPlan sp;
 			sp.read = (uint32_t)ri;
 			sp.seed = (uint32_t)si;
@@ -94,7 +165,7 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 			int nodeId = std::get<0>(hit);
 			size_t pos = std::get<1>(hit);
 			bool backwards = std::get<2>(hit);
-			if (badChar || !graph.HasNode(nodeId * 2) || !graph.HasNode(nodeId * 2 + 1) || pos >= seq.size())
+			if (badChar[ri] || !graph.HasNode(nodeId * 2) || !graph.HasNode(nodeId * 2 + 1) || pos >= len || pos + overlap > len)
 			{
 				sp.invalid = true;
 				seeds.push_back(sp);
@@ -105,96 +176,60 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 			size_t backwardNode = graph.Lookup(backwards ? nodeId * 2 : nodeId * 2 + 1);
 			if (pos > 0)
 			{
+				// backward part = reverse complement of read[0 .. pos + overlap), 'N'-padded to a multiple of 64
+				size_t partLen = pos + overlap;
 				ga_stream_in in;
 				in.startNode = (uint32_t)backwardNode;
-				appendPart(parts, ReverseComplement(seq.substr(0, pos + graph.DBGOverlap)), in);
+				in.seqOff = top;
+				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
+				in.trimRows = (uint32_t)pos;                       // GraphAligner.h:3086-3089
+				in.reserved = 0;
+				top += in.partLen;
 				sp.bwStream = (int64_t)streams.size();
 				streams.push_back(in);
+				jobs.push_back(Job { (uint32_t)ri, 1, pos });
 			}
-			if (pos < seq.size() - 1)
+			if (pos < len - 1)
 			{
+				size_t partLen = len - pos;
 				ga_stream_in in;
 				in.startNode = (uint32_t)forwardNode;
-				appendPart(parts, seq.substr(pos), in);
+				in.seqOff = top;
+				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
+				in.trimRows = (uint32_t)(len - pos - overlap);     // GraphAligner.h:3063-3066
+				in.reserved = 0;
+				top += in.partLen;
 				sp.fwStream = (int64_t)streams.size();
 				streams.push_back(in);
+				jobs.push_back(Job { (uint32_t)ri, 0, pos });
 			}
 			seeds.push_back(sp);
 		}
 	}
 	firstSeedOfRead.push_back((uint32_t)seeds.size());
-}
-
-DirectionTrace DecodeStream(const AlignmentGraph& graph, const ga_stream_in& in, const ga_stream_out& out, const uint32_t* arena)
-{
-	(void)in;
-	DirectionTrace result;
-	if (out.status != GA_OK || out.nSlices <= 0) return result;
-	result.present = true;
-	result.score = out.score;
-	result.nSlices = (size_t)out.nSlices;
-	const uint32_t* moves = arena + out.traceOff;
-	const uint32_t* path = moves + (out.nMoves + 15) / 16;
-	std::vector<MatrixPos>& t = result.trace;
-	t.reserve(out.nMoves + 1);
-	MatrixPos cur;
-	cur.node = out.endNode;
-	cur.off = out.endOff;
-	cur.j = (size_t)out.nSlices * 64 - 1;
-	t.push_back(cur);
-	uint32_t nextPath = 0;
-	for (uint32_t m = 0; m < out.nMoves; m++)
-	{
-		uint32_t move = (moves[m >> 4] >> ((m & 15) * 2)) & 3u;
-		if (move == GA_MOVE_END) break;   // the step to row -1 is popped again by the reference (GraphAligner.h:949-951)
-		if (move != GA_MOVE_V)
+	parts.resize(top);
+	ParallelFor(jobs.size(), [&](size_t k) {
+		const Job& job = jobs[k];
+		const ga_stream_in& in = streams[k];
+		const ReadInput& r = reads[job.read];
+		uint8_t* dst = parts.data() + in.seqOff;
+		size_t real;
+		if (job.backward)
 		{
-			if (cur.off == 0)
-			{
-				cur.node = path[nextPath++];
-				cur.off = (uint32_t)graph.NodeLength(cur.node) - 1;
-			}
-			else
-			{
-				cur.off--;
-			}
+			real = job.pos + overlap;
+			for (size_t i = 0; i < real; i++) dst[i] = (uint8_t)complementOf(r.seq[real - 1 - i]);
 		}
-		if (move != GA_MOVE_H) cur.j--;
-		t.push_back(cur);
-	}
-	std::reverse(t.begin(), t.end());
-	return result;
+		else
+		{
+			real = r.seqLen - job.pos;
+			memcpy(dst, r.seq + job.pos, real);
+		}
+		memset(dst + real, 'N', in.partLen - real);
+	});
 }
 
 namespace
 {
-
-struct PiecewiseTrace
-{
-	int32_t fwScore = 0, bwScore = 0;
-	std::vector<MatrixPos> fw, bw;
-	size_t estimatedCorrectlyAligned = 0;
-	uint64_t wordColumns = 0;
-};
-
-// addAlignmentNodes, GraphAligner.h:594-634
-void addTried(std::vector<std::tuple<size_t, size_t, size_t>>& tried, const std::vector<MatrixPos>& trace)
-{
-	if (trace.empty()) return;
-	size_t oldNode = trace[0].node;
-	size_t startIndex = trace[0].j, endIndex = trace[0].j;
-	for (size_t i = 1; i < trace.size(); i++)
-	{
-		if (trace[i].node != oldNode)
-		{
-			tried.emplace_back(startIndex, endIndex, oldNode);
-			startIndex = trace[i].j;
-			oldNode = trace[i].node;
-		}
-		endIndex = trace[i].j;
-	}
-	tried.emplace_back(startIndex, endIndex, oldNode);
-}
 
 bool charMatch(char readChar, char graphChar)
 {
@@ -220,8 +255,154 @@ bool charMatch(char readChar, char graphChar)
 	}
 }
 
+
+// same-node runs of one stream's trimmed trace, in forward (ascending row) order
+void decodeRuns(const ga_stream_out& out, const uint32_t* arena, std::vector<TraceRun>& runs)
+{
+	runs.clear();
+	if (out.status != GA_OK || out.nSlices <= 0) return;
+	const uint32_t* rec = arena + out.traceOff + (out.nMoves + 15) / 16 + out.nPathNodes;
+	runs.resize(out.nRuns);
+	for (uint32_t k = 0; k < out.nRuns; k++)
+	{
+		const uint32_t* r = rec + (size_t)(out.nRuns - 1 - k) * GA_RUN_WORDS;
+		runs[k] = TraceRun { r[0], r[1], r[2], (size_t)r[3], (size_t)r[4] };
+	}
+}
+
+// every position of one stream's trimmed trace in forward order (only needed for TraceItems)
+void decodePositions(const AlignmentGraph& graph, const ga_stream_in& in, const ga_stream_out& out, const uint32_t* arena, std::vector<MatrixPos>& t)
+{
+	t.clear();
+	if (out.status != GA_OK || out.nSlices <= 0) return;
+	const uint32_t* moves = arena + out.traceOff;
+	const uint32_t* path = moves + (out.nMoves + 15) / 16;
+	t.reserve(out.nPositions);
+	MatrixPos cur;
+	cur.node = out.endNode;
+	cur.off = out.endOff;
+	cur.j = (size_t)out.nSlices * 64 - 1;
+	if (cur.j < in.trimRows) t.push_back(cur);
+	uint32_t nextPath = 0;
+	for (uint32_t m = 0; m < out.nMoves; m++)
+	{
+		uint32_t move = (moves[m >> 4] >> ((m & 15) * 2)) & 3u;
+		if (move == GA_MOVE_END) break;   // the step to row -1 is popped again by the reference (GraphAligner.h:949-951)
+		if (move != GA_MOVE_V)
+		{
+			if (cur.off == 0)
+			{
+				cur.node = path[nextPath++];
+				cur.off = (uint32_t)graph.NodeLength(cur.node) - 1;
+			}
+			else
+			{
+				cur.off--;
+			}
+		}
+		if (move != GA_MOVE_H) cur.j--;
+		if (cur.j < in.trimRows) t.push_back(cur);
+	}
+	std::reverse(t.begin(), t.end());
+}
+
+// reverseTrace (GraphAligner.h:3026-3037) on runs: order reversed, positions mapped to the other strand,
+// rows mirrored around `end`
+void reverseRuns(const AlignmentGraph& graph, std::vector<TraceRun>& runs, size_t end)
+{
+	std::reverse(runs.begin(), runs.end());
+	for (auto& r : runs)
+	{
+		size_t other = graph.GetReverseNode(r.node);
+		uint32_t len = (uint32_t)graph.NodeLength(other);
+		TraceRun n;
+		n.node = (uint32_t)other;
+		n.firstOff = len - 1 - r.lastOff;
+		n.lastOff = len - 1 - r.firstOff;
+		n.firstJ = end - r.lastJ;
+		n.lastJ = end - r.firstJ;
+		r = n;
+	}
+}
+
+AlignmentResult emptyAlignment()
+{
+	AlignmentResult r;
+	r.alignment.score = std::numeric_limits<int32_t>::max();
+	r.alignmentFailed = true;
+	return r;
+}
+
+// traceToAlignment, GraphAligner.h:782-847, from runs: one Mapping per run with exactly one Edit; non-final
+// mappings get from_length = end - start + 1, the final one end - start; only the first mapping has an offset
+AlignmentResult runsToAlignment(const AlignmentGraph& graph, const ReadInput& read, int32_t score, const std::vector<TraceRun>& runs, bool keepSequences)
+{
+	AlignmentResult r;
+	r.alignment.score = score;
+	r.alignmentFailed = true;
+	if (keepSequences)
+	{
+		r.alignment.name.assign(read.name, read.nameLen);
+		r.alignment.sequence.assign(read.seq, read.seqLen);
+	}
+	if (runs.empty()) return r;
+	size_t k = 0;
+	while (runs[k].node == graph.DummyNodeStart())
+	{
+		k++;
+		if (k == runs.size()) return emptyAlignment();
+	}
+	if (runs[k].node == graph.DummyNodeEnd()) return emptyAlignment();
+	size_t last = k;
+	while (last + 1 < runs.size() && runs[last + 1].node != graph.DummyNodeEnd()) last++;
+	r.alignment.path.mapping.resize(last - k + 1);
+	size_t beforeJ = runs[k].firstJ;
+	for (size_t i = k; i <= last; i++)
+	{
+		vg::Mapping& m = r.alignment.path.mapping[i - k];
+		m.rank = (int64_t)(i - k);
+		m.position.node_id = graph.NodeID(runs[i].node);
+		m.position.is_reverse = graph.Reverse(runs[i].node);
+		if (i == k) m.position.offset = runs[i].firstOff;
+		vg::Edit e;
+		e.from_length = (int32_t)(runs[i].lastOff - runs[i].firstOff) + (i == last ? 0 : 1);
+		e.to_length = (int32_t)(runs[i].lastJ - beforeJ);
+		e.read_start = runs[i].firstJ;
+		if (runs[i].firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");
+		if (keepSequences) e.sequence.assign(read.seq + runs[i].firstJ, std::min<size_t>((size_t)e.to_length, read.seqLen - runs[i].firstJ));
+		m.edit.push_back(std::move(e));
+		beforeJ = runs[i].lastJ;
+	}
+	r.alignmentFailed = false;
+	return r;
+}
+
+// mergeAlignments, GraphAligner.h:648-688
+AlignmentResult mergeAlignments(const AlignmentGraph& graph, AlignmentResult& first, AlignmentResult& second)
+{
+	if (first.alignmentFailed) return std::move(second);
+	if (second.alignmentFailed) return std::move(first);
+	if (first.alignment.path.mapping.empty()) return std::move(second);
+	if (second.alignment.path.mapping.empty()) return std::move(first);
+	AlignmentResult fin;
+	fin.alignmentFailed = false;
+	int32_t score = first.alignment.score + second.alignment.score;
+	const vg::Position firstEnd = first.alignment.path.mapping.back().position;
+	const vg::Position secondStart = second.alignment.path.mapping.front().position;
+	size_t firstEndNode = graph.Lookup((int)firstEnd.node_id);
+	size_t secondStartNode = graph.Lookup((int)secondStart.node_id);
+	size_t start = 0;
+	if (firstEnd.node_id == secondStart.node_id && firstEnd.is_reverse == secondStart.is_reverse) start = 1;
+	else if (graph.HasOutNeighbor(firstEndNode, secondStartNode)) start = 0;
+	// else: the reference only logs "Piecewise alignments can't be merged!" and appends everything
+	fin.alignment = std::move(first.alignment);
+	fin.alignment.score = score;
+	for (size_t i = start; i < second.alignment.path.mapping.size(); i++) fin.alignment.path.mapping.push_back(std::move(second.alignment.path.mapping[i]));
+	return fin;
+}
+
 // getTraceInfoInner, GraphAligner.h:718-780
-void traceInfoInner(const AlignmentGraph& graph, const std::string& sequence, const std::vector<MatrixPos>& trace, std::vector<AlignmentResult::TraceItem>& result)
+void traceInfoInner(const AlignmentGraph& graph, const ReadInput& read, const std::vector<MatrixPos>& trace, std::vector<AlignmentResult::TraceItem>& result)
 {
 	for (size_t i = 1; i < trace.size(); i++)
 	{
@@ -240,140 +421,44 @@ void traceInfoInner(const AlignmentGraph& graph, const std::string& sequence, co
 		item.offset = np.off;
 		item.readpos = np.j;
 		item.graphChar = graph.NodeSequences(graph.NodeStart(np.node) + np.off);
-		item.readChar = sequence[np.j];
+		item.readChar = np.j < read.seqLen ? read.seq[np.j] : '\0';
 		if (np.j == op.j) item.type = AlignmentResult::DELETION;
 		else if (sameColumn && !diagonal) item.type = AlignmentResult::INSERTION;
-		else item.type = charMatch(sequence[np.j], item.graphChar) ? AlignmentResult::MATCH : AlignmentResult::MISMATCH;
+		else item.type = charMatch(item.readChar, item.graphChar) ? AlignmentResult::MATCH : AlignmentResult::MISMATCH;
 		result.push_back(item);
 	}
 }
 
-AlignmentResult emptyAlignment()
-{
-	AlignmentResult r;
-	r.alignment.score = std::numeric_limits<int32_t>::max();
-	r.alignmentFailed = true;
-	return r;
 }
 
-// traceToAlignment, GraphAligner.h:782-847 (one Mapping per node run, one Edit per mapping, final mapping's
-// from_length without the +1)
-AlignmentResult traceToAlignment(const AlignmentGraph& graph, const std::string& seq_id, const std::string& sequence, int32_t score, const std::vector<MatrixPos>& trace)
+ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
+	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, bool keepSequences)
 {
-	AlignmentResult r;
-	r.alignment.name = seq_id;
-	r.alignment.score = score;
-	r.alignment.sequence = sequence;
-	r.alignmentFailed = true;
-	if (trace.empty()) return r;
-	size_t pos = 0;
-	size_t oldNode = trace[0].node;
-	while (oldNode == graph.DummyNodeStart())
-	{
-		pos++;
-		if (pos == trace.size()) return emptyAlignment();
-		oldNode = trace[pos].node;
-	}
-	if (oldNode == graph.DummyNodeEnd()) return emptyAlignment();
-	int rank = 0;
-	r.alignment.path.mapping.emplace_back();
-	{
-		vg::Mapping& m = r.alignment.path.mapping.back();
-		m.rank = rank;
-		m.position.node_id = graph.NodeID(oldNode);
-		m.position.is_reverse = graph.Reverse(oldNode);
-		m.position.offset = trace[pos].off;
-	}
-	MatrixPos btNodeStart = trace[pos], btNodeEnd = trace[pos], btBeforeNode = trace[pos];
-	for (; pos < trace.size(); pos++)
-	{
-		if (trace[pos].node == graph.DummyNodeEnd()) break;
-		if (trace[pos].node == oldNode)
-		{
-			btNodeEnd = trace[pos];
-			continue;
-		}
-		vg::Edit e;
-		e.from_length = (int32_t)(btNodeEnd.off - btNodeStart.off + 1);
-		e.to_length = (int32_t)(btNodeEnd.j - btBeforeNode.j);
-		e.sequence = sequence.substr(btNodeStart.j, btNodeEnd.j - btBeforeNode.j);
-		e.read_start = btNodeStart.j;
-		r.alignment.path.mapping.back().edit.push_back(e);
-		oldNode = trace[pos].node;
-		btBeforeNode = btNodeEnd;
-		btNodeStart = trace[pos];
-		btNodeEnd = trace[pos];
-		rank++;
-		r.alignment.path.mapping.emplace_back();
-		vg::Mapping& m = r.alignment.path.mapping.back();
-		m.rank = rank;
-		m.position.node_id = graph.NodeID(oldNode);
-		m.position.is_reverse = graph.Reverse(oldNode);
-	}
-	vg::Edit e;
-	e.from_length = (int32_t)(btNodeEnd.off - btNodeStart.off);
-	e.to_length = (int32_t)(btNodeEnd.j - btBeforeNode.j);
-	e.sequence = sequence.substr(btNodeStart.j, btNodeEnd.j - btBeforeNode.j);
-	e.read_start = btNodeStart.j;
-	r.alignment.path.mapping.back().edit.push_back(e);
-	r.alignmentFailed = false;
-	return r;
-}
-
-// mergeAlignments, GraphAligner.h:648-688
-AlignmentResult mergeAlignments(const AlignmentGraph& graph, const AlignmentResult& first, const AlignmentResult& second)
-{
-	if (first.alignmentFailed) return second;
-	if (second.alignmentFailed) return first;
-	if (first.alignment.path.mapping.empty()) return second;
-	if (second.alignment.path.mapping.empty()) return first;
-	AlignmentResult fin;
-	fin.alignmentFailed = false;
-	fin.alignment = first.alignment;
-	fin.alignment.score = first.alignment.score + second.alignment.score;
-	size_t start = 0;
-	const vg::Position& firstEnd = first.alignment.path.mapping.back().position;
-	const vg::Position& secondStart = second.alignment.path.mapping.front().position;
-	size_t firstEndNode = graph.Lookup((int)firstEnd.node_id);
-	size_t secondStartNode = graph.Lookup((int)secondStart.node_id);
-	if (firstEnd.node_id == secondStart.node_id && firstEnd.is_reverse == secondStart.is_reverse) start = 1;
-	else if (graph.HasOutNeighbor(firstEndNode, secondStartNode)) start = 0;
-	// else: the reference only logs "Piecewise alignments can't be merged!" and appends everything
-	for (size_t i = start; i < second.alignment.path.mapping.size(); i++) fin.alignment.path.mapping.push_back(second.alignment.path.mapping[i]);
-	return fin;
-}
-
-}
-
-AlignmentResult AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena)
-{
-	const std::string& sequence = *read.sequence;
+	ReadAssembly as;
+	as.result = emptyAlignment();
 	uint32_t first = plan.firstSeedOfRead[readIndex], last = plan.firstSeedOfRead[readIndex + 1];
+	for (uint32_t k = first; k < last; k++)
+	{
+		const BatchPlan::SeedPlan& sp = plan.seeds[k];
+		if (sp.fwStream >= 0) as.wordColumns += outs[sp.fwStream].wordColumns;
+		if (sp.bwStream >= 0) as.wordColumns += outs[sp.bwStream].wordColumns;
+	}
+	as.result.wordColumns = as.wordColumns;
 	std::vector<std::tuple<size_t, size_t, size_t>> tried;
 	bool hasAlignment = false;
-	PiecewiseTrace best;
-	size_t bestSeedPos = 0;
-	uint32_t flags = 0;
-	uint64_t wordColumns = 0;
+	std::vector<TraceRun> fw, bw, bestFw, bestBw;
+	int32_t bestFwScore = 0, bestBwScore = 0;
+	size_t bestEstimated = 0, bestSeedPos = 0, bestFwN = 0, bestBwN = 0;
 	for (uint32_t k = first; k < last; k++)
 	{
 		const BatchPlan::SeedPlan& sp = plan.seeds[k];
-		if (sp.fwStream >= 0) wordColumns += outs[sp.fwStream].wordColumns;
-		if (sp.bwStream >= 0) wordColumns += outs[sp.bwStream].wordColumns;
-	}
-	for (uint32_t k = first; k < last; k++)
-	{
-		const BatchPlan::SeedPlan& sp = plan.seeds[k];
-		const SeedHit& hit = (*read.seeds)[sp.seed];
+		const SeedHit& hit = read.seeds[sp.seed];
 		if (sp.invalid)
 		{
 			// reference: nodeLookup.at / substr throw std::out_of_range (GraphAligner.h:423), or abort on a bad character
-			AlignmentResult r = emptyAlignment();
-			bool badChar = false;
-			for (char c : sequence) badChar = badChar || !ValidReadChar(c);
-			r.flags = badChar ? FLAG_BAD_CHAR : FLAG_BAD_SEED;
-			return r;
+			as.flags |= plan.badChar[readIndex] ? FLAG_BAD_CHAR : FLAG_BAD_SEED;
+			as.result.flags = as.flags;
+			return as;
 		}
 		size_t nodeIndex = graph.Lookup(std::get<0>(hit) * 2);
 		size_t pos = std::get<1>(hit);
@@ -383,81 +468,117 @@ AlignmentResult AssembleRead(const AlignmentGraph& graph, const ReadInput& read,
 			if (std::get<0>(t) <= pos && std::get<1>(t) >= pos && std::get<2>(t) == nodeIndex) { already = true; break; }
 		}
 		if (already) continue;   // "seed i already aligned", GraphAligner.h:425-429
-		PiecewiseTrace pw;
 		// getPiecewiseTracesFromSplit, GraphAligner.h:3039-3098
-		size_t splitIndex = pos;
-		bool streamError = false;
-		size_t fwSlices = 0, bwSlices = 0;
+		const size_t splitIndex = pos;
+		bool streamError = false, shifted = false;
+		size_t fwSlices = 0, bwSlices = 0, fwN = 0, bwN = 0;
+		int32_t fwScore = 0, bwScore = 0;
+		fw.clear();
+		bw.clear();
 		if (sp.fwStream >= 0)
 		{
 			const ga_stream_out& o = outs[sp.fwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
-			if (o.cyclicSlices) flags |= FLAG_CYCLIC;
-			DirectionTrace d = DecodeStream(graph, plan.streams[sp.fwStream], o, arena.data());
-			if (d.present)
+			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.status == GA_OK && o.nSlices > 0)
 			{
-				fwSlices = d.nSlices;
-				pw.fwScore = d.score;
-				pw.fw.swap(d.trace);
-				size_t backtraceableSize = sequence.size() - splitIndex - graph.DBGOverlap;
-				while (!pw.fw.empty() && pw.fw.back().j >= backtraceableSize) pw.fw.pop_back();
+				fwSlices = (size_t)o.nSlices;
+				fwScore = o.score;
+				fwN = o.nPositions;
+				decodeRuns(o, arena.data(), fw);
 			}
 		}
 		if (sp.bwStream >= 0)
 		{
 			const ga_stream_out& o = outs[sp.bwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
-			if (o.cyclicSlices) flags |= FLAG_CYCLIC;
-			DirectionTrace d = DecodeStream(graph, plan.streams[sp.bwStream], o, arena.data());
-			if (d.present)
+			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.status == GA_OK && o.nSlices > 0)
 			{
-				bwSlices = d.nSlices;
-				pw.bwScore = d.score;
-				pw.bw.swap(d.trace);
-				while (!pw.bw.empty() && pw.bw.back().j >= splitIndex) pw.bw.pop_back();
-				// reverseTrace, GraphAligner.h:3026-3037
-				std::reverse(pw.bw.begin(), pw.bw.end());
-				for (auto& p : pw.bw)
-				{
-					size_t other = graph.GetReverseNode(p.node);
-					p.off = (uint32_t)(graph.NodeLength(other) - 1 - p.off);
-					p.node = (uint32_t)other;
-					p.j = (splitIndex - 1) - p.j;
-				}
+				bwSlices = (size_t)o.nSlices;
+				bwScore = o.score;
+				bwN = o.nPositions;
+				decodeRuns(o, arena.data(), bw);
+				reverseRuns(graph, bw, splitIndex - 1);
 				// the forward rows are shifted only inside this branch in the reference (GraphAligner.h:3090-3093)
-				for (auto& p : pw.fw) p.j += splitIndex;
+				for (auto& r : fw) { r.firstJ += splitIndex; r.lastJ += splitIndex; }
+				shifted = true;
 			}
 		}
 		if (streamError)
 		{
-			AlignmentResult r = emptyAlignment();
-			r.flags = flags | FLAG_STREAM_ERROR;
-			r.wordColumns = wordColumns;
-			return r;
+			as.flags |= FLAG_STREAM_ERROR;
+			as.result.flags = as.flags;
+			return as;
 		}
-		pw.estimatedCorrectlyAligned = (fwSlices + bwSlices) * 64;
-		addTried(tried, pw.fw);
-		addTried(tried, pw.bw);
-		if (!hasAlignment || pw.estimatedCorrectlyAligned > best.estimatedCorrectlyAligned)
+		size_t estimated = (fwSlices + bwSlices) * 64;
+		// addAlignmentNodes, GraphAligner.h:594-634
+		for (auto& r : fw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+		for (auto& r : bw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+		if (!hasAlignment || estimated > bestEstimated)
 		{
-			best = std::move(pw);
+			bestFw.swap(fw);
+			bestBw.swap(bw);
+			bestFwScore = fwScore;
+			bestBwScore = bwScore;
+			bestFwN = fwN;
+			bestBwN = bwN;
+			bestEstimated = estimated;
 			bestSeedPos = pos;
 			hasAlignment = true;
+			as.fwStream = fwN > 0 ? sp.fwStream : -1;
+			as.bwStream = bwN > 0 ? sp.bwStream : -1;
+			as.splitIndex = splitIndex;
+			as.fwShifted = shifted;
 		}
 	}
-	if (!hasAlignment)
-	{
-		AlignmentResult r = emptyAlignment();
-		r.flags = flags;
-		r.wordColumns = wordColumns;
-		return r;
-	}
+	as.result.flags = as.flags;
+	if (!hasAlignment) return as;
+	AlignmentResult fwresult = runsToAlignment(graph, read, bestFwScore, bestFw, keepSequences);
+	AlignmentResult bwresult = runsToAlignment(graph, read, bestBwScore, bestBw, keepSequences);
+	if (fwresult.alignmentFailed && bwresult.alignmentFailed) return as;
+	AlignmentResult result = mergeAlignments(graph, bwresult, fwresult);
+	size_t lastAligned = !bestBw.empty() ? bestBw[0].firstJ : bestSeedPos;
+	result.alignment.query_position = (int32_t)lastAligned;
+	result.alignmentStart = lastAligned;
+	result.alignmentEnd = lastAligned + bestEstimated;
+	result.flags = as.flags;
+	result.wordColumns = as.wordColumns;
+	as.nTraceItems = (bestBwN > 0 ? bestBwN - 1 : 0) + ((bestBwN > 0 && bestFwN > 0) ? 1 : 0) + (bestFwN > 0 ? bestFwN - 1 : 0);
+	as.failed = false;
+	as.result = std::move(result);
+	return as;
+}
+
+void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const std::vector<ga_stream_in>& streams,
+	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, std::vector<AlignmentResult::TraceItem>& items)
+{
 	// getTraceInfo, GraphAligner.h:690-716
-	std::vector<AlignmentResult::TraceItem> traceVector;
-	if (!best.bw.empty()) traceInfoInner(graph, sequence, best.bw, traceVector);
-	if (!best.bw.empty() && !best.fw.empty())
+	items.clear();
+	if (as.failed) return;
+	std::vector<MatrixPos> fw, bw;
+	if (as.fwStream >= 0)
 	{
-		const MatrixPos& p = best.fw[0];
+		decodePositions(graph, streams[as.fwStream], outs[as.fwStream], arena.data(), fw);
+		if (as.fwShifted) for (auto& p : fw) p.j += as.splitIndex;
+	}
+	if (as.bwStream >= 0)
+	{
+		decodePositions(graph, streams[as.bwStream], outs[as.bwStream], arena.data(), bw);
+		std::reverse(bw.begin(), bw.end());
+		for (auto& p : bw)
+		{
+			size_t other = graph.GetReverseNode(p.node);
+			p.off = (uint32_t)(graph.NodeLength(other) - 1 - p.off);
+			p.node = (uint32_t)other;
+			p.j = (as.splitIndex - 1) - p.j;
+		}
+	}
+	items.reserve(as.nTraceItems);
+	if (!bw.empty()) traceInfoInner(graph, read, bw, items);
+	if (!bw.empty() && !fw.empty())
+	{
+		const MatrixPos& p = fw[0];
 		AlignmentResult::TraceItem item;
 		item.type = AlignmentResult::FORWARDBACKWARDSPLIT;
 		item.nodeID = graph.NodeID(p.node) / 2;
@@ -465,29 +586,10 @@ AlignmentResult AssembleRead(const AlignmentGraph& graph, const ReadInput& read,
 		item.offset = p.off;
 		item.readpos = p.j;
 		item.graphChar = graph.NodeSequences(graph.NodeStart(p.node) + p.off);
-		item.readChar = sequence[p.j];
-		traceVector.push_back(item);
+		item.readChar = p.j < read.seqLen ? read.seq[p.j] : '\0';
+		items.push_back(item);
 	}
-	if (!best.fw.empty()) traceInfoInner(graph, sequence, best.fw, traceVector);
-
-	AlignmentResult fwresult = traceToAlignment(graph, *read.name, sequence, best.fwScore, best.fw);
-	AlignmentResult bwresult = traceToAlignment(graph, *read.name, sequence, best.bwScore, best.bw);
-	if (fwresult.alignmentFailed && bwresult.alignmentFailed)
-	{
-		AlignmentResult r = emptyAlignment();
-		r.flags = flags;
-		r.wordColumns = wordColumns;
-		return r;
-	}
-	AlignmentResult result = mergeAlignments(graph, bwresult, fwresult);
-	result.trace.swap(traceVector);
-	size_t lastAligned = !best.bw.empty() ? best.bw[0].j : bestSeedPos;
-	result.alignment.query_position = (int32_t)lastAligned;
-	result.alignmentStart = lastAligned;
-	result.alignmentEnd = lastAligned + best.estimatedCorrectlyAligned;
-	result.flags = flags;
-	result.wordColumns = wordColumns;
-	return result;
+	if (!fw.empty()) traceInfoInner(graph, read, fw, items);
 }
 
 std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats)
@@ -498,15 +600,16 @@ std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& gr
 	std::vector<uint32_t> arena;
 	ExecuteStreams(ctx, plan.streams, plan.parts, initialBandwidth, rampBandwidth, outs, arena, stats);
 	std::vector<AlignmentResult> results(reads.size());
-	for (size_t i = 0; i < reads.size(); i++)
-	{
-		if (reads[i].seeds->empty())
+	ParallelFor(reads.size(), [&](size_t i) {
+		if (reads[i].nSeeds == 0)
 		{
 			results[i] = emptyAlignment();   // Aligner.cpp:131-138 "has no seed hits"
-			continue;
+			return;
 		}
-		results[i] = AssembleRead(graph, reads[i], plan, (uint32_t)i, outs, arena);
-	}
+		ReadAssembly as = AssembleRead(graph, reads[i], plan, (uint32_t)i, outs, arena, true);
+		BuildTraceItems(graph, reads[i], as, plan.streams, outs, arena, as.result.trace);
+		results[i] = std::move(as.result);
+	});
 	if (stats)
 	{
 		stats->streams += plan.streams.size();

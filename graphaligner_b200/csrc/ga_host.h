@@ -4,6 +4,7 @@
 #define GA_HOST_H
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -87,11 +88,15 @@ struct DeviceCtx;   // defined in ga_kernels.cu
 
 typedef std::tuple<int, size_t, bool> SeedHit;   // (bigraph node id, read position, reverse)
 
+// one read of a batch; nothing is copied, the caller's buffers must outlive the batch
 struct ReadInput
 {
-	const std::string* name;
-	const std::string* sequence;
-	const std::vector<SeedHit>* seeds;
+	const char* name;
+	size_t nameLen;
+	const char* seq;
+	size_t seqLen;
+	const SeedHit* seeds;
+	size_t nSeeds;
 };
 
 struct MatrixPos
@@ -101,12 +106,12 @@ struct MatrixPos
 	size_t j;
 };
 
-struct DirectionTrace
+// maximal run of consecutive trace positions on the same node (what traceToAlignment turns into one Mapping)
+struct TraceRun
 {
-	int32_t score = 0;
-	bool present = false;          // the direction was run and kept >= 1 slice
-	size_t nSlices = 0;
-	std::vector<MatrixPos> trace;  // ascending rows, like getTraceFromTable's result
+	uint32_t node;
+	uint32_t firstOff, lastOff;
+	size_t firstJ, lastJ;
 };
 
 struct BatchStats
@@ -123,13 +128,15 @@ struct BatchStats
 // Reference reverse complement incl. its IUPAC table and the 'H' fall-through (CommonUtils.cpp:60-136).
 std::string ReverseComplement(const std::string& s);
 bool ValidReadChar(char c);
+unsigned HostThreads();   // worker threads for the host-side passes (GA_HOST_THREADS or hardware_concurrency)
 
-// Plans the streams of a batch (two per seed: backward part, forward part).
+// Plans the streams of a batch (two per seed: backward part, forward part) and writes the padded parts.
 class BatchPlan
 {
 public:
 	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads);
 	std::vector<ga_stream_in> streams;
+	// padded parts of all streams; lives in `parts` unless the caller supplies pinned memory via AllocParts
 	std::vector<uint8_t> parts;
 	struct SeedPlan
 	{
@@ -137,25 +144,43 @@ public:
 		uint32_t seed;
 		int64_t fwStream;   // -1 if the direction does not exist
 		int64_t bwStream;
-		bool invalid;       // unknown node / position outside the read: reference throws out_of_range
+		bool invalid;       // unknown node / position outside the read / bad character
 	};
 	std::vector<SeedPlan> seeds;
 	std::vector<uint32_t> firstSeedOfRead;   // size reads+1
+	std::vector<uint8_t> badChar;            // per read
 };
 
-// Rebuilds the (node, offset, row) trace of one stream from the device's move/path record.
-DirectionTrace DecodeStream(const AlignmentGraph& graph, const ga_stream_in& in, const ga_stream_out& out, const uint32_t* arena);
+// What the seeded AlignOneWay decided for one read (GraphAligner.h:408-491): enough to build the
+// vg::Alignment now and the TraceItems later, on demand.
+struct ReadAssembly
+{
+	bool failed = true;
+	uint32_t flags = 0;
+	uint64_t wordColumns = 0;
+	int64_t fwStream = -1, bwStream = -1;   // streams of the chosen seed that contributed a trace
+	size_t splitIndex = 0;
+	bool fwShifted = false;                 // forward rows were shifted by splitIndex (GraphAligner.h:3090-3093)
+	size_t nTraceItems = 0;
+	AlignmentResult result;                 // alignment, start/end, flags; trace left empty
+};
 
-// The seed loop and result assembly of the reference's seeded AlignOneWay (GraphAligner.h:408-491) given the
-// per-seed direction traces.
-AlignmentResult AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena);
+ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
+	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, bool keepSequences);
+
+// AlignmentResult::trace of an assembled read (getTraceInfo, GraphAligner.h:690-780), decoded from the device's move record
+void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const std::vector<ga_stream_in>& streams,
+	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, std::vector<AlignmentResult::TraceItem>& items);
 
 // Implemented by the CUDA translation unit: runs all streams on the device behind ctx.
 void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth,
 	std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats);
 
+// C++ batch entry: full AlignmentResults including trace items (the C ABI materialises those lazily instead)
 std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+
+// runs f(i) for i in [0,n) on HostThreads() workers
+void ParallelFor(size_t n, const std::function<void(size_t)>& f);
 
 }
 

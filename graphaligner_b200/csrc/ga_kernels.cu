@@ -28,11 +28,13 @@ struct WarpDesc
 	uint64_t hnBase;
 	uint64_t movesBase;
 	uint64_t pathBase;
+	uint64_t runsBase;
 	uint64_t warpCols;
 	uint32_t maxSlices;
 	uint32_t histNodes;
 	uint32_t maxMoves;
 	uint32_t maxPathNodes;
+	uint32_t maxRuns;
 };
 
 struct ScratchPtrs
@@ -47,6 +49,7 @@ struct ScratchPtrs
 	uint4* col;         // [warp slab][2][S]
 	uint32_t* moves;
 	uint32_t* pathNodes;
+	uint32_t* runs;
 	const uint4* peq;   // [stream][slice][2]
 	const uint64_t* peqOff;  // per stream: first uint4 of its masks
 	uint32_t ubktSize;
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	wc.warpCols = wd.warpCols;
 	wc.maxMoves = wd.maxMoves;
 	wc.maxPathNodes = wd.maxPathNodes;
+	wc.maxRuns = wd.maxRuns;
 	GaLaneMem mem;
 	{
 		size_t w = warp;
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 		mem.col = sp.col + wd.colBase * 2 * S + ml;
 		mem.moves = sp.moves + wd.movesBase + ml;
 		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
+		mem.runs = sp.runs + wd.runsBase + ml;
 		mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
 	}
 	ga_stream_out* out = active ? outs + stream : nullptr;
@@ -121,7 +126,8 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	if (!active) return;
 	// compact this stream's trace record into the arena
 	uint32_t moveWords = (out->nMoves + 15) / 16;
-	uint32_t words = moveWords + out->nPathNodes;
+	uint32_t runWords = out->nRuns * GA_RUN_WORDS;
+	uint32_t words = moveWords + out->nPathNodes + runWords;
 	unsigned long long off = atomicAdd(arenaTop, (unsigned long long)words);
 	out->traceOff = off;
 	if (off + words > arenaCap)
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	}
 	for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * S];
 	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * S];
+	for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + out->nPathNodes + i] = mem.runs[(size_t)i * S];
 }
 
 // INT32 roofline probe: 8 independent dependency chains per thread of alternating LOP3 / IADD3, no memory traffic.
@@ -186,7 +193,7 @@ struct DeviceCtx
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bArena, bArenaTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
@@ -290,7 +297,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bArena, &ctx->bArenaTop };
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop };
 	for (Buffer* b : all) b->release();
 	if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -425,7 +432,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	const uint64_t nodesGuess = (colsGuess / 6 + 16);
 	std::vector<WarpDesc> wds(nWarps);
 	std::vector<uint64_t> peqOff(n);
-	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0, peqTop = 0;
+	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0, runsTop = 0, peqTop = 0;
 	sb->arenaCap = 0;
 	for (size_t w = 0; w < nWarps; w++)
 	{
@@ -433,7 +440,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		for (size_t i = w * S; i < std::min(n, w * S + S); i++)
 		{
 			maxLen = std::max(maxLen, sb->sorted[i].partLen);
-			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + (uint64_t)sb->sorted[i].partLen * 2 + 64;
+			// moves (2 bits each, ~1.2 per row) + crossed nodes + runs; nodes are assumed >= 4 bp on average, the retry path covers the rest
+			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + ((uint64_t)sb->sorted[i].partLen / 3 * scale + 258) * (1 + GA_RUN_WORDS) + 8;
 			peqOff[i] = peqTop;
 			peqTop += (uint64_t)(sb->sorted[i].partLen / 64) * 2;
 		}
@@ -443,7 +451,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		d.histNodes = (uint32_t)std::min<uint64_t>(0xfffffff0u, (uint64_t)nslices * nodesGuess + caps.maxNodes + 8);
 		d.warpCols = (uint64_t)nslices * colsGuess + caps.maxCols;
 		d.maxMoves = maxLen * 3 + 256;
-		d.maxPathNodes = maxLen * 2 + 256;
+		d.maxPathNodes = (uint32_t)std::min<uint64_t>(0x7fffffffu, (uint64_t)maxLen / 3 * scale + 256);
+		d.maxRuns = d.maxPathNodes + 2;
 		d.colBase = colTop;
 		colTop += d.warpCols;
 		d.hdrBase = hdrTop;
@@ -454,6 +463,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		movesTop += (uint64_t)(d.maxMoves / 16 + 1) * S;
 		d.pathBase = pathTop;
 		pathTop += (uint64_t)d.maxPathNodes * S;
+		d.runsBase = runsTop;
+		runsTop += (uint64_t)d.maxRuns * GA_RUN_WORDS * S;
 	}
 	sb->peqWords = peqTop;
 	uint32_t ubktSize = 13;
@@ -479,6 +490,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ctx->bPeqOff.ensure(n * sizeof(uint64_t));
 	ctx->bMoves.ensure(movesTop * sizeof(uint32_t));
 	ctx->bPath.ensure(pathTop * sizeof(uint32_t));
+	ctx->bRuns.ensure(runsTop * sizeof(uint32_t));
 	ctx->bArena.ensure(sb->arenaCap * sizeof(uint32_t));
 	ctx->bArenaTop.ensure(sizeof(unsigned long long));
 	sb->sp.tiny = (uint32_t*)ctx->bTiny.ptr;
@@ -494,6 +506,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.peqOff = (const uint64_t*)ctx->bPeqOff.ptr;
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
+	sb->sp.runs = (uint32_t*)ctx->bRuns.ptr;
 	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts->data(), sb->hostParts->size(), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));

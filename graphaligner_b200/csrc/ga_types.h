@@ -28,6 +28,8 @@ typedef struct ga_stream_in
 	uint64_t seqOff;     // byte offset of the padded part in the parts buffer
 	uint32_t partLen;    // padded length (multiple of 64) = reference sequence.size()
 	uint32_t startNode;  // graph node index whose columns are all 0 in the initial slice
+	uint32_t trimRows;   // trace positions with row >= trimRows are dropped (padding / DBG overlap, GraphAligner.h:3063-3066,3086-3089)
+	uint32_t reserved;
 } ga_stream_in;
 
 enum
@@ -58,12 +60,16 @@ typedef struct ga_stream_out
 	uint32_t endOff;
 	uint32_t nMoves;        // number of 2-bit moves in the trace (backward order)
 	uint32_t nPathNodes;    // node indices crossed into, backward order
+	uint32_t nRuns;         // maximal same-node runs of the trimmed trace, backward order, GA_RUN_WORDS words each
+	uint32_t nPositions;    // trace positions left after trimming
 	uint64_t traceOff;      // offset (in 32-bit words) of this stream's record in the trace arena
 	uint32_t nTies;         // cells of the last retained slice tied at the minimum (incl. the chosen one)
 	uint32_t cyclicSlices;  // slices whose band held a cyclic component
 	uint32_t tieNode[GA_MAX_TIES];
 	uint32_t tieOff[GA_MAX_TIES];
 } ga_stream_out;
+
+#define GA_RUN_WORDS 5   /* node, firstOff, lastOff, firstRow, lastRow (first = smallest row) */
 
 // moves (2 bits each, backward from the end cell)
 enum { GA_MOVE_H = 0, GA_MOVE_D = 1, GA_MOVE_V = 2, GA_MOVE_END = 3 };
@@ -79,6 +85,7 @@ typedef struct ga_caps
 	uint64_t warpCols;      // column-history capacity per warp, in columns (x lanes x 20 B)
 	uint32_t maxMoves;      // per-stream temporary trace capacity (moves)
 	uint32_t maxPathNodes;
+	uint32_t maxRuns;
 } ga_caps;
 
 #endif

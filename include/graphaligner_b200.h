@@ -78,8 +78,8 @@ typedef struct ga_read_result
 	uint32_t flags;                 /* GA_FLAG_* */
 	uint64_t mapping_offset;        /* first entry in ga_results_mappings() */
 	uint64_t n_mappings;            /* alignment.path().mapping_size() */
-	uint64_t trace_offset;          /* first entry in ga_results_trace() */
-	uint64_t n_trace;               /* AlignmentResult::trace.size() */
+	uint64_t reserved;
+	uint64_t n_trace;               /* AlignmentResult::trace.size(); the items come from ga_results_read_trace() */
 	uint64_t word_columns;          /* forward-pass word updates spent on this read (all seeds, both directions) */
 } ga_read_result;
 
@@ -112,7 +112,8 @@ typedef struct ga_trace_item        /* AlignmentResult::TraceItem */
 	uint32_t reserved;
 } ga_trace_item;
 
-/* host buffers in, host results out: H2D of the reads, kernels, traceback, D2H, result assembly */
+/* host buffers in, host results out: H2D of the reads, kernels, traceback, D2H, result assembly.
+ * The buffers behind `batch` are referenced, not copied: keep them valid until the results are freed. */
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch);
 
 /* the same in three steps, so that a caller can keep inputs resident in HBM and time the GPU part alone */
@@ -126,7 +127,10 @@ void* ga_cuda_stream(ga_ctx* ctx);                                      /* cudaS
 size_t ga_results_count(const ga_results* r);
 const ga_read_result* ga_results_reads(const ga_results* r);
 const ga_mapping* ga_results_mappings(const ga_results* r);
-const ga_trace_item* ga_results_trace(const ga_results* r);
+/* AlignmentResult::trace of read i, materialised on demand from the device's compact move record: writes up to
+ * `capacity` items and returns the read's item count (call with buffer == NULL to query it).  The ga_batch buffers the
+ * results came from must still be valid. */
+size_t ga_results_read_trace(const ga_results* r, size_t read_index, ga_trace_item* buffer, size_t capacity);
 void ga_results_free(ga_results* r);
 /* FNV-1a 64 over (node_id, offset, reverse, readpos, type) of read i's trace items, each as a little-endian u64:
  * a compact fingerprint of the whole path for differential tests */
