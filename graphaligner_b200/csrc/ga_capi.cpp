@@ -1,5 +1,8 @@
 // extern "C" layer (include/graphaligner_b200.h) over the C++ host code.  Exceptions stop here.
 #include "../../include/graphaligner_b200.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <limits>
@@ -33,8 +36,8 @@ struct ga_results
 	const AlignmentGraph* graph = nullptr;
 	std::vector<ga::ReadInput> inputs;
 	std::vector<ga_stream_in> streams;
-	std::vector<ga_stream_out> outs;
-	std::vector<uint32_t> arena;
+	ga::RawBuffer<ga_stream_out> outs;
+	ga::RawBuffer<uint32_t> arena;
 	struct Lazy
 	{
 		int64_t fwStream, bwStream;
@@ -56,6 +59,21 @@ struct ga_staged
 };
 
 static thread_local std::string g_globalError;
+
+// GA_TIMING=1: per-stage host timings on stderr
+struct StageTimer
+{
+	bool on;
+	std::chrono::steady_clock::time_point t;
+	StageTimer() : on(getenv("GA_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+	void lap(const char* what)
+	{
+		if (!on) return;
+		auto n = std::chrono::steady_clock::now();
+		fprintf(stderr, "[ga timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+		t = n;
+	}
+};
 
 template <typename F>
 static int guarded(ga_ctx* ctx, F&& f)
@@ -204,40 +222,36 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 	out->reads.resize(n);
 	out->lazy.resize(n);
 	std::vector<uint64_t> mapOff(n + 1, 0);
-	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].result.alignment.path.mapping.size());
+	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].mappings.size());
 	out->mappings.resize(mapOff[n]);
 	ga::ParallelFor(n, [&](size_t i) {
 		const ga::ReadAssembly& a = as[i];
-		const AlignmentResult& r = a.result;
 		ga_read_result& o = out->reads[i];
 		memset(&o, 0, sizeof(o));
 		o.failed = a.failed ? 1 : 0;
-		o.score = a.failed ? std::numeric_limits<int32_t>::max() : r.alignment.score;
+		o.score = a.failed ? std::numeric_limits<int32_t>::max() : a.score;
 		o.flags = a.flags;
 		o.word_columns = a.wordColumns;
 		o.mapping_offset = mapOff[i];
 		out->lazy[i] = ga_results::Lazy { a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
 		if (a.failed) return;
-		o.alignment_start = r.alignmentStart;
-		o.alignment_end = r.alignmentEnd;
-		o.query_position = r.alignment.query_position;
-		o.n_mappings = r.alignment.path.mapping.size();
+		o.alignment_start = a.alignmentStart;
+		o.alignment_end = a.alignmentEnd;
+		o.query_position = a.queryPosition;
+		o.n_mappings = a.mappings.size();
 		o.n_trace = a.nTraceItems;
 		ga_mapping* dst = out->mappings.data() + mapOff[i];
-		for (auto& m : r.alignment.path.mapping)
+		for (auto& m : a.mappings)
 		{
 			ga_mapping gm;
 			memset(&gm, 0, sizeof(gm));
-			gm.node_id = m.position.node_id;
-			gm.offset = m.position.offset;
+			gm.node_id = m.node_id;
+			gm.offset = m.offset;
 			gm.rank = m.rank;
-			gm.is_reverse = m.position.is_reverse ? 1 : 0;
-			if (!m.edit.empty())
-			{
-				gm.from_length = m.edit[0].from_length;
-				gm.to_length = m.edit[0].to_length;
-				gm.read_start = m.edit[0].read_start;
-			}
+			gm.is_reverse = m.is_reverse ? 1 : 0;
+			gm.from_length = m.from_length;
+			gm.to_length = m.to_length;
+			gm.read_start = m.read_start;
 			*dst++ = gm;
 		}
 	});
@@ -248,9 +262,14 @@ ga_staged* ga_stage_batch(ga_ctx* ctx, const ga_batch* batch)
 	ga_staged* st = new ga_staged();
 	int rc = guarded(ctx, [&]() {
 		if (!ctx->graph) throw std::logic_error("ga_stage_batch: no graph uploaded");
+		StageTimer tm;
 		fillStaged(st, batch);
-		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads));
-		st->device = ga::StageAndUpload(ctx->dev, st->plan->streams, st->plan->parts, st->b, st->B, &ctx->stats);
+		tm.lap("stage: marshal reads");
+		ga::DeviceCtx* dev = ctx->dev;
+		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads, [dev](size_t bytes) { return ga::AllocPinnedParts(dev, bytes); }));
+		tm.lap("stage: plan + build parts");
+		st->device = ga::StageAndUpload(ctx->dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats);
+		tm.lap("stage: layout + H2D");
 	});
 	if (rc != 0)
 	{
@@ -274,24 +293,24 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 {
 	ga_results* res = new ga_results();
 	int rc = guarded(ctx, [&]() {
+		StageTimer tm;
 		ga::FinishStaged(ctx->dev, st->device, res->outs, res->arena, &ctx->stats);
+		tm.lap("finish: wait kernel + D2H");
 		const AlignmentGraph& graph = ctx->graph->graph;
 		const size_t n = st->reads.size();
 		std::vector<ga::ReadAssembly> as(n);
 		ga::ParallelFor(n, [&](size_t i) {
-			if (st->reads[i].nSeeds == 0)
-			{
-				as[i].result.alignment.score = std::numeric_limits<int32_t>::max();   // "has no seed hits" (Aligner.cpp:131-138)
-				return;
-			}
-			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, res->outs, res->arena, false);
+			if (st->reads[i].nSeeds == 0) return;   // stays failed: "has no seed hits" (Aligner.cpp:131-138)
+			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, res->outs.data(), res->arena.data());
 		});
+		tm.lap("finish: assemble reads");
 		ctx->stats.streams += st->plan->streams.size();
-		for (auto& o : res->outs) ctx->stats.wordColumns += o.wordColumns;
+		for (size_t i = 0; i < res->outs.size(); i++) ctx->stats.wordColumns += res->outs.data()[i].wordColumns;
 		packResults(res, as);
 		res->graph = &graph;
 		res->inputs = st->reads;
 		res->streams = st->plan->streams;
+		tm.lap("finish: pack results");
 	});
 	if (rc != 0)
 	{
@@ -335,7 +354,7 @@ static void materializeTrace(const ga_results* r, size_t i, std::vector<Alignmen
 	as.splitIndex = lz.splitIndex;
 	as.fwShifted = lz.fwShifted;
 	as.nTraceItems = lz.nTraceItems;
-	ga::BuildTraceItems(*r->graph, r->inputs[i], as, r->streams, r->outs, r->arena, items);
+	ga::BuildTraceItems(*r->graph, r->inputs[i], as, r->streams.data(), r->outs.data(), r->arena.data(), items);
 }
 
 size_t ga_results_read_trace(const ga_results* r, size_t i, ga_trace_item* buffer, size_t capacity)

@@ -27,11 +27,13 @@ size_t GraphBytesOnDevice(DeviceCtx* ctx);
 double MeasureInt32Peak(DeviceCtx* ctx);
 
 // plans the per-warp memory layout and copies parts + stream descriptors to the device.  `parts` must outlive the batch.
-StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+// pinned host memory for a batch's padded parts (grow-only, owned by the context, reused by the next batch)
+uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes);
 // launches the alignment kernel(s) on the context's stream (asynchronous); returns number of launches
 int RunStaged(DeviceCtx* ctx, StagedBatch* batch);
 // waits, copies results back, re-runs streams that overflowed their scratch with larger capacities
-void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats);
+void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats);
 void FreeStaged(DeviceCtx* ctx, StagedBatch* batch);
 void* DeviceStream(DeviceCtx* ctx);   // cudaStream_t
 void SyncDevice(DeviceCtx* ctx);

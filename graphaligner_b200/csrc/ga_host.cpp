@@ -133,7 +133,7 @@ static char complementOf(char c)
 	}
 }
 
-BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads)
+BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts)
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
@@ -207,12 +207,18 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 		}
 	}
 	firstSeedOfRead.push_back((uint32_t)seeds.size());
-	parts.resize(top);
+	partsBytes = top;
+	if (allocParts) parts = allocParts(top + 64);
+	else
+	{
+		ownedParts.resize(top + 64);
+		parts = ownedParts.data();
+	}
 	ParallelFor(jobs.size(), [&](size_t k) {
 		const Job& job = jobs[k];
 		const ga_stream_in& in = streams[k];
 		const ReadInput& r = reads[job.read];
-		uint8_t* dst = parts.data() + in.seqOff;
+		uint8_t* dst = parts + in.seqOff;
 		size_t real;
 		if (job.backward)
 		{
@@ -334,71 +340,59 @@ AlignmentResult emptyAlignment()
 }
 
 // traceToAlignment, GraphAligner.h:782-847, from runs: one Mapping per run with exactly one Edit; non-final
-// mappings get from_length = end - start + 1, the final one end - start; only the first mapping has an offset
-AlignmentResult runsToAlignment(const AlignmentGraph& graph, const ReadInput& read, int32_t score, const std::vector<TraceRun>& runs, bool keepSequences)
+// mappings get from_length = end - start + 1, the final one end - start; only the first mapping has an offset.
+// Returns false for a failed (empty) direction.
+bool runsToMappings(const AlignmentGraph& graph, const ReadInput& read, const std::vector<TraceRun>& runs, std::vector<FlatMapping>& out)
 {
-	AlignmentResult r;
-	r.alignment.score = score;
-	r.alignmentFailed = true;
-	if (keepSequences)
-	{
-		r.alignment.name.assign(read.name, read.nameLen);
-		r.alignment.sequence.assign(read.seq, read.seqLen);
-	}
-	if (runs.empty()) return r;
+	out.clear();
+	if (runs.empty()) return false;
 	size_t k = 0;
 	while (runs[k].node == graph.DummyNodeStart())
 	{
 		k++;
-		if (k == runs.size()) return emptyAlignment();
+		if (k == runs.size()) return false;
 	}
-	if (runs[k].node == graph.DummyNodeEnd()) return emptyAlignment();
+	if (runs[k].node == graph.DummyNodeEnd()) return false;
 	size_t last = k;
 	while (last + 1 < runs.size() && runs[last + 1].node != graph.DummyNodeEnd()) last++;
-	r.alignment.path.mapping.resize(last - k + 1);
+	out.resize(last - k + 1);
 	size_t beforeJ = runs[k].firstJ;
 	for (size_t i = k; i <= last; i++)
 	{
-		vg::Mapping& m = r.alignment.path.mapping[i - k];
+		FlatMapping& m = out[i - k];
 		m.rank = (int64_t)(i - k);
-		m.position.node_id = graph.NodeID(runs[i].node);
-		m.position.is_reverse = graph.Reverse(runs[i].node);
-		if (i == k) m.position.offset = runs[i].firstOff;
-		vg::Edit e;
-		e.from_length = (int32_t)(runs[i].lastOff - runs[i].firstOff) + (i == last ? 0 : 1);
-		e.to_length = (int32_t)(runs[i].lastJ - beforeJ);
-		e.read_start = runs[i].firstJ;
-		if (runs[i].firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");
-		if (keepSequences) e.sequence.assign(read.seq + runs[i].firstJ, std::min<size_t>((size_t)e.to_length, read.seqLen - runs[i].firstJ));
-		m.edit.push_back(std::move(e));
+		m.node_id = graph.NodeID(runs[i].node);
+		m.is_reverse = graph.Reverse(runs[i].node);
+		m.offset = i == k ? runs[i].firstOff : 0;
+		m.from_length = (int32_t)(runs[i].lastOff - runs[i].firstOff) + (i == last ? 0 : 1);
+		m.to_length = (int32_t)(runs[i].lastJ - beforeJ);
+		m.read_start = runs[i].firstJ;
+		if (runs[i].firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");   // what sequence.substr would do
 		beforeJ = runs[i].lastJ;
 	}
-	r.alignmentFailed = false;
-	return r;
+	return true;
 }
 
-// mergeAlignments, GraphAligner.h:648-688
-AlignmentResult mergeAlignments(const AlignmentGraph& graph, AlignmentResult& first, AlignmentResult& second)
+// mergeAlignments, GraphAligner.h:648-688, on flat mappings: bw first, then fw without its first mapping when both
+// meet on the same node
+void mergeMappings(const AlignmentGraph& graph, bool firstOk, std::vector<FlatMapping>& first, int32_t firstScore, bool secondOk, std::vector<FlatMapping>& second,
+	int32_t secondScore, std::vector<FlatMapping>& out, int32_t& score)
 {
-	if (first.alignmentFailed) return std::move(second);
-	if (second.alignmentFailed) return std::move(first);
-	if (first.alignment.path.mapping.empty()) return std::move(second);
-	if (second.alignment.path.mapping.empty()) return std::move(first);
-	AlignmentResult fin;
-	fin.alignmentFailed = false;
-	int32_t score = first.alignment.score + second.alignment.score;
-	const vg::Position firstEnd = first.alignment.path.mapping.back().position;
-	const vg::Position secondStart = second.alignment.path.mapping.front().position;
+	if (!firstOk) { out.swap(second); score = secondScore; return; }
+	if (!secondOk) { out.swap(first); score = firstScore; return; }
+	if (first.empty()) { out.swap(second); score = secondScore; return; }
+	if (second.empty()) { out.swap(first); score = firstScore; return; }
+	score = firstScore + secondScore;
+	const FlatMapping& firstEnd = first.back();
+	const FlatMapping& secondStart = second.front();
 	size_t firstEndNode = graph.Lookup((int)firstEnd.node_id);
 	size_t secondStartNode = graph.Lookup((int)secondStart.node_id);
 	size_t start = 0;
 	if (firstEnd.node_id == secondStart.node_id && firstEnd.is_reverse == secondStart.is_reverse) start = 1;
 	else if (graph.HasOutNeighbor(firstEndNode, secondStartNode)) start = 0;
 	// else: the reference only logs "Piecewise alignments can't be merged!" and appends everything
-	fin.alignment = std::move(first.alignment);
-	fin.alignment.score = score;
-	for (size_t i = start; i < second.alignment.path.mapping.size(); i++) fin.alignment.path.mapping.push_back(std::move(second.alignment.path.mapping[i]));
-	return fin;
+	out.swap(first);
+	out.insert(out.end(), second.begin() + start, second.end());
 }
 
 // getTraceInfoInner, GraphAligner.h:718-780
@@ -432,10 +426,9 @@ void traceInfoInner(const AlignmentGraph& graph, const ReadInput& read, const st
 }
 
 ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, bool keepSequences)
+	const ga_stream_out* outs, const uint32_t* arena)
 {
 	ReadAssembly as;
-	as.result = emptyAlignment();
 	uint32_t first = plan.firstSeedOfRead[readIndex], last = plan.firstSeedOfRead[readIndex + 1];
 	for (uint32_t k = first; k < last; k++)
 	{
@@ -443,7 +436,6 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		if (sp.fwStream >= 0) as.wordColumns += outs[sp.fwStream].wordColumns;
 		if (sp.bwStream >= 0) as.wordColumns += outs[sp.bwStream].wordColumns;
 	}
-	as.result.wordColumns = as.wordColumns;
 	std::vector<std::tuple<size_t, size_t, size_t>> tried;
 	bool hasAlignment = false;
 	std::vector<TraceRun> fw, bw, bestFw, bestBw;
@@ -457,7 +449,6 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		{
 			// reference: nodeLookup.at / substr throw std::out_of_range (GraphAligner.h:423), or abort on a bad character
 			as.flags |= plan.badChar[readIndex] ? FLAG_BAD_CHAR : FLAG_BAD_SEED;
-			as.result.flags = as.flags;
 			return as;
 		}
 		size_t nodeIndex = graph.Lookup(std::get<0>(hit) * 2);
@@ -485,7 +476,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 				fwSlices = (size_t)o.nSlices;
 				fwScore = o.score;
 				fwN = o.nPositions;
-				decodeRuns(o, arena.data(), fw);
+				decodeRuns(o, arena, fw);
 			}
 		}
 		if (sp.bwStream >= 0)
@@ -498,7 +489,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 				bwSlices = (size_t)o.nSlices;
 				bwScore = o.score;
 				bwN = o.nPositions;
-				decodeRuns(o, arena.data(), bw);
+				decodeRuns(o, arena, bw);
 				reverseRuns(graph, bw, splitIndex - 1);
 				// the forward rows are shifted only inside this branch in the reference (GraphAligner.h:3090-3093)
 				for (auto& r : fw) { r.firstJ += splitIndex; r.lastJ += splitIndex; }
@@ -508,7 +499,6 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		if (streamError)
 		{
 			as.flags |= FLAG_STREAM_ERROR;
-			as.result.flags = as.flags;
 			return as;
 		}
 		size_t estimated = (fwSlices + bwSlices) * 64;
@@ -532,26 +522,55 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			as.fwShifted = shifted;
 		}
 	}
-	as.result.flags = as.flags;
 	if (!hasAlignment) return as;
-	AlignmentResult fwresult = runsToAlignment(graph, read, bestFwScore, bestFw, keepSequences);
-	AlignmentResult bwresult = runsToAlignment(graph, read, bestBwScore, bestBw, keepSequences);
-	if (fwresult.alignmentFailed && bwresult.alignmentFailed) return as;
-	AlignmentResult result = mergeAlignments(graph, bwresult, fwresult);
+	std::vector<FlatMapping> fwMap, bwMap;
+	bool fwOk = runsToMappings(graph, read, bestFw, fwMap);
+	bool bwOk = runsToMappings(graph, read, bestBw, bwMap);
+	if (!fwOk && !bwOk) return as;
+	mergeMappings(graph, bwOk, bwMap, bestBwScore, fwOk, fwMap, bestFwScore, as.mappings, as.score);
 	size_t lastAligned = !bestBw.empty() ? bestBw[0].firstJ : bestSeedPos;
-	result.alignment.query_position = (int32_t)lastAligned;
-	result.alignmentStart = lastAligned;
-	result.alignmentEnd = lastAligned + bestEstimated;
-	result.flags = as.flags;
-	result.wordColumns = as.wordColumns;
+	as.queryPosition = (int32_t)lastAligned;
+	as.alignmentStart = lastAligned;
+	as.alignmentEnd = lastAligned + bestEstimated;
 	as.nTraceItems = (bestBwN > 0 ? bestBwN - 1 : 0) + ((bestBwN > 0 && bestFwN > 0) ? 1 : 0) + (bestFwN > 0 ? bestFwN - 1 : 0);
 	as.failed = false;
-	as.result = std::move(result);
 	return as;
 }
 
-void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const std::vector<ga_stream_in>& streams,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, std::vector<AlignmentResult::TraceItem>& items)
+AlignmentResult ToAlignmentResult(const ReadInput& read, const ReadAssembly& as, bool keepSequences)
+{
+	AlignmentResult r = emptyAlignment();
+	r.flags = as.flags;
+	r.wordColumns = as.wordColumns;
+	if (as.failed) return r;
+	r.alignmentFailed = false;
+	r.alignment.score = as.score;
+	r.alignment.query_position = as.queryPosition;
+	r.alignmentStart = as.alignmentStart;
+	r.alignmentEnd = as.alignmentEnd;
+	r.alignment.name.assign(read.name, read.nameLen);
+	if (keepSequences) r.alignment.sequence.assign(read.seq, read.seqLen);
+	r.alignment.path.mapping.resize(as.mappings.size());
+	for (size_t i = 0; i < as.mappings.size(); i++)
+	{
+		const FlatMapping& f = as.mappings[i];
+		vg::Mapping& m = r.alignment.path.mapping[i];
+		m.rank = f.rank;
+		m.position.node_id = f.node_id;
+		m.position.offset = f.offset;
+		m.position.is_reverse = f.is_reverse;
+		vg::Edit e;
+		e.from_length = f.from_length;
+		e.to_length = f.to_length;
+		e.read_start = f.read_start;
+		if (keepSequences && f.read_start <= read.seqLen) e.sequence.assign(read.seq + f.read_start, std::min<size_t>((size_t)std::max(0, f.to_length), read.seqLen - f.read_start));
+		m.edit.push_back(std::move(e));
+	}
+	return r;
+}
+
+void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_in* streams,
+	const ga_stream_out* outs, const uint32_t* arena, std::vector<AlignmentResult::TraceItem>& items)
 {
 	// getTraceInfo, GraphAligner.h:690-716
 	items.clear();
@@ -559,12 +578,12 @@ void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const R
 	std::vector<MatrixPos> fw, bw;
 	if (as.fwStream >= 0)
 	{
-		decodePositions(graph, streams[as.fwStream], outs[as.fwStream], arena.data(), fw);
+		decodePositions(graph, streams[as.fwStream], outs[as.fwStream], arena, fw);
 		if (as.fwShifted) for (auto& p : fw) p.j += as.splitIndex;
 	}
 	if (as.bwStream >= 0)
 	{
-		decodePositions(graph, streams[as.bwStream], outs[as.bwStream], arena.data(), bw);
+		decodePositions(graph, streams[as.bwStream], outs[as.bwStream], arena, bw);
 		std::reverse(bw.begin(), bw.end());
 		for (auto& p : bw)
 		{
@@ -596,9 +615,9 @@ std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& gr
 {
 	if (!graph.Finalized()) throw std::logic_error("AlignBatch: graph not finalized");
 	BatchPlan plan(graph, reads);
-	std::vector<ga_stream_out> outs;
-	std::vector<uint32_t> arena;
-	ExecuteStreams(ctx, plan.streams, plan.parts, initialBandwidth, rampBandwidth, outs, arena, stats);
+	RawBuffer<ga_stream_out> outs;
+	RawBuffer<uint32_t> arena;
+	ExecuteStreams(ctx, plan.streams, plan.parts, plan.partsBytes, initialBandwidth, rampBandwidth, outs, arena, stats);
 	std::vector<AlignmentResult> results(reads.size());
 	ParallelFor(reads.size(), [&](size_t i) {
 		if (reads[i].nSeeds == 0)
@@ -606,14 +625,14 @@ std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& gr
 			results[i] = emptyAlignment();   // Aligner.cpp:131-138 "has no seed hits"
 			return;
 		}
-		ReadAssembly as = AssembleRead(graph, reads[i], plan, (uint32_t)i, outs, arena, true);
-		BuildTraceItems(graph, reads[i], as, plan.streams, outs, arena, as.result.trace);
-		results[i] = std::move(as.result);
+		ReadAssembly as = AssembleRead(graph, reads[i], plan, (uint32_t)i, outs.data(), arena.data());
+		results[i] = ToAlignmentResult(reads[i], as, true);
+		BuildTraceItems(graph, reads[i], as, plan.streams.data(), outs.data(), arena.data(), results[i].trace);
 	});
 	if (stats)
 	{
 		stats->streams += plan.streams.size();
-		for (auto& o : outs) stats->wordColumns += o.wordColumns;
+		for (size_t i = 0; i < outs.size(); i++) stats->wordColumns += outs.data()[i].wordColumns;
 	}
 	return results;
 }

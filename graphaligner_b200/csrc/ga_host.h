@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -99,6 +100,23 @@ struct ReadInput
 	size_t nSeeds;
 };
 
+// heap buffer without value-initialisation (a 100 MB std::vector costs ~25 ms just to zero)
+template <typename T>
+class RawBuffer
+{
+public:
+	RawBuffer() : n(0) {}
+	void resize(size_t count) { p.reset(count ? new T[count] : nullptr); n = count; }
+	T* data() { return p.get(); }
+	const T* data() const { return p.get(); }
+	size_t size() const { return n; }
+	void clear() { p.reset(); n = 0; }
+	void swap(RawBuffer& o) { p.swap(o.p); std::swap(n, o.n); }
+private:
+	std::unique_ptr<T[]> p;
+	size_t n;
+};
+
 struct MatrixPos
 {
 	uint32_t node;
@@ -134,10 +152,13 @@ unsigned HostThreads();   // worker threads for the host-side passes (GA_HOST_TH
 class BatchPlan
 {
 public:
-	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads);
+	// allocParts(bytes) may hand out pinned host memory for the padded parts (it must stay valid until the batch has
+	// been uploaded); with no allocator the plan owns the storage
+	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts = nullptr);
 	std::vector<ga_stream_in> streams;
-	// padded parts of all streams; lives in `parts` unless the caller supplies pinned memory via AllocParts
-	std::vector<uint8_t> parts;
+	uint8_t* parts = nullptr;       // padded parts of all streams, back to back
+	size_t partsBytes = 0;
+	RawBuffer<uint8_t> ownedParts;
 	struct SeedPlan
 	{
 		uint32_t read;
@@ -153,6 +174,18 @@ public:
 
 // What the seeded AlignOneWay decided for one read (GraphAligner.h:408-491): enough to build the
 // vg::Alignment now and the TraceItems later, on demand.
+// one vg::Mapping with its single Edit, flattened (see runsToAlignment)
+struct FlatMapping
+{
+	int64_t node_id;
+	int64_t offset;
+	int64_t rank;
+	int32_t from_length;
+	int32_t to_length;
+	uint64_t read_start;
+	bool is_reverse;
+};
+
 struct ReadAssembly
 {
 	bool failed = true;
@@ -162,19 +195,25 @@ struct ReadAssembly
 	size_t splitIndex = 0;
 	bool fwShifted = false;                 // forward rows were shifted by splitIndex (GraphAligner.h:3090-3093)
 	size_t nTraceItems = 0;
-	AlignmentResult result;                 // alignment, start/end, flags; trace left empty
+	int32_t score = 0x7fffffff;
+	int32_t queryPosition = 0;
+	size_t alignmentStart = 0, alignmentEnd = 0;
+	std::vector<FlatMapping> mappings;
 };
 
+// the reference-shaped AlignmentResult (vg::Alignment with names / sequences / edits) of an assembled read
+AlignmentResult ToAlignmentResult(const ReadInput& read, const ReadAssembly& as, bool keepSequences);
+
 ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, bool keepSequences);
+	const ga_stream_out* outs, const uint32_t* arena);
 
 // AlignmentResult::trace of an assembled read (getTraceInfo, GraphAligner.h:690-780), decoded from the device's move record
-void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const std::vector<ga_stream_in>& streams,
-	const std::vector<ga_stream_out>& outs, const std::vector<uint32_t>& arena, std::vector<AlignmentResult::TraceItem>& items);
+void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_in* streams,
+	const ga_stream_out* outs, const uint32_t* arena, std::vector<AlignmentResult::TraceItem>& items);
 
 // Implemented by the CUDA translation unit: runs all streams on the device behind ctx.
-void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth,
-	std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats);
+void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth,
+	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats);
 
 // C++ batch entry: full AlignmentResults including trace items (the C ABI materialises those lazily instead)
 std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats);

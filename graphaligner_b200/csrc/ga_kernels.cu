@@ -198,9 +198,30 @@ struct DeviceCtx
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
 	int smCount = 148;
-	// pinned staging
-	void* pinnedOut = nullptr;
-	size_t pinnedOutCap = 0;
+	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
+	struct Pinned
+	{
+		void* ptr = nullptr;
+		size_t cap = 0;
+		void* ensure(size_t bytes)
+		{
+			if (bytes <= cap) return ptr;
+			if (ptr) cudaFreeHost(ptr);
+			ptr = nullptr;
+			cap = 0;
+			size_t want = bytes + bytes / 8 + 4096;
+			GA_CUDA(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+			cap = want;
+			return ptr;
+		}
+		void release()
+		{
+			if (ptr) cudaFreeHost(ptr);
+			ptr = nullptr;
+			cap = 0;
+		}
+	};
+	Pinned pinParts, pinOuts, pinArena;
 };
 
 struct StagedBatch
@@ -214,7 +235,8 @@ struct StagedBatch
 	size_t nWarps = 0;
 	int launches = 0;
 	// host copy of the inputs, kept for retries
-	const std::vector<uint8_t>* hostParts = nullptr;
+	const uint8_t* hostParts = nullptr;
+	size_t hostPartsBytes = 0;
 	int capScale = 1;
 	int S = 32;            // streams per warp
 	size_t peqWords = 0;
@@ -299,7 +321,9 @@ void DestroyDevice(DeviceCtx* ctx)
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
 		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop };
 	for (Buffer* b : all) b->release();
-	if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
+	ctx->pinParts.release();
+	ctx->pinOuts.release();
+	ctx->pinArena.release();
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -389,14 +413,15 @@ static ga_caps defaultCaps(int b, int B, int scale)
 	return c;
 }
 
-StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth, BatchStats* stats)
+StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats)
 {
 	if (!ctx->hasGraph) throw std::logic_error("StageStreams: no graph uploaded to this device");
 	GA_CUDA(cudaSetDevice(ctx->device));
 	StagedBatch* sb = new StagedBatch();
 	sb->b = initialBandwidth;
 	sb->B = rampBandwidth;
-	sb->hostParts = &parts;
+	sb->hostParts = parts;
+	sb->hostPartsBytes = partsBytes;
 	const size_t n = streams.size();
 	// longest streams first: the 32 streams of a warp iterate as long as the longest of them
 	sb->perm.resize(n);
@@ -474,7 +499,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		if (ctx->sched.buckets[i] >= caps.maxNodes) break;
 	}
 	ubktSize = std::max(ubktSize, caps.maxNodes);
-	ctx->bParts.ensure(sb->hostParts->size() + 64);
+	ctx->bParts.ensure(sb->hostPartsBytes + 64);
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
 	ctx->bOut.ensure(n * sizeof(ga_stream_out));
 	ctx->bWd.ensure(nWarps * sizeof(WarpDesc));
@@ -507,12 +532,12 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
 	sb->sp.runs = (uint32_t*)ctx->bRuns.ptr;
-	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts->data(), sb->hostParts->size(), cudaMemcpyHostToDevice, ctx->stream));
+	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts, sb->hostPartsBytes, cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bPeqOff.ptr, peqOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));   // wds / peqOff are locals
-	if (stats) stats->h2dBytes += sb->hostParts->size() + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc) + n * sizeof(uint64_t);
+	if (stats) stats->h2dBytes += sb->hostPartsBytes + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc) + n * sizeof(uint64_t);
 }
 
 template <int S>
@@ -559,62 +584,89 @@ static bool isOverflow(int32_t status)
 	return status == GA_ERR_NODE_OVERFLOW || status == GA_ERR_COL_OVERFLOW || status == GA_ERR_QUEUE_OVERFLOW || status == GA_ERR_HIST_OVERFLOW || status == GA_ERR_TRACE_OVERFLOW;
 }
 
-void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats)
+void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
 	const size_t n = sb->sorted.size();
-	outs.assign(n, ga_stream_out());
+	outs.resize(n);
 	arena.clear();
 	if (n == 0) return;
-	std::vector<ga_stream_out> sortedOuts(n);
-	unsigned long long top = 0;
-	GA_CUDA(cudaMemcpyAsync(sortedOuts.data(), ctx->bOut.ptr, n * sizeof(ga_stream_out), cudaMemcpyDeviceToHost, ctx->stream));
-	GA_CUDA(cudaMemcpyAsync(&top, ctx->bArenaTop.ptr, sizeof(top), cudaMemcpyDeviceToHost, ctx->stream));
+	// D2H through pinned staging, then a parallel copy into the caller's buffers
+	ga_stream_out* pinOuts = (ga_stream_out*)ctx->pinOuts.ensure(n * sizeof(ga_stream_out) + sizeof(unsigned long long));
+	unsigned long long* pinTop = (unsigned long long*)(pinOuts + n);
+	GA_CUDA(cudaMemcpyAsync(pinOuts, ctx->bOut.ptr, n * sizeof(ga_stream_out), cudaMemcpyDeviceToHost, ctx->stream));
+	GA_CUDA(cudaMemcpyAsync(pinTop, ctx->bArenaTop.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	unsigned long long top = *pinTop;
 	if (top > sb->arenaCap) top = sb->arenaCap;
-	arena.resize(top);
-	if (top) GA_CUDA(cudaMemcpyAsync(arena.data(), ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	uint32_t* pinArena = (uint32_t*)ctx->pinArena.ensure(top * sizeof(uint32_t) + 16);
+	if (top) GA_CUDA(cudaMemcpyAsync(pinArena, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	arena.resize(top);
+	{
+		const size_t chunk = 1 << 20;
+		const size_t nChunks = (top + chunk - 1) / chunk;
+		uint32_t* dst = arena.data();
+		ParallelFor(nChunks, [&](size_t c) {
+			size_t begin = c * chunk, end = std::min<size_t>(top, begin + chunk);
+			memcpy(dst + begin, pinArena + begin, (end - begin) * sizeof(uint32_t));
+		});
+	}
 	if (stats)
 	{
 		stats->d2hBytes += n * sizeof(ga_stream_out) + top * sizeof(uint32_t) + sizeof(top);
 		stats->launches += sb->launches;
+		sb->launches = 0;
 	}
-	for (size_t i = 0; i < n; i++) outs[sb->perm[i]] = sortedOuts[i];
 	// streams that ran out of scratch are re-run with larger capacities (never on the CPU)
 	std::vector<uint32_t> again;
 	for (size_t i = 0; i < n; i++)
 	{
-		if (isOverflow(outs[i].status)) again.push_back((uint32_t)i);
+		if (isOverflow(outs.data()[i].status)) again.push_back((uint32_t)i);
 	}
 	if (!again.empty() && sb->capScale < 64)
 	{
-		std::vector<ga_stream_in> sub;
-		for (uint32_t i : again)
-		{
-			// find the original descriptor: perm maps sorted -> original, so invert lazily
-			sub.push_back(ga_stream_in());
-		}
 		std::vector<uint32_t> inv(n);
 		for (size_t i = 0; i < n; i++) inv[sb->perm[i]] = (uint32_t)i;
+		std::vector<ga_stream_in> sub(again.size());
 		for (size_t k = 0; k < again.size(); k++) sub[k] = sb->sorted[inv[again[k]]];
-		StagedBatch* retry = StageStreams(ctx, sub, *sb->hostParts, sb->b, sb->B, stats);
+		// NOTE: the retry reuses the context's device buffers, so the staged batch cannot be run again afterwards
+		StagedBatch* retry = StageStreams(ctx, sub, sb->hostParts, sb->hostPartsBytes, sb->b, sb->B, stats);
 		retry->capScale = sb->capScale * 4;
-		layoutAndUpload(ctx, retry, stats);
-		RunStaged(ctx, retry);
-		std::vector<ga_stream_out> subOuts;
-		std::vector<uint32_t> subArena;
-		FinishStaged(ctx, retry, subOuts, subArena, stats);
+		RawBuffer<ga_stream_out> subOuts;
+		RawBuffer<uint32_t> subArena;
+		try
+		{
+			layoutAndUpload(ctx, retry, stats);
+			RunStaged(ctx, retry);
+			FinishStaged(ctx, retry, subOuts, subArena, stats);
+		}
+		catch (...)
+		{
+			delete retry;
+			throw;
+		}
 		delete retry;
 		if (stats) stats->retries += again.size();
+		RawBuffer<uint32_t> merged;
+		merged.resize(arena.size() + subArena.size());
+		if (arena.size()) memcpy(merged.data(), arena.data(), arena.size() * sizeof(uint32_t));
+		if (subArena.size()) memcpy(merged.data() + arena.size(), subArena.data(), subArena.size() * sizeof(uint32_t));
 		uint64_t base = arena.size();
-		arena.insert(arena.end(), subArena.begin(), subArena.end());
+		arena.swap(merged);
 		for (size_t k = 0; k < again.size(); k++)
 		{
-			outs[again[k]] = subOuts[k];
-			outs[again[k]].traceOff += base;
+			outs.data()[again[k]] = subOuts.data()[k];
+			outs.data()[again[k]].traceOff += base;
 		}
 	}
+}
+
+uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	return (uint8_t*)ctx->pinParts.ensure(bytes);
 }
 
 void FreeStaged(DeviceCtx* ctx, StagedBatch* sb)
@@ -624,17 +676,25 @@ void FreeStaged(DeviceCtx* ctx, StagedBatch* sb)
 }
 
 // exposed for ga_device users: layout + upload happen at stage time
-StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int b, int B, BatchStats* stats)
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int b, int B, BatchStats* stats)
 {
-	StagedBatch* sb = StageStreams(ctx, streams, parts, b, B, stats);
-	layoutAndUpload(ctx, sb, stats);
+	StagedBatch* sb = StageStreams(ctx, streams, parts, partsBytes, b, B, stats);
+	try
+	{
+		layoutAndUpload(ctx, sb, stats);
+	}
+	catch (...)
+	{
+		delete sb;
+		throw;
+	}
 	return sb;
 }
 
-void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const std::vector<uint8_t>& parts, int initialBandwidth, int rampBandwidth,
-	std::vector<ga_stream_out>& outs, std::vector<uint32_t>& arena, BatchStats* stats)
+void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth,
+	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats)
 {
-	StagedBatch* sb = StageAndUpload(ctx, streams, parts, initialBandwidth, rampBandwidth, stats);
+	StagedBatch* sb = StageAndUpload(ctx, streams, parts, partsBytes, initialBandwidth, rampBandwidth, stats);
 	try
 	{
 		RunStaged(ctx, sb);
