@@ -152,7 +152,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from graphaligner_b200 import api
+    from graphaligner_b200 import api, multi_gpu
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -192,23 +192,17 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    res = aligner.finish(staged)
+    res = aligner.finish(staged, keepalive=packed)
     aligned_bp = int(sum(len(case.reads[i][1]) for i in range(len(case.reads)) if not res.reads["failed"][i]))
     word_columns = int(res.reads["word_columns"].sum())
     failed = int(res.reads["failed"].sum())
     stats = aligner.stats()
     res.free()
     aligner.free_staged(staged)
-    dev_ms = sum(kernel_ms)
-    if world > 1:
-        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-        tot = torch.tensor([aligned_bp, word_columns, failed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        aligned_bp_all, word_columns_all, failed_all = (float(x) for x in tot.tolist())
-    else:
-        aligned_bp_all, word_columns_all, failed_all = aligned_bp, word_columns, failed
+    # device time of the K steps: MAX over ranks; work: SUM over ranks (no data-path collective anywhere else)
+    d = dist if world > 1 else None
+    dev_ms = multi_gpu.reduce_max(d, sum(kernel_ms), device="cuda")
+    aligned_bp_all, word_columns_all, failed_all = multi_gpu.reduce_sum(d, [aligned_bp, word_columns, failed], device="cuda")
     ms_per_step = dev_ms / args.steps
     value = aligned_bp_all / (ms_per_step * 1e-3)
     gcups = word_columns_all * 64 / (ms_per_step * 1e-3) / 1e9
@@ -226,10 +220,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     st = aligner.stats()
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = multi_gpu.reduce_max(d, e2e_s, device="cuda")
     e2e_val = aligned_bp_all * args.steps / e2e_s
 
     line = None

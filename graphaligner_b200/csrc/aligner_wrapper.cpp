@@ -1,0 +1,87 @@
+#include "aligner_wrapper.h"
+#include <chrono>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include "ga_device.h"
+
+namespace
+{
+struct Engine
+{
+	ga::DeviceCtx* ctx = nullptr;
+	std::mutex mutex;   // a device context is not thread-safe; the reference's workers call AlignOneWay concurrently
+};
+std::mutex g_enginesMutex;
+std::map<std::pair<const AlignmentGraph*, int>, Engine*> g_engines;
+
+Engine* engineFor(const AlignmentGraph& graph, int device)
+{
+	std::lock_guard<std::mutex> lock(g_enginesMutex);
+	auto key = std::make_pair(&graph, device);
+	auto found = g_engines.find(key);
+	if (found != g_engines.end()) return found->second;
+	Engine* e = new Engine();
+	e->ctx = ga::CreateDevice(device);
+	ga::UploadGraph(e->ctx, graph);
+	g_engines[key] = e;
+	return e;
+}
+}
+
+void ReleaseAlignerEngine(const AlignmentGraph& graph)
+{
+	std::lock_guard<std::mutex> lock(g_enginesMutex);
+	for (auto it = g_engines.begin(); it != g_engines.end();)
+	{
+		if (it->first.first == &graph)
+		{
+			ga::DestroyDevice(it->second->ctx);
+			delete it->second;
+			it = g_engines.erase(it);
+		}
+		else ++it;
+	}
+}
+
+std::vector<AlignmentResult> AlignReads(const AlignmentGraph& graph, const std::vector<AlignerRead>& reads, int initialBandwidth, int rampBandwidth, int device)
+{
+	Engine* e = engineFor(graph, device);
+	std::vector<ga::ReadInput> inputs(reads.size());
+	for (size_t i = 0; i < reads.size(); i++)
+	{
+		inputs[i] = ga::ReadInput { reads[i].name.data(), reads[i].name.size(), reads[i].sequence.data(), reads[i].sequence.size(), reads[i].seedHits.data(), reads[i].seedHits.size() };
+	}
+	std::lock_guard<std::mutex> lock(e->mutex);
+	return ga::AlignBatch(e->ctx, graph, inputs, initialBandwidth, rampBandwidth, nullptr);
+}
+
+AlignmentResult AlignOneWay(const AlignmentGraph& graph, const std::string& seq_id, const std::string& sequence, int initialBandwidth, int rampBandwidth, size_t dynamicRowStart,
+	const std::vector<std::tuple<int, size_t, bool>>& seedHits)
+{
+	(void)dynamicRowStart;   // parsed but unused by the reference's algorithm as well
+	auto t0 = std::chrono::system_clock::now();
+	// the reference dereferences nodeLookup.at() and substr() and lets std::out_of_range escape (GraphAligner.h:423)
+	for (auto& hit : seedHits)
+	{
+		if (!graph.HasNode(std::get<0>(hit) * 2)) throw std::out_of_range("AlignOneWay: seed node not in graph");
+		if (std::get<1>(hit) >= sequence.size()) throw std::out_of_range("AlignOneWay: seed position outside the read");
+	}
+	std::vector<AlignerRead> one(1);
+	one[0].name = seq_id;
+	one[0].sequence = sequence;
+	one[0].seedHits = seedHits;
+	AlignmentResult r = std::move(AlignReads(graph, one, initialBandwidth, rampBandwidth)[0]);
+	r.elapsedMilliseconds = (size_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now() - t0).count();
+	return r;
+}
+
+AlignmentResult AlignOneWay(const AlignmentGraph& graph, const std::string& seq_id, const std::string& sequence, int initialBandwidth, int rampBandwidth, size_t dynamicRowStart)
+{
+	(void)graph; (void)seq_id; (void)sequence; (void)initialBandwidth; (void)rampBandwidth; (void)dynamicRowStart;
+	AlignmentResult r;
+	r.alignmentFailed = true;
+	r.alignment.score = std::numeric_limits<int32_t>::max();
+	return r;
+}

@@ -30,8 +30,8 @@ struct ga_ctx
 
 struct ga_results
 {
-	std::vector<ga_read_result> reads;
-	std::vector<ga_mapping> mappings;
+	ga::RawBuffer<ga_read_result> reads;
+	ga::RawBuffer<ga_mapping> mappings;
 	// kept for the lazy trace items (ga_results_read_trace): what the device returned and what was decided per read
 	const AlignmentGraph* graph = nullptr;
 	std::vector<ga::ReadInput> inputs;
@@ -226,7 +226,7 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 	out->mappings.resize(mapOff[n]);
 	ga::ParallelFor(n, [&](size_t i) {
 		const ga::ReadAssembly& a = as[i];
-		ga_read_result& o = out->reads[i];
+		ga_read_result& o = out->reads.data()[i];
 		memset(&o, 0, sizeof(o));
 		o.failed = a.failed ? 1 : 0;
 		o.score = a.failed ? std::numeric_limits<int32_t>::max() : a.score;
@@ -359,7 +359,7 @@ static void materializeTrace(const ga_results* r, size_t i, std::vector<Alignmen
 
 size_t ga_results_read_trace(const ga_results* r, size_t i, ga_trace_item* buffer, size_t capacity)
 {
-	if (i >= r->reads.size() || r->lazy[i].failed) return 0;
+	if (i >= r->lazy.size() || r->lazy[i].failed) return 0;
 	if (buffer == nullptr || capacity < r->lazy[i].nTraceItems) return r->lazy[i].nTraceItems;
 	std::vector<AlignmentResult::TraceItem> items;
 	try
@@ -390,7 +390,7 @@ size_t ga_results_read_trace(const ga_results* r, size_t i, ga_trace_item* buffe
 uint64_t ga_results_trace_hash(const ga_results* r, size_t i)
 {
 	uint64_t h = 14695981039346656037ull;
-	if (i >= r->reads.size() || r->lazy[i].failed) return h;
+	if (i >= r->lazy.size() || r->lazy[i].failed) return h;
 	auto mix = [&h](uint64_t v) {
 		for (int b = 0; b < 8; b++)
 		{

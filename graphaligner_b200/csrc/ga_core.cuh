@@ -996,10 +996,12 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	int s = nSlices - 1;
 	int row = 63;
 	const int32_t maxv = (int32_t)st.partLen;
-	uint32_t colBase = 0;    // per (slice, node): index of the node's first column in the slab
+	const uint32_t ABSENT = 0xffffffffu;
+	uint32_t colBase = 0;      // per (slice, node): index of the node's first column in the slab
+	uint32_t prevBase = ABSENT; // the same node's first column in slice s-1, if it is in that band
 	uint64_t wStart = 0;
-	uint32_t seqWord = 0;    // 16 graph bases around the current column
-	bool reload = true;      // slice or node changed: re-resolve colBase and reload both columns
+	uint32_t seqWord = 0;      // 16 graph bases around the current column
+	bool reload = true;        // slice or node changed: re-resolve the bases and reload both columns
 	GaCol cur, left;
 	cur.VP = cur.VN = 0; cur.sbs = cur.scoreEnd = 0;
 	left = cur;
@@ -1013,6 +1015,13 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
 			if (slot < 0) { st.status = GA_ERR_TRACE; break; }
 			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
+			prevBase = ABSENT;
+			if (s > 0)
+			{
+				uint32_t pNodeOff = GA_HDR(s - 1, 2);
+				int pslot = ga_slice_find<LANES>(mem, pNodeOff, GA_HDR(s - 1, 3), node);
+				if (pslot >= 0) prevBase = GA_HDR(s - 1, 0) + GA_HN(pNodeOff + pslot, 1);
+			}
 			wStart = g.nodeStart[node];
 			seqWord = g.seq2[(wStart + off) >> 4];
 			cur = ga_col_load<LANES>(mem, colBase + off);
@@ -1052,57 +1061,64 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
 		const int32_t match = (int32_t)((eqWord >> row) & 1);
 		const int32_t diagWant = here - 1 + match;
-		if (off > 0 && row > 0)
+		const bool firstRow = s == 0 && row == 0;
+		if (firstRow && node == st.startNode && (here == 0 || here == 1))
 		{
-			// fast path: strictly inside a node and inside a slice; the three candidates come from two register-held columns
+			move = GA_MOVE_END;   // GraphAligner.h:500
+		}
+		else if (off > 0)
+		{
+			// inside a node: the candidates come from the two register-held columns (and, on row 0, from the same two
+			// columns' end scores one slice up)
 			const uint64_t maskRow = ~(uint64_t)0 >> (63 - row);
 			const int32_t hs = left.sbs + (int32_t)GA_POPC(left.VP & maskRow) - (int32_t)GA_POPC(left.VN & maskRow);
-			const int32_t ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
-			const int32_t us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+			int32_t ds, us;
+			if (row > 0)
+			{
+				ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
+				us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+			}
+			else if (s == 0)
+			{
+				ds = us = node == st.startNode ? 0 : maxv;   // the initial slice: seed node all zero
+			}
+			else if (prevBase == ABSENT)
+			{
+				ds = us = maxv;
+			}
+			else
+			{
+				ds = (int32_t)mem.col[(size_t)((prevBase + off - 1) * 2 + 1) * LANES].y;   // scoreEnd = row 63 of the slice above
+				us = (int32_t)mem.col[(size_t)((prevBase + off) * 2 + 1) * LANES].y;
+			}
 			if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
 			else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
 			else if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
 		}
 		else
 		{
-			const bool firstRow = s == 0 && row == 0;
-			if (firstRow && node == st.startNode && (here == 0 || here == 1))
+			// first column of a node: in-neighbours in inNeighbors order, horizontal before diagonal (GraphAligner.h:501-533)
+			for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 			{
-				move = GA_MOVE_END;
+				uint32_t u = g.inAdj[e];
+				uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+				int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
+				if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
+				int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
+				if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
 			}
-			else
+			if (move == 4)
 			{
-				if (off == 0)
-				{
-					for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
-					{
-						uint32_t u = g.inAdj[e];
-						uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-						int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
-						if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
-						int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
-						if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
-					}
-				}
-				else
-				{
-					int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
-					if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
-					else
-					{
-						int32_t ds = ga_hist_value<LANES>(mem, st, s - 1, node, off - 1, 63, maxv);   // row == 0 here
-						if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
-					}
-				}
-				if (move == 4)
-				{
-					int32_t us = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, node, off, 63, maxv) : ga_col_value(cur.VP, cur.VN, cur.sbs, row - 1);
-					if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
-				}
-				// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
-				if (firstRow && move != GA_MOVE_H && move != 4) move = GA_MOVE_END;
+				int32_t us;
+				if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+				else if (s == 0) us = node == st.startNode ? 0 : maxv;
+				else if (prevBase == ABSENT) us = maxv;
+				else us = (int32_t)mem.col[(size_t)((prevBase + off) * 2 + 1) * LANES].y;
+				if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
 			}
 		}
+		// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
+		if (firstRow && (move == GA_MOVE_D || move == GA_MOVE_V)) move = GA_MOVE_END;
 #ifdef GA_HOST_DEBUG
 		if (move == 4) fprintf(stderr, "trace fail at node %u off %u s %d row %d here %d\n", node, off, s, row, here);
 #endif

@@ -44,3 +44,16 @@ def test_reference_oracle_reproduces_golden(golden_dir, name):
     expected = load_expected(os.path.join(golden_dir, name + ".expected"))
     got, _ = run_reference(os.path.join(golden_dir, name + ".gacase"))
     assert_same(got, expected, name)
+
+
+RESTATEMENT = os.path.join(ROOT, "oracle", "_ref", "ga_oracle")
+
+
+@pytest.mark.skipif(not os.path.exists(RESTATEMENT), reason="oracle restatement not built (python __graft_entry__.py)")
+@pytest.mark.parametrize("name", GOLDEN)
+def test_restatement_oracle_reproduces_golden(golden_dir, name):
+    # oracle/ga_oracle.cpp (cell-by-cell restatement) pinned against outputs of the unmodified reference
+    import subprocess
+    res = subprocess.run([RESTATEMENT, os.path.join(golden_dir, name + ".gacase")], capture_output=True, text=True, check=True)
+    got, _ = gacase.parse_ref_output(res.stdout)
+    assert_same(got, load_expected(os.path.join(golden_dir, name + ".expected")), name)
