@@ -114,6 +114,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks graph and read count (testing only; 1.0 = BASELINE config)")
     ap.add_argument("--cpu-sample", type=int, default=800)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicate", type=int, default=1, help="align R copies of the read set per step (batch-size study only; not the BASELINE config)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -163,6 +164,9 @@ def main():
     g, case = make_workload(rank, n_reads, args.scale)
     graph = api.Graph.from_case(case)
     aligner = api.Aligner(graph, device=local_rank)
+    if args.replicate > 1:
+        case.reads = [("%s_c%d" % (n, c), s_, sd) for c in range(args.replicate) for (n, s_, sd) in case.reads]
+        workload["workload"] += " x%d replicated (batch-size study)" % args.replicate
     packed = api.PackedReads(case.reads, case.b, case.B)
     total_bp = packed.total_bp
 

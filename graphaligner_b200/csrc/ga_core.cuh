@@ -25,11 +25,13 @@
 
 #ifdef __CUDACC__
 #define GA_DEV __device__ __forceinline__
-#define GA_DEV_NOINLINE __device__ __noinline__
+#define GA_DEV_NOINLINE __device__ __forceinline__   /* a real call would cap the kernel at 96 registers (ABI) and spill in the hot loops */
 #define GA_POPC(x) __popcll(x)
 #define GA_CTZ(x) (__ffsll((long long)(x)) - 1)
 #define GA_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
 #define GA_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+// one allocation per warp from a global bump pointer; every lane gets the same offset
+#define GA_POOL_ALLOC(ptr, n) __shfl_sync(0xffffffffu, ((threadIdx.x & 31) == 0) ? atomicAdd((ptr), (unsigned long long)(n)) : 0ull, 0)
 #else
 #define GA_DEV inline
 #define GA_DEV_NOINLINE inline
@@ -37,11 +39,16 @@
 #define GA_CTZ(x) __builtin_ctzll(x)
 #define GA_WARP_MAX(x) (x)
 #define GA_WARP_ANY(x) (x)
+#define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
 #define GA_HDR_WORDS 6u         // slabOff, ncols, nodeOff, nNodes, minScore, flags
 #define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
+
+#ifdef GA_HOST_DEBUG
+static unsigned long long g_dbgFast = 0, g_dbgOuter = 0, g_dbgGeneral = 0, g_dbgNodeStart = 0, g_dbgRow0 = 0, g_dbgMerged = 0, g_dbgReload = 0;
+#endif
 
 struct GaHmmTables
 {
@@ -68,7 +75,9 @@ struct GaLaneMem
 	uint32_t* nPcs;
 	uint32_t* hdr;
 	uint32_t* histNode;
-	uint4* col;          // column history, two 16-byte halves per column: {VP, VN} and {sbs, scoreEnd, -, -}
+	uint4* col;          // column history pool (shared by all warps), four 16-byte quarters per column:
+	                     // {VP, VN} {sbs, scoreEnd, -, -} {H, D0} {EQ, flags, -}   (H, D0, EQ: traceback masks, see ga_node_columns)
+	unsigned long long* colPoolTop;   // bump pointer of the pool, in columns (x LANES lanes)
 	uint32_t* moves;
 	uint32_t* pathNodes;
 	uint32_t* runs;      // GA_RUN_WORDS words per run
@@ -88,21 +97,27 @@ struct GaCol
 	int32_t sbs, scoreEnd;
 };
 
+#define GA_COL_Q 4u   /* 16-byte quarters per column record */
+
+// stores a column without traceback masks (node starts, merged columns, resets): flags = 0 sends the traceback
+// through the exact general path for this column
 template <int LANES>
 GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c)
 {
-	uint4 a, b;
+	uint4 a, b, z;
 	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
 	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
-	mem.col[(size_t)(col * 2) * LANES] = a;
-	mem.col[(size_t)(col * 2 + 1) * LANES] = b;
+	z.x = z.y = z.z = z.w = 0;
+	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
+	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
+	mem.col[(size_t)(col * GA_COL_Q + 3) * LANES] = z;
 }
 
 template <int LANES>
 GA_DEV GaCol ga_col_load(const GaLaneMem& mem, uint32_t col)
 {
-	uint4 a = mem.col[(size_t)(col * 2) * LANES];
-	uint4 b = mem.col[(size_t)(col * 2 + 1) * LANES];
+	uint4 a = mem.col[(size_t)(col * GA_COL_Q) * LANES];
+	uint4 b = mem.col[(size_t)(col * GA_COL_Q + 1) * LANES];
 	GaCol c;
 	c.VP = (uint64_t)a.x | ((uint64_t)a.y << 32);
 	c.VN = (uint64_t)a.z | ((uint64_t)a.w << 32);
@@ -114,7 +129,7 @@ GA_DEV GaCol ga_col_load(const GaLaneMem& mem, uint32_t col)
 template <int LANES>
 GA_DEV int32_t ga_col_load_sbs(const GaLaneMem& mem, uint32_t col)
 {
-	return (int32_t)mem.col[(size_t)(col * 2 + 1) * LANES].x;
+	return (int32_t)mem.col[(size_t)(col * GA_COL_Q + 1) * LANES].x;
 }
 
 template <int LANES>
@@ -122,14 +137,28 @@ GA_DEV void ga_col_store_sbs(const GaLaneMem& mem, uint32_t col, int32_t sbs)
 {
 	uint4 b;
 	b.x = (uint32_t)sbs; b.y = 0; b.z = 0; b.w = 0;
-	mem.col[(size_t)(col * 2 + 1) * LANES] = b;
+	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
+}
+
+// The traceback is a chain of dependent loads into a history far larger than L2.  Whole nodes are requested into L2
+// when the walk enters them, and the next few columns are pulled into L1 just ahead of the walk.
+template <int LANES>
+GA_DEV void ga_col_prefetch_l2(const GaLaneMem& mem, uint32_t col)
+{
+#ifdef __CUDACC__
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 2) * LANES));
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
+#else
+	(void)mem; (void)col;
+#endif
 }
 
 template <int LANES>
-GA_DEV void ga_col_prefetch(const GaLaneMem& mem, uint32_t col)
+GA_DEV void ga_col_prefetch_l1(const GaLaneMem& mem, uint32_t col)
 {
 #ifdef __CUDACC__
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * 2) * LANES));
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 2) * LANES));
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
 #else
 	(void)mem; (void)col;
 #endif
@@ -151,7 +180,13 @@ GA_DEV uint32_t ga_base(const ga_graph_view& g, uint64_t w)
 }
 
 // Myers word step without the confirmedRows bookkeeping (GraphAligner.h:1349-1399).
-GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftInside, bool diagInside, bool previousEq, int32_t upleftRow62)
+// H = rows where this column is one above its left neighbour (horizontal delta +1), D0 = rows whose diagonal delta is 0.
+// topScore = end score of this column in the previous slice (or INT_MAX): the reference takes the word step from
+// the left neighbour and then min-merges the result with the vertical ramp from topScore when the step's row -1 score
+// is larger (GraphAligner.h:1541-1546).  That minimum IS the word step whose row -1 score is topScore - same
+// recurrence, lower entry value - so whenever topScore - L.sbs is a legal horizontal delta (-1 or 0) the step is taken
+// with it directly, which also keeps H and D0 exact for the traceback.  needMerge reports the rare other case.
+GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftInside, bool diagInside, bool previousEq, int32_t upleftRow62, int32_t topScore, uint64_t& H, uint64_t& D0, bool& needMerge)
 {
 	GaCol r;
 	if (!leftSbE || !diagInside) Eq &= ~(uint64_t)1;
@@ -161,12 +196,20 @@ GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftI
 		int32_t d = upleftRow62 + (previousEq ? 0 : 1);
 		if (d < sbs) sbs = d;
 	}
+	needMerge = false;
+	if (topScore < sbs)
+	{
+		if (topScore - L.sbs >= -1) sbs = topScore;
+		else needMerge = true;
+	}
 	int32_t hin = sbs - L.sbs;
 	uint64_t Xv = Eq | L.VN;
 	if (hin < 0) Eq |= 1;
 	uint64_t Xh = (((Eq & L.VP) + L.VP) ^ L.VP) | Eq;
 	uint64_t Ph = L.VN | ~(Xh | L.VP);
 	uint64_t Mh = L.VP & Xh;
+	H = Ph;
+	D0 = Xh | L.VN;
 	r.scoreEnd = L.scoreEnd + (int32_t)(Ph >> 63) - (int32_t)(Mh >> 63);
 	Ph <<= 1;
 	Mh <<= 1;
@@ -544,7 +587,7 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 	uint64_t w = wStart + 1;
 	uint32_t seqWord = g.seq2[w >> 4];
 	uint32_t shift = (uint32_t)(w & 15) * 2;
-	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * 2) * LANES;
+	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * GA_COL_Q) * LANES;
 	uint32_t* tinyPtr = cx.tinyCur + (size_t)(cs + 1) * LANES;
 	const uint32_t* prevPtr = cx.tinyPrev + (size_t)(pcs + 2) * LANES;   // next column to prefetch
 	const uint32_t* seqPtr = g.seq2 + (w >> 4) + 1;
@@ -556,9 +599,12 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		const uint64_t lo = (base & 1u) ? cx.BC : cx.BA;
 		const uint64_t hi = (base & 1u) ? cx.BT : cx.BG;
 		const uint64_t Eq = (base & 2u) ? hi : lo;
+		const uint64_t EqTrue = Eq;   // IUPAC match mask of this column's base, untouched by the band-edge rules
 		const bool previousEq = ((prevMask >> base) & 1u) != 0;
 		GaCol c;
 		bool sbE = false;
+		uint64_t H, D0;
+		uint32_t flags = 1;   // traceback masks valid: this column is a plain word step from its left neighbour
 		if (INPREV)
 		{
 			const uint32_t oldTiny = oldTinyNext;
@@ -568,20 +614,46 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 			const int32_t oldScore = ga_tiny_score(oldTiny);
 			// forced row -1 score = min(left + 1, previous slice's end score); the flag says the latter attains it
 			sbE = forced ? (oldScore == (int32_t)colPtr[LANES].x) : (oldScore <= L.sbs + 1);
-			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft));
-			if (c.sbs > oldScore) ga_vertical_merge(c, oldScore);
+			bool needMerge;
+			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), oldScore, H, D0, needMerge);
+			if (needMerge) { ga_vertical_merge(c, oldScore); flags = 0; }
+#ifdef GA_HOST_DEBUG
+			{
+				// the shortcut must equal the reference's step-then-merge bit for bit
+				uint64_t h2, d2; bool m2;
+				GaCol ref = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), 0x7fffffff, h2, d2, m2);
+				if (ref.sbs > oldScore) ga_vertical_merge(ref, oldScore);
+				if (ref.VP != c.VP || ref.VN != c.VN || ref.sbs != c.sbs || ref.scoreEnd != c.scoreEnd) { fprintf(stderr, "vertical-merge shortcut mismatch\n"); abort(); }
+			}
+#endif
 			oldTinyLeft = oldTiny;
 		}
 		else
 		{
-			c = ga_next_col(Eq, L, LsbE, false, LsbE, previousEq, 0);
+			bool needMerge;
+			c = ga_next_col(Eq, L, LsbE, false, LsbE, previousEq, 0, 0x7fffffff, H, D0, needMerge);
 		}
-		uint4 ra, rb;
+#ifdef GA_HOST_DEBUG
+		if (flags)
+		{
+			// the masks must agree with the cell values for every row >= 1 (row 0 is never taken from them)
+			for (int r = 1; r < 64; r++)
+			{
+				int32_t here = ga_col_value(c.VP, c.VN, c.sbs, r), lft = ga_col_value(L.VP, L.VN, L.sbs, r), diag = ga_col_value(L.VP, L.VN, L.sbs, r - 1);
+				if ((((H >> r) & 1) != 0) != (here - lft == 1) || (((D0 >> r) & 1) != 0) != (here == diag)) { fprintf(stderr, "traceback mask mismatch row %d\n", r); abort(); }
+			}
+		}
+#endif
+		uint4 ra, rb, rc, rd;
 		ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
 		rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = 0; rb.w = 0;
+		rc.x = (uint32_t)H; rc.y = (uint32_t)(H >> 32); rc.z = (uint32_t)D0; rc.w = (uint32_t)(D0 >> 32);
+		rd.x = (uint32_t)EqTrue; rd.y = (uint32_t)(EqTrue >> 32); rd.z = flags; rd.w = 0;
 		colPtr[0] = ra;
 		colPtr[LANES] = rb;
-		colPtr += 2 * LANES;
+		colPtr[2 * LANES] = rc;
+		colPtr[3 * LANES] = rd;
+		colPtr += GA_COL_Q * LANES;
 		*tinyPtr = ga_tiny_pack(c, sbE);
 		tinyPtr += LANES;
 		if (c.scoreEnd < nodeMin) nodeMin = c.scoreEnd;
@@ -592,7 +664,8 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 }
 
 #define GA_MAX_CACHED_IN 6
-#define GA_TRACE_PREFETCH 40u
+#define GA_TRACE_PREFETCH 64u   /* columns requested into L2 on entering a node */
+#define GA_TRACE_NEAR 4u        /* columns kept ahead in L1 */
 
 // Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
 // forced = the node belongs to a cyclic block whose row -1 scores were already forced into the column records
@@ -699,7 +772,9 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				LsbE = true;
 				EqHere &= 1;
 			}
-			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny));
+			uint64_t hIgnored, dIgnored;
+			bool mIgnored;
+			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), 0x7fffffff, hIgnored, dIgnored, mIgnored);
 			if (k == 0) c0 = cand;
 			else c0 = ga_merge_cols(c0, cand);
 			k++;
@@ -986,34 +1061,45 @@ GA_DEV int32_t ga_hist_value(const GaLaneMem& mem, const GaStreamState& st, int 
 }
 
 template <int LANES>
-GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
+GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool doTrace, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
 {
-	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-	// current same-node run of the trimmed trace (walked backwards: 'last' is seen first)
+	// Called by every lane of the warp (doTrace = this lane has a trace to walk).  One loop iteration = one step of
+	// every walking lane, with a warp vote at the loop head: diverged lanes would otherwise serialise their chains of
+	// dependent loads, which is what a traceback is made of.
+	bool walking = doTrace;
+	uint32_t nMoves = 0, nPath = 0, nRuns = 0;
+	// Same-node runs of the trimmed trace, walked backwards.  A run is opened at the first untrimmed position seen on a
+	// node ('last' in read order) and closed when the walk leaves the node; its other end is the position left from.
 	bool runOpen = false;
-	uint32_t runNode = 0, runFirstOff = 0, runLastOff = 0, runFirstRow = 0, runLastRow = 0;
+	uint32_t runNode = 0, runLastOff = 0, runLastRow = 0;
+	uint32_t skipped = 0;        // positions dropped because their row lies in the trimmed tail
 	uint32_t curWord = 0;
 	int s = nSlices - 1;
 	int row = 63;
 	const int32_t maxv = (int32_t)st.partLen;
 	const uint32_t ABSENT = 0xffffffffu;
-	uint32_t colBase = 0;      // per (slice, node): index of the node's first column in the slab
+	uint32_t colBase = 0;       // per (slice, node): index of the node's first column in the history pool
 	uint32_t prevBase = ABSENT; // the same node's first column in slice s-1, if it is in that band
-	uint64_t wStart = 0;
-	uint32_t seqWord = 0;      // 16 graph bases around the current column
-	bool reload = true;        // slice or node changed: re-resolve the bases and reload both columns
-	GaCol cur, left;
-	cur.VP = cur.VN = 0; cur.sbs = cur.scoreEnd = 0;
-	left = cur;
+	const uint4* colPtr = nullptr;   // record of the current column
+	bool reload = true;         // slice or node changed: re-resolve the bases
+	// traceback masks of the current column (valid iff flags & 1): H = rows one above the left neighbour,
+	// D0 = rows with diagonal delta 0, EQ = rows whose read character matches this column's base
+	uint64_t mH = 0, mD0 = 0, mEQ = 0;
+	uint32_t flags = 0;
 	int32_t here = 0;
 	bool haveHere = false;
-	while (true)
+	const uint32_t maxMoves = caps.maxMoves;
+	while (GA_WARP_ANY(walking))
 	{
+		if (!walking) continue;
 		if (reload)
 		{
+#ifdef GA_HOST_DEBUG
+			g_dbgReload++;
+#endif
 			uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
 			int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
-			if (slot < 0) { st.status = GA_ERR_TRACE; break; }
+			if (slot < 0) { st.status = GA_ERR_TRACE; walking = false; continue; }
 			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
 			prevBase = ABSENT;
 			if (s > 0)
@@ -1022,128 +1108,184 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				int pslot = ga_slice_find<LANES>(mem, pNodeOff, GA_HDR(s - 1, 3), node);
 				if (pslot >= 0) prevBase = GA_HDR(s - 1, 0) + GA_HN(pNodeOff + pslot, 1);
 			}
-			wStart = g.nodeStart[node];
-			seqWord = g.seq2[(wStart + off) >> 4];
-			cur = ga_col_load<LANES>(mem, colBase + off);
-			if (off > 0) left = ga_col_load<LANES>(mem, colBase + off - 1);
-			// the history is far larger than L2: start fetching the rest of this node's columns now, so that one
-			// HBM round trip is paid per node and slice instead of per step
-			for (uint32_t t = 2; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch<LANES>(mem, colBase + off - t);
-			if (!haveHere) { here = ga_col_value(cur.VP, cur.VN, cur.sbs, row); haveHere = true; }
+			colPtr = mem.col + (size_t)((colBase + off) * GA_COL_Q) * LANES;
+			// the history is far larger than L2: request the rest of this node's columns now, so that one HBM round
+			// trip is paid per node and slice instead of per step
+			for (uint32_t t = 1; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch_l2<LANES>(mem, colBase + off - t);
+			if (!haveHere)
+			{
+				GaCol c = ga_col_load<LANES>(mem, colBase + off);
+				here = ga_col_value(c.VP, c.VN, c.sbs, row);
+				haveHere = true;
+			}
+			{
+				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
+				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
+				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+				flags = q3.z;
+			}
 			reload = false;
 		}
-		// record the position we stand on (unless it lies in the trimmed tail)
+		if (!runOpen)
 		{
+			// still inside the trimmed tail, or a run was just closed: open one at the first untrimmed position
 			const uint32_t j = (uint32_t)s * 64u + (uint32_t)row;
-			if (j < st.trimRows)
-			{
-				if (runOpen && runNode != node)
-				{
-					if (nRuns >= caps.maxRuns) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
-					uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
-					r[0] = runNode; r[LANES] = runFirstOff; r[2 * LANES] = runLastOff; r[3 * LANES] = runFirstRow; r[4 * LANES] = runLastRow;
-					nRuns++;
-					runOpen = false;
-				}
-				if (!runOpen) { runOpen = true; runNode = node; runLastOff = off; runLastRow = j; }
-				runFirstOff = off;
-				runFirstRow = j;
-				nPos++;
-			}
+			if (j < st.trimRows) { runOpen = true; runNode = node; runLastOff = off; runLastRow = j; }
+			else skipped++;
 		}
-		const uint64_t w = wStart + off;
+		// ---- fast step: inside the node, inside the slice, on a word-step column (about nine steps in ten).  The three
+		// candidates of pickBacktracePredecessor reduce to three bit tests, taken in the reference's order: horizontal,
+		// diagonal, vertical.  Nothing here can fail or change node / slice / run.
+		if (runOpen && off > 1 && row > 1 && (flags & 1u) && nMoves < maxMoves)
+		{
+#ifdef GA_HOST_DEBUG
+			g_dbgFast++;
+#endif
+			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
+			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
+			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
+			// diagonal delta = 1 - D0 must equal the mismatch cost 1 - EQ
+			const uint32_t mv = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
+			here = here - 1 + (int32_t)((mv == GA_MOVE_D) ? d0 : 0u);
+			curWord |= mv << ((nMoves & 15) * 2);
+			nMoves++;
+			if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
+			if (mv != GA_MOVE_V)
+			{
+				off--;
+				colPtr -= GA_COL_Q * LANES;
+				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
+				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
+				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+				flags = q3.z;
+			}
+			row -= (mv != GA_MOVE_H) ? 1 : 0;
+			continue;
+		}
+#ifdef GA_HOST_DEBUG
+		g_dbgOuter++;
+		if (!(off > 0 && row > 0 && (flags & 1u))) { g_dbgGeneral++; if (off == 0) g_dbgNodeStart++; else if (row == 0) g_dbgRow0++; else g_dbgMerged++; }
+#endif
 		uint32_t move = 4;
 		uint32_t nnode = node, noff = off;
 		int32_t nhere = 0;
-		// read character vs graph base through the slice's precomputed match masks (same IUPAC table)
-		const uint32_t base = (seqWord >> ((uint32_t)(w & 15) * 2)) & 3u;
-		const uint4 pq = mem.peq[(size_t)s * 2 + (base >> 1)];
-		const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
-		const int32_t match = (int32_t)((eqWord >> row) & 1);
-		const int32_t diagWant = here - 1 + match;
-		const bool firstRow = s == 0 && row == 0;
-		if (firstRow && node == st.startNode && (here == 0 || here == 1))
+		if (off > 0 && row > 0 && (flags & 1u))
 		{
-			move = GA_MOVE_END;   // GraphAligner.h:500
-		}
-		else if (off > 0)
-		{
-			// inside a node: the candidates come from the two register-held columns (and, on row 0, from the same two
-			// columns' end scores one slice up)
-			const uint64_t maskRow = ~(uint64_t)0 >> (63 - row);
-			const int32_t hs = left.sbs + (int32_t)GA_POPC(left.VP & maskRow) - (int32_t)GA_POPC(left.VN & maskRow);
-			int32_t ds, us;
-			if (row > 0)
-			{
-				ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
-				us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
-			}
-			else if (s == 0)
-			{
-				ds = us = node == st.startNode ? 0 : maxv;   // the initial slice: seed node all zero
-			}
-			else if (prevBase == ABSENT)
-			{
-				ds = us = maxv;
-			}
-			else
-			{
-				ds = (int32_t)mem.col[(size_t)((prevBase + off - 1) * 2 + 1) * LANES].y;   // scoreEnd = row 63 of the slice above
-				us = (int32_t)mem.col[(size_t)((prevBase + off) * 2 + 1) * LANES].y;
-			}
-			if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
-			else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
-			else if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+			// fast path: an unmerged word-step column, away from node and slice borders.  The three candidates of
+			// pickBacktracePredecessor reduce to three bit tests, in the reference's order: horizontal, diagonal, vertical
+			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
+			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
+			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
+			// diagonal delta = 1 - D0 must equal the mismatch cost 1 - EQ
+			move = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
+			nhere = here - 1 + (int32_t)((move == GA_MOVE_D) ? d0 : 0u);
+			noff = off - (move != GA_MOVE_V ? 1u : 0u);
 		}
 		else
 		{
-			// first column of a node: in-neighbours in inNeighbors order, horizontal before diagonal (GraphAligner.h:501-533)
-			for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
+			// general path (node starts, slice borders, merged columns): evaluate the candidates from the stored columns
+			const GaCol cur = ga_col_load<LANES>(mem, colBase + off);
+			const uint64_t w = g.nodeStart[node] + off;
+			const uint32_t base = ga_base(g, w);
+			const uint4 pq = mem.peq[(size_t)s * 2 + (base >> 1)];
+			const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
+			const int32_t match = (int32_t)((eqWord >> row) & 1);
+			const int32_t diagWant = here - 1 + match;
+			const bool firstRow = s == 0 && row == 0;
+			if (firstRow && node == st.startNode && (here == 0 || here == 1))
 			{
-				uint32_t u = g.inAdj[e];
-				uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-				int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
-				if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
-				int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
-				if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
+				move = GA_MOVE_END;   // GraphAligner.h:500
 			}
-			if (move == 4)
+			else if (off > 0)
 			{
-				int32_t us;
-				if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
-				else if (s == 0) us = node == st.startNode ? 0 : maxv;
-				else if (prevBase == ABSENT) us = maxv;
-				else us = (int32_t)mem.col[(size_t)((prevBase + off) * 2 + 1) * LANES].y;
-				if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+				const GaCol left = ga_col_load<LANES>(mem, colBase + off - 1);
+				const int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
+				int32_t ds, us;
+				if (row > 0)
+				{
+					ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
+					us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+				}
+				else if (s == 0)
+				{
+					ds = us = node == st.startNode ? 0 : maxv;   // the initial slice: seed node all zero
+				}
+				else if (prevBase == ABSENT)
+				{
+					ds = us = maxv;
+				}
+				else
+				{
+					ds = (int32_t)mem.col[(size_t)((prevBase + off - 1) * GA_COL_Q + 1) * LANES].y;   // scoreEnd = row 63 of the slice above
+					us = (int32_t)mem.col[(size_t)((prevBase + off) * GA_COL_Q + 1) * LANES].y;
+				}
+				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
+				else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
+				else if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
 			}
-		}
-		// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
-		if (firstRow && (move == GA_MOVE_D || move == GA_MOVE_V)) move = GA_MOVE_END;
+			else
+			{
+				// first column of a node: in-neighbours in inNeighbors order, horizontal before diagonal (GraphAligner.h:501-533)
+				for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
+				{
+					uint32_t u = g.inAdj[e];
+					uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+					int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
+					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
+					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
+					if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
+				}
+				if (move == 4)
+				{
+					int32_t us;
+					if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
+					else if (s == 0) us = node == st.startNode ? 0 : maxv;
+					else if (prevBase == ABSENT) us = maxv;
+					else us = (int32_t)mem.col[(size_t)((prevBase + off) * GA_COL_Q + 1) * LANES].y;
+					if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+				}
+			}
+			// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
+			if (firstRow && (move == GA_MOVE_D || move == GA_MOVE_V)) move = GA_MOVE_END;
 #ifdef GA_HOST_DEBUG
-		if (move == 4) fprintf(stderr, "trace fail at node %u off %u s %d row %d here %d\n", node, off, s, row, here);
+			if (move == 4) fprintf(stderr, "trace fail at node %u off %u s %d row %d here %d\n", node, off, s, row, here);
 #endif
-		if (move == 4) { st.status = GA_ERR_TRACE; break; }   // reference: assert(false); std::abort()
-		if (nMoves >= caps.maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+			if (move == 4) { st.status = GA_ERR_TRACE; walking = false; continue; }   // reference: assert(false); std::abort()
+		}
+		if (nMoves >= maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
 		curWord |= move << ((nMoves & 15) * 2);
 		nMoves++;
 		if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
-		if (move == GA_MOVE_END) break;
+		// leaving the node (or ending): close the open run; its first position is the one we stand on
+		if (runOpen && (move == GA_MOVE_END || nnode != node))
+		{
+			if (nRuns >= caps.maxRuns) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
+			uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
+			r[0] = runNode; r[LANES] = off; r[2 * LANES] = runLastOff; r[3 * LANES] = (uint32_t)s * 64u + (uint32_t)row; r[4 * LANES] = runLastRow;
+			nRuns++;
+			runOpen = false;
+		}
+		if (move == GA_MOVE_END) { walking = false; continue; }
 		here = nhere;
 		if (move != GA_MOVE_V)
 		{
 			if (off == 0)
 			{
-				if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; break; }
+				if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
 				mem.pathNodes[(size_t)nPath * LANES] = nnode;
 				nPath++;
 				reload = true;
 			}
 			else
 			{
-				cur = left;
-				if (noff > 0) left = ga_col_load<LANES>(mem, colBase + noff - 1);
-				if (noff >= GA_TRACE_PREFETCH) ga_col_prefetch<LANES>(mem, colBase + noff - GA_TRACE_PREFETCH);
-				if (((wStart + noff) & 15) == 15) seqWord = g.seq2[(wStart + noff) >> 4];
+				colPtr -= GA_COL_Q * LANES;
+				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
+				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
+				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+				flags = q3.z;
 			}
 		}
 		if (move != GA_MOVE_H)
@@ -1154,21 +1296,12 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		node = nnode;
 		off = noff;
 	}
-	if (nMoves & 15) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
-	if (runOpen && st.status == GA_OK)
-	{
-		if (nRuns >= caps.maxRuns) st.status = GA_ERR_TRACE_OVERFLOW;
-		else
-		{
-			uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
-			r[0] = runNode; r[LANES] = runFirstOff; r[2 * LANES] = runLastOff; r[3 * LANES] = runFirstRow; r[4 * LANES] = runLastRow;
-			nRuns++;
-		}
-	}
+	if (doTrace && (nMoves & 15)) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
 	nMovesOut = nMoves;
 	nPathOut = nPath;
 	nRunsOut = nRuns;
-	nPosOut = nPos;
+	// positions = the start cell plus one per move except the terminating one, minus the trimmed tail
+	nPosOut = nMoves > skipped ? nMoves - skipped : 0;
 }
 
 // Iterative Tarjan over the band of slice sl in the reference's visiting order (band order, outNeighbors order,
@@ -1310,7 +1443,6 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			st.histNodeTop = 1;
 		}
 	}
-	uint64_t warpColTop = 0;
 	for (int s = 0; ; s++)
 	{
 		bool run = !st.done && (uint32_t)s < st.nslices;
@@ -1328,10 +1460,10 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], stampPrev, mem.hash[tc], stampCur, nodeOff, ncols);
 			if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 		}
+		// this slice's columns for all lanes of the warp: one chunk of the global history pool
 		uint32_t maxc = GA_WARP_MAX(ncols);
-		uint64_t slabOff = warpColTop;
-		warpColTop += maxc;
-		if (warpColTop > caps.warpCols)
+		uint64_t slabOff = GA_POOL_ALLOC(mem.colPoolTop, maxc);
+		if (slabOff + maxc > caps.warpCols)
 		{
 			if (run) { st.status = GA_ERR_COL_OVERFLOW; st.done = true; }
 			break;   // warp-uniform
@@ -1366,84 +1498,97 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			}
 		}
 	}
-	if (!active) return;
-	out->nSlicesRun = (int32_t)slicesRun;
-	out->wordColumns = st.wordColumns;
-	out->cyclicSlices = st.cyclicSlices;
-	out->nMoves = 0;
-	out->nPathNodes = 0;
-	out->nRuns = 0;
-	out->nPositions = 0;
-	out->nTies = 0;
-	out->nSlices = 0;
-	out->score = 0;
-	out->endNode = 0;
-	out->endOff = 0;
-	if (st.status != GA_OK) { out->status = st.status; return; }
-
-	// removeWronglyAlignedEnd (GraphAligner.h:2554-2569)
-	int n = (int)st.slicesPushed;
-	if (n > 0)
+	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------
+	bool doTrace = false;
+	int n = 0;
+	uint32_t endNode = 0, endOff = 0;
+	if (active)
 	{
-		bool currentlyCorrect = (GA_HDR(n - 1, 5) & 1u) != 0;
-		while (!currentlyCorrect)
+		out->nSlicesRun = (int32_t)slicesRun;
+		out->wordColumns = st.wordColumns;
+		out->cyclicSlices = st.cyclicSlices;
+		out->nMoves = 0;
+		out->nPathNodes = 0;
+		out->nRuns = 0;
+		out->nPositions = 0;
+		out->nTies = 0;
+		out->nSlices = 0;
+		out->score = 0;
+		out->endNode = 0;
+		out->endOff = 0;
+		out->status = st.status;
+	}
+	if (active && st.status == GA_OK)
+	{
+		// removeWronglyAlignedEnd (GraphAligner.h:2554-2569)
+		n = (int)st.slicesPushed;
+		if (n > 0)
 		{
-			n--;
-			if (n == 0) break;
-			currentlyCorrect = (GA_HDR(n - 1, 5) & 2u) != 0;   // FalseFromCorrect of the new last slice, as the reference reads it
+			bool currentlyCorrect = (GA_HDR(n - 1, 5) & 1u) != 0;
+			while (!currentlyCorrect)
+			{
+				n--;
+				if (n == 0) break;
+				currentlyCorrect = (GA_HDR(n - 1, 5) & 2u) != 0;   // FalseFromCorrect of the new last slice, as the reference reads it
+			}
+		}
+		out->nSlices = n;
+		if (n == 0) out->status = GA_EMPTY;
+		else
+		{
+			// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
+			// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
+			// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
+			const int sl = n - 1;
+			const int32_t minScore = (int32_t)GA_HDR(sl, 4);
+			const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
+			uint32_t nTies = 0;
+			for (uint32_t slot = 0; slot < nNodes; slot++)
+			{
+				if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
+				uint32_t node = GA_HN(nodeOff + slot, 0);
+				uint32_t cs = GA_HN(nodeOff + slot, 1);
+				uint32_t len = GA_HN(nodeOff + slot, 3);
+				for (uint32_t k = 0; k < len; k++)
+				{
+					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+					int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
+					if (v != minScore) continue;
+					if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
+					nTies++;
+				}
+			}
+			int endSlot = nTies > 0 ? ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore) : -1;
+			if (endSlot < 0) out->status = GA_ERR_INTERNAL;
+			else
+			{
+				endNode = GA_HN(nodeOff + endSlot, 0);
+				uint32_t cs = GA_HN(nodeOff + endSlot, 1);
+				uint32_t len = GA_HN(nodeOff + endSlot, 3);
+				for (uint32_t k = 0; k < len; k++)
+				{
+					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+					int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
+					if (v == minScore) endOff = k;
+				}
+				out->nTies = nTies;
+				out->score = minScore;
+				out->endNode = endNode;
+				out->endOff = endOff;
+				doTrace = !(debugFlags & 1u);
+			}
 		}
 	}
-	out->nSlices = n;
-	if (n == 0) { out->status = GA_EMPTY; return; }
-	// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
-	// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
-	// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
+	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+	ga_traceback<LANES>(g, caps, mem, st, doTrace, n, endNode, endOff, nMoves, nPath, nRuns, nPos);
+	if (doTrace)
 	{
-		const int sl = n - 1;
-		const int32_t minScore = (int32_t)GA_HDR(sl, 4);
-		const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
-		uint32_t nTies = 0;
-		for (uint32_t slot = 0; slot < nNodes; slot++)
-		{
-			if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
-			uint32_t node = GA_HN(nodeOff + slot, 0);
-			uint32_t cs = GA_HN(nodeOff + slot, 1);
-			uint32_t len = GA_HN(nodeOff + slot, 3);
-			for (uint32_t k = 0; k < len; k++)
-			{
-				GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
-				int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
-				if (v != minScore) continue;
-				if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
-				nTies++;
-			}
-		}
-		if (nTies == 0) { out->status = GA_ERR_INTERNAL; return; }
-		int endSlot = ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore);
-		if (endSlot < 0) { out->status = GA_ERR_INTERNAL; return; }
-		uint32_t endNode = GA_HN(nodeOff + endSlot, 0), endOff = 0;
-		{
-			uint32_t cs = GA_HN(nodeOff + endSlot, 1);
-			uint32_t len = GA_HN(nodeOff + endSlot, 3);
-			for (uint32_t k = 0; k < len; k++)
-			{
-				GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
-				int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
-				if (v == minScore) endOff = k;
-			}
-		}
-		out->nTies = nTies;
-		out->score = minScore;
-		out->endNode = endNode;
-		out->endOff = endOff;
-		uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-		if (!(debugFlags & 1u)) ga_traceback<LANES>(g, caps, mem, st, n, endNode, endOff, nMoves, nPath, nRuns, nPos);
 		out->nMoves = nMoves;
 		out->nPathNodes = nPath;
 		out->nRuns = nRuns;
 		out->nPositions = nPos;
+		out->status = st.status;
 	}
-	out->status = st.status;
 }
 
 #endif

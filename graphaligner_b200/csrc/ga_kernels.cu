@@ -23,13 +23,11 @@ namespace ga
 
 struct WarpDesc
 {
-	uint64_t colBase;      // first column of this warp's slab (units: columns, x LANES elements)
 	uint64_t hdrBase;      // element offsets into the pooled arrays (already x LANES)
 	uint64_t hnBase;
 	uint64_t movesBase;
 	uint64_t pathBase;
 	uint64_t runsBase;
-	uint64_t warpCols;
 	uint32_t maxSlices;
 	uint32_t histNodes;
 	uint32_t maxMoves;
@@ -52,20 +50,22 @@ struct ScratchPtrs
 	uint32_t* runs;
 	const uint4* peq;   // [stream][slice][2]
 	const uint64_t* peqOff;  // per stream: first uint4 of its masks
+	unsigned long long* colPoolTop;
+	uint64_t colPoolCap;
 	uint32_t ubktSize;
 };
 
 __constant__ GaHmmTables c_hmm;
 __constant__ GaUmapSchedule c_sched;
 
-// Match masks for every 64-row slice of every stream: one thread per (stream, slice), 64 bytes in, 32 bytes out.
+// Match masks for every 64-row slice of every stream: one block per stream, one thread per slice, 64 bytes in, 32 bytes out.
 __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq)
 {
-	const uint32_t stream = blockIdx.y;
+	const uint32_t stream = blockIdx.x;
 	if (stream >= nStreams) return;
 	const uint32_t nslices = streams[stream].partLen / 64;
 	const uint8_t* base = parts + streams[stream].seqOff;
-	for (uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x; sl < nslices; sl += gridDim.x * blockDim.x)
+	for (uint32_t sl = threadIdx.x; sl < nslices; sl += blockDim.x)
 	{
 		uint64_t A, C, G, T;
 		ga_peq_words(base + (size_t)sl * 64, A, C, G, T);
@@ -78,7 +78,7 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 // S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
 // less divergence; big batches run with S = 32 for full lane utilisation.
 template <int S>
-__global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
+__global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
 	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
 	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 	ga_caps wc = caps;
 	wc.maxSlices = wd.maxSlices;
 	wc.histNodes = wd.histNodes;
-	wc.warpCols = wd.warpCols;
+	wc.warpCols = sp.colPoolCap;
 	wc.maxMoves = wd.maxMoves;
 	wc.maxPathNodes = wd.maxPathNodes;
 	wc.maxRuns = wd.maxRuns;
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(64) ga_align_kernel(ga_graph_view g, ga_caps c
 		mem.ubkt = sp.ubkt + w * sp.ubktSize * S + ml;
 		mem.hdr = sp.hdr + wd.hdrBase + ml;
 		mem.histNode = sp.histNode + wd.hnBase + ml;
-		mem.col = sp.col + wd.colBase * 2 * S + ml;
+		mem.col = sp.col + ml;
+		mem.colPoolTop = sp.colPoolTop;
 		mem.moves = sp.moves + wd.movesBase + ml;
 		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
 		mem.runs = sp.runs + wd.runsBase + ml;
@@ -171,7 +172,12 @@ struct Buffer
 		ptr = nullptr;
 		cap = 0;
 		size_t want = bytes + bytes / 8 + 256;
-		GA_CUDA(cudaMalloc(&ptr, want));
+		cudaError_t e = cudaMalloc(&ptr, want);
+		if (e != cudaSuccess)
+		{
+			ptr = nullptr;
+			throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " + std::to_string(want >> 20) + " MiB of device memory");
+		}
 		cap = want;
 	}
 	void release()
@@ -193,11 +199,13 @@ struct DeviceCtx
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
+	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
 	int smCount = 148;
+	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
 	struct Pinned
 	{
@@ -240,6 +248,7 @@ struct StagedBatch
 	int capScale = 1;
 	int S = 32;            // streams per warp
 	size_t peqWords = 0;
+	uint64_t colPoolCap = 0;
 };
 
 static GaHmmTables makeHmmTables()
@@ -309,6 +318,8 @@ DeviceCtx* CreateDevice(int device)
 		cudaDeviceProp prop;
 		GA_CUDA(cudaGetDeviceProperties(&prop, device));
 		ctx->smCount = prop.multiProcessorCount;
+		int blocks = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, ga_align_kernel<4>, 64, 0) == cudaSuccess && blocks > 0) ctx->warpsPerSm = blocks * 2;
 	}
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
 	return ctx;
@@ -319,7 +330,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop };
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
 	for (Buffer* b : all) b->release();
 	ctx->pinParts.release();
 	ctx->pinOuts.release();
@@ -382,6 +393,7 @@ void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
 	GA_CUDA(cudaSetDevice(ctx->device));
 	ctx->graphBytes = 0;
 	ctx->view.nNodes = (uint32_t)graph.NodeSize();
+	ctx->avgNodeLen = (double)graph.SizeInBp() / (double)std::max<size_t>(1, graph.NodeSize());
 	ctx->view.nodeStart = uploadVec(ctx, ctx->gNodeStart, graph.NodeStarts());
 	ctx->view.seq2 = uploadVec(ctx, ctx->gSeq, graph.Seq2());
 	ctx->view.inOff = uploadVec(ctx, ctx->gInOff, graph.InOff());
@@ -436,9 +448,11 @@ static int pickStreamsPerWarp(DeviceCtx* ctx, size_t nStreams)
 {
 	// enough warps to give every SM sub-partition several to switch between; full warps once the batch is large
 	if (ctx->forceS > 0) return ctx->forceS;
-	const size_t wantWarps = (size_t)ctx->smCount * 16;
-	int S = 32;
-	while (S > 4 && (nStreams + S - 1) / S < wantWarps) S >>= 1;
+	// as many warps as fit on the GPU in ONE wave (a second, nearly empty wave would double the run time of a kernel
+	// whose warps all take about equally long), but never fewer than 4 streams per warp
+	const size_t resident = (size_t)ctx->smCount * ctx->warpsPerSm;
+	int S = 4;
+	while (S < 32 && (nStreams + S - 1) / S > resident) S <<= 1;
 	return S;
 }
 
@@ -453,11 +467,13 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	const size_t nWarps = (n + S - 1) / S;
 	sb->nWarps = nWarps;
 	const int bw = std::max(sb->b, sb->B);
-	const uint64_t colsGuess = (uint64_t)(3 * (bw + 64) + 96) * scale;
-	const uint64_t nodesGuess = (colsGuess / 6 + 16);
+	// expected band per slice: ~2 x (bandwidth + 64) columns plus a node or two of slack; nodes from the graph's mean node length
+	const double avgNodeLen = std::max(1.0, ctx->avgNodeLen);
+	const uint64_t colsGuess = (uint64_t)((2 * (bw + 64) + 2 * std::min(avgNodeLen, 256.0) + 32) * scale);
+	const uint64_t nodesGuess = (uint64_t)(colsGuess / avgNodeLen * 1.5 + 8);
 	std::vector<WarpDesc> wds(nWarps);
 	std::vector<uint64_t> peqOff(n);
-	uint64_t colTop = 0, hdrTop = 0, hnTop = 0, movesTop = 0, pathTop = 0, runsTop = 0, peqTop = 0;
+	uint64_t colTop = 0, hdrTop = 0, totalSlices = 0, hnTop = 0, movesTop = 0, pathTop = 0, runsTop = 0, peqTop = 0;
 	sb->arenaCap = 0;
 	for (size_t w = 0; w < nWarps; w++)
 	{
@@ -466,7 +482,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		{
 			maxLen = std::max(maxLen, sb->sorted[i].partLen);
 			// moves (2 bits each, ~1.2 per row) + crossed nodes + runs; nodes are assumed >= 4 bp on average, the retry path covers the rest
-			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + ((uint64_t)sb->sorted[i].partLen / 3 * scale + 258) * (1 + GA_RUN_WORDS) + 8;
+			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + ((uint64_t)(sb->sorted[i].partLen * 1.3 / avgNodeLen * 2.0 * scale) + 66) * (1 + GA_RUN_WORDS) + 8;
 			peqOff[i] = peqTop;
 			peqTop += (uint64_t)(sb->sorted[i].partLen / 64) * 2;
 		}
@@ -474,12 +490,11 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		WarpDesc& d = wds[w];
 		d.maxSlices = nslices;
 		d.histNodes = (uint32_t)std::min<uint64_t>(0xfffffff0u, (uint64_t)nslices * nodesGuess + caps.maxNodes + 8);
-		d.warpCols = (uint64_t)nslices * colsGuess + caps.maxCols;
+		colTop += (uint64_t)nslices * colsGuess + 64;
+		totalSlices += nslices;
 		d.maxMoves = maxLen * 3 + 256;
-		d.maxPathNodes = (uint32_t)std::min<uint64_t>(0x7fffffffu, (uint64_t)maxLen / 3 * scale + 256);
+		d.maxPathNodes = (uint32_t)std::min<uint64_t>(0x7fffffffu, (uint64_t)(maxLen * 1.3 / avgNodeLen * 2.0 * scale) + 64);
 		d.maxRuns = d.maxPathNodes + 2;
-		d.colBase = colTop;
-		colTop += d.warpCols;
 		d.hdrBase = hdrTop;
 		hdrTop += (uint64_t)d.maxSlices * GA_HDR_WORDS * S;
 		d.hnBase = hnTop;
@@ -510,7 +525,11 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ctx->bUbkt.ensure(nWarps * (size_t)ubktSize * S * sizeof(uint32_t));
 	ctx->bHdr.ensure(hdrTop * sizeof(uint32_t));
 	ctx->bHn.ensure(hnTop * sizeof(uint32_t));
-	ctx->bCol.ensure(colTop * 2 * S * sizeof(uint4));
+	colTop += caps.maxCols;
+	if (colTop >= 0xffffffffull) throw std::runtime_error("batch too large for one launch: column-history pool would exceed 2^32 columns; split the batch");
+	sb->colPoolCap = colTop;
+	ctx->bCol.ensure(colTop * GA_COL_Q * S * sizeof(uint4));
+	ctx->bColTop.ensure(sizeof(unsigned long long));
 	ctx->bPeq.ensure(std::max<uint64_t>(peqTop, 1) * sizeof(uint4));
 	ctx->bPeqOff.ensure(n * sizeof(uint64_t));
 	ctx->bMoves.ensure(movesTop * sizeof(uint32_t));
@@ -527,6 +546,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.hdr = (uint32_t*)ctx->bHdr.ptr;
 	sb->sp.histNode = (uint32_t*)ctx->bHn.ptr;
 	sb->sp.col = (uint4*)ctx->bCol.ptr;
+	sb->sp.colPoolTop = (unsigned long long*)ctx->bColTop.ptr;
+	sb->sp.colPoolCap = colTop;
 	sb->sp.peq = (const uint4*)ctx->bPeq.ptr;
 	sb->sp.peqOff = (const uint64_t*)ctx->bPeqOff.ptr;
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
@@ -559,9 +580,9 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	// the node -> slot tables rely on stamps; clear what an earlier batch left behind
 	GA_CUDA(cudaMemsetAsync(ctx->bHash.ptr, 0, sb->nWarps * 2 * (size_t)sb->caps.hashSize * sb->S * sizeof(uint64_t), ctx->stream));
 	GA_CUDA(cudaMemsetAsync(ctx->bArenaTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
+	GA_CUDA(cudaMemsetAsync(ctx->bColTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
 	{
-		dim3 grid(4, (unsigned)n);
-		ga_peq_kernel<<<grid, 64, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
+		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
 		GA_CUDA(cudaGetLastError());
 	}
 	switch (sb->S)

@@ -82,7 +82,7 @@ typedef struct ga_caps
 	uint32_t maxQueue;      // heap / ready-queue entries
 	uint32_t maxSlices;     // slice headers per stream
 	uint32_t histNodes;     // node-list history entries per stream
-	uint64_t warpCols;      // column-history capacity per warp, in columns (x lanes x 20 B)
+	uint64_t warpCols;      // capacity of the shared column-history pool, in columns (x lanes x 32 B); must stay below 2^32
 	uint32_t maxMoves;      // per-stream temporary trace capacity (moves)
 	uint32_t maxPathNodes;
 	uint32_t maxRuns;
