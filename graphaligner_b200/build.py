@@ -59,6 +59,17 @@ def build(verbose=False, force=False):
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link failed")
+    # the reference-compatible command line, linked against the in-tree library
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    exe = os.path.join(bindir, "Aligner")
+    main_src = os.path.join(CSRC, "aligner_main.cpp")
+    if force or _newer(exe, [main_src, LIB] + headers):
+        cmd = ["g++"] + CXX_FLAGS + ["-o", exe, main_src, "-L" + HERE, "-lgraphaligner_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath," + os.path.join(CUDA_HOME, "lib64"), "-pthread"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("Aligner link failed")
     return LIB
 
 

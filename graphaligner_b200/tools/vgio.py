@@ -174,3 +174,96 @@ def load_fastq(path):
         out.append((lines[i][1:], lines[i + 1]))
         i += 4
     return out
+
+
+# ---- writers (tests build .vg / .gam inputs for the loaders and the CLI with these) ----------------------------
+
+def _put_varint(out, v):
+    if v < 0:
+        v += 1 << 64
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+
+
+def _put_int(out, field, v):
+    if v:
+        _put_varint(out, field << 3)
+        _put_varint(out, int(v))
+
+
+def _put_bytes(out, field, b, always=False):
+    if b or always:
+        _put_varint(out, field << 3 | 2)
+        _put_varint(out, len(b))
+        out.extend(b)
+
+
+def encode_graph(nodes, edges):
+    """nodes: [(id, sequence)], edges: [(from, from_start, to, to_end)]"""
+    out = bytearray()
+    for nid, seq in nodes:
+        m = bytearray()
+        _put_bytes(m, 1, seq.encode())
+        _put_int(m, 3, nid)
+        _put_bytes(out, 1, bytes(m), True)
+    for a, fs, b, te in edges:
+        m = bytearray()
+        _put_int(m, 1, a)
+        _put_int(m, 2, b)
+        _put_int(m, 3, 1 if fs else 0)
+        _put_int(m, 4, 1 if te else 0)
+        _put_bytes(out, 2, bytes(m), True)
+    return bytes(out)
+
+
+def encode_seed(name, node_id, query_position, is_reverse):
+    """A seed hit as the aligner reads it: Alignment{name, query_position, path.mapping[0].position}"""
+    pos = bytearray()
+    _put_int(pos, 1, node_id)
+    _put_int(pos, 4, 1 if is_reverse else 0)
+    mapping = bytearray()
+    _put_bytes(mapping, 1, bytes(pos), True)
+    path = bytearray()
+    _put_bytes(path, 2, bytes(mapping), True)
+    out = bytearray()
+    _put_bytes(out, 2, bytes(path), True)
+    _put_bytes(out, 3, name.encode())
+    _put_int(out, 7, query_position)
+    return bytes(out)
+
+
+def write_stream(path, records, group=1000):
+    """gzip members of: varint count, then (varint length, message) x count (stream.hpp:24-51)"""
+    with open(path, "wb") as f:
+        for i in range(0, len(records), group):
+            chunk = records[i:i + group]
+            raw = bytearray()
+            _put_varint(raw, len(chunk))
+            for r in chunk:
+                _put_varint(raw, len(r))
+                raw.extend(r)
+            f.write(gzip.compress(bytes(raw)))
+        if not records:
+            f.write(gzip.compress(b""))
+
+
+def write_case_files(case, prefix):
+    """Writes <prefix>.vg (or .gfa), <prefix>.fastq, <prefix>_seeds.gam for the reference-style command line."""
+    if case.gfa_overlap is None:
+        graph_path = prefix + ".vg"
+        write_stream(graph_path, [encode_graph(case.nodes, case.edges)])
+    else:
+        graph_path = prefix + ".gfa"
+        with open(graph_path, "w") as f:
+            for nid, seq in case.nodes:
+                f.write("S\t%d\t%s\n" % (nid, seq))
+            for a, fs, b, te in case.edges:
+                f.write("L\t%d\t%s\t%d\t%s\t%dM\n" % (a, "-" if fs else "+", b, "-" if te else "+", case.gfa_overlap))
+    with open(prefix + ".fastq", "w") as f:
+        for name, seq, _ in case.reads:
+            f.write("@%s\n%s\n+\n%s\n" % (name, seq, "!" * len(seq)))
+    seeds = [encode_seed(name, node, pos, rev) for name, _, ss in case.reads for node, pos, rev in ss]
+    write_stream(prefix + "_seeds.gam", seeds)
+    return graph_path, prefix + ".fastq", prefix + "_seeds.gam"
