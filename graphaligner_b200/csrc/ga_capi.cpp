@@ -1,5 +1,6 @@
 // extern "C" layer (include/graphaligner_b200.h) over the C++ host code.  Exceptions stop here.
 #include "../../include/graphaligner_b200.h"
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -32,14 +33,20 @@ struct ga_results
 {
 	ga::RawBuffer<ga_read_result> reads;
 	ga::RawBuffer<ga_mapping> mappings;
-	// kept for the lazy trace items (ga_results_read_trace): what the device returned and what was decided per read
+	// kept for the lazy trace items (ga_results_read_trace): what the device returned and what was decided per read.
+	// A batch too large for the device is aligned in several launches (chunks of reads); each keeps its own buffers.
 	const AlignmentGraph* graph = nullptr;
 	std::vector<ga::ReadInput> inputs;
-	std::vector<ga_stream_in> streams;
-	ga::RawBuffer<ga_stream_out> outs;
-	ga::RawBuffer<uint32_t> arena;
+	struct Chunk
+	{
+		std::vector<ga_stream_in> streams;
+		ga::RawBuffer<ga_stream_out> outs;
+		ga::RawBuffer<uint32_t> arena;
+	};
+	std::vector<std::unique_ptr<Chunk>> chunks;
 	struct Lazy
 	{
+		uint32_t chunk;
 		int64_t fwStream, bwStream;
 		size_t splitIndex;
 		bool fwShifted;
@@ -190,9 +197,11 @@ static void fillStaged(ga_staged* st, const ga_batch* batch)
 	// nothing is copied: ReadInput points into the caller's buffers, which must stay valid until the results
 	// (and any lazily requested trace items) are no longer needed
 	const size_t n = batch->n_reads;
-	const uint64_t nSeeds = n ? batch->seed_offsets[n] : 0;
+	// offsets are absolute into the seed arrays and need not start at 0 (a sub-batch is the same arrays, shifted)
+	const uint64_t seedBase = n ? batch->seed_offsets[0] : 0;
+	const uint64_t nSeeds = n ? batch->seed_offsets[n] - seedBase : 0;
 	st->seeds.resize(nSeeds);
-	for (uint64_t k = 0; k < nSeeds; k++) st->seeds[k] = ga::SeedHit((int)batch->seed_node[k], (size_t)batch->seed_pos[k], batch->seed_reverse[k] != 0);
+	for (uint64_t k = 0; k < nSeeds; k++) st->seeds[k] = ga::SeedHit((int)batch->seed_node[seedBase + k], (size_t)batch->seed_pos[seedBase + k], batch->seed_reverse[seedBase + k] != 0);
 	st->reads.resize(n);
 	for (size_t i = 0; i < n; i++)
 	{
@@ -209,7 +218,7 @@ static void fillStaged(ga_staged* st, const ga_batch* batch)
 			r.name = "";
 			r.nameLen = 0;
 		}
-		r.seeds = st->seeds.data() + batch->seed_offsets[i];
+		r.seeds = st->seeds.data() + (batch->seed_offsets[i] - seedBase);
 		r.nSeeds = (size_t)(batch->seed_offsets[i + 1] - batch->seed_offsets[i]);
 	}
 	st->b = batch->initial_bandwidth;
@@ -233,7 +242,7 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 		o.flags = a.flags;
 		o.word_columns = a.wordColumns;
 		o.mapping_offset = mapOff[i];
-		out->lazy[i] = ga_results::Lazy { a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
+		out->lazy[i] = ga_results::Lazy { 0, a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
 		if (a.failed) return;
 		o.alignment_start = a.alignmentStart;
 		o.alignment_end = a.alignmentEnd;
@@ -294,22 +303,24 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 	ga_results* res = new ga_results();
 	int rc = guarded(ctx, [&]() {
 		StageTimer tm;
-		ga::FinishStaged(ctx->dev, st->device, res->outs, res->arena, &ctx->stats);
+		res->chunks.emplace_back(new ga_results::Chunk());
+		ga_results::Chunk& ch = *res->chunks.back();
+		ga::FinishStaged(ctx->dev, st->device, ch.outs, ch.arena, &ctx->stats);
 		tm.lap("finish: wait kernel + D2H");
 		const AlignmentGraph& graph = ctx->graph->graph;
 		const size_t n = st->reads.size();
 		std::vector<ga::ReadAssembly> as(n);
 		ga::ParallelFor(n, [&](size_t i) {
 			if (st->reads[i].nSeeds == 0) return;   // stays failed: "has no seed hits" (Aligner.cpp:131-138)
-			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, res->outs.data(), res->arena.data());
+			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, ch.outs.data(), ch.arena.data());
 		});
 		tm.lap("finish: assemble reads");
 		ctx->stats.streams += st->plan->streams.size();
-		for (size_t i = 0; i < res->outs.size(); i++) ctx->stats.wordColumns += res->outs.data()[i].wordColumns;
+		for (size_t i = 0; i < ch.outs.size(); i++) ctx->stats.wordColumns += ch.outs.data()[i].wordColumns;
 		packResults(res, as);
 		res->graph = &graph;
 		res->inputs = st->reads;
-		res->streams = st->plan->streams;
+		ch.streams = st->plan->streams;
 		tm.lap("finish: pack results");
 	});
 	if (rc != 0)
@@ -329,14 +340,87 @@ void ga_staged_free(ga_ctx* ctx, ga_staged* st)
 
 void* ga_cuda_stream(ga_ctx* ctx) { return ga::DeviceStream(ctx->dev); }
 
+// appends the results of one chunk (reads [first, first + part->lazy.size())) to the combined results
+static void appendChunk(ga_results* all, ga_results* part, size_t first)
+{
+	const uint32_t chunkIndex = (uint32_t)all->chunks.size();
+	const uint64_t mapBase = all->mappings.size();
+	ga::RawBuffer<ga_mapping> merged;
+	merged.resize(mapBase + part->mappings.size());
+	if (mapBase) memcpy(merged.data(), all->mappings.data(), mapBase * sizeof(ga_mapping));
+	if (part->mappings.size()) memcpy(merged.data() + mapBase, part->mappings.data(), part->mappings.size() * sizeof(ga_mapping));
+	all->mappings.swap(merged);
+	for (size_t i = 0; i < part->lazy.size(); i++)
+	{
+		all->reads.data()[first + i] = part->reads.data()[i];
+		all->reads.data()[first + i].mapping_offset += mapBase;
+		all->lazy[first + i] = part->lazy[i];
+		all->lazy[first + i].chunk = chunkIndex;
+		all->inputs[first + i] = part->inputs[i];
+	}
+	all->chunks.push_back(std::move(part->chunks[0]));
+}
+
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 {
-	ga_staged* st = ga_stage_batch(ctx, batch);
-	if (!st) return nullptr;
-	ga_results* res = nullptr;
-	if (ga_run_staged(ctx, st) == 0) res = ga_finish_staged(ctx, st);
-	ga_staged_free(ctx, st);
-	return res;
+	// split the batch when its DP history would not fit the device (the history is ~64 B per band column and slice)
+	std::vector<size_t> cuts;   // chunk boundaries in reads
+	int rc = guarded(ctx, [&]() {
+		if (!ctx->graph) throw std::logic_error("ga_align_batch: no graph uploaded");
+		const size_t budget = (size_t)(ga::FreeDeviceBytes(ctx->dev) * 0.8);
+		const int bw = std::max(batch->initial_bandwidth, batch->ramp_bandwidth);
+		size_t used = 0;
+		cuts.push_back(0);
+		for (size_t i = 0; i < batch->n_reads; i++)
+		{
+			const size_t len = (size_t)(batch->seq_offsets[i + 1] - batch->seq_offsets[i]);
+			const size_t nSeeds = (size_t)(batch->seed_offsets[i + 1] - batch->seed_offsets[i]);
+			const size_t need = nSeeds * ga::EstimateStreamBytes(ctx->dev, len + 64, bw);
+			if (used + need > budget && i > cuts.back())
+			{
+				cuts.push_back(i);
+				used = 0;
+			}
+			used += need;
+		}
+		cuts.push_back(batch->n_reads);
+	});
+	if (rc != 0) return nullptr;
+	if (cuts.size() <= 2)
+	{
+		ga_staged* st = ga_stage_batch(ctx, batch);
+		if (!st) return nullptr;
+		ga_results* res = nullptr;
+		if (ga_run_staged(ctx, st) == 0) res = ga_finish_staged(ctx, st);
+		ga_staged_free(ctx, st);
+		return res;
+	}
+	ga_results* all = new ga_results();
+	all->reads.resize(batch->n_reads);
+	all->lazy.resize(batch->n_reads);
+	all->inputs.resize(batch->n_reads);
+	all->graph = &ctx->graph->graph;
+	for (size_t c = 0; c + 1 < cuts.size(); c++)
+	{
+		// a sub-batch is the same arrays with shifted offsets pointers: offsets are absolute, so only the bases move
+		ga_batch sub = *batch;
+		sub.n_reads = cuts[c + 1] - cuts[c];
+		sub.seq_offsets = batch->seq_offsets + cuts[c];
+		sub.name_offsets = batch->name_offsets ? batch->name_offsets + cuts[c] : nullptr;
+		sub.seed_offsets = batch->seed_offsets + cuts[c];
+		ga_staged* st = ga_stage_batch(ctx, &sub);
+		ga_results* part = nullptr;
+		if (st && ga_run_staged(ctx, st) == 0) part = ga_finish_staged(ctx, st);
+		if (st) ga_staged_free(ctx, st);
+		if (!part)
+		{
+			delete all;
+			return nullptr;
+		}
+		appendChunk(all, part, cuts[c]);
+		delete part;
+	}
+	return all;
 }
 
 size_t ga_results_count(const ga_results* r) { return r->reads.size(); }
@@ -354,7 +438,8 @@ static void materializeTrace(const ga_results* r, size_t i, std::vector<Alignmen
 	as.splitIndex = lz.splitIndex;
 	as.fwShifted = lz.fwShifted;
 	as.nTraceItems = lz.nTraceItems;
-	ga::BuildTraceItems(*r->graph, r->inputs[i], as, r->streams.data(), r->outs.data(), r->arena.data(), items);
+	const ga_results::Chunk& ch = *r->chunks[lz.chunk];
+	ga::BuildTraceItems(*r->graph, r->inputs[i], as, ch.streams.data(), ch.outs.data(), ch.arena.data(), items);
 }
 
 size_t ga_results_read_trace(const ga_results* r, size_t i, ga_trace_item* buffer, size_t capacity)

@@ -21,6 +21,7 @@
 #ifndef GA_CORE_CUH
 #define GA_CORE_CUH
 #include <stdint.h>
+#include <string.h>
 #include "ga_types.h"
 
 #ifdef __CUDACC__
@@ -43,7 +44,7 @@
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
-#define GA_HDR_WORDS 6u         // slabOff, ncols, nodeOff, nNodes, minScore, flags
+#define GA_HDR_WORDS 10u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles)
 #define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
 
 #ifdef GA_HOST_DEBUG
@@ -265,6 +266,28 @@ GA_DEV_NOINLINE GaCol ga_merge_cols(const GaCol& A, const GaCol& B)
 	r.VP = VP;
 	r.VN = VN;
 	return r;
+}
+
+GA_DEV uint64_t ga_double_to_bits(double d)
+{
+#ifdef __CUDACC__
+	return (uint64_t)__double_as_longlong(d);
+#else
+	uint64_t u;
+	memcpy(&u, &d, sizeof(u));
+	return u;
+#endif
+}
+
+GA_DEV double ga_bits_to_double(uint64_t u)
+{
+#ifdef __CUDACC__
+	return __longlong_as_double((long long)u);
+#else
+	double d;
+	memcpy(&d, &u, sizeof(d));
+	return d;
+#endif
 }
 
 GA_DEV int32_t ga_col_value(uint64_t VP, uint64_t VN, int32_t sbs, int row)
@@ -930,11 +953,18 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 	}
 }
 
+struct GaSliceResult
+{
+	int32_t minScore;
+	double hmmC, hmmF;
+	bool correctFromCorrect, falseFromCorrect, currentlyCorrect;
+};
+
 // One slice for one stream, after band selection: topological pass (Kahn) over the acyclic part, fix-point
 // sweeps over what is left (cyclic components and everything downstream of them), slice minimum, HMM step.
-// Returns false when the stream stops (error or early stop).
+// Returns false on error; the slice's minimum and HMM step come back in res (the caller applies the stop / ramp rules).
 template <int LANES>
-GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, GaStreamState& st, GaSliceCtx& cx, uint32_t ncols)
+GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, GaStreamState& st, GaSliceCtx& cx, uint32_t ncols, GaSliceResult& res)
 {
 	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t nc = cx.nNodes;
@@ -1017,17 +1047,12 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	if (m < 0 || m > 64) { st.status = GA_ERR_INTERNAL; return false; }
 	double cc = st.hmmC + hmm.c2c, fc = st.hmmF + hmm.f2c;
 	double cf = st.hmmC + hmm.c2f, ff = st.hmmF + hmm.f2f;
-	bool correctFromCorrect = cc >= fc;
-	bool falseFromCorrect = cf >= ff;
-	double nc2 = (cc > fc ? cc : fc) + hmm.correctMul[m];
-	double nf2 = (cf > ff ? cf : ff) + hmm.falseMul[m];
-	GA_HDR(cx.s, 4) = (uint32_t)minScore;
-	if (!correctFromCorrect) return false;   // GraphAligner.h:2640-2647: stop, slice not recorded
-	st.hmmC = nc2;
-	st.hmmF = nf2;
-	GA_HDR(cx.s, 5) = (nc2 > nf2 ? 1u : 0u) | (falseFromCorrect ? 2u : 0u);
-	st.prevMin = minScore;
-	st.slicesPushed = (uint32_t)cx.s + 1;
+	res.correctFromCorrect = cc >= fc;
+	res.falseFromCorrect = cf >= ff;
+	res.hmmC = (cc > fc ? cc : fc) + hmm.correctMul[m];
+	res.hmmF = (cf > ff ? cf : ff) + hmm.falseMul[m];
+	res.currentlyCorrect = res.hmmC > res.hmmF;
+	res.minScore = minScore;
 	return true;
 }
 
@@ -1443,22 +1468,33 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			st.histNodeTop = 1;
 		}
 	}
-	for (int s = 0; ; s++)
+	// per-lane slice cursor and ramp state (GraphAligner.h:2602-2719); the warp iterates until every lane is done
+	int ls = 0;
+	int rampUntil = 0, rampRedoIndex = -1;
+	uint32_t gen = 1;          // stamp generator for the node -> slot tables (stamp 1 = the initial slice in table 0)
+	int tp = 0;                // table holding the previous slice
+	uint32_t stampPrev = 1;
+	while (true)
 	{
-		bool run = !st.done && (uint32_t)s < st.nslices;
+		bool run = !st.done && (uint32_t)ls < st.nslices;
 		if (!GA_WARP_ANY(run)) break;
-		// table (s+1)&1 holds slice s, table s&1 holds slice s-1
-		const int tc = (s + 1) & 1, tp = s & 1;
-		const uint32_t stampCur = (uint32_t)((s + 1) >> 1) + 1, stampPrev = (uint32_t)(s >> 1) + 1;
+		const int s = ls;
+		const int tc = tp ^ 1;
+		uint32_t stampCur = 0;
 		uint32_t ncols = 0;
 		int nc = 0;
 		uint32_t nodeOff = st.histNodeTop;
 		if (run)
 		{
-			// slice 0 always runs with rampBandwidth (rampUntil = 0, GraphAligner.h:2612)
-			int bandwidth = (s == 0) ? rampBandwidth : initialBandwidth;
-			nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], stampPrev, mem.hash[tc], stampCur, nodeOff, ncols);
-			if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
+			if (gen >= 0xfffeu) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; run = false; }
+			else
+			{
+				stampCur = ++gen;
+				// slices up to rampUntil run with rampBandwidth; rampUntil starts at 0, so slice 0 always does (GraphAligner.h:2612)
+				int bandwidth = (rampUntil >= s) ? rampBandwidth : initialBandwidth;
+				nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], stampPrev, mem.hash[tc], stampCur, nodeOff, ncols);
+				if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
+			}
 		}
 		// this slice's columns for all lanes of the warp: one chunk of the global history pool
 		uint32_t maxc = GA_WARP_MAX(ncols);
@@ -1468,35 +1504,84 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if (run) { st.status = GA_ERR_COL_OVERFLOW; st.done = true; }
 			break;   // warp-uniform
 		}
-		if (run)
+		if (!run) continue;
+		slicesRun++;
+		GaSliceCtx cx;
+		cx.s = s;
+		cx.nodeOff = nodeOff;
+		cx.nNodes = (uint32_t)nc;
+		cx.pNodeOff = pNodeOff;
+		cx.pNodes = pNodes;
+		cx.slabOff = (uint32_t)slabOff;
+		cx.tinyCur = mem.tiny[tc];
+		cx.tinyPrev = mem.tiny[tp];
+		cx.hashCur = mem.hash[tc];
+		cx.hashPrev = mem.hash[tp];
+		cx.stampCur = stampCur;
+		cx.stampPrev = stampPrev;
+		GA_HDR(s, 0) = (uint32_t)slabOff;
+		GA_HDR(s, 1) = ncols;
+		GA_HDR(s, 2) = nodeOff;
+		GA_HDR(s, 3) = (uint32_t)nc;
+		GaSliceResult res;
+		if (!ga_fill_slice<LANES>(g, caps, hmm, mem, st, cx, ncols, res)) { st.done = true; continue; }
+		// remember where a ramp would restart from (GraphAligner.h:2630-2634)
+		if (rampUntil == s - 1 || (rampUntil < s && res.currentlyCorrect && res.falseFromCorrect)) rampRedoIndex = s - 1;
+		if (!res.correctFromCorrect) { st.done = true; continue; }   // GraphAligner.h:2640-2647: stop, slice not recorded
+		if (!res.currentlyCorrect && rampUntil < s && rampBandwidth > initialBandwidth)
 		{
-			slicesRun++;
-			GaSliceCtx cx;
-			cx.s = s;
-			cx.nodeOff = nodeOff;
-			cx.nNodes = (uint32_t)nc;
-			cx.pNodeOff = pNodeOff;
-			cx.pNodes = pNodes;
-			cx.slabOff = (uint32_t)slabOff;
-			cx.tinyCur = mem.tiny[tc];
-			cx.tinyPrev = mem.tiny[tp];
-			cx.hashCur = mem.hash[tc];
-			cx.hashPrev = mem.hash[tp];
-			cx.stampCur = stampCur;
-			cx.stampPrev = stampPrev;
-			GA_HDR(s, 0) = (uint32_t)slabOff;
-			GA_HDR(s, 1) = ncols;
-			GA_HDR(s, 2) = nodeOff;
-			GA_HDR(s, 3) = (uint32_t)nc;
-			bool cont = ga_fill_slice<LANES>(g, caps, hmm, mem, st, cx, ncols);
-			if (!cont) st.done = true;
-			else
+			// ramp: redo from the remembered slice with the wide band up to here (GraphAligner.h:2648-2719)
+			const int target = rampRedoIndex;
+			rampUntil = s;
+			rampRedoIndex = s;
+			if (target < 0) { st.status = GA_ERR_INTERNAL; st.done = true; continue; }
+			// the previous slice becomes slice `target` again: state from its header, tables rebuilt from the history
+			st.prevMin = (int32_t)GA_HDR(target, 4);
 			{
-				pNodeOff = nodeOff;
-				pNodes = (uint32_t)nc;
-				st.histNodeTop = nodeOff + (uint32_t)nc;
+				uint64_t c = (uint64_t)GA_HDR(target, 6) | ((uint64_t)GA_HDR(target, 7) << 32);
+				uint64_t f = (uint64_t)GA_HDR(target, 8) | ((uint64_t)GA_HDR(target, 9) << 32);
+				st.hmmC = ga_bits_to_double(c);
+				st.hmmF = ga_bits_to_double(f);
 			}
+			pNodeOff = GA_HDR(target, 2);
+			pNodes = GA_HDR(target, 3);
+			st.histNodeTop = nodeOff + (uint32_t)nc;   // abandoned entries are simply left behind
+			st.slicesPushed = (uint32_t)target + 1;
+			stampPrev = ++gen;
+			{
+				const uint32_t tSlab = GA_HDR(target, 0);
+				for (uint32_t i = 0; i < pNodes; i++)
+				{
+					ga_hash_insert<LANES>(mem.hash[tp], hashMask, stampPrev, GA_HN(pNodeOff + i, 0), i);
+					const uint32_t cs = GA_HN(pNodeOff + i, 1), len = GA_HN(pNodeOff + i, 3);
+					for (uint32_t k = 0; k < len; k++)
+					{
+						GaCol c = ga_col_load<LANES>(mem, tSlab + cs + k);
+						mem.tiny[tp][(size_t)(cs + k) * LANES] = ga_tiny_pack(c, false);
+					}
+				}
+			}
+			ls = target + 1;
+			continue;
 		}
+		// the slice is kept
+		st.hmmC = res.hmmC;
+		st.hmmF = res.hmmF;
+		st.prevMin = res.minScore;
+		GA_HDR(s, 4) = (uint32_t)res.minScore;
+		GA_HDR(s, 5) = (res.currentlyCorrect ? 1u : 0u) | (res.falseFromCorrect ? 2u : 0u);
+		{
+			uint64_t c = ga_double_to_bits(res.hmmC), f = ga_double_to_bits(res.hmmF);
+			GA_HDR(s, 6) = (uint32_t)c; GA_HDR(s, 7) = (uint32_t)(c >> 32);
+			GA_HDR(s, 8) = (uint32_t)f; GA_HDR(s, 9) = (uint32_t)(f >> 32);
+		}
+		st.slicesPushed = (uint32_t)s + 1;
+		pNodeOff = nodeOff;
+		pNodes = (uint32_t)nc;
+		st.histNodeTop = nodeOff + (uint32_t)nc;
+		tp = tc;
+		stampPrev = stampCur;
+		ls = s + 1;
 	}
 	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------
 	bool doTrace = false;

@@ -30,6 +30,9 @@ double MeasureInt32Peak(DeviceCtx* ctx);
 StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats);
 // pinned host memory for a batch's padded parts (grow-only, owned by the context, reused by the next batch)
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes);
+// sizing helpers for splitting a batch that would not fit the device in one launch
+size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth);
+size_t FreeDeviceBytes(DeviceCtx* ctx);
 // launches the alignment kernel(s) on the context's stream (asynchronous); returns number of launches
 int RunStaged(DeviceCtx* ctx, StagedBatch* batch);
 // waits, copies results back, re-runs streams that overflowed their scratch with larger capacities

@@ -684,6 +684,28 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	}
 }
 
+size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
+{
+	// dominant terms of layoutAndUpload per stream: column history + fixed scratch + trace buffers
+	const double avgNodeLen = std::max(1.0, ctx->avgNodeLen);
+	const double colsGuess = 2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32;
+	const double slices = (double)((partLen + 63) / 64);
+	return (size_t)(slices * colsGuess * GA_COL_Q * sizeof(uint4) * 1.15 + 96.0 * 1024 + partLen * 12.0);
+}
+
+size_t FreeDeviceBytes(DeviceCtx* ctx)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	size_t freeB = 0, totalB = 0;
+	GA_CUDA(cudaMemGetInfo(&freeB, &totalB));
+	// the context's grow-only pools are reusable, so count them as available
+	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq,
+		&ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena };
+	for (Buffer* b : all) freeB += b->cap;
+	if (const char* e = getenv("GA_MEM_BUDGET_MB")) freeB = std::min<size_t>(freeB, (size_t)atoll(e) << 20);   // testing: force batch splitting
+	return freeB;
+}
+
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));

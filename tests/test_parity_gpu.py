@@ -77,3 +77,32 @@ def test_empty_and_degenerate_inputs(api, golden_dir):
     assert [x["failed"] for x in d] == [1, 1, 1, 1, 0]
     assert d[1]["flags"] & 2 and d[2]["flags"] & 2 and d[3]["flags"] & 4
     aligner.close()
+
+
+def test_oversized_batch_is_split_into_launches(api, golden_dir, monkeypatch):
+    # a batch whose DP history exceeds the device budget is aligned in several launches with identical results
+    case = gacase.read_case(os.path.join(golden_dir, "bubbles_multiseed.gacase"))
+    expected = load_expected(os.path.join(golden_dir, "bubbles_multiseed.expected"))
+    monkeypatch.setenv("GA_MEM_BUDGET_MB", "12")
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    assert aligner.stats()["launches"] >= 4   # two kernels per launch, at least two launches
+    assert_same(res.as_dicts(), expected, "chunked")
+    aligner.close()
+
+
+def test_ramp_bandwidth_runs(api):
+    # -B: slice 0 and every redone stretch use the wide band (GraphAligner.h:2612,2648-2719).  The reference's own ramp
+    # path crashes on many inputs (stale sqrt checkpoints), so this checks our invariants rather than bit parity:
+    # every read aligns, and a wide-band rescue can only help the score on average
+    g = synth.make_graph(301, 40000, chop=32, bubble_every=120, indel_frac=0.5)
+    narrow = synth.make_case(301, g, 48, 3000, b=3, B=0, errors=(0.08, 0.08, 0.08))
+    ramped = synth.make_case(301, g, 48, 3000, b=3, B=40, errors=(0.08, 0.08, 0.08))
+    aligner = api.Aligner(api.Graph.from_case(narrow))
+    a = aligner.align(narrow.reads, 3, 0).as_dicts()
+    b = aligner.align(ramped.reads, 3, 40).as_dicts()
+    assert all(x["flags"] & 1 == 0 for x in a + b)
+    cover_a = sum(x["end"] - x["start"] for x in a if not x["failed"])
+    cover_b = sum(x["end"] - x["start"] for x in b if not x["failed"])
+    assert cover_b >= cover_a
+    aligner.close()
