@@ -137,12 +137,26 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
-	ParallelFor(n, [&](size_t i) {
-		const char* p = reads[i].seq;
-		for (size_t k = 0; k < reads[i].seqLen; k++)
+	// 256-entry tables: validity (the reference aborts on anything outside its IUPAC switch) and complement
+	static const struct Tables
+	{
+		uint8_t valid[256];
+		uint8_t comp[256];
+		Tables()
 		{
-			if (!ValidReadChar(p[k])) { badChar[i] = 1; break; }
+			for (int c = 0; c < 256; c++)
+			{
+				valid[c] = ValidReadChar((char)c) ? 1 : 0;
+				comp[c] = (uint8_t)complementOf((char)c);
+			}
 		}
+	} tables;
+	ParallelFor(n, [&](size_t i) {
+		const uint8_t* p = (const uint8_t*)reads[i].seq;
+		const size_t len = reads[i].seqLen;
+		uint8_t ok = 1;
+		for (size_t k = 0; k < len; k++) ok &= tables.valid[p[k]];
+		badChar[i] = ok ? 0 : 1;
 	});
 	struct Job { uint32_t read; uint32_t backward; size_t pos; };
 	std::vector<Job> jobs;
@@ -223,7 +237,8 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 		if (job.backward)
 		{
 			real = job.pos + overlap;
-			for (size_t i = 0; i < real; i++) dst[i] = (uint8_t)complementOf(r.seq[real - 1 - i]);
+			const uint8_t* src = (const uint8_t*)r.seq;
+			for (size_t i = 0; i < real; i++) dst[i] = tables.comp[src[real - 1 - i]];
 		}
 		else
 		{
