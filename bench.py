@@ -28,8 +28,17 @@ READS_PER_GPU = 10_000
 READ_LEN = 10_000
 BAND = 10
 # algorithmic work per forward word update (64 cells), DESIGN.md "Roofline":
-BYTES_PER_WORD_COLUMN = 28.25    # 0.25 sequence + 4 previous-slice end state + 4 end state out + 16 VP/VN + 4 row -1 score
+BYTES_PER_WORD_COLUMN = 72.25    # 0.25 bases + 4 previous-slice end state in + 4 end state out + 64-byte history record (VP, VN, scores, traceback masks)
 LANE_OPS_PER_WORD_COLUMN = 50.0
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
 
 
 def load_peaks():
@@ -241,8 +250,9 @@ def main():
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_val, "unit": "bp/s", "h2d_bytes_per_step": st["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st["d2h_bytes"] // args.steps,
                         "ms_per_step": e2e_s / args.steps * 1e3},
-                "gpu_launches": stats["launches"] if stats["launches"] else args.steps,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                # kernels of ours launched inside the timed region: ga_peq_kernel + ga_align_kernel per step
+                "gpu_launches": int(st["launches"]) if st["launches"] else 2 * args.steps,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": load_traffic(),
                              "peak_source": peak_kind, "kernel": "ga_align_kernel", "kernel_ms": mean_kernel_s * 1e3,
                              "int_alu": {"achieved_lane_ops_per_s": lane_ops / mean_kernel_s, "peak_lane_ops_per_s": int_peak,
                                          "frac": (lane_ops / mean_kernel_s / int_peak) if int_peak else None,
