@@ -160,6 +160,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # host worker threads per rank: the ranks of one box share its cores
+    os.environ.setdefault("GA_HOST_THREADS", str(max(1, cores // max(1, world))))
     import torch
     import torch.distributed as dist
     from graphaligner_b200 import api, multi_gpu

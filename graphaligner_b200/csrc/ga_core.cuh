@@ -44,7 +44,7 @@
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
-#define GA_HDR_WORDS 10u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles)
+#define GA_HDR_WORDS 12u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles), last minimum cell (slot, column)
 #define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
 
 #ifdef GA_HOST_DEBUG
@@ -74,6 +74,10 @@ struct GaLaneMem
 	uint32_t* nWlo;      // per band node of the current slice: nodeStart (low / high word) and its first column
 	uint32_t* nWhi;      //   in the previous slice's tiny array (0xffffffff = not in the previous band)
 	uint32_t* nPcs;
+	uint32_t* cmpOf;     // cyclic slices only: Tarjan component of each band node (top bit: on the work list)
+	uint32_t* emit;      //   band slots in Tarjan emission order (components are contiguous)
+	uint32_t* wl;        //   the reference's UniqueQueue (a LIFO)
+	uint32_t* conf;      //   per band column: confirmedRows (rows | partial << 8), GraphAligner.h:1355-1416
 	uint32_t* hdr;
 	uint32_t* histNode;
 	uint4* col;          // column history pool (shared by all warps), four 16-byte quarters per column:
@@ -847,18 +851,308 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	return true;
 }
 
+
+// ================================================================================================================
+// Exact emulation of the reference's evaluation of a CYCLIC band component (GraphAligner.h:1349-1427, 1457-1573,
+// 2360-2420; WordSlice.h:361-510).  Cell values of a cyclic component are a fix point and could be had any way, but
+// two things the reference feeds into later slices are artefacts of HOW it iterates: the per-node minimum it stores
+// is the one of the LAST calculateNode call on that node (which covers only the columns that call confirmed), and the
+// order of tied minimum cells follows its work list.  So for these components the confirmedRows schedule is replayed.
+// ================================================================================================================
+struct GaExCol
+{
+	uint64_t VP, VN;
+	int32_t sbs, scoreEnd;
+	int32_t rows;      // confirmedRows.rows
+	bool partial;      // confirmedRows.partial
+	bool sbE;          // scoreBeforeExists
+};
+
+GA_DEV bool ga_conf_gt(int ra, bool pa, int rb, bool pb) { return ra > rb || (ra == rb && pa && !pb); }   // RowConfirmation::operator>
+GA_DEV bool ga_conf_eq(int ra, bool pa, int rb, bool pb) { return ra == rb && pa == pb; }
+
+// getNextSlice with the confirmedRows bookkeeping (GraphAligner.h:1349-1427).  Shift counts follow x86 (masked to 6 bits),
+// which is what the reference's build does with rows == 64 and rows == 0.
+GA_DEV GaExCol ga_ex_next(uint64_t Eq, GaExCol slice, bool upInside, bool upleftInside, bool diagInside, bool previousEq, int32_t prevScoreEnd, uint32_t prevVP63, uint32_t prevVN63)
+{
+	const int32_t oldValue = slice.sbs;
+	const uint64_t confirmedMask = (uint64_t)1 << (slice.rows & 63);
+	const uint64_t prevConfirmedMask = (uint64_t)1 << ((slice.rows - 1) & 63);
+	bool confirmOneMore = false;
+	if (!slice.sbE) Eq &= ~(uint64_t)1;
+	slice.sbE = upInside;
+	if (!diagInside) Eq &= ~(uint64_t)1;
+	if (!upleftInside) slice.sbs += 1;
+	else
+	{
+		int32_t d = prevScoreEnd - (int32_t)prevVP63 + (int32_t)prevVN63 + (previousEq ? 0 : 1);
+		slice.sbs = slice.sbs + 1 < d ? slice.sbs + 1 : d;
+	}
+	const int32_t hin = slice.sbs - oldValue;
+	uint64_t Xv = Eq | slice.VN;
+	if (hin < 0) Eq |= 1;
+	uint64_t Xh = (((Eq & slice.VP) + slice.VP) ^ slice.VP) | Eq;
+	uint64_t Ph = slice.VN | ~(Xh | slice.VP);
+	uint64_t Mh = slice.VP & Xh;
+	int32_t diagonalDiff = hin;
+	if (slice.rows > 0) diagonalDiff = ((Ph & prevConfirmedMask) ? 1 : 0) - ((Mh & prevConfirmedMask) ? 1 : 0);
+	if (slice.rows > 0 && (Mh & prevConfirmedMask)) confirmOneMore = true;
+	else if (slice.rows == 0 && hin == -1) confirmOneMore = true;
+	const uint64_t lastBitMask = (uint64_t)1 << 63;
+	if (Ph & lastBitMask) slice.scoreEnd += 1;
+	else if (Mh & lastBitMask) slice.scoreEnd -= 1;
+	if (slice.partial && (~Ph & confirmedMask)) confirmOneMore = true;
+	Ph <<= 1;
+	Mh <<= 1;
+	if (hin < 0) Mh |= 1; else if (hin > 0) Ph |= 1;
+	slice.VP = Mh | ~(Xv | Ph);
+	slice.VN = Ph & Xv;
+	diagonalDiff += ((slice.VP & confirmedMask) ? 1 : 0) - ((slice.VN & confirmedMask) ? 1 : 0);
+	if (diagonalDiff <= 0) confirmOneMore = true;
+	else if (slice.VN & confirmedMask) confirmOneMore = true;
+	if (confirmOneMore)
+	{
+		if (slice.rows + 1 <= 64) slice.rows += 1;
+		slice.partial = false;
+	}
+	else if (!slice.partial && slice.rows < 64) slice.partial = true;
+	return slice;
+}
+
+// position of the rank-th set bit of a 128-bit value (low word first), WordSlice.h:46-98
+GA_DEV int ga_bit_position64(uint64_t number, int rank)
+{
+	int total = (int)GA_POPC(number);
+	if (rank >= total) return 64 + (rank - total);
+	for (int i = 0; i < rank; i++) number &= number - 1;
+	return (int)GA_CTZ(number);
+}
+GA_DEV int ga_bit_position(uint64_t low, uint64_t high, int rank)
+{
+	int result = ga_bit_position64(low, rank);
+	if (result < 64) return result;
+	return 64 + ga_bit_position64(high, result - 64);
+}
+// bits of x on the even positions, bits of y on the odd ones (WordSlice.h:111-131)
+GA_DEV uint64_t ga_interleave(uint64_t x, uint64_t y)
+{
+	x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; x = (x | (x << 8)) & 0x00FF00FF00FF00FFull; x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x << 2)) & 0x3333333333333333ull; x = (x | (x << 1)) & 0x5555555555555555ull;
+	y = (y | (y << 16)) & 0x0000FFFF0000FFFFull; y = (y | (y << 8)) & 0x00FF00FF00FF00FFull; y = (y | (y << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	y = (y | (y << 2)) & 0x3333333333333333ull; y = (y | (y << 1)) & 0x5555555555555555ull;
+	return x | (y << 1);
+}
+
+// confirmedRowsInMerged, WordSlice.h:423-510
+GA_DEV void ga_ex_conf_merged(GaExCol left, GaExCol right, int32_t& rowsOut, bool& partialOut)
+{
+	if (ga_conf_eq(left.rows, left.partial, right.rows, right.partial)) { rowsOut = left.rows; partialOut = left.partial; return; }
+	if (ga_conf_gt(right.rows, right.partial, left.rows, left.partial)) { GaExCol t = left; left = right; right = t; }
+	int32_t leftScore = left.sbs, rightScore = right.sbs;
+	const uint64_t confirmedMask = ~(~(uint64_t)0 << (right.rows & 63));   // rows == 64 shifts by 0 on x86, like the reference's build
+	leftScore += (int32_t)GA_POPC(left.VP & confirmedMask) - (int32_t)GA_POPC(left.VN & confirmedMask);
+	rightScore += (int32_t)GA_POPC(right.VP & confirmedMask) - (int32_t)GA_POPC(right.VN & confirmedMask);
+	if (right.rows == left.rows)
+	{
+		const uint64_t mask = (uint64_t)1 << (left.rows & 63);
+		rightScore -= 1;
+		if (!(left.VP & mask)) leftScore -= 1;
+		rowsOut = left.rows;
+		partialOut = leftScore <= rightScore;
+		return;
+	}
+	const uint64_t premask = (uint64_t)1 << (right.rows & 63);
+	leftScore += (left.VP & premask) ? 1 : 0;
+	leftScore -= (left.VN & premask) ? 1 : 0;
+	if (!(right.partial && (right.VP & premask))) rightScore -= 1;
+	if (leftScore == rightScore + 1) { rowsOut = right.rows; partialOut = true; return; }
+	if (leftScore > rightScore + 1) { rowsOut = right.rows; partialOut = right.partial; return; }
+	if (left.rows > right.rows + 1)
+	{
+		uint64_t partiallyConfirmedMask = 0;
+		if (left.rows < 64) partiallyConfirmedMask = ~(uint64_t)0 << left.rows;
+		partiallyConfirmedMask = ~partiallyConfirmedMask;
+		partiallyConfirmedMask &= ~(uint64_t)0 << (right.rows + 1);
+		const uint64_t low = left.VP & partiallyConfirmedMask;
+		const uint64_t high = ~left.VN & partiallyConfirmedMask;
+		const uint64_t mortonLow = ga_interleave(low & 0xFFFFFFFFull, high & 0xFFFFFFFFull);
+		const uint64_t mortonHigh = ga_interleave(low >> 32, high >> 32);
+		const int pos = ga_bit_position(mortonLow, mortonHigh, rightScore - leftScore);
+		if (pos / 2 < left.rows)
+		{
+			const int nextpos = ga_bit_position(mortonLow, mortonHigh, rightScore - leftScore + 1);
+			rowsOut = pos / 2;
+			partialOut = nextpos / 2 > pos / 2;
+			return;
+		}
+		leftScore += (int32_t)GA_POPC(left.VP & partiallyConfirmedMask) - (int32_t)GA_POPC(left.VN & partiallyConfirmedMask);
+		rightScore -= left.rows - right.rows - 1;
+	}
+	if (!left.partial) { rowsOut = left.rows; partialOut = left.partial; return; }
+	const uint64_t postmask = (uint64_t)1 << (left.rows & 63);
+	rightScore -= 1;
+	if (left.VP & postmask)
+	{
+		if (leftScore <= rightScore) { rowsOut = left.rows; partialOut = left.partial; return; }
+	}
+	else
+	{
+		rowsOut = left.rows;
+		partialOut = left.partial;
+		return;
+	}
+	rowsOut = left.rows;
+	partialOut = false;
+}
+
+// WordSlice::mergeWith -> mergeTwoSlices, WordSlice.h:202-206,361-421 (values by exact minimum, flags by the reference's rules)
+GA_DEV GaExCol ga_ex_merge(GaExCol left, GaExCol right)
+{
+	if (left.sbs > right.sbs) { GaExCol t = left; left = right; right = t; }
+	GaExCol result;
+	ga_ex_conf_merged(left, right, result.rows, result.partial);
+	GaCol a, b;
+	a.VP = left.VP; a.VN = left.VN; a.sbs = left.sbs; a.scoreEnd = left.scoreEnd;
+	b.VP = right.VP; b.VN = right.VN; b.sbs = right.sbs; b.scoreEnd = right.scoreEnd;
+	GaCol m = ga_merge_cols(a, b);
+	result.VP = m.VP; result.VN = m.VN; result.sbs = m.sbs; result.scoreEnd = m.scoreEnd;
+	if (left.sbs < right.sbs) result.sbE = left.sbE;
+	else result.sbE = left.sbE || right.sbE;   // equal after the swap
+	return result;
+}
+
+template <int LANES>
+GA_DEV GaExCol ga_ex_load(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col)
+{
+	GaCol c = ga_col_load<LANES>(mem, cx.slabOff + col);
+	uint32_t t = cx.tinyCur[(size_t)col * LANES];
+	uint32_t cf = mem.conf[(size_t)col * LANES];
+	GaExCol e;
+	e.VP = c.VP; e.VN = c.VN; e.sbs = c.sbs; e.scoreEnd = c.scoreEnd;
+	e.rows = (int32_t)(cf & 0xffu);
+	e.partial = (cf & 0x100u) != 0;
+	e.sbE = (t & 4u) != 0;
+	return e;
+}
+
+template <int LANES>
+GA_DEV void ga_ex_store(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col, const GaExCol& e)
+{
+	GaCol c;
+	c.VP = e.VP; c.VN = e.VN; c.sbs = e.sbs; c.scoreEnd = e.scoreEnd;
+	ga_col_store<LANES>(mem, cx.slabOff + col, c);
+	cx.tinyCur[(size_t)col * LANES] = ga_tiny_pack(c, e.sbE);
+	mem.conf[(size_t)col * LANES] = (uint32_t)e.rows | (e.partial ? 0x100u : 0u);
+}
+
+// calculateNode for a member of a cyclic component (GraphAligner.h:1457-1573).  Returns the minimum scoreEnd over the
+// columns this call fully confirmed (INT_MAX if none) and the last such column attaining it.
+template <int LANES>
+GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, uint32_t& lastMinCol)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
+	const uint32_t len = GA_HN(cx.nodeOff + slot, 3);
+	const uint64_t wStart = (uint64_t)mem.nWlo[(size_t)slot * LANES] | ((uint64_t)mem.nWhi[(size_t)slot * LANES] << 32);
+	const uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
+	const bool inPrev = pcs != GA_NOT_IN_PREV;
+	int32_t minScore = 0x7fffffff;
+	lastMinCol = 0xffffffffu;
+	GaExCol cur0 = ga_ex_load<LANES>(mem, cx, cs);
+	if (cur0.rows == 64) return minScore;
+	const int32_t oldRows0 = cur0.rows;
+	const bool oldPartial0 = cur0.partial;
+	uint32_t base = ga_base(g, wStart);
+	uint64_t Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
+	bool previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
+	// getNodeStartSlice, GraphAligner.h:1270-1315
+	GaExCol res;
+	bool foundOne = false;
+	for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
+	{
+		uint32_t u = g.inAdj[e];
+		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
+		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+		if (cu < 0 && pu < 0) continue;
+		uint64_t EqHere = Eq;
+		const bool foundOneUp = pu >= 0;
+		uint32_t upTiny = 0;
+		if (foundOneUp) upTiny = cx.tinyPrev[(size_t)(GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1) * LANES];
+		GaExCol previous;
+		if (cu >= 0) previous = ga_ex_load<LANES>(mem, cx, GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1);
+		else
+		{
+			const int32_t es = ga_tiny_score(upTiny);
+			previous.VP = ~(uint64_t)0; previous.VN = 0; previous.scoreEnd = es + 64; previous.sbs = es; previous.rows = 64; previous.partial = false; previous.sbE = true;
+			EqHere &= 1;
+		}
+		GaExCol here = ga_ex_next(EqHere, previous, cur0.sbE, cur0.sbE && foundOneUp, foundOneUp, previousEq, ga_tiny_score(upTiny), upTiny & 1u, (upTiny >> 1) & 1u);
+		if (!foundOne) { res = here; foundOne = true; }
+		else res = ga_ex_merge(res, here);
+	}
+	uint32_t oldTiny = inPrev ? cx.tinyPrev[(size_t)pcs * LANES] : 0;
+	if (!foundOne)
+	{
+		// source node downstream of nothing (GraphAligner.h:1317-1347,1475-1488): final at once
+		if (!inPrev) { st.status = GA_ERR_INTERNAL; return minScore; }
+		const int32_t ps = ga_tiny_score(oldTiny);
+		uint64_t mismatch = 1;
+		if (cx.firstSlice) mismatch = ((ga_iupac_mask(st.seq[0]) >> base) & 1u) ? 0 : 1;
+		res.VP = (~(uint64_t)1) | mismatch; res.VN = 0; res.scoreEnd = ps + 63 + (int32_t)mismatch; res.sbs = ps;
+		res.rows = 64; res.partial = false; res.sbE = true;
+	}
+	else if (inPrev && res.sbs > ga_tiny_score(oldTiny))
+	{
+		GaExCol mergable;
+		mergable.VP = ~(uint64_t)0; mergable.VN = 0; mergable.sbs = ga_tiny_score(oldTiny); mergable.scoreEnd = mergable.sbs + 64; mergable.rows = 64; mergable.partial = false; mergable.sbE = true;
+		res = ga_ex_merge(res, mergable);
+	}
+	ga_ex_store<LANES>(mem, cx, cs, res);
+	if (res.rows == 64 && res.scoreEnd < minScore) minScore = res.scoreEnd;
+	if (res.rows == 64 && res.scoreEnd == minScore) lastMinCol = 0;
+	if (ga_conf_eq(res.rows, res.partial, oldRows0, oldPartial0)) return minScore;
+	GaExCol leftCol = res;
+	uint32_t oldTinyLeft = oldTiny;
+	for (uint32_t k = 1; k < len; k++)
+	{
+		GaExCol c = ga_ex_load<LANES>(mem, cx, cs + k);
+		if (c.rows == 64) return minScore;
+		const int32_t oldRows = c.rows;
+		const bool oldPartial = c.partial;
+		base = ga_base(g, wStart + k);
+		Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
+		previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
+		oldTiny = inPrev ? cx.tinyPrev[(size_t)(pcs + k) * LANES] : 0;
+		GaExCol n = ga_ex_next(Eq, leftCol, c.sbE, c.sbE, leftCol.sbE, previousEq, ga_tiny_score(oldTinyLeft), oldTinyLeft & 1u, (oldTinyLeft >> 1) & 1u);
+		if (inPrev && n.sbs > ga_tiny_score(oldTiny))
+		{
+			GaExCol mergable;
+			mergable.VP = ~(uint64_t)0; mergable.VN = 0; mergable.sbs = ga_tiny_score(oldTiny); mergable.scoreEnd = mergable.sbs + 64; mergable.rows = 64; mergable.partial = false; mergable.sbE = true;
+			n = ga_ex_merge(n, mergable);
+		}
+		ga_ex_store<LANES>(mem, cx, cs + k, n);
+		if (n.rows == 64 && n.scoreEnd < minScore) minScore = n.scoreEnd;
+		if (n.rows == 64 && n.scoreEnd == minScore) lastMinCol = k;
+		if (ga_conf_eq(n.rows, n.partial, oldRows, oldPartial)) return minScore;
+		leftCol = n;
+		oldTinyLeft = oldTiny;
+	}
+	return minScore;
+}
+
 // Row -1 scores for a cyclic block of band nodes (the slots listed in order[from..to)) by shortest paths over
 // the block (forceComponentZeroRow, GraphAligner.h:1903-1995), then reset every column to the all-ones ramp.
 template <int LANES>
-GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to)
+GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to, uint32_t comp)
 {
 	const uint32_t hashMask = caps.hashSize - 1;
 	const int32_t INF = 0x3fffffff;
 	uint32_t heapN = 0;
-	// indeg[slot] != 0 marks block membership at this point (Kahn left these nodes unresolved)
+	// the component's members are emit[from..to); cmpOf[slot] == comp tests membership
 	for (uint32_t q = from; q < to; q++)
 	{
-		uint32_t slot = mem.order[(size_t)q * LANES];
+		uint32_t slot = mem.emit[(size_t)q * LANES];
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
 		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
@@ -870,7 +1164,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			uint32_t u = g.inAdj[e];
 			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
 			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
-			if (cu >= 0 && mem.indeg[(size_t)cu * LANES] == 0)
+			if (cu >= 0 && (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp)
 			{
 				uint32_t ucol = GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1;
 				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + ucol) + 1;
@@ -902,7 +1196,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 			{
 				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
-				if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
+				if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp) continue;
 				if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 				ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(v + 1) << 32) | (uint32_t)cu);
 			}
@@ -927,15 +1221,15 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 		{
 			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
-			if (cu < 0 || mem.indeg[(size_t)cu * LANES] == 0) continue;
+			if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp) continue;
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)score << 32) | (uint32_t)cu);
 		}
 	}
-	// reset columns to {VP = all ones, VN = 0, scoreEnd = sbs + 64, scoreBeforeExists} (GraphAligner.h:1981-1993)
+	// reset columns to {VP = all ones, VN = 0, scoreEnd = sbs + 64, confirmedRows = 0, scoreBeforeExists} (GraphAligner.h:1981-1993)
 	for (uint32_t q = from; q < to; q++)
 	{
-		uint32_t slot = mem.order[(size_t)q * LANES];
+		uint32_t slot = mem.emit[(size_t)q * LANES];
 		uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
 		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
 		uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
@@ -951,8 +1245,83 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			bool sbE = inPrev && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
 			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c);
 			cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
+			mem.conf[(size_t)(cs + k) * LANES] = 0;
 		}
 	}
+}
+
+
+// Tarjan over the whole band in the reference's visiting order (band order, outNeighbors order, GraphAligner.h:1759-1856).
+// Fills emit[] with the band slots in emission order (the members of a component are contiguous, in the order the
+// reference's component vector holds them) and cmpOf[slot] with the component number (emission order).  Returns the
+// number of components.  Scratch: indeg = DFS index | on-stack bit, order = low link, uorder = Tarjan stack,
+// unext = call-stack slots, ubkt = call-stack edge cursors.  (The hash table of the slice resolves neighbours.)
+template <int LANES>
+GA_DEV uint32_t ga_tarjan_components(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, const GaSliceCtx& cx)
+{
+	const uint32_t hashMask = caps.hashSize - 1;
+	const uint32_t nNodes = cx.nNodes;
+	const uint32_t ONSTACK = 0x80000000u;
+	for (uint32_t i = 0; i < nNodes; i++) mem.indeg[(size_t)i * LANES] = 0;
+	uint32_t counter = 0, tstack = 0, emitted = 0, nComp = 0;
+	for (uint32_t root = 0; root < nNodes; root++)
+	{
+		if (mem.indeg[(size_t)root * LANES] != 0) continue;
+		uint32_t depth = 0;
+		mem.unext[0] = root;
+		mem.ubkt[0] = g.outOff[GA_HN(cx.nodeOff + root, 0)];
+		counter++;
+		mem.indeg[(size_t)root * LANES] = counter | ONSTACK;
+		mem.order[(size_t)root * LANES] = counter;
+		mem.uorder[(size_t)(tstack++) * LANES] = root;
+		while (true)
+		{
+			uint32_t slot = mem.unext[(size_t)depth * LANES];
+			uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+			uint32_t e = mem.ubkt[(size_t)depth * LANES];
+			if (e < g.outOff[node + 1])
+			{
+				mem.ubkt[(size_t)depth * LANES] = e + 1;
+				int nb = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+				if (nb < 0) continue;
+				uint32_t mark = mem.indeg[(size_t)nb * LANES];
+				if (mark == 0)
+				{
+					depth++;
+					mem.unext[(size_t)depth * LANES] = (uint32_t)nb;
+					mem.ubkt[(size_t)depth * LANES] = g.outOff[GA_HN(cx.nodeOff + nb, 0)];
+					counter++;
+					mem.indeg[(size_t)nb * LANES] = counter | ONSTACK;
+					mem.order[(size_t)nb * LANES] = counter;
+					mem.uorder[(size_t)(tstack++) * LANES] = (uint32_t)nb;
+				}
+				else if (mark & ONSTACK)
+				{
+					uint32_t idx = mark & ~ONSTACK;
+					if (idx < mem.order[(size_t)slot * LANES]) mem.order[(size_t)slot * LANES] = idx;
+				}
+				continue;
+			}
+			uint32_t low = mem.order[(size_t)slot * LANES];
+			if (low == (mem.indeg[(size_t)slot * LANES] & ~ONSTACK))
+			{
+				while (true)
+				{
+					uint32_t back = mem.uorder[(size_t)(--tstack) * LANES];
+					mem.indeg[(size_t)back * LANES] &= ~ONSTACK;
+					mem.emit[(size_t)(emitted++) * LANES] = back;
+					mem.cmpOf[(size_t)back * LANES] = nComp;
+					if (back == slot) break;
+				}
+				nComp++;
+			}
+			if (depth == 0) break;
+			depth--;
+			uint32_t parent = mem.unext[(size_t)depth * LANES];
+			if (low < mem.order[(size_t)parent * LANES]) mem.order[(size_t)parent * LANES] = low;
+		}
+	}
+	return nComp;
 }
 
 struct GaSliceResult
@@ -1009,40 +1378,139 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if (d == 0) mem.order[(size_t)(ready++) * LANES] = (uint32_t)cu;
 		}
 	}
-	if (done < nc)
+	int32_t minScore = 0x7fffffff;
+	uint32_t lastMinSlot = 0xffffffffu, lastMinCol = 0;
+	if (done == nc)
 	{
-		// cyclic remainder: indeg != 0 marks membership
-		st.cyclicSlices++;
-		uint32_t from = ready;
+		// acyclic band: slice minimum over the per-node minima (GraphAligner.h:2375,2410-2418); the order of tied cells is
+		// resolved later, only for the slice the traceback starts from (ga_first_emitted_min_node)
 		for (uint32_t slot = 0; slot < nc; slot++)
 		{
-			if (mem.indeg[(size_t)slot * LANES] != 0) mem.order[(size_t)(ready++) * LANES] = slot;
-		}
-		ga_force_block<LANES>(g, caps, mem, st, cx, from, ready);
-		if (st.status != GA_OK) return false;
-		bool first = true;
-		uint32_t sweeps = 0;
-		while (true)
-		{
-			bool changed = false;
-			for (uint32_t q = from; q < ready; q++)
-			{
-				bool c = ga_calc_node<LANES>(g, caps, mem, st, cx, mem.order[(size_t)q * LANES], true, first);
-				if (st.status != GA_OK) return false;
-				changed = changed || c;
-			}
-			if (!changed && !first) break;
-			first = false;
-			if (++sweeps > 64u * (ready - from) + 64u) { st.status = GA_ERR_CYCLE_ITER; return false; }
+			int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + slot, 2);
+			if (nodeMin < minScore) minScore = nodeMin;
 		}
 	}
-	// slice minimum over the per-node minima ga_calc_node recorded (GraphAligner.h:2375,2410-2418; all rows are final)
-	int32_t minScore = 0x7fffffff;
-	for (uint32_t slot = 0; slot < nc; slot++)
+	else
 	{
-		int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + slot, 2);
-		if (nodeMin < minScore) minScore = nodeMin;
+		// The band holds a cycle.  Components in the reference's order (reverse Tarjan emission = topological); acyclic
+		// ones that Kahn's pass did not reach are evaluated like any other node, cyclic ones replay the reference's
+		// confirmedRows work list.  The slice minimum and its last tied cell are tracked in evaluation order.
+		st.cyclicSlices++;
+		// mark the nodes Kahn's pass evaluated (indeg is about to be reused by Tarjan)
+		for (uint32_t slot = 0; slot < nc; slot++) mem.wl[(size_t)slot * LANES] = 0;
+		for (uint32_t q = 0; q < done; q++) mem.wl[(size_t)mem.order[(size_t)q * LANES] * LANES] = 1;
+		// wl doubles as the "already evaluated" flag array until the work list needs it: copy the flags into cmpOf's top bit
+		const uint32_t nComp = ga_tarjan_components<LANES>(g, caps, mem, cx);
+		// columns outside cyclic components are final when a component reads them: confirmedRows = 64
+		for (uint32_t c = 0; c < ncols; c++) mem.conf[(size_t)c * LANES] = 64;
+		for (uint32_t slot = 0; slot < nc; slot++)
+		{
+			if (mem.wl[(size_t)slot * LANES]) mem.cmpOf[(size_t)slot * LANES] |= 0x40000000u;
+		}
+		bool sawCyclic = false;
+		uint32_t compEnd = nc;   // emit[compStart..compEnd) = current component, walking emission order backwards
+		for (uint32_t ci = nComp; ci-- > 0;)
+		{
+			uint32_t compStart = compEnd;
+			while (compStart > 0 && (mem.cmpOf[(size_t)mem.emit[(size_t)(compStart - 1) * LANES] * LANES] & 0x3fffffffu) == ci) compStart--;
+			const uint32_t firstSlot = mem.emit[(size_t)compStart * LANES];
+			bool cyclic = compEnd - compStart > 1;
+			if (!cyclic)
+			{
+				const uint32_t node = GA_HN(cx.nodeOff + firstSlot, 0);
+				for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++) cyclic = cyclic || g.outAdj[e] == node;
+			}
+			// once a cyclic component has been evaluated, everything after it may read columns the reference left
+			// partly confirmed, so it replays the reference's path as well
+			const bool exact = cyclic || sawCyclic;
+			sawCyclic = sawCyclic || cyclic;
+			if (!exact)
+			{
+				if (!(mem.cmpOf[(size_t)firstSlot * LANES] & 0x40000000u))
+				{
+					ga_calc_node<LANES>(g, caps, mem, st, cx, firstSlot, false, true);
+					if (st.status != GA_OK) return false;
+				}
+				const int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + firstSlot, 2);
+				if (nodeMin <= minScore)
+				{
+					// minScoreIndex gets this node's tied columns in ascending order: the last one is the highest
+					const uint32_t cs = GA_HN(cx.nodeOff + firstSlot, 1), len = GA_HN(cx.nodeOff + firstSlot, 3);
+					for (uint32_t k = 0; k < len; k++)
+					{
+						if (ga_tiny_score(cx.tinyCur[(size_t)(cs + k) * LANES]) == nodeMin) lastMinCol = k;
+					}
+					minScore = nodeMin;
+					lastMinSlot = firstSlot;
+				}
+			}
+			else
+			{
+				// forceComponentZeroRow, then the UniqueQueue work list (GraphAligner.h:2360-2420, UniqueQueue.h)
+				ga_force_block<LANES>(g, caps, mem, st, cx, compStart, compEnd, ci);
+				if (st.status != GA_OK) return false;
+				uint32_t wlN = 0;
+				const uint32_t INQ = 0x80000000u;
+				for (uint32_t q = compStart; q < compEnd; q++)
+				{
+					const uint32_t slot = mem.emit[(size_t)q * LANES];
+					mem.wl[(size_t)(wlN++) * LANES] = slot;
+					mem.cmpOf[(size_t)slot * LANES] |= INQ;
+				}
+				uint32_t guard = 0;
+				while (wlN > 0)
+				{
+					const uint32_t slot = mem.wl[(size_t)(--wlN) * LANES];
+					mem.cmpOf[(size_t)slot * LANES] &= ~INQ;
+					const uint32_t cs = GA_HN(cx.nodeOff + slot, 1), len = GA_HN(cx.nodeOff + slot, 3);
+					const uint32_t oldEndConf = mem.conf[(size_t)(cs + len - 1) * LANES];
+					uint32_t callLastCol = 0;
+					const int32_t callMin = ga_ex_calc_node<LANES>(g, caps, mem, st, cx, slot, callLastCol);
+					if (st.status != GA_OK) return false;
+					GA_HN(cx.nodeOff + slot, 2) = (uint32_t)callMin;   // setMinScore: the LAST call's value stays (GraphAligner.h:2375)
+					const uint32_t newEndConf = mem.conf[(size_t)(cs + len - 1) * LANES];
+					const int32_t endSbs = ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + len - 1);
+					if (endSbs < (int32_t)st.partLen && ga_conf_gt((int)(newEndConf & 0xffu), (newEndConf & 0x100u) != 0, (int)(oldEndConf & 0xffu), (oldEndConf & 0x100u) != 0))
+					{
+						const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
+						for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
+						{
+							int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+							if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != ci) continue;
+							if ((mem.conf[(size_t)GA_HN(cx.nodeOff + cu, 1) * LANES] & 0xffu) >= 64) continue;
+							if (mem.cmpOf[(size_t)cu * LANES] & INQ) continue;
+							mem.cmpOf[(size_t)cu * LANES] |= INQ;
+							mem.wl[(size_t)(wlN++) * LANES] = (uint32_t)cu;
+						}
+					}
+					if (callMin < minScore || (callMin == minScore && callMin != 0x7fffffff))
+					{
+						minScore = callMin;
+						lastMinSlot = slot;
+						lastMinCol = callLastCol;
+					}
+					if (++guard > 200u * (compEnd - compStart) + 1000u) { st.status = GA_ERR_CYCLE_ITER; return false; }
+				}
+			}
+			compEnd = compStart;
+		}
 	}
+	GA_HDR(cx.s, 10) = lastMinSlot;
+	GA_HDR(cx.s, 11) = lastMinCol;
+#ifdef GA_HOST_DEBUG
+	if (getenv("GA_DBG"))
+	{
+		std::vector<std::pair<uint32_t, std::pair<int, int>>> v;
+		for (uint32_t slot = 0; slot < nc; slot++)
+		{
+			uint32_t cs = GA_HN(cx.nodeOff + slot, 1), len = GA_HN(cx.nodeOff + slot, 3);
+			v.push_back({GA_HN(cx.nodeOff + slot, 0), {(int)GA_HN(cx.nodeOff + slot, 2), ga_tiny_score(cx.tinyCur[(size_t)(cs + len - 1) * LANES])}});
+		}
+		std::sort(v.begin(), v.end());
+		fprintf(stderr, "SLICE j=%d min=%d n=%d last=%d\n", (int)cx.s * 64, minScore, (int)nc, lastMinSlot == 0xffffffffu ? -2 : (int)(g.nodeStart[GA_HN(cx.nodeOff + lastMinSlot, 0)] + lastMinCol));
+		for (auto& p : v) fprintf(stderr, "N %d %d %d\n", (int)p.first, p.second.first, p.second.second);
+	}
+#endif
 	st.wordColumns += ncols;
 	// correctness HMM (AlignmentCorrectnessEstimation.cpp:71-89); doubles are only added and compared
 	int32_t m = minScore - st.prevMin;
@@ -1647,18 +2115,24 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 					nTies++;
 				}
 			}
-			int endSlot = nTies > 0 ? ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore) : -1;
+			// a slice with a cyclic component recorded its last minimum cell while replaying the reference's schedule
+			const uint32_t recSlot = GA_HDR(sl, 10);
+			int endSlot = recSlot != 0xffffffffu ? (int)recSlot : (nTies > 0 ? ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore) : -1);
 			if (endSlot < 0) out->status = GA_ERR_INTERNAL;
 			else
 			{
 				endNode = GA_HN(nodeOff + endSlot, 0);
 				uint32_t cs = GA_HN(nodeOff + endSlot, 1);
 				uint32_t len = GA_HN(nodeOff + endSlot, 3);
-				for (uint32_t k = 0; k < len; k++)
+				if (recSlot != 0xffffffffu) endOff = GA_HDR(sl, 11);
+				else
 				{
-					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
-					int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
-					if (v == minScore) endOff = k;
+					for (uint32_t k = 0; k < len; k++)
+					{
+						GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+						int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
+						if (v == minScore) endOff = k;
+					}
 				}
 				out->nTies = nTies;
 				out->score = minScore;

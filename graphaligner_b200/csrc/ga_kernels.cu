@@ -37,10 +37,10 @@ struct WarpDesc
 
 struct ScratchPtrs
 {
-	uint32_t* tiny;     // [warp][2][maxCols][S]
+	uint32_t* tiny;     // [warp][3][maxCols][S]  tiny x2, confirmedRows (cyclic slices)
 	uint64_t* hash;     // [warp][2][hashSize][S]
 	uint64_t* heap;     // [warp][maxQueue][S]
-	uint32_t* nodeTmp;  // [warp][7][maxNodes][S]  indeg, order, unext, uorder, nWlo, nWhi, nPcs
+	uint32_t* nodeTmp;  // [warp][10][maxNodes][S]  indeg, order, unext, uorder, nWlo, nWhi, nPcs, cmpOf, emit, wl
 	uint32_t* ubkt;     // [warp][ubktSize][S]
 	uint32_t* hdr;
 	uint32_t* histNode;
@@ -100,18 +100,22 @@ __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_ca
 	GaLaneMem mem;
 	{
 		size_t w = warp;
-		mem.tiny[0] = sp.tiny + (w * 2 + 0) * caps.maxCols * S + ml;
-		mem.tiny[1] = sp.tiny + (w * 2 + 1) * caps.maxCols * S + ml;
+		mem.tiny[0] = sp.tiny + (w * 3 + 0) * caps.maxCols * S + ml;
+		mem.tiny[1] = sp.tiny + (w * 3 + 1) * caps.maxCols * S + ml;
+		mem.conf = sp.tiny + (w * 3 + 2) * caps.maxCols * S + ml;
 		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S + ml;
 		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S + ml;
 		mem.heap = sp.heap + w * caps.maxQueue * S + ml;
-		mem.indeg = sp.nodeTmp + (w * 7 + 0) * caps.maxNodes * S + ml;
-		mem.order = sp.nodeTmp + (w * 7 + 1) * caps.maxNodes * S + ml;
-		mem.unext = sp.nodeTmp + (w * 7 + 2) * caps.maxNodes * S + ml;
-		mem.uorder = sp.nodeTmp + (w * 7 + 3) * caps.maxNodes * S + ml;
-		mem.nWlo = sp.nodeTmp + (w * 7 + 4) * caps.maxNodes * S + ml;
-		mem.nWhi = sp.nodeTmp + (w * 7 + 5) * caps.maxNodes * S + ml;
-		mem.nPcs = sp.nodeTmp + (w * 7 + 6) * caps.maxNodes * S + ml;
+		mem.indeg = sp.nodeTmp + (w * 10 + 0) * caps.maxNodes * S + ml;
+		mem.order = sp.nodeTmp + (w * 10 + 1) * caps.maxNodes * S + ml;
+		mem.unext = sp.nodeTmp + (w * 10 + 2) * caps.maxNodes * S + ml;
+		mem.uorder = sp.nodeTmp + (w * 10 + 3) * caps.maxNodes * S + ml;
+		mem.nWlo = sp.nodeTmp + (w * 10 + 4) * caps.maxNodes * S + ml;
+		mem.nWhi = sp.nodeTmp + (w * 10 + 5) * caps.maxNodes * S + ml;
+		mem.nPcs = sp.nodeTmp + (w * 10 + 6) * caps.maxNodes * S + ml;
+		mem.cmpOf = sp.nodeTmp + (w * 10 + 7) * caps.maxNodes * S + ml;
+		mem.emit = sp.nodeTmp + (w * 10 + 8) * caps.maxNodes * S + ml;
+		mem.wl = sp.nodeTmp + (w * 10 + 9) * caps.maxNodes * S + ml;
 		mem.ubkt = sp.ubkt + w * sp.ubktSize * S + ml;
 		mem.hdr = sp.hdr + wd.hdrBase + ml;
 		mem.histNode = sp.histNode + wd.hnBase + ml;
@@ -518,10 +522,10 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
 	ctx->bOut.ensure(n * sizeof(ga_stream_out));
 	ctx->bWd.ensure(nWarps * sizeof(WarpDesc));
-	ctx->bTiny.ensure(nWarps * 2 * caps.maxCols * S * sizeof(uint32_t));
+	ctx->bTiny.ensure(nWarps * 3 * caps.maxCols * S * sizeof(uint32_t));
 	ctx->bHash.ensure(nWarps * 2 * (size_t)caps.hashSize * S * sizeof(uint64_t));
 	ctx->bHeap.ensure(nWarps * (size_t)caps.maxQueue * S * sizeof(uint64_t));
-	ctx->bNodeTmp.ensure(nWarps * 7 * (size_t)caps.maxNodes * S * sizeof(uint32_t));
+	ctx->bNodeTmp.ensure(nWarps * 10 * (size_t)caps.maxNodes * S * sizeof(uint32_t));
 	ctx->bUbkt.ensure(nWarps * (size_t)ubktSize * S * sizeof(uint32_t));
 	ctx->bHdr.ensure(hdrTop * sizeof(uint32_t));
 	ctx->bHn.ensure(hnTop * sizeof(uint32_t));

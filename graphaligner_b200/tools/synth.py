@@ -247,10 +247,16 @@ def make_case(seed, graph, n_reads, read_len, b=10, B=0, seed_offsets=(0,), deco
     rng = np.random.default_rng(seed + 7919)
     reads = []
     i = 0
+    misses = 0
     while len(reads) < n_reads:
         ln = read_len if not len_jitter else int(read_len + rng.integers(-len_jitter, len_jitter + 1))
         r = simulate_read(rng, graph, max(2, ln), errors[0], errors[1], errors[2])
         if r is None:
+            # the graph has no walk this long from the nodes tried: shorten instead of looping forever
+            misses += 1
+            if misses % 8 == 0:
+                read_len = max(2, read_len // 2)
+                len_jitter = min(len_jitter, read_len // 4)
             continue
         read, real, walk, mp = r
         offs = [o if o >= 0 else len(real) + o for o in seed_offsets]
