@@ -28,6 +28,21 @@ def smallexample():
                        [(name, seq, by.get(name, [])) for name, seq in reads], 10, 0)
 
 
+def fuzz_case(it):
+    """The differential fuzzer's recipe for seed `it` (kind 3: bubbles + short cycles)."""
+    import numpy as np
+    rng = np.random.default_rng(it)
+    assert it % 6 == 3
+    L = int(rng.integers(2000, 20000))
+    chop = int(rng.choice([4, 8, 16, 32, 64, 100]))
+    g = synth.make_graph(it, L, chop=chop, bubble_every=int(rng.integers(20, 300)), cycle_every=int(rng.integers(100, 1500)))
+    rl = int(rng.choice([70, 150, 300, 1000, 3000]))
+    b = int(rng.choice([2, 5, 10, 20, 35, 50, 100]))
+    offs = [(0,), (0, rl // 2, -50), (rl // 3,), (-1,), (1,)][int(rng.integers(0, 5))]
+    err = float(rng.choice([0.0, 0.02, 0.05, 0.1]))
+    return synth.make_case(it, g, 12, rl, b=b, seed_offsets=offs, decoys=int(rng.integers(0, 2)), errors=(err, err, err), len_jitter=min(rl // 4, 40))
+
+
 def cases():
     yield "smallexample", smallexample()
     # config-2 style: chopped backbone, SNP bubble per 1000 bp, seed at read offset 0
@@ -46,6 +61,11 @@ def cases():
     # short reads / ragged lengths around the 64-row slice boundary, tiny nodes, error-free and noisy
     yield "ragged_short", synth.make_case(16, synth.make_graph(16, 6000, chop=8, bubble_every=40), 24, 100, b=5, len_jitter=40, seed_offsets=(0, 50))
     yield "wide_band", synth.make_case(17, synth.make_graph(17, 20000, chop=16, bubble_every=60, indel_frac=0.5), 8, 1500, b=100)
+    # cyclic band components whose result depends on HOW the reference iterates them: a work list that stops with columns
+    # confirmed to 47 of 64 rows (their nodes then carry minScore INT_MAX into the next band selection), and per-node minima
+    # left by the last calculateNode call
+    yield "cyclic_partial_confirm", fuzz_case(11205)
+    yield "cyclic_last_call_min", fuzz_case(1605)
     yield "ramp", synth.make_case(18, synth.make_graph(18, 20000, chop=32, bubble_every=100), 8, 2000, b=5, B=30, errors=(0.08, 0.08, 0.08))
 
 
