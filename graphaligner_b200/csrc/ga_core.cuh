@@ -48,7 +48,7 @@
 #define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
 
 #ifdef GA_HOST_DEBUG
-static unsigned long long g_dbgFast = 0, g_dbgOuter = 0, g_dbgGeneral = 0, g_dbgNodeStart = 0, g_dbgRow0 = 0, g_dbgMerged = 0, g_dbgReload = 0;
+static unsigned long long g_dbgFast = 0, g_dbgOuter = 0, g_dbgGeneral = 0, g_dbgNodeStart = 0, g_dbgRow0 = 0, g_dbgMerged = 0, g_dbgReload = 0, g_dbgLink = 0;
 #endif
 
 struct GaHmmTables
@@ -81,7 +81,7 @@ struct GaLaneMem
 	uint32_t* hdr;
 	uint32_t* histNode;
 	uint4* col;          // column history pool (shared by all warps), four 16-byte quarters per column:
-	                     // {VP, VN} {sbs, scoreEnd, -, -} {H, D0} {EQ, flags, -}   (H, D0, EQ: traceback masks, see ga_node_columns)
+	                     // {VP, VN} {sbs, scoreEnd, linkNode, linkCol} {H, D0} {EQ, flags, prevCol}   (H, D0, EQ: traceback masks, see ga_node_columns)
 	unsigned long long* colPoolTop;   // bump pointer of the pool, in columns (x LANES lanes)
 	uint32_t* moves;
 	uint32_t* pathNodes;
@@ -106,16 +106,46 @@ struct GaCol
 
 // stores a column without traceback masks (node starts, merged columns, resets): flags = 0 sends the traceback
 // through the exact general path for this column
+// prevCol = pool index of the same graph column in the slice above (GA_NO_COL if the node is not in that band): the
+// traceback crosses slice borders through it without searching
+#define GA_NO_COL 0xffffffffu
 template <int LANES>
-GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c)
+GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint32_t prevCol)
 {
 	uint4 a, b, z;
 	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
 	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
-	z.x = z.y = z.z = z.w = 0;
+	z.x = z.y = z.z = 0; z.w = prevCol;
 	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
 	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
 	mem.col[(size_t)(col * GA_COL_Q + 3) * LANES] = z;
+}
+
+// values only: the record's flags / prevCol quarter stays as ga_force_block wrote it
+template <int LANES>
+GA_DEV void ga_col_store_values(const GaLaneMem& mem, uint32_t col, const GaCol& c)
+{
+	uint4 a, b;
+	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
+	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
+	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
+	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
+}
+
+// first column of a node that is a plain word step from its single in-neighbour's last column: masks as for any other
+// column (flags bit 0) plus the link to that neighbour (flags bit 1): its node index and the pool index of its last column
+template <int LANES>
+GA_DEV void ga_col_store_linked(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint64_t H, uint64_t D0, uint64_t EQ, uint32_t flags, uint32_t linkNode, uint32_t linkCol, uint32_t prevCol)
+{
+	uint4 ra, rb, rc, rd;
+	ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
+	rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = linkNode; rb.w = linkCol;
+	rc.x = (uint32_t)H; rc.y = (uint32_t)(H >> 32); rc.z = (uint32_t)D0; rc.w = (uint32_t)(D0 >> 32);
+	rd.x = (uint32_t)EQ; rd.y = (uint32_t)(EQ >> 32); rd.z = flags; rd.w = prevCol;
+	mem.col[(size_t)(col * GA_COL_Q) * LANES] = ra;
+	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = rb;
+	mem.col[(size_t)(col * GA_COL_Q + 2) * LANES] = rc;
+	mem.col[(size_t)(col * GA_COL_Q + 3) * LANES] = rd;
 }
 
 template <int LANES>
@@ -594,6 +624,8 @@ struct GaSliceCtx
 	uint32_t nodeOff, nNodes;     // this slice's node list in the node history
 	uint32_t pNodeOff, pNodes;    // previous slice's
 	uint32_t slabOff;             // this slice's first column in the warp slab
+	uint32_t pSlabOff;            // the previous slice's (unused when !hasPrevSlab: slice 0 follows the initial slice)
+	bool hasPrevSlab;
 	uint32_t* tinyCur;
 	const uint32_t* tinyPrev;
 	uint64_t* hashCur;
@@ -675,7 +707,7 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
 		rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = 0; rb.w = 0;
 		rc.x = (uint32_t)H; rc.y = (uint32_t)(H >> 32); rc.z = (uint32_t)D0; rc.w = (uint32_t)(D0 >> 32);
-		rd.x = (uint32_t)EqTrue; rd.y = (uint32_t)(EqTrue >> 32); rd.z = flags; rd.w = 0;
+		rd.x = (uint32_t)EqTrue; rd.y = (uint32_t)(EqTrue >> 32); rd.z = flags; rd.w = (INPREV && cx.hasPrevSlab) ? cx.pSlabOff + pcs + k : GA_NO_COL;
 		colPtr[0] = ra;
 		colPtr[LANES] = rb;
 		colPtr[2 * LANES] = rc;
@@ -722,6 +754,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	// current slab / in the previous tiny array (0xffffffff = absent)
 	uint32_t inCur[GA_MAX_CACHED_IN], inPrevCol[GA_MAX_CACHED_IN];
 	uint32_t nIn = 0;
+	uint32_t firstIn = 0;   // the first band in-neighbour (the only one when nIn == 1)
 	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
 	int32_t sbs0 = forced ? ga_col_load_sbs<LANES>(mem, cx.slabOff + cs) : (inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff);
 	const uint32_t eBegin = g.inOff[node], eEnd = g.inOff[node + 1];
@@ -751,11 +784,17 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			}
 		}
 		if (nIn < GA_MAX_CACHED_IN) { inCur[nIn] = curCol; inPrevCol[nIn] = prevCol; }
+		if (nIn == 0) firstIn = u;
 		nIn++;
 	}
 	const bool sbE0 = inPrev && ga_tiny_score(oldTiny0) == sbs0;
 	GaCol c0;
 	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
+	// A node whose only band in-neighbour is in this slice starts with a plain word step from that neighbour's last column:
+	// it gets traceback masks and a link like any inner column (the walk then crosses the node border on the fast path)
+	const bool single = !forced && nIn == 1 && inCur[0] != 0xffffffffu;
+	uint64_t H0 = 0, D00 = 0;
+	uint32_t flags0 = 0;
 	if (nIn > 0)
 	{
 		uint32_t k = 0;
@@ -801,14 +840,36 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				LsbE = true;
 				EqHere &= 1;
 			}
-			uint64_t hIgnored, dIgnored;
-			bool mIgnored;
-			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), 0x7fffffff, hIgnored, dIgnored, mIgnored);
+			uint64_t hCand, dCand;
+			bool needMerge;
+			// single: the vertical merge rides on the step as in ga_node_columns (same recurrence, lower entry score)
+			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), (single && inPrev) ? ga_tiny_score(oldTiny0) : 0x7fffffff, hCand, dCand, needMerge);
+			if (single)
+			{
+				H0 = hCand; D00 = dCand; flags0 = 3;
+				if (needMerge) { ga_vertical_merge(cand, ga_tiny_score(oldTiny0)); flags0 = 0; }
+#ifdef GA_HOST_DEBUG
+				{
+					uint64_t h2, d2; bool m2;
+					GaCol ref = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), 0x7fffffff, h2, d2, m2);
+					if (inPrev && ref.sbs > ga_tiny_score(oldTiny0)) ga_vertical_merge(ref, ga_tiny_score(oldTiny0));
+					if (ref.VP != cand.VP || ref.VN != cand.VN || ref.sbs != cand.sbs || ref.scoreEnd != cand.scoreEnd) { fprintf(stderr, "node-start shortcut mismatch\n"); abort(); }
+					if (flags0)
+					{
+						for (int r = 1; r < 64; r++)
+						{
+							int32_t here = ga_col_value(cand.VP, cand.VN, cand.sbs, r), lft = ga_col_value(L.VP, L.VN, L.sbs, r), diag = ga_col_value(L.VP, L.VN, L.sbs, r - 1);
+							if ((((H0 >> r) & 1) != 0) != (here - lft == 1) || (((D00 >> r) & 1) != 0) != (here == diag)) { fprintf(stderr, "node-start mask mismatch row %d\n", r); abort(); }
+						}
+					}
+				}
+#endif
+			}
 			if (k == 0) c0 = cand;
 			else c0 = ga_merge_cols(c0, cand);
 			k++;
 		}
-		if (inPrev && c0.sbs > ga_tiny_score(oldTiny0)) ga_vertical_merge(c0, ga_tiny_score(oldTiny0));
+		if (!single && inPrev && c0.sbs > ga_tiny_score(oldTiny0)) ga_vertical_merge(c0, ga_tiny_score(oldTiny0));
 	}
 	else
 	{
@@ -834,7 +895,11 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		GaCol old = ga_col_load<LANES>(mem, cx.slabOff + cs);
 		if (old.VP == c0.VP && old.VN == c0.VN) return false;   // nothing upstream changed
 	}
-	ga_col_store<LANES>(mem, cx.slabOff + cs, c0);
+	{
+		const uint32_t prevCol0 = (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs : GA_NO_COL;
+		if (flags0) ga_col_store_linked<LANES>(mem, cx.slabOff + cs, c0, H0, D00, Eq, flags0, firstIn, cx.slabOff + inCur[0], prevCol0);
+		else ga_col_store<LANES>(mem, cx.slabOff + cs, c0, prevCol0);
+	}
 	cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
 
 	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
@@ -1040,7 +1105,7 @@ GA_DEV void ga_ex_store(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col
 {
 	GaCol c;
 	c.VP = e.VP; c.VN = e.VN; c.sbs = e.sbs; c.scoreEnd = e.scoreEnd;
-	ga_col_store<LANES>(mem, cx.slabOff + col, c);
+	ga_col_store_values<LANES>(mem, cx.slabOff + col, c);
 	cx.tinyCur[(size_t)col * LANES] = ga_tiny_pack(c, e.sbE);
 	mem.conf[(size_t)col * LANES] = (uint32_t)e.rows | (e.partial ? 0x100u : 0u);
 }
@@ -1243,7 +1308,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			if (c.sbs >= INF) { st.status = GA_ERR_INTERNAL; return; }
 			c.scoreEnd = c.sbs + 64;
 			bool sbE = inPrev && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
-			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c);
+			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c, (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs + k : GA_NO_COL);
 			cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
 			mem.conf[(size_t)(cs + k) * LANES] = 0;
 		}
@@ -1572,18 +1637,33 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	int s = nSlices - 1;
 	int row = 63;
 	const int32_t maxv = (int32_t)st.partLen;
-	const uint32_t ABSENT = 0xffffffffu;
 	uint32_t colBase = 0;       // per (slice, node): index of the node's first column in the history pool
-	uint32_t prevBase = ABSENT; // the same node's first column in slice s-1, if it is in that band
 	const uint4* colPtr = nullptr;   // record of the current column
-	bool reload = true;         // slice or node changed: re-resolve the bases
+	bool reload = true;         // slice or node changed without a stored link: re-resolve the base
 	// traceback masks of the current column (valid iff flags & 1): H = rows one above the left neighbour,
-	// D0 = rows with diagonal delta 0, EQ = rows whose read character matches this column's base
+	// D0 = rows with diagonal delta 0, EQ = rows whose read character matches this column's base;
+	// prevCol = the same graph column in the slice above
 	uint64_t mH = 0, mD0 = 0, mEQ = 0;
-	uint32_t flags = 0;
+	uint32_t flags = 0, prevCol = GA_NO_COL;
 	int32_t here = 0;
 	bool haveHere = false;
 	const uint32_t maxMoves = caps.maxMoves;
+#define GA_TRACE_LOAD_MASKS() \
+	{ \
+		const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES]; \
+		mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32); \
+		mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32); \
+		mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32); \
+		flags = q3.z; \
+		prevCol = q3.w; \
+	}
+	// the history is far larger than L2: on entering a node request the rest of its columns, so that one HBM round
+	// trip is paid per node and slice instead of per step
+#if GA_TRACE_PREFETCH > 0
+#define GA_TRACE_PREFETCH_NODE() for (uint32_t t = 1; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch_l2<LANES>(mem, colBase + off - t);
+#else
+#define GA_TRACE_PREFETCH_NODE()
+#endif
 	while (GA_WARP_ANY(walking))
 	{
 		if (!walking) continue;
@@ -1596,32 +1676,15 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
 			if (slot < 0) { st.status = GA_ERR_TRACE; walking = false; continue; }
 			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
-			prevBase = ABSENT;
-			if (s > 0)
-			{
-				uint32_t pNodeOff = GA_HDR(s - 1, 2);
-				int pslot = ga_slice_find<LANES>(mem, pNodeOff, GA_HDR(s - 1, 3), node);
-				if (pslot >= 0) prevBase = GA_HDR(s - 1, 0) + GA_HN(pNodeOff + pslot, 1);
-			}
 			colPtr = mem.col + (size_t)((colBase + off) * GA_COL_Q) * LANES;
-			// the history is far larger than L2: request the rest of this node's columns now, so that one HBM round
-			// trip is paid per node and slice instead of per step
-#if GA_TRACE_PREFETCH > 0
-			for (uint32_t t = 1; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch_l2<LANES>(mem, colBase + off - t);
-#endif
+			GA_TRACE_PREFETCH_NODE();
 			if (!haveHere)
 			{
 				GaCol c = ga_col_load<LANES>(mem, colBase + off);
 				here = ga_col_value(c.VP, c.VN, c.sbs, row);
 				haveHere = true;
 			}
-			{
-				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
-				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
-				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
-				flags = q3.z;
-			}
+			GA_TRACE_LOAD_MASKS();
 			reload = false;
 		}
 		if (!runOpen)
@@ -1631,10 +1694,10 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			if (j < st.trimRows) { runOpen = true; runNode = node; runLastOff = off; runLastRow = j; }
 			else skipped++;
 		}
-		// ---- fast step: inside the node, inside the slice, on a word-step column (about nine steps in ten).  The three
+		// ---- fast step: inside the node, inside the slice, on a word-step column (nine steps in ten).  The three
 		// candidates of pickBacktracePredecessor reduce to three bit tests, taken in the reference's order: horizontal,
 		// diagonal, vertical.  Nothing here can fail or change node / slice / run.
-		if (runOpen && off > 1 && row > 1 && (flags & 1u) && nMoves < maxMoves)
+		if (runOpen && off > 0 && row > 0 && (flags & 1u) && nMoves < maxMoves)
 		{
 #ifdef GA_HOST_DEBUG
 			g_dbgFast++;
@@ -1652,11 +1715,44 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			{
 				off--;
 				colPtr -= GA_COL_Q * LANES;
-				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
-				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
-				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
-				flags = q3.z;
+				GA_TRACE_LOAD_MASKS();
+			}
+			row -= (mv != GA_MOVE_H) ? 1 : 0;
+			continue;
+		}
+		// ---- link step: first column of a node whose only band in-neighbour is in this slice.  The column is a word step
+		// from that neighbour's last column, so the same three bit tests apply (in-neighbour horizontal, in-neighbour
+		// diagonal, vertical: GraphAligner.h:501-533 with one neighbour); the record holds where the neighbour's column is.
+		// here < maxv: an in-neighbour outside the band reads as maxv in the reference and must not be able to match.
+		if (runOpen && off == 0 && row > 0 && (flags & 2u) && here < maxv && nMoves < maxMoves && nPath < caps.maxPathNodes && nRuns < caps.maxRuns)
+		{
+#ifdef GA_HOST_DEBUG
+			g_dbgLink++;
+#endif
+			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
+			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
+			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
+			const uint32_t mv = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
+			here = here - 1 + (int32_t)((mv == GA_MOVE_D) ? d0 : 0u);
+			curWord |= mv << ((nMoves & 15) * 2);
+			nMoves++;
+			if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
+			if (mv != GA_MOVE_V)
+			{
+				// leaving the node: close the run on the position we stand on, cross into the neighbour
+				uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
+				r[0] = runNode; r[LANES] = 0; r[2 * LANES] = runLastOff; r[3 * LANES] = (uint32_t)s * 64u + (uint32_t)row; r[4 * LANES] = runLastRow;
+				nRuns++;
+				runOpen = false;
+				const uint4 q1 = colPtr[LANES];
+				node = q1.z;
+				off = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]) - 1;
+				colBase = q1.w - off;
+				colPtr = mem.col + (size_t)(q1.w * GA_COL_Q) * LANES;
+				mem.pathNodes[(size_t)nPath * LANES] = node;
+				nPath++;
+				GA_TRACE_PREFETCH_NODE();
+				GA_TRACE_LOAD_MASKS();
 			}
 			row -= (mv != GA_MOVE_H) ? 1 : 0;
 			continue;
@@ -1668,14 +1764,13 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		uint32_t move = 4;
 		uint32_t nnode = node, noff = off;
 		int32_t nhere = 0;
+		uint32_t upCol = GA_NO_COL;   // where the walk lands in the slice above, when the stored index tells
 		if (off > 0 && row > 0 && (flags & 1u))
 		{
-			// fast path: an unmerged word-step column, away from node and slice borders.  The three candidates of
-			// pickBacktracePredecessor reduce to three bit tests, in the reference's order: horizontal, diagonal, vertical
+			// the fast step's tests, outside an open run (trimmed tail) or at a capacity limit
 			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
 			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
 			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
-			// diagonal delta = 1 - D0 must equal the mismatch cost 1 - EQ
 			move = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
 			nhere = here - 1 + (int32_t)((move == GA_MOVE_D) ? d0 : 0u);
 			noff = off - (move != GA_MOVE_V ? 1u : 0u);
@@ -1709,18 +1804,19 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				{
 					ds = us = node == st.startNode ? 0 : maxv;   // the initial slice: seed node all zero
 				}
-				else if (prevBase == ABSENT)
+				else if (prevCol == GA_NO_COL)
 				{
 					ds = us = maxv;
 				}
 				else
 				{
-					ds = (int32_t)mem.col[(size_t)((prevBase + off - 1) * GA_COL_Q + 1) * LANES].y;   // scoreEnd = row 63 of the slice above
-					us = (int32_t)mem.col[(size_t)((prevBase + off) * GA_COL_Q + 1) * LANES].y;
+					// scoreEnd = row 63 of the slice above; a node's columns are contiguous there too
+					ds = (int32_t)mem.col[(size_t)((prevCol - 1) * GA_COL_Q + 1) * LANES].y;
+					us = (int32_t)mem.col[(size_t)(prevCol * GA_COL_Q + 1) * LANES].y;
 				}
 				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
-				else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; }
-				else if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+				else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; if (row == 0 && s > 0 && prevCol != GA_NO_COL) upCol = prevCol - 1; }
+				else if (us == here - 1) { move = GA_MOVE_V; nhere = us; if (row == 0 && s > 0) upCol = prevCol; }
 			}
 			else
 			{
@@ -1739,9 +1835,9 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 					int32_t us;
 					if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
 					else if (s == 0) us = node == st.startNode ? 0 : maxv;
-					else if (prevBase == ABSENT) us = maxv;
-					else us = (int32_t)mem.col[(size_t)((prevBase + off) * GA_COL_Q + 1) * LANES].y;
-					if (us == here - 1) { move = GA_MOVE_V; nhere = us; }
+					else if (prevCol == GA_NO_COL) us = maxv;
+					else us = (int32_t)mem.col[(size_t)(prevCol * GA_COL_Q + 1) * LANES].y;
+					if (us == here - 1) { move = GA_MOVE_V; nhere = us; if (row == 0 && s > 0) upCol = prevCol; }
 				}
 			}
 			// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
@@ -1775,24 +1871,36 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				nPath++;
 				reload = true;
 			}
-			else
+			else if (row > 0 || move == GA_MOVE_H)
 			{
 				colPtr -= GA_COL_Q * LANES;
-				const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES];
-				mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-				mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
-				mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
-				flags = q3.z;
+				GA_TRACE_LOAD_MASKS();
 			}
 		}
 		if (move != GA_MOVE_H)
 		{
 			row--;
-			if (row < 0) { row = 63; s--; reload = true; }
+			if (row < 0)
+			{
+				row = 63;
+				s--;
+				if (upCol != GA_NO_COL && !reload)
+				{
+					// same node, slice above: the stored index replaces the search
+					colBase = upCol - noff;
+					colPtr = mem.col + (size_t)(upCol * GA_COL_Q) * LANES;
+					off = noff;
+					GA_TRACE_PREFETCH_NODE();
+					GA_TRACE_LOAD_MASKS();
+				}
+				else reload = true;
+			}
 		}
 		node = nnode;
 		off = noff;
 	}
+#undef GA_TRACE_LOAD_MASKS
+#undef GA_TRACE_PREFETCH_NODE
 	if (doTrace && (nMoves & 15)) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
 	nMovesOut = nMoves;
 	nPathOut = nPath;
@@ -1985,6 +2093,8 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.pNodeOff = pNodeOff;
 		cx.pNodes = pNodes;
 		cx.slabOff = (uint32_t)slabOff;
+		cx.hasPrevSlab = s > 0;
+		cx.pSlabOff = s > 0 ? GA_HDR(s - 1, 0) : 0;
 		cx.tinyCur = mem.tiny[tc];
 		cx.tinyPrev = mem.tiny[tp];
 		cx.hashCur = mem.hash[tc];
