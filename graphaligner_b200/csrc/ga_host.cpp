@@ -5,6 +5,8 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 namespace ga
@@ -73,6 +75,69 @@ unsigned HostThreads()
 	return n;
 }
 
+// ---- worker pool -------------------------------------------------------------------------------------------------
+// The host passes of a batch are a handful of short parallel loops; starting threads for each costs as much as the loop.
+// One process-wide pool (never torn down: workers sleep on a condition variable) runs them.  A second caller arriving
+// while the pool is busy (one host thread per GPU) falls back to threads of its own.
+namespace
+{
+struct WorkerPool
+{
+	std::mutex jobMutex;              // one job at a time
+	std::mutex m;
+	std::condition_variable cvStart, cvDone;
+	uint64_t generation = 0;
+	const std::function<void()>* job = nullptr;
+	unsigned wanted = 0, taken = 0, pending = 0;
+	std::vector<std::thread> workers;
+
+	void workerMain()
+	{
+		uint64_t seen = 0;
+		std::unique_lock<std::mutex> lock(m);
+		while (true)
+		{
+			cvStart.wait(lock, [&]() { return generation != seen; });
+			seen = generation;
+			if (taken >= wanted) continue;
+			taken++;
+			const std::function<void()>* j = job;
+			lock.unlock();
+			(*j)();
+			lock.lock();
+			if (--pending == 0) cvDone.notify_all();
+		}
+	}
+	// runs job on `extra` pool workers and on the caller
+	void run(unsigned extra, const std::function<void()>& j)
+	{
+		{
+			std::lock_guard<std::mutex> lock(m);
+			while (workers.size() < extra)
+			{
+				workers.emplace_back([this]() { workerMain(); });
+				workers.back().detach();
+			}
+			job = &j;
+			wanted = extra;
+			taken = 0;
+			pending = extra;
+			generation++;
+		}
+		cvStart.notify_all();
+		j();
+		std::unique_lock<std::mutex> lock(m);
+		cvDone.wait(lock, [&]() { return pending == 0; });
+		job = nullptr;
+	}
+};
+WorkerPool& workerPool()
+{
+	static WorkerPool* pool = new WorkerPool();   // leaked on purpose: detached workers outlive static destruction
+	return *pool;
+}
+}
+
 void ParallelFor(size_t n, const std::function<void(size_t)>& f)
 {
 	unsigned threads = (unsigned)std::min<size_t>(HostThreads(), n);
@@ -83,10 +148,9 @@ void ParallelFor(size_t n, const std::function<void(size_t)>& f)
 	}
 	std::atomic<size_t> next(0);
 	const size_t chunk = std::max<size_t>(1, n / (threads * 8));
-	std::vector<std::thread> pool;
 	std::exception_ptr error;
 	std::atomic<bool> failed(false);
-	auto work = [&]() {
+	std::function<void()> work = [&]() {
 		try
 		{
 			while (!failed.load())
@@ -102,10 +166,99 @@ void ParallelFor(size_t n, const std::function<void(size_t)>& f)
 			if (!failed.exchange(true)) error = std::current_exception();
 		}
 	};
-	for (unsigned t = 0; t + 1 < threads; t++) pool.emplace_back(work);
-	work();
-	for (auto& t : pool) t.join();
+	WorkerPool& wp = workerPool();
+	std::unique_lock<std::mutex> jobLock(wp.jobMutex, std::try_to_lock);
+	if (jobLock.owns_lock())
+	{
+		wp.run(threads - 1, work);
+	}
+	else
+	{
+		std::vector<std::thread> own;
+		for (unsigned t = 0; t + 1 < threads; t++) own.emplace_back(work);
+		work();
+		for (auto& t : own) t.join();
+	}
 	if (error) std::rethrow_exception(error);
+}
+
+// ---- block cache ---------------------------------------------------------------------------------------------------
+// Result buffers are 100 MB-class and live for one batch.  glibc hands such blocks straight to mmap / munmap, so every
+// batch would fault all of its pages in again (tens of thousands of faults); freed blocks are kept for the next batch.
+namespace
+{
+struct BlockCache
+{
+	std::mutex m;
+	std::vector<std::pair<void*, size_t>> blocks;   // oldest first
+	size_t cached = 0;
+	size_t limit;
+	BlockCache()
+	{
+		limit = (size_t)1024 << 20;
+		if (const char* e = getenv("GA_HOST_CACHE_MB")) limit = (size_t)std::max(0ll, atoll(e)) << 20;
+	}
+};
+BlockCache& blockCache()
+{
+	static BlockCache* c = new BlockCache();
+	return *c;
+}
+const size_t kBigBlock = (size_t)1 << 20;
+}
+
+void* BigAlloc(size_t bytes, size_t& capOut)
+{
+	if (bytes < kBigBlock)
+	{
+		capOut = bytes;
+		void* p = malloc(bytes ? bytes : 1);
+		if (!p) throw std::bad_alloc();
+		return p;
+	}
+	BlockCache& c = blockCache();
+	{
+		std::lock_guard<std::mutex> lock(c.m);
+		size_t best = c.blocks.size();
+		for (size_t i = 0; i < c.blocks.size(); i++)
+		{
+			const size_t cap = c.blocks[i].second;
+			if (cap >= bytes && cap <= 2 * bytes + (8u << 20) && (best == c.blocks.size() || cap < c.blocks[best].second)) best = i;
+		}
+		if (best != c.blocks.size())
+		{
+			void* p = c.blocks[best].first;
+			capOut = c.blocks[best].second;
+			c.cached -= capOut;
+			c.blocks.erase(c.blocks.begin() + best);
+			return p;
+		}
+	}
+	const size_t round = (size_t)4 << 20;
+	capOut = (bytes + bytes / 16 + round - 1) / round * round;
+	void* p = malloc(capOut);
+	if (!p) throw std::bad_alloc();
+	return p;
+}
+
+void BigFree(void* p, size_t cap)
+{
+	if (!p) return;
+	if (cap < kBigBlock) { free(p); return; }
+	BlockCache& c = blockCache();
+	std::vector<void*> drop;
+	{
+		std::lock_guard<std::mutex> lock(c.m);
+		c.blocks.emplace_back(p, cap);
+		c.cached += cap;
+		while (c.cached > c.limit && !c.blocks.empty())
+		{
+			drop.push_back(c.blocks.front().first);
+			c.cached -= c.blocks.front().second;
+			c.blocks.erase(c.blocks.begin());
+		}
+	}
+	for (void* d : drop) free(d);
 }
 
 static char complementOf(char c)

@@ -100,21 +100,48 @@ struct ReadInput
 	size_t nSeeds;
 };
 
-// heap buffer without value-initialisation (a 100 MB std::vector costs ~25 ms just to zero)
+// 1 MiB+ blocks are recycled through a process-wide cache instead of going back to the OS (ga_host.cpp)
+void* BigAlloc(size_t bytes, size_t& capOut);
+void BigFree(void* p, size_t cap);
+
+// heap buffer without value-initialisation (a 100 MB std::vector costs ~25 ms just to zero) for trivially copyable T.
+// adopt() takes over a block from elsewhere (pinned host memory a device copy landed in) together with its release function.
 template <typename T>
 class RawBuffer
 {
 public:
-	RawBuffer() : n(0) {}
-	void resize(size_t count) { p.reset(count ? new T[count] : nullptr); n = count; }
-	T* data() { return p.get(); }
-	const T* data() const { return p.get(); }
+	typedef void (*ReleaseFn)(void* p, size_t capBytes);
+	RawBuffer() : p(nullptr), n(0), cap(0), rel(nullptr) {}
+	~RawBuffer() { clear(); }
+	RawBuffer(const RawBuffer&) = delete;
+	RawBuffer& operator=(const RawBuffer&) = delete;
+	RawBuffer(RawBuffer&& o) noexcept : p(o.p), n(o.n), cap(o.cap), rel(o.rel) { o.p = nullptr; o.n = 0; o.cap = 0; o.rel = nullptr; }
+	RawBuffer& operator=(RawBuffer&& o) noexcept { if (this != &o) { clear(); swap(o); } return *this; }
+	void resize(size_t count)
+	{
+		if (!rel && p && count * sizeof(T) <= cap) { n = count; return; }
+		clear();
+		if (count) p = (T*)BigAlloc(count * sizeof(T), cap);
+		n = count;
+	}
+	void adopt(T* block, size_t count, size_t capBytes, ReleaseFn release)
+	{
+		clear();
+		p = block; n = count; cap = capBytes; rel = release;
+	}
+	T* data() { return p; }
+	const T* data() const { return p; }
 	size_t size() const { return n; }
-	void clear() { p.reset(); n = 0; }
-	void swap(RawBuffer& o) { p.swap(o.p); std::swap(n, o.n); }
+	void clear()
+	{
+		if (p) { if (rel) rel(p, cap); else BigFree(p, cap); }
+		p = nullptr; n = 0; cap = 0; rel = nullptr;
+	}
+	void swap(RawBuffer& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); std::swap(rel, o.rel); }
 private:
-	std::unique_ptr<T[]> p;
-	size_t n;
+	T* p;
+	size_t n, cap;
+	ReleaseFn rel;
 };
 
 struct MatrixPos

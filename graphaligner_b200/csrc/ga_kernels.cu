@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <mutex>
 #include <vector>
 #include "ga_core.cuh"
 #include "ga_device.h"
@@ -609,6 +610,74 @@ static bool isOverflow(int32_t status)
 	return status == GA_ERR_NODE_OVERFLOW || status == GA_ERR_COL_OVERFLOW || status == GA_ERR_QUEUE_OVERFLOW || status == GA_ERR_HIST_OVERFLOW || status == GA_ERR_TRACE_OVERFLOW;
 }
 
+// ---- pinned host blocks for results -------------------------------------------------------------------------------
+namespace
+{
+struct PinnedPool
+{
+	std::mutex m;
+	std::vector<std::pair<void*, size_t>> blocks;   // oldest first
+	size_t cached = 0;
+	size_t limit;
+	PinnedPool()
+	{
+		limit = (size_t)1024 << 20;
+		if (const char* e = getenv("GA_PINNED_CACHE_MB")) limit = (size_t)std::max(0ll, atoll(e)) << 20;
+	}
+};
+PinnedPool& pinnedPool()
+{
+	static PinnedPool* p = new PinnedPool();   // never destroyed: results may be freed during static destruction
+	return *p;
+}
+
+void* pinnedAcquire(size_t bytes, size_t& capOut)
+{
+	PinnedPool& pool = pinnedPool();
+	{
+		std::lock_guard<std::mutex> lock(pool.m);
+		size_t best = pool.blocks.size();
+		for (size_t i = 0; i < pool.blocks.size(); i++)
+		{
+			const size_t cap = pool.blocks[i].second;
+			if (cap >= bytes && cap <= 2 * bytes + (8u << 20) && (best == pool.blocks.size() || cap < pool.blocks[best].second)) best = i;
+		}
+		if (best != pool.blocks.size())
+		{
+			void* p = pool.blocks[best].first;
+			capOut = pool.blocks[best].second;
+			pool.cached -= capOut;
+			pool.blocks.erase(pool.blocks.begin() + best);
+			return p;
+		}
+	}
+	const size_t round = (size_t)4 << 20;
+	capOut = (bytes + bytes / 8 + round - 1) / round * round;
+	void* p = nullptr;
+	GA_CUDA(cudaHostAlloc(&p, capOut, cudaHostAllocPortable));
+	return p;
+}
+
+void pinnedRelease(void* p, size_t cap)
+{
+	if (!p) return;
+	PinnedPool& pool = pinnedPool();
+	std::vector<void*> drop;
+	{
+		std::lock_guard<std::mutex> lock(pool.m);
+		pool.blocks.emplace_back(p, cap);
+		pool.cached += cap;
+		while (pool.cached > pool.limit && !pool.blocks.empty())
+		{
+			drop.push_back(pool.blocks.front().first);
+			pool.cached -= pool.blocks.front().second;
+			pool.blocks.erase(pool.blocks.begin());
+		}
+	}
+	for (void* d : drop) cudaFreeHost(d);
+}
+}
+
 void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
@@ -624,20 +693,17 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 	unsigned long long top = *pinTop;
 	if (top > sb->arenaCap) top = sb->arenaCap;
-	uint32_t* pinArena = (uint32_t*)ctx->pinArena.ensure(top * sizeof(uint32_t) + 16);
-	if (top) GA_CUDA(cudaMemcpyAsync(pinArena, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	// the trace arena lands in a pinned block that the results then own (recycled through a process-wide pool): no
+	// second pass over ~100 MB, no fresh pages to fault in
+	if (top)
+	{
+		size_t cap = 0;
+		uint32_t* pin = (uint32_t*)pinnedAcquire(top * sizeof(uint32_t) + 16, cap);
+		arena.adopt(pin, (size_t)top, cap, pinnedRelease);
+		GA_CUDA(cudaMemcpyAsync(pin, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	}
 	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
-	arena.resize(top);
-	{
-		const size_t chunk = 1 << 20;
-		const size_t nChunks = (top + chunk - 1) / chunk;
-		uint32_t* dst = arena.data();
-		ParallelFor(nChunks, [&](size_t c) {
-			size_t begin = c * chunk, end = std::min<size_t>(top, begin + chunk);
-			memcpy(dst + begin, pinArena + begin, (end - begin) * sizeof(uint32_t));
-		});
-	}
 	if (stats)
 	{
 		stats->d2hBytes += n * sizeof(ga_stream_out) + top * sizeof(uint32_t) + sizeof(top);
