@@ -365,6 +365,7 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 {
 	// split the batch when its DP history would not fit the device (the history is ~64 B per band column and slice)
 	std::vector<size_t> cuts;   // chunk boundaries in reads
+	StageTimer tmAll;
 	int rc = guarded(ctx, [&]() {
 		if (!ctx->graph) throw std::logic_error("ga_align_batch: no graph uploaded");
 		const size_t budget = (size_t)(ga::FreeDeviceBytes(ctx->dev) * 0.8);
@@ -386,13 +387,19 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 		cuts.push_back(batch->n_reads);
 	});
 	if (rc != 0) return nullptr;
+	tmAll.lap("align: split plan");
 	if (cuts.size() <= 2)
 	{
 		ga_staged* st = ga_stage_batch(ctx, batch);
 		if (!st) return nullptr;
 		ga_results* res = nullptr;
-		if (ga_run_staged(ctx, st) == 0) res = ga_finish_staged(ctx, st);
+		tmAll.lap("align: stage (total)");
+		int rrc = ga_run_staged(ctx, st);
+		tmAll.lap("align: launch");
+		if (rrc == 0) res = ga_finish_staged(ctx, st);
+		tmAll.lap("align: finish (total)");
 		ga_staged_free(ctx, st);
+		tmAll.lap("align: free staged");
 		return res;
 	}
 	ga_results* all = new ga_results();

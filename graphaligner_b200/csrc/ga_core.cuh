@@ -33,6 +33,9 @@
 #define GA_WARP_ANY(x) __any_sync(0xffffffffu, (x))
 // one allocation per warp from a global bump pointer; every lane gets the same offset
 #define GA_POOL_ALLOC(ptr, n) __shfl_sync(0xffffffffu, ((threadIdx.x & 31) == 0) ? atomicAdd((ptr), (unsigned long long)(n)) : 0ull, 0)
+// traceback-mask quarters of the column history: written once, read once much later by the traceback -> keep them out of
+// L1 (st.global.cg), which the per-slice scratch (node tables, hash windows, tiny arrays) and the value quarters need
+#define GA_ST_HIST(ptr, v) __stcg((ptr), (v))
 #else
 #define GA_DEV inline
 #define GA_DEV_NOINLINE inline
@@ -41,6 +44,7 @@
 #define GA_WARP_MAX(x) (x)
 #define GA_WARP_ANY(x) (x)
 #define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
+#define GA_ST_HIST(ptr, v) (*(ptr) = (v))
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
@@ -118,7 +122,7 @@ GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c, uin
 	z.x = z.y = z.z = 0; z.w = prevCol;
 	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
 	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
-	mem.col[(size_t)(col * GA_COL_Q + 3) * LANES] = z;
+	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 3) * LANES], z);
 }
 
 // values only: the record's flags / prevCol quarter stays as ga_force_block wrote it
@@ -144,8 +148,8 @@ GA_DEV void ga_col_store_linked(const GaLaneMem& mem, uint32_t col, const GaCol&
 	rd.x = (uint32_t)EQ; rd.y = (uint32_t)(EQ >> 32); rd.z = flags; rd.w = prevCol;
 	mem.col[(size_t)(col * GA_COL_Q) * LANES] = ra;
 	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = rb;
-	mem.col[(size_t)(col * GA_COL_Q + 2) * LANES] = rc;
-	mem.col[(size_t)(col * GA_COL_Q + 3) * LANES] = rd;
+	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 2) * LANES], rc);
+	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 3) * LANES], rd);
 }
 
 template <int LANES>
@@ -182,7 +186,8 @@ GA_DEV void ga_col_prefetch_l2(const GaLaneMem& mem, uint32_t col)
 {
 #ifdef __CUDACC__
 	asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 2) * LANES));
-	asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
+	// with up to 4 lanes the two mask quarters of a column share a 128-byte line
+	if (LANES > 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
 #else
 	(void)mem; (void)col;
 #endif
@@ -334,7 +339,7 @@ GA_DEV int32_t ga_col_value(uint64_t VP, uint64_t VN, int32_t sbs, int row)
 template <int LANES>
 GA_DEV int ga_hash_find(const uint64_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node)
 {
-	uint32_t h = (node * 2654435761u) & hashMask;
+	uint32_t h = ((node * 2654435761u) >> 15) & hashMask;
 	while (true)
 	{
 		uint64_t e = table[(size_t)h * LANES];
@@ -347,9 +352,20 @@ GA_DEV int ga_hash_find(const uint64_t* table, uint32_t hashMask, uint32_t stamp
 template <int LANES>
 GA_DEV void ga_hash_insert(uint64_t* table, uint32_t hashMask, uint32_t stamp, uint32_t node, uint32_t slot)
 {
-	uint32_t h = (node * 2654435761u) & hashMask;
+	uint32_t h = ((node * 2654435761u) >> 15) & hashMask;
 	while (((uint32_t)(table[(size_t)h * LANES] >> 16) & 0xffffu) == stamp) h = (h + 1) & hashMask;
 	table[(size_t)h * LANES] = ((uint64_t)node << 32) | ((uint64_t)stamp << 16) | slot;
+}
+
+// A band is a handful of nodes, the table is sized for the largest band allowed: a slice only uses the first `window`
+// entries (mask = window - 1), so the tables of all resident warps stay in L1.  Lookups for a stamp must use the mask the
+// stamp was inserted with; ga_band_add widens the window (under a fresh stamp) when a band outgrows it.
+GA_DEV uint32_t ga_hash_window(uint32_t expectedNodes, uint32_t hashSize)
+{
+	uint32_t size = 32;
+	while (size < expectedNodes * 4 && size < hashSize) size <<= 1;
+	if (size > hashSize) size = hashSize;
+	return size - 1;
 }
 
 // ---- std::priority_queue<NodeWithPriority, vector, greater<>> as libstdc++ implements it ----------------------
@@ -547,18 +563,28 @@ GA_DEV uint32_t ga_exact_code(uint8_t c)
 // Returns the number of band nodes.
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES>
-GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, uint64_t* hashCur, uint32_t stampCur,
+GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, uint64_t* hashCur, uint32_t& maskCur, uint32_t& stampCur, uint32_t& gen,
 	uint32_t nodeOff, uint32_t& nc, uint32_t& ncols, uint32_t node, uint64_t wStart, uint32_t len, uint32_t pcs)
 {
 	if (nc >= caps.maxNodes) { st.status = GA_ERR_NODE_OVERFLOW; return false; }
 	if (nodeOff + nc >= caps.histNodes) { st.status = GA_ERR_HIST_OVERFLOW; return false; }
+	if ((nc + 1) * 2 > maskCur + 1 && maskCur + 1 < caps.hashSize)
+	{
+		// the table outgrew the window it was given (ga_hash_window): re-insert under a fresh stamp with a wider mask
+		if (gen >= 0xfffeu) { st.status = GA_ERR_HIST_OVERFLOW; return false; }
+		uint32_t size = maskCur + 1;
+		while (size < (nc + 1) * 4 && size < caps.hashSize) size <<= 1;
+		maskCur = size - 1;
+		stampCur = ++gen;
+		for (uint32_t i = 0; i < nc; i++) ga_hash_insert<LANES>(hashCur, maskCur, stampCur, GA_HN(nodeOff + i, 0), i);
+	}
 	GA_HN(nodeOff + nc, 0) = node;
 	GA_HN(nodeOff + nc, 1) = ncols;
 	GA_HN(nodeOff + nc, 3) = len;
 	mem.nWlo[(size_t)nc * LANES] = (uint32_t)wStart;
 	mem.nWhi[(size_t)nc * LANES] = (uint32_t)(wStart >> 32);
 	mem.nPcs[(size_t)nc * LANES] = pcs;
-	ga_hash_insert<LANES>(hashCur, caps.hashSize - 1, stampCur, node, nc);
+	ga_hash_insert<LANES>(hashCur, maskCur, stampCur, node, nc);
 	nc++;
 	ncols += len;
 	if (ncols >= GA_ALT_CUTOFF) { st.status = GA_ERR_ALT_METHOD; return false; }
@@ -567,9 +593,9 @@ GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLan
 
 template <int LANES>
 GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaUmapSchedule& sch, const GaLaneMem& mem, GaStreamState& st, int bandwidth,
-	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, const uint64_t* hashPrev, uint32_t stampPrev, uint64_t* hashCur, uint32_t stampCur, uint32_t nodeOff, uint32_t& ncolsOut)
+	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, const uint64_t* hashPrev, uint32_t maskPrev, uint32_t stampPrev, uint64_t* hashCur, uint32_t& maskCur, uint32_t& stampCur, uint32_t& gen,
+	uint32_t nodeOff, uint32_t& ncolsOut)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const int32_t expand = bandwidth + 64;
 	uint32_t nc = 0;
 	uint32_t ncols = 0;
@@ -584,7 +610,7 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		uint32_t node = GA_HN(pNodeOff + i, 0);
 		uint32_t pcs = GA_HN(pNodeOff + i, 1);
 		uint32_t len = GA_HN(pNodeOff + i, 3);
-		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, stampCur, nodeOff, nc, ncols, node, g.nodeStart[node], len, pcs)) return -1;
+		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, g.nodeStart[node], len, pcs)) return -1;
 		int32_t endscore = ga_tiny_score(tinyPrev[(size_t)(pcs + len - 1) * LANES]);
 		if (endscore > st.prevMin + expand) continue;
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
@@ -600,13 +626,13 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		if (prio > expand) break;
 		ga_heap_pop<LANES>(mem.heap, heapN);
 		uint32_t node = (uint32_t)top;
-		if (ga_hash_find<LANES>(hashCur, hashMask, stampCur, node) >= 0) continue;
+		if (ga_hash_find<LANES>(hashCur, maskCur, stampCur, node) >= 0) continue;
 		uint64_t wStart = g.nodeStart[node];
 		uint32_t len = (uint32_t)(g.nodeStart[node + 1] - wStart);
 		// not kept, but it may still sit in the previous band (its minimum was outside the bandwidth)
-		int pslot = ga_hash_find<LANES>(hashPrev, hashMask, stampPrev, node);
+		int pslot = ga_hash_find<LANES>(hashPrev, maskPrev, stampPrev, node);
 		uint32_t pcs = pslot >= 0 ? GA_HN(pNodeOff + pslot, 1) : GA_NOT_IN_PREV;
-		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, stampCur, nodeOff, nc, ncols, node, wStart, len, pcs)) return -1;
+		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, wStart, len, pcs)) return -1;
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
@@ -631,6 +657,7 @@ struct GaSliceCtx
 	uint64_t* hashCur;
 	const uint64_t* hashPrev;
 	uint32_t stampCur, stampPrev;
+	uint32_t maskCur, maskPrev;   // hash windows of the two tables (ga_hash_window)
 	uint64_t BA, BC, BG, BT;
 	uint32_t prevCharCode;        // exact code of sequence[j0-1], 4 = matches nothing
 	bool firstSlice;
@@ -710,8 +737,8 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		rd.x = (uint32_t)EqTrue; rd.y = (uint32_t)(EqTrue >> 32); rd.z = flags; rd.w = (INPREV && cx.hasPrevSlab) ? cx.pSlabOff + pcs + k : GA_NO_COL;
 		colPtr[0] = ra;
 		colPtr[LANES] = rb;
-		colPtr[2 * LANES] = rc;
-		colPtr[3 * LANES] = rd;
+		GA_ST_HIST(colPtr + 2 * LANES, rc);
+		GA_ST_HIST(colPtr + 3 * LANES, rd);
 		colPtr += GA_COL_Q * LANES;
 		*tinyPtr = ga_tiny_pack(c, sbE);
 		tinyPtr += LANES;
@@ -734,7 +761,6 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 template <int LANES>
 GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, bool forced, bool first)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
 	const uint32_t len = GA_HN(cx.nodeOff + slot, 3);
@@ -754,20 +780,22 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	// current slab / in the previous tiny array (0xffffffff = absent)
 	uint32_t inCur[GA_MAX_CACHED_IN], inPrevCol[GA_MAX_CACHED_IN];
 	uint32_t nIn = 0;
-	uint32_t firstIn = 0;   // the first band in-neighbour (the only one when nIn == 1)
+	uint32_t firstIn = 0, firstInLen = 1;   // the first band in-neighbour (the only one when nIn == 1) and its length
 	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
 	int32_t sbs0 = forced ? ga_col_load_sbs<LANES>(mem, cx.slabOff + cs) : (inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff);
 	const uint32_t eBegin = g.inOff[node], eEnd = g.inOff[node + 1];
 	for (uint32_t e = eBegin; e < eEnd; e++)
 	{
 		uint32_t u = g.inAdj[e];
-		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
-		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+		int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, u);
+		int pu = ga_hash_find<LANES>(cx.hashPrev, cx.maskPrev, cx.stampPrev, u);
 		if (cu < 0 && pu < 0) continue;
 		uint32_t curCol = 0xffffffffu, prevCol = 0xffffffffu;
 		if (cu >= 0)
 		{
-			curCol = GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1;
+			const uint32_t ulen = GA_HN(cx.nodeOff + cu, 3);
+			curCol = GA_HN(cx.nodeOff + cu, 1) + ulen - 1;
+			if (nIn == 0) firstInLen = ulen;
 			if (!forced)
 			{
 				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + curCol) + 1;
@@ -811,8 +839,8 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			{
 				// high in-degree: look the neighbour up again instead of caching
 				uint32_t u = g.inAdj[e];
-				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
-				int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+				int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, u);
+				int pu = ga_hash_find<LANES>(cx.hashPrev, cx.maskPrev, cx.stampPrev, u);
 				if (cu < 0 && pu < 0) continue;
 				curCol = cu >= 0 ? GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1 : 0xffffffffu;
 				prevCol = pu >= 0 ? GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1 : 0xffffffffu;
@@ -846,7 +874,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), (single && inPrev) ? ga_tiny_score(oldTiny0) : 0x7fffffff, hCand, dCand, needMerge);
 			if (single)
 			{
-				H0 = hCand; D00 = dCand; flags0 = 3;
+				H0 = hCand; D00 = dCand; flags0 = 3u | ((firstInLen - 1) << 2);   // bits 2..: the neighbour's last offset
 				if (needMerge) { ga_vertical_merge(cand, ga_tiny_score(oldTiny0)); flags0 = 0; }
 #ifdef GA_HOST_DEBUG
 				{
@@ -1115,7 +1143,6 @@ GA_DEV void ga_ex_store(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col
 template <int LANES>
 GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, uint32_t& lastMinCol)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
 	const uint32_t len = GA_HN(cx.nodeOff + slot, 3);
@@ -1137,8 +1164,8 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 	for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 	{
 		uint32_t u = g.inAdj[e];
-		int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
-		int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+		int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, u);
+		int pu = ga_hash_find<LANES>(cx.hashPrev, cx.maskPrev, cx.stampPrev, u);
 		if (cu < 0 && pu < 0) continue;
 		uint64_t EqHere = Eq;
 		const bool foundOneUp = pu >= 0;
@@ -1211,7 +1238,6 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 template <int LANES>
 GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to, uint32_t comp)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const int32_t INF = 0x3fffffff;
 	uint32_t heapN = 0;
 	// the component's members are emit[from..to); cmpOf[slot] == comp tests membership
@@ -1227,8 +1253,8 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
 		{
 			uint32_t u = g.inAdj[e];
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, u);
-			int pu = ga_hash_find<LANES>(cx.hashPrev, hashMask, cx.stampPrev, u);
+			int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, u);
+			int pu = ga_hash_find<LANES>(cx.hashPrev, cx.maskPrev, cx.stampPrev, u);
 			if (cu >= 0 && (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp)
 			{
 				uint32_t ucol = GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1;
@@ -1260,7 +1286,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		{
 			for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 			{
-				int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+				int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.outAdj[e]);
 				if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp) continue;
 				if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 				ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(v + 1) << 32) | (uint32_t)cu);
@@ -1285,7 +1311,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		if (!endUpdated) continue;
 		for (uint32_t e = g.outOff[node]; e < g.outOff[node + 1]; e++)
 		{
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+			int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.outAdj[e]);
 			if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != comp) continue;
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return; }
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)score << 32) | (uint32_t)cu);
@@ -1324,7 +1350,6 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 template <int LANES>
 GA_DEV uint32_t ga_tarjan_components(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, const GaSliceCtx& cx)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t nNodes = cx.nNodes;
 	const uint32_t ONSTACK = 0x80000000u;
 	for (uint32_t i = 0; i < nNodes; i++) mem.indeg[(size_t)i * LANES] = 0;
@@ -1347,7 +1372,7 @@ GA_DEV uint32_t ga_tarjan_components(const ga_graph_view& g, const ga_caps& caps
 			if (e < g.outOff[node + 1])
 			{
 				mem.ubkt[(size_t)depth * LANES] = e + 1;
-				int nb = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+				int nb = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.outAdj[e]);
 				if (nb < 0) continue;
 				uint32_t mark = mem.indeg[(size_t)nb * LANES];
 				if (mark == 0)
@@ -1402,7 +1427,6 @@ struct GaSliceResult
 template <int LANES>
 GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, GaStreamState& st, GaSliceCtx& cx, uint32_t ncols, GaSliceResult& res)
 {
-	const uint32_t hashMask = caps.hashSize - 1;
 	const uint32_t nc = cx.nNodes;
 	// Peq words for the 64 read characters of this slice (GraphAligner.h:2338-2351), precomputed by ga_peq_kernel
 	{
@@ -1422,7 +1446,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		uint32_t d = 0;
 		for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 		{
-			if (ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.inAdj[e]) >= 0) d++;
+			if (ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.inAdj[e]) >= 0) d++;
 		}
 		mem.indeg[(size_t)slot * LANES] = d;
 		if (d == 0) mem.order[(size_t)(ready++) * LANES] = slot;
@@ -1436,7 +1460,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
-			int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+			int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.outAdj[e]);
 			if (cu < 0) continue;
 			uint32_t d = mem.indeg[(size_t)cu * LANES] - 1;
 			mem.indeg[(size_t)cu * LANES] = d;
@@ -1540,7 +1564,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 						const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 						for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 						{
-							int cu = ga_hash_find<LANES>(cx.hashCur, hashMask, cx.stampCur, g.outAdj[e]);
+							int cu = ga_hash_find<LANES>(cx.hashCur, cx.maskCur, cx.stampCur, g.outAdj[e]);
 							if (cu < 0 || (mem.cmpOf[(size_t)cu * LANES] & 0x3fffffffu) != ci) continue;
 							if ((mem.conf[(size_t)GA_HN(cx.nodeOff + cu, 1) * LANES] & 0xffu) >= 64) continue;
 							if (mem.cmpOf[(size_t)cu * LANES] & INQ) continue;
@@ -1621,7 +1645,8 @@ GA_DEV int32_t ga_hist_value(const GaLaneMem& mem, const GaStreamState& st, int 
 }
 
 template <int LANES>
-GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool doTrace, int nSlices, uint32_t node, uint32_t off, uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
+GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool doTrace, int nSlices, uint32_t node, uint32_t off,
+	uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
 {
 	// Called by every lane of the warp (doTrace = this lane has a trace to walk).  One loop iteration = one step of
 	// every walking lane, with a warp vote at the loop head: diverged lanes would otherwise serialise their chains of
@@ -1746,7 +1771,7 @@ GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				runOpen = false;
 				const uint4 q1 = colPtr[LANES];
 				node = q1.z;
-				off = (uint32_t)(g.nodeStart[node + 1] - g.nodeStart[node]) - 1;
+				off = flags >> 2;
 				colBase = q1.w - off;
 				colPtr = mem.col + (size_t)(q1.w * GA_COL_Q) * LANES;
 				mem.pathNodes[(size_t)nPath * LANES] = node;
@@ -2027,7 +2052,6 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	st.cyclicSlices = 0;
 	uint32_t slicesRun = 0;
 	if (active && st.nslices > caps.maxSlices) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; }
-	const uint32_t hashMask = caps.hashSize - 1;
 
 	// initial slice (getInitialSliceOnlyOneNode, GraphAligner.h:2945-2960): the seed node, every column 0.
 	// It lives at node-history entry 0 and in tiny table 0 / hash table 0 with stamp 1.
@@ -2042,7 +2066,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			GA_HN(0, 1) = 0;
 			GA_HN(0, 2) = 0;
 			GA_HN(0, 3) = len;
-			ga_hash_insert<LANES>(mem.hash[0], hashMask, 1, st.startNode, 0);
+			ga_hash_insert<LANES>(mem.hash[0], ga_hash_window(1, caps.hashSize), 1, st.startNode, 0);
 			for (uint32_t k = 0; k < len; k++) mem.tiny[0][(size_t)k * LANES] = 0;
 			pNodes = 1;
 			st.histNodeTop = 1;
@@ -2054,6 +2078,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	uint32_t gen = 1;          // stamp generator for the node -> slot tables (stamp 1 = the initial slice in table 0)
 	int tp = 0;                // table holding the previous slice
 	uint32_t stampPrev = 1;
+	uint32_t maskPrev = ga_hash_window(1, caps.hashSize);
 	while (true)
 	{
 		bool run = !st.done && (uint32_t)ls < st.nslices;
@@ -2061,6 +2086,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		const int s = ls;
 		const int tc = tp ^ 1;
 		uint32_t stampCur = 0;
+		uint32_t maskCur = ga_hash_window(pNodes, caps.hashSize);   // bands change slowly: sized from the previous one
 		uint32_t ncols = 0;
 		int nc = 0;
 		uint32_t nodeOff = st.histNodeTop;
@@ -2072,7 +2098,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 				stampCur = ++gen;
 				// slices up to rampUntil run with rampBandwidth; rampUntil starts at 0, so slice 0 always does (GraphAligner.h:2612)
 				int bandwidth = (rampUntil >= s) ? rampBandwidth : initialBandwidth;
-				nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], stampPrev, mem.hash[tc], stampCur, nodeOff, ncols);
+				nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], maskPrev, stampPrev, mem.hash[tc], maskCur, stampCur, gen, nodeOff, ncols);
 				if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 			}
 		}
@@ -2101,6 +2127,8 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.hashPrev = mem.hash[tp];
 		cx.stampCur = stampCur;
 		cx.stampPrev = stampPrev;
+		cx.maskCur = maskCur;
+		cx.maskPrev = maskPrev;
 		GA_HDR(s, 0) = (uint32_t)slabOff;
 		GA_HDR(s, 1) = ncols;
 		GA_HDR(s, 2) = nodeOff;
@@ -2130,11 +2158,12 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			st.histNodeTop = nodeOff + (uint32_t)nc;   // abandoned entries are simply left behind
 			st.slicesPushed = (uint32_t)target + 1;
 			stampPrev = ++gen;
+			maskPrev = ga_hash_window(pNodes, caps.hashSize);
 			{
 				const uint32_t tSlab = GA_HDR(target, 0);
 				for (uint32_t i = 0; i < pNodes; i++)
 				{
-					ga_hash_insert<LANES>(mem.hash[tp], hashMask, stampPrev, GA_HN(pNodeOff + i, 0), i);
+					ga_hash_insert<LANES>(mem.hash[tp], maskPrev, stampPrev, GA_HN(pNodeOff + i, 0), i);
 					const uint32_t cs = GA_HN(pNodeOff + i, 1), len = GA_HN(pNodeOff + i, 3);
 					for (uint32_t k = 0; k < len; k++)
 					{
@@ -2163,6 +2192,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		st.histNodeTop = nodeOff + (uint32_t)nc;
 		tp = tc;
 		stampPrev = stampCur;
+		maskPrev = maskCur;
 		ls = s + 1;
 	}
 	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------

@@ -76,13 +76,21 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 	}
 }
 
+// shared-memory scratch per stream in small-band mode
+#define GA_SMEM_NODES 16u
+#define GA_SMEM_HASH 32u
+#define GA_SMEM_HEAP 32u
+#define GA_SMEM_UBKT 32u
+#define GA_SMEM_WORDS64 (2 * GA_SMEM_HASH + GA_SMEM_HEAP + (7 * GA_SMEM_NODES + GA_SMEM_UBKT) / 2)
+
 // S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
 // less divergence; big batches run with S = 32 for full lane utilisation.
 template <int S>
 __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
-	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
+	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, uint32_t smemScratch,
 	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
+	extern __shared__ __align__(16) unsigned long long gaShared[];
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t warp = tid >> 5;
 	const uint32_t lane = tid & 31;
@@ -126,6 +134,27 @@ __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_ca
 		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
 		mem.runs = sp.runs + wd.runsBase + ml;
 		mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
+		if (smemScratch)
+		{
+			// Small-band mode (host: caps.maxNodes = GA_SMEM_NODES, hashSize = GA_SMEM_HASH, maxQueue = GA_SMEM_HEAP): the per-slice
+			// scratch that is written and read back within a slice lives in shared memory.  A global store invalidates its L1
+			// line, so in global memory every such read-after-write is an L2 round trip on the stream's critical path.
+			unsigned long long* base64 = gaShared + (size_t)(threadIdx.x >> 5) * (GA_SMEM_WORDS64 * S);
+			for (uint32_t i = lane; i < (2 * GA_SMEM_HASH) * S; i += 32) base64[i] = 0;   // the stamped tables start empty
+			__syncwarp();
+			mem.hash[0] = (uint64_t*)base64 + ml;
+			mem.hash[1] = (uint64_t*)base64 + GA_SMEM_HASH * S + ml;
+			mem.heap = (uint64_t*)base64 + 2 * GA_SMEM_HASH * S + ml;
+			uint32_t* base32 = (uint32_t*)(base64 + (2 * GA_SMEM_HASH + GA_SMEM_HEAP) * S);
+			mem.indeg = base32 + 0 * GA_SMEM_NODES * S + ml;
+			mem.order = base32 + 1 * GA_SMEM_NODES * S + ml;
+			mem.unext = base32 + 2 * GA_SMEM_NODES * S + ml;
+			mem.uorder = base32 + 3 * GA_SMEM_NODES * S + ml;
+			mem.nWlo = base32 + 4 * GA_SMEM_NODES * S + ml;
+			mem.nWhi = base32 + 5 * GA_SMEM_NODES * S + ml;
+			mem.nPcs = base32 + 6 * GA_SMEM_NODES * S + ml;
+			mem.ubkt = base32 + 7 * GA_SMEM_NODES * S + ml;
+		}
 	}
 	ga_stream_out* out = active ? outs + stream : nullptr;
 	ga_run_stream<S>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
@@ -252,6 +281,7 @@ struct StagedBatch
 	size_t hostPartsBytes = 0;
 	int capScale = 1;
 	int S = 32;            // streams per warp
+	bool smemScratch = false;   // small-band mode: per-slice scratch in shared memory
 	size_t peqWords = 0;
 	uint64_t colPoolCap = 0;
 };
@@ -469,6 +499,18 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ga_caps& caps = sb->caps;
 	sb->S = pickStreamsPerWarp(ctx, n);
 	const size_t S = (size_t)sb->S;
+	{
+		// small-band mode: few streams per warp (shared memory per SM) and a graph whose bands hold a handful of nodes; a stream
+		// that outgrows the fixed capacities reports an overflow and is re-run with the general layout (capScale > 1)
+		const double bandNodes = 2.0 * (std::max(sb->b, sb->B) + 64) / std::max(1.0, ctx->avgNodeLen) + 2;
+		sb->smemScratch = scale == 1 && sb->S <= 4 && bandNodes <= 10 && getenv("GA_NO_SMEM") == nullptr;
+		if (sb->smemScratch)
+		{
+			caps.maxNodes = GA_SMEM_NODES;
+			caps.hashSize = GA_SMEM_HASH;
+			caps.maxQueue = GA_SMEM_HEAP;
+		}
+	}
 	const size_t nWarps = (n + S - 1) / S;
 	sb->nWarps = nWarps;
 	const int bw = std::max(sb->b, sb->B);
@@ -518,6 +560,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		ubktSize = ctx->sched.buckets[i];
 		if (ctx->sched.buckets[i] >= caps.maxNodes) break;
 	}
+	if (sb->smemScratch && ubktSize > GA_SMEM_UBKT) throw std::logic_error("unordered_map bucket schedule does not fit the shared-memory scratch");
 	ubktSize = std::max(ubktSize, caps.maxNodes);
 	ctx->bParts.ensure(sb->hostPartsBytes + 64);
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
@@ -572,8 +615,9 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 	const size_t n = sb->sorted.size();
 	const int threads = 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
-	ga_align_kernel<S><<<blocks, threads, 0, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
+	const size_t smemBytes = sb->smemScratch ? (size_t)(threads / 32) * GA_SMEM_WORDS64 * S * sizeof(unsigned long long) : 0;
+	ga_align_kernel<S><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, sb->smemScratch ? 1u : 0u, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
 		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 
