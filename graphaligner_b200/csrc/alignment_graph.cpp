@@ -125,6 +125,7 @@ void AlignmentGraph::Finalize(int wordSize)
 	pendingEdges.clear();
 	pendingEdges.shrink_to_fit();
 	// keep one spare word so a 16-base window read at the very end stays in bounds
+	seq2.push_back(0);   // two words of padding: the device reads 32 bases (three words) at a time
 	seq2.push_back(0);
 	size_t special = 0;
 	for (size_t i = 0; i < n; i++)

@@ -36,6 +36,7 @@
 // traceback-mask quarters of the column history: written once, read once much later by the traceback -> keep them out of
 // L1 (st.global.cg), which the per-slice scratch (node tables, hash windows, tiny arrays) and the value quarters need
 #define GA_ST_HIST(ptr, v) __stcg((ptr), (v))
+#define GA_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
 #else
 #define GA_DEV inline
 #define GA_DEV_NOINLINE inline
@@ -45,6 +46,7 @@
 #define GA_WARP_ANY(x) (x)
 #define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
 #define GA_ST_HIST(ptr, v) (*(ptr) = (v))
+#define GA_FUNNEL_R(lo, hi, s) ((uint32_t)(((((uint64_t)(hi)) << 32) | (uint64_t)(lo)) >> ((s) & 31)))
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
@@ -84,6 +86,7 @@ struct GaLaneMem
 	uint32_t* conf;      //   per band column: confirmedRows (rows | partial << 8), GraphAligner.h:1355-1416
 	uint32_t* hdr;
 	uint32_t* histNode;
+	uint64_t* eqTab;     // four match words of the current slice, [base][lane] (shared memory on the device)
 	uint4* col;          // column history pool (shared by all warps), four 16-byte quarters per column:
 	                     // {VP, VN} {sbs, scoreEnd, linkNode, linkCol} {H, D0} {EQ, flags, prevCol}   (H, D0, EQ: traceback masks, see ga_node_columns)
 	unsigned long long* colPoolTop;   // bump pointer of the pool, in columns (x LANES lanes)
@@ -659,6 +662,7 @@ struct GaSliceCtx
 	uint32_t stampCur, stampPrev;
 	uint32_t maskCur, maskPrev;   // hash windows of the two tables (ga_hash_window)
 	uint64_t BA, BC, BG, BT;
+	uint64_t* eqTab;              // the same four words indexed by base: [base][lane], shared memory on the device
 	uint32_t prevCharCode;        // exact code of sequence[j0-1], 4 = matches nothing
 	bool firstSlice;
 };
@@ -670,21 +674,22 @@ template <int LANES, bool INPREV>
 GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, const GaSliceCtx& cx, uint64_t wStart, uint32_t len, uint32_t cs, uint32_t pcs,
 	uint32_t prevMask, bool forced, GaCol L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin)
 {
-	uint64_t w = wStart + 1;
-	uint32_t seqWord = g.seq2[w >> 4];
-	uint32_t shift = (uint32_t)(w & 15) * 2;
 	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * GA_COL_Q) * LANES;
 	uint32_t* tinyPtr = cx.tinyCur + (size_t)(cs + 1) * LANES;
 	const uint32_t* prevPtr = cx.tinyPrev + (size_t)(pcs + 2) * LANES;   // next column to prefetch
+	const uint64_t w = wStart + 1;
 	const uint32_t* seqPtr = g.seq2 + (w >> 4) + 1;
+	uint32_t seqWord = g.seq2[w >> 4];
+	uint32_t shift = (uint32_t)(w & 15) * 2;
 	for (uint32_t k = 1; k < len; k++)
 	{
+		// one loop for all lanes, refill test inside: per-word or per-32-base inner loops end at different columns per
+		// lane (nodes start anywhere inside a sequence word) and were measured slower (divergence, exposed refill load)
 		const uint32_t base = (seqWord >> shift) & 3u;
 		shift += 2;
 		if (shift == 32) { seqWord = *seqPtr++; shift = 0; }
-		const uint64_t lo = (base & 1u) ? cx.BC : cx.BA;
-		const uint64_t hi = (base & 1u) ? cx.BT : cx.BG;
-		const uint64_t Eq = (base & 2u) ? hi : lo;
+		// match mask of this column's base from the slice's table (shared memory: the address depends only on the base)
+		const uint64_t Eq = cx.eqTab[(size_t)base * LANES];
 		const uint64_t EqTrue = Eq;   // IUPAC match mask of this column's base, untouched by the band-edge rules
 		const bool previousEq = ((prevMask >> base) & 1u) != 0;
 		GaCol c;
@@ -1435,6 +1440,8 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.BC = (uint64_t)a.z | ((uint64_t)a.w << 32);
 		cx.BG = (uint64_t)b.x | ((uint64_t)b.y << 32);
 		cx.BT = (uint64_t)b.z | ((uint64_t)b.w << 32);
+		cx.eqTab = mem.eqTab;
+		cx.eqTab[0] = cx.BA; cx.eqTab[LANES] = cx.BC; cx.eqTab[2 * LANES] = cx.BG; cx.eqTab[3 * LANES] = cx.BT;
 		cx.prevCharCode = cx.s > 0 ? ga_exact_code(st.seq[(size_t)cx.s * 64 - 1]) : 4;
 		cx.firstSlice = cx.s == 0;
 	}

@@ -134,12 +134,14 @@ __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_ca
 		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
 		mem.runs = sp.runs + wd.runsBase + ml;
 		mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
+		// every launch: four match words per stream, [warp in block][base][lane]
+		mem.eqTab = (uint64_t*)gaShared + (size_t)(threadIdx.x >> 5) * (4 * S) + ml;
 		if (smemScratch)
 		{
 			// Small-band mode (host: caps.maxNodes = GA_SMEM_NODES, hashSize = GA_SMEM_HASH, maxQueue = GA_SMEM_HEAP): the per-slice
 			// scratch that is written and read back within a slice lives in shared memory.  A global store invalidates its L1
 			// line, so in global memory every such read-after-write is an L2 round trip on the stream's critical path.
-			unsigned long long* base64 = gaShared + (size_t)(threadIdx.x >> 5) * (GA_SMEM_WORDS64 * S);
+			unsigned long long* base64 = gaShared + (size_t)(blockDim.x >> 5) * (4 * S) + (size_t)(threadIdx.x >> 5) * (GA_SMEM_WORDS64 * S);
 			for (uint32_t i = lane; i < (2 * GA_SMEM_HASH) * S; i += 32) base64[i] = 0;   // the stamped tables start empty
 			__syncwarp();
 			mem.hash[0] = (uint64_t*)base64 + ml;
@@ -615,7 +617,7 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 	const size_t n = sb->sorted.size();
 	const int threads = 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
-	const size_t smemBytes = sb->smemScratch ? (size_t)(threads / 32) * GA_SMEM_WORDS64 * S * sizeof(unsigned long long) : 0;
+	const size_t smemBytes = (size_t)(threads / 32) * (4 + (sb->smemScratch ? GA_SMEM_WORDS64 : 0)) * S * sizeof(unsigned long long);
 	ga_align_kernel<S><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
 		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, sb->smemScratch ? 1u : 0u, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
 		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
