@@ -106,3 +106,46 @@ def test_ramp_bandwidth_runs(api):
     cover_b = sum(x["end"] - x["start"] for x in b if not x["failed"])
     assert cover_b >= cover_a
     aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+def test_small_band_overflow_reruns_with_general_layout(api, tmp_path, monkeypatch):
+    # 32-bp nodes and band 10 select the small-band layout (16 nodes per band in shared memory); tangles hold far more
+    # nodes per band, so those streams must report an overflow and be re-run with the general layout - same results
+    g = synth.make_graph(105, 60000, chop=32, snp_every=1000, tangle_every=12000, tangle_levels=12, tangle_width=4, tangle_node=2)
+    case = synth.make_case(105, g, 48, 3000, b=10, seed_offsets=(0,))
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    assert aligner.stats()["retries"] > 0
+    assert_same(res.as_dicts(), expected, "small-band overflow")
+    res.free()
+    # and the general layout alone gives the same answer
+    monkeypatch.setenv("GA_NO_SMEM", "1")
+    res = aligner.align(case.reads, case.b, case.B)
+    assert_same(res.as_dicts(), expected, "general layout")
+    aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,kw,rl,b", [
+    (106, dict(chop=16, bubble_every=120, cycle_every=400), 2000, 10),
+    (107, dict(chop=32, snp_every=150, cycle_every=300, inversion_every=900), 3000, 20),
+    (108, dict(chop=8, bubble_every=60, cycle_every=250), 1000, 5),
+])
+def test_cyclic_graphs_against_reference_run_here(api, tmp_path, seed, kw, rl, b):
+    # short cycles inside the band: scores and paths depend on how the reference iterates a cyclic component
+    # (last-call node minima, partly confirmed columns); the device replays that schedule
+    g = synth.make_graph(seed, 40000, **kw)
+    case = synth.make_case(seed, g, 40, rl, b=b, seed_offsets=(0, rl // 3))
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    d = res.as_dicts()
+    assert any(x["flags"] & 8 for x in d), "no read met a cyclic band: the case does not test what it says"
+    assert_same(d, expected, "seed %d" % seed)
+    aligner.close()
