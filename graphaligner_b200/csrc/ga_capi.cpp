@@ -62,6 +62,7 @@ struct ga_staged
 	std::vector<ga::ReadInput> reads;
 	std::unique_ptr<ga::BatchPlan> plan;
 	ga::StagedBatch* device = nullptr;
+	ga::DeviceCtx* dev = nullptr;   // the context it was staged on
 	int b = 0, B = 0;
 };
 
@@ -266,18 +267,18 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 	});
 }
 
-ga_staged* ga_stage_batch(ga_ctx* ctx, const ga_batch* batch)
+static ga_staged* stageOn(ga_ctx* ctx, ga::DeviceCtx* dev, const ga_batch* batch)
 {
 	ga_staged* st = new ga_staged();
 	int rc = guarded(ctx, [&]() {
 		if (!ctx->graph) throw std::logic_error("ga_stage_batch: no graph uploaded");
 		StageTimer tm;
+		st->dev = dev;
 		fillStaged(st, batch);
 		tm.lap("stage: marshal reads");
-		ga::DeviceCtx* dev = ctx->dev;
 		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads, [dev](size_t bytes) { return ga::AllocPinnedParts(dev, bytes); }));
 		tm.lap("stage: plan + build parts");
-		st->device = ga::StageAndUpload(ctx->dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats);
+		st->device = ga::StageAndUpload(dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats);
 		tm.lap("stage: layout + H2D");
 	});
 	if (rc != 0)
@@ -288,9 +289,11 @@ ga_staged* ga_stage_batch(ga_ctx* ctx, const ga_batch* batch)
 	return st;
 }
 
+ga_staged* ga_stage_batch(ga_ctx* ctx, const ga_batch* batch) { return stageOn(ctx, ctx->dev, batch); }
+
 int ga_run_staged(ga_ctx* ctx, ga_staged* st)
 {
-	return guarded(ctx, [&]() { ga::RunStaged(ctx->dev, st->device); });
+	return guarded(ctx, [&]() { ga::RunStaged(st->dev, st->device); });
 }
 
 int ga_sync(ga_ctx* ctx)
@@ -305,7 +308,7 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 		StageTimer tm;
 		res->chunks.emplace_back(new ga_results::Chunk());
 		ga_results::Chunk& ch = *res->chunks.back();
-		ga::FinishStaged(ctx->dev, st->device, ch.outs, ch.arena, &ctx->stats);
+		ga::FinishStaged(st->dev, st->device, ch.outs, ch.arena, &ctx->stats);
 		tm.lap("finish: wait kernel + D2H");
 		const AlignmentGraph& graph = ctx->graph->graph;
 		const size_t n = st->reads.size();
@@ -334,31 +337,66 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 void ga_staged_free(ga_ctx* ctx, ga_staged* st)
 {
 	if (!st) return;
-	if (st->device) ga::FreeStaged(ctx->dev, st->device);
+	if (st->device) ga::FreeStaged(st->dev, st->device);
 	delete st;
 }
 
 void* ga_cuda_stream(ga_ctx* ctx) { return ga::DeviceStream(ctx->dev); }
 
-// appends the results of one chunk (reads [first, first + part->lazy.size())) to the combined results
-static void appendChunk(ga_results* all, ga_results* part, size_t first)
+// Combines the results of consecutive sub-batches (part k holds reads [cuts[k], cuts[k + 1])) into one result set:
+// one allocation for all mappings, parts copied in parallel.
+static ga_results* mergeParts(ga_ctx* ctx, std::vector<ga_results*>& parts, const std::vector<size_t>& cuts)
 {
-	const uint32_t chunkIndex = (uint32_t)all->chunks.size();
-	const uint64_t mapBase = all->mappings.size();
-	ga::RawBuffer<ga_mapping> merged;
-	merged.resize(mapBase + part->mappings.size());
-	if (mapBase) memcpy(merged.data(), all->mappings.data(), mapBase * sizeof(ga_mapping));
-	if (part->mappings.size()) memcpy(merged.data() + mapBase, part->mappings.data(), part->mappings.size() * sizeof(ga_mapping));
-	all->mappings.swap(merged);
-	for (size_t i = 0; i < part->lazy.size(); i++)
+	ga_results* all = new ga_results();
+	const size_t n = cuts.back();
+	all->reads.resize(n);
+	all->lazy.resize(n);
+	all->inputs.resize(n);
+	all->graph = &ctx->graph->graph;
+	std::vector<uint64_t> mapBase(parts.size() + 1, 0);
+	for (size_t k = 0; k < parts.size(); k++) mapBase[k + 1] = mapBase[k] + parts[k]->mappings.size();
+	all->mappings.resize(mapBase.back());
+	// copy jobs of ~1 MiB so that the worker pool shares the work evenly
+	struct Job { size_t part; size_t begin, end; };
+	std::vector<Job> jobs;
+	const size_t step = ((size_t)1 << 20) / sizeof(ga_mapping);
+	for (size_t k = 0; k < parts.size(); k++)
 	{
-		all->reads.data()[first + i] = part->reads.data()[i];
-		all->reads.data()[first + i].mapping_offset += mapBase;
-		all->lazy[first + i] = part->lazy[i];
-		all->lazy[first + i].chunk = chunkIndex;
-		all->inputs[first + i] = part->inputs[i];
+		for (size_t b0 = 0; b0 < parts[k]->mappings.size(); b0 += step) jobs.push_back(Job { k, b0, std::min(parts[k]->mappings.size(), b0 + step) });
 	}
-	all->chunks.push_back(std::move(part->chunks[0]));
+	ga::ParallelFor(jobs.size(), [&](size_t j) {
+		const Job& job = jobs[j];
+		memcpy(all->mappings.data() + mapBase[job.part] + job.begin, parts[job.part]->mappings.data() + job.begin, (job.end - job.begin) * sizeof(ga_mapping));
+	});
+	for (size_t k = 0; k < parts.size(); k++)
+	{
+		ga_results* part = parts[k];
+		const uint32_t chunkIndex = (uint32_t)all->chunks.size();
+		const size_t first = cuts[k];
+		for (size_t i = 0; i < part->lazy.size(); i++)
+		{
+			all->reads.data()[first + i] = part->reads.data()[i];
+			all->reads.data()[first + i].mapping_offset += mapBase[k];
+			all->lazy[first + i] = part->lazy[i];
+			all->lazy[first + i].chunk = chunkIndex;
+			all->inputs[first + i] = part->inputs[i];
+		}
+		all->chunks.push_back(std::move(part->chunks[0]));
+		delete part;
+		parts[k] = nullptr;
+	}
+	return all;
+}
+
+// a sub-batch is the same arrays with shifted offsets pointers: offsets are absolute, so only the bases move
+static ga_batch subBatch(const ga_batch* batch, size_t first, size_t last)
+{
+	ga_batch sub = *batch;
+	sub.n_reads = last - first;
+	sub.seq_offsets = batch->seq_offsets + first;
+	sub.name_offsets = batch->name_offsets ? batch->name_offsets + first : nullptr;
+	sub.seed_offsets = batch->seed_offsets + first;
+	return sub;
 }
 
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
@@ -388,46 +426,36 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 	});
 	if (rc != 0) return nullptr;
 	tmAll.lap("align: split plan");
+	std::vector<ga_results*> parts;
+	auto fail = [&]() -> ga_results* {
+		for (ga_results* p : parts) delete p;
+		return nullptr;
+	};
 	if (cuts.size() <= 2)
 	{
+		// (Running two half-batches through two sets of device buffers and streams, to overlap staging and assembly with the
+		// kernel, was measured: each half's kernel takes as long as the whole batch's - a stream's time is a chain of
+		// latencies, not a share of the GPU - so nothing is gained.)
 		ga_staged* st = ga_stage_batch(ctx, batch);
 		if (!st) return nullptr;
 		ga_results* res = nullptr;
-		tmAll.lap("align: stage (total)");
-		int rrc = ga_run_staged(ctx, st);
-		tmAll.lap("align: launch");
-		if (rrc == 0) res = ga_finish_staged(ctx, st);
-		tmAll.lap("align: finish (total)");
+		if (ga_run_staged(ctx, st) == 0) res = ga_finish_staged(ctx, st);
 		ga_staged_free(ctx, st);
-		tmAll.lap("align: free staged");
 		return res;
 	}
-	ga_results* all = new ga_results();
-	all->reads.resize(batch->n_reads);
-	all->lazy.resize(batch->n_reads);
-	all->inputs.resize(batch->n_reads);
-	all->graph = &ctx->graph->graph;
 	for (size_t c = 0; c + 1 < cuts.size(); c++)
 	{
-		// a sub-batch is the same arrays with shifted offsets pointers: offsets are absolute, so only the bases move
-		ga_batch sub = *batch;
-		sub.n_reads = cuts[c + 1] - cuts[c];
-		sub.seq_offsets = batch->seq_offsets + cuts[c];
-		sub.name_offsets = batch->name_offsets ? batch->name_offsets + cuts[c] : nullptr;
-		sub.seed_offsets = batch->seed_offsets + cuts[c];
+		ga_batch sub = subBatch(batch, cuts[c], cuts[c + 1]);
 		ga_staged* st = ga_stage_batch(ctx, &sub);
 		ga_results* part = nullptr;
 		if (st && ga_run_staged(ctx, st) == 0) part = ga_finish_staged(ctx, st);
 		if (st) ga_staged_free(ctx, st);
-		if (!part)
-		{
-			delete all;
-			return nullptr;
-		}
-		appendChunk(all, part, cuts[c]);
-		delete part;
+		if (!part) return fail();
+		parts.push_back(part);
 	}
-	return all;
+	ga_results* all = nullptr;
+	rc = guarded(ctx, [&]() { all = mergeParts(ctx, parts, cuts); });
+	return rc == 0 ? all : fail();
 }
 
 size_t ga_results_count(const ga_results* r) { return r->reads.size(); }

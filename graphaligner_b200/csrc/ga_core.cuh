@@ -36,7 +36,6 @@
 // traceback-mask quarters of the column history: written once, read once much later by the traceback -> keep them out of
 // L1 (st.global.cg), which the per-slice scratch (node tables, hash windows, tiny arrays) and the value quarters need
 #define GA_ST_HIST(ptr, v) __stcg((ptr), (v))
-#define GA_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
 #else
 #define GA_DEV inline
 #define GA_DEV_NOINLINE inline
@@ -46,7 +45,6 @@
 #define GA_WARP_ANY(x) (x)
 #define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
 #define GA_ST_HIST(ptr, v) (*(ptr) = (v))
-#define GA_FUNNEL_R(lo, hi, s) ((uint32_t)(((((uint64_t)(hi)) << 32) | (uint64_t)(lo)) >> ((s) & 31)))
 #endif
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10

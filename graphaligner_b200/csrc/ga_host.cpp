@@ -671,8 +671,12 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		}
 		size_t estimated = (fwSlices + bwSlices) * 64;
 		// addAlignmentNodes, GraphAligner.h:594-634
-		for (auto& r : fw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
-		for (auto& r : bw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+		if (k + 1 < last)   // only a later seed of this read ever looks at them
+		{
+			tried.reserve(tried.size() + fw.size() + bw.size());
+			for (auto& r : fw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+			for (auto& r : bw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+		}
 		if (!hasAlignment || estimated > bestEstimated)
 		{
 			bestFw.swap(fw);
