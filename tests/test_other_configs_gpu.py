@@ -1,0 +1,47 @@
+"""BASELINE configs 3 and 5 at a size the reference finishes in seconds on the box's host cores: a variation graph with
+multi-seed reads and decoy seeds, and 50 kbp reads through tangle-heavy regions over a sweep of band widths.
+The CUDA path (through the C ABI) must reproduce the reference bit for bit (score, range, every mapping, trace fingerprint)."""
+import os
+
+import pytest
+
+from graphaligner_b200.tools import gacase, synth
+from helpers import REF_ALIGN, assert_same, run_reference
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from graphaligner_b200 import api as a
+    a.load_library()
+    return a
+
+
+def _check(api, tmp_path, case, what):
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=os.cpu_count() or 4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    got = res.as_dicts()
+    assert sum(1 for x in got if not x["failed"]) >= len(got) * 0.9, what
+    assert_same(got, expected, what)
+    res.free()
+    aligner.close()
+
+
+def test_config3_variation_graph_multiseed(api, tmp_path):
+    # configs[2] scaled: 1 Mbp variation graph (SNP / indel bubbles every 100 bp, inversions), 400 reads x 10 kbp,
+    # seeds at read offsets 0 / 5000 / end-300 plus a decoy seed each (the seed loop's "already aligned" pruning)
+    g, kw = synth.config3(scale=0.01)
+    case = synth.make_case(3, g, 400, kw["read_len"], b=kw["b"], seed_offsets=kw["seed_offsets"], decoys=kw["decoys"], errors=(0.05, 0.05, 0.05))
+    _check(api, tmp_path, case, "config 3")
+
+
+@pytest.mark.parametrize("band", [5, 20, 50, 100])
+def test_config5_ultralong_reads_band_sweep(api, tmp_path, band):
+    # configs[4] scaled: 50 kbp reads (782 slices) over a 1 Mbp graph with a tangle every 100 kbp, band 5 .. 100
+    g = synth.make_graph(5, 1_000_000, chop=32, bubble_every=100, indel_frac=0.2, tangle_every=100_000)
+    case = synth.make_case(5, g, 16, 50_000, b=band, errors=(0.05, 0.05, 0.05))
+    _check(api, tmp_path, case, "config 5, band %d" % band)
