@@ -13,6 +13,10 @@ HOST_SOURCES = ["ga_host.cpp", "alignment_graph.cpp", "bigraph_to_digraph.cpp", 
 CUDA_SOURCES = ["ga_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-I" + os.path.join(CUDA_HOME, "include")]
+# profiling builds: GA_EXTRA_FLAGS="-DGA_PHASE_TIMING" python graphaligner_b200/build.py --force (both compilers see the flags: shared structs)
+_EXTRA = os.environ.get("GA_EXTRA_FLAGS", "").split()
+NVCC_FLAGS += _EXTRA
+CXX_FLAGS += _EXTRA
 
 
 def _newer(target, deps):

@@ -47,6 +47,16 @@
 #define GA_ST_HIST(ptr, v) (*(ptr) = (v))
 #endif
 
+// -DGA_PHASE_TIMING: per-stream cycle counters per phase (profiling builds only: GA_EXTRA_FLAGS in build.py; the sums are
+// printed by FinishStaged).  A lane's counter also collects the time it waits for the other lanes of its warp.
+#if defined(GA_PHASE_TIMING) && defined(__CUDACC__)
+#define GA_T0(st) (st).tLast = clock64()
+#define GA_TLAP(st, i) { long long n_ = clock64(); (st).phase[i] += (unsigned long long)(n_ - (st).tLast); (st).tLast = n_; }
+#else
+#define GA_T0(st)
+#define GA_TLAP(st, i)
+#endif
+
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
 #define GA_HDR_WORDS 12u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles), last minimum cell (slot, column)
 #define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
@@ -518,6 +528,10 @@ struct GaStreamState
 	uint32_t slicesPushed;
 	uint64_t wordColumns;
 	uint32_t cyclicSlices;
+#ifdef GA_PHASE_TIMING
+	long long tLast;
+	unsigned long long phase[16];  // see the names in FinishStaged
+#endif
 };
 
 // IUPAC match masks (bit0 A, bit1 C, bit2 G, bit3 T), GraphAligner.h:2039-2110; 0 = invalid character
@@ -602,7 +616,9 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 	uint32_t ncols = 0;
 	uint32_t heapN = 0;
 	// the reference walks the previous slice's unordered_map (GraphAligner.h:1117)
+	GA_TLAP(st, 0);
 	ga_umap_order<LANES>(sch, mem, pNodeOff, pNodes);
+	GA_TLAP(st, 8);
 	for (uint32_t it = 0; it < pNodes; it++)
 	{
 		const uint32_t i = mem.uorder[(size_t)it * LANES];
@@ -620,6 +636,7 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(endscore - st.prevMin + 1) << 32) | g.outAdj[e]);
 		}
 	}
+	GA_TLAP(st, 9);
 	while (heapN > 0)
 	{
 		uint64_t top = mem.heap[0];
@@ -640,6 +657,7 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 			ga_heap_push<LANES>(mem.heap, heapN, ((uint64_t)(uint32_t)(prio + (int32_t)len) << 32) | g.outAdj[e]);
 		}
 	}
+	GA_TLAP(st, 10);
 	if (ncols > caps.maxCols) { st.status = GA_ERR_COL_OVERFLOW; return -1; }
 	ncolsOut = ncols;
 	return (int)nc;
@@ -818,6 +836,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		if (nIn == 0) firstIn = u;
 		nIn++;
 	}
+	GA_TLAP(st, 11);
 	const bool sbE0 = inPrev && ga_tiny_score(oldTiny0) == sbs0;
 	GaCol c0;
 	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
@@ -926,6 +945,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		GaCol old = ga_col_load<LANES>(mem, cx.slabOff + cs);
 		if (old.VP == c0.VP && old.VN == c0.VN) return false;   // nothing upstream changed
 	}
+	GA_TLAP(st, 12);
 	{
 		const uint32_t prevCol0 = (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs : GA_NO_COL;
 		if (flags0) ga_col_store_linked<LANES>(mem, cx.slabOff + cs, c0, H0, D00, Eq, flags0, firstIn, cx.slabOff + inCur[0], prevCol0);
@@ -934,6 +954,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
 
 	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
+	GA_TLAP(st, 2);
 	int32_t nodeMin = c0.scoreEnd;
 	if (len > 1)
 	{
@@ -1443,6 +1464,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.prevCharCode = cx.s > 0 ? ga_exact_code(st.seq[(size_t)cx.s * 64 - 1]) : 4;
 		cx.firstSlice = cx.s == 0;
 	}
+	GA_TLAP(st, 13);
 	// in-degrees inside the band
 	uint32_t ready = 0;   // order[0..ready) = nodes whose predecessors are all evaluated (FIFO)
 	for (uint32_t slot = 0; slot < nc; slot++)
@@ -1457,10 +1479,12 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		if (d == 0) mem.order[(size_t)(ready++) * LANES] = slot;
 	}
 	uint32_t done = 0;
+	GA_TLAP(st, 1);
 	while (done < ready)
 	{
 		uint32_t slot = mem.order[(size_t)(done++) * LANES];
 		ga_calc_node<LANES>(g, caps, mem, st, cx, slot, false, true);
+		GA_TLAP(st, 3);
 		if (st.status != GA_OK) return false;
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
@@ -1471,6 +1495,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			mem.indeg[(size_t)cu * LANES] = d;
 			if (d == 0) mem.order[(size_t)(ready++) * LANES] = (uint32_t)cu;
 		}
+		GA_TLAP(st, 4);
 	}
 	int32_t minScore = 0x7fffffff;
 	uint32_t lastMinSlot = 0xffffffffu, lastMinCol = 0;
@@ -2055,6 +2080,10 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	st.slicesPushed = 0;
 	st.wordColumns = 0;
 	st.cyclicSlices = 0;
+#ifdef GA_PHASE_TIMING
+	for (int i = 0; i < 16; i++) st.phase[i] = 0;
+#endif
+	GA_T0(st);
 	uint32_t slicesRun = 0;
 	if (active && st.nslices > caps.maxSlices) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; }
 
@@ -2086,6 +2115,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	uint32_t maskPrev = ga_hash_window(1, caps.hashSize);
 	while (true)
 	{
+		GA_TLAP(st, 5);
 		bool run = !st.done && (uint32_t)ls < st.nslices;
 		if (!GA_WARP_ANY(run)) break;
 		const int s = ls;
@@ -2107,6 +2137,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 				if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 			}
 		}
+		GA_TLAP(st, 0);
 		// this slice's columns for all lanes of the warp: one chunk of the global history pool
 		uint32_t maxc = GA_WARP_MAX(ncols);
 		uint64_t slabOff = GA_POOL_ALLOC(mem.colPoolTop, maxc);
@@ -2115,6 +2146,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if (run) { st.status = GA_ERR_COL_OVERFLOW; st.done = true; }
 			break;   // warp-uniform
 		}
+		GA_TLAP(st, 14);
 		if (!run) continue;
 		slicesRun++;
 		GaSliceCtx cx;
@@ -2288,7 +2320,12 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		}
 	}
 	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+	GA_TLAP(st, 7);
 	ga_traceback<LANES>(g, caps, mem, st, doTrace, n, endNode, endOff, nMoves, nPath, nRuns, nPos);
+	GA_TLAP(st, 6);
+#ifdef GA_PHASE_TIMING
+	if (active) for (int i = 0; i < 16; i++) out->phase[i] = st.phase[i];
+#endif
 	if (doTrace)
 	{
 		out->nMoves = nMoves;

@@ -750,6 +750,17 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	}
 	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+#ifdef GA_PHASE_TIMING
+	{
+		static const char* names[16] = { "slice start: lock-step wait", "in-degrees", "node start: store + rest", "word-step loop", "successors", "slice end: minima, HMM, headers, wait", "traceback", "trace start",
+			"band: map order", "band: kept nodes", "band: heap walk", "node start: in-edges", "node start: candidates", "slice: masks, setup", "slice: pool alloc", "-" };
+		double sum[16] = { 0 }, total = 0;
+		for (size_t i = 0; i < n; i++) for (int k = 0; k < 16; k++) sum[k] += (double)pinOuts[i].phase[k];
+		for (int k = 0; k < 16; k++) total += sum[k];
+		fprintf(stderr, "[ga phases] mean cycles per stream: total %.0f\n", total / n);
+		for (int k = 0; k < 15; k++) fprintf(stderr, "[ga phases]   %-40s %12.0f  %5.1f %%\n", names[k], sum[k] / n, 100.0 * sum[k] / total);
+	}
+#endif
 	if (stats)
 	{
 		stats->d2hBytes += n * sizeof(ga_stream_out) + top * sizeof(uint32_t) + sizeof(top);

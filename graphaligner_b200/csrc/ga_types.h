@@ -67,6 +67,9 @@ typedef struct ga_stream_out
 	uint32_t cyclicSlices;  // slices whose band held a cyclic component
 	uint32_t tieNode[GA_MAX_TIES];
 	uint32_t tieOff[GA_MAX_TIES];
+#ifdef GA_PHASE_TIMING
+	unsigned long long phase[16];  /* profiling builds: cycles per phase, see ga_core.cuh */
+#endif
 } ga_stream_out;
 
 #define GA_RUN_WORDS 5   /* node, firstOff, lastOff, firstRow, lastRow (first = smallest row) */
