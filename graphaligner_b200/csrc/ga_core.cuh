@@ -688,7 +688,7 @@ struct GaSliceCtx
 // Returns the minimum scoreEnd over the node.
 template <int LANES, bool INPREV>
 GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, const GaSliceCtx& cx, uint64_t wStart, uint32_t len, uint32_t cs, uint32_t pcs,
-	uint32_t prevMask, bool forced, GaCol L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin)
+	uint32_t prevMask, GaCol L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin)
 {
 	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * GA_COL_Q) * LANES;
 	uint32_t* tinyPtr = cx.tinyCur + (size_t)(cs + 1) * LANES;
@@ -719,8 +719,8 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 			if (k + 1 < len) oldTinyNext = *prevPtr;
 			prevPtr += LANES;
 			const int32_t oldScore = ga_tiny_score(oldTiny);
-			// forced row -1 score = min(left + 1, previous slice's end score); the flag says the latter attains it
-			sbE = forced ? (oldScore == (int32_t)colPtr[LANES].x) : (oldScore <= L.sbs + 1);
+			// row -1 score = min(left + 1, previous slice's end score); the flag says the latter attains it
+			sbE = oldScore <= L.sbs + 1;
 			bool needMerge;
 			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), oldScore, H, D0, needMerge);
 			if (needMerge) { ga_vertical_merge(c, oldScore); flags = 0; }
@@ -776,11 +776,11 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 #endif
 #define GA_TRACE_NEAR 4u        /* columns kept ahead in L1 */
 
-// Evaluate one band node: first column from its in-neighbours (or as a source), the rest by the word step.
-// forced = the node belongs to a cyclic block whose row -1 scores were already forced into the column records
-// (ga_force_block); first = its columns hold no computed value yet.  Returns true if the node's columns changed.
+// Evaluate one band node whose band predecessors are final (the acyclic part of a band, in topological order): first column
+// from its in-neighbours (or as a source), the rest by the word step.  Members of cyclic components go through
+// ga_ex_calc_node instead.
 template <int LANES>
-GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, bool forced, bool first)
+GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot)
 {
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
 	const uint32_t cs = GA_HN(cx.nodeOff + slot, 1);
@@ -803,7 +803,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	uint32_t nIn = 0;
 	uint32_t firstIn = 0, firstInLen = 1;   // the first band in-neighbour (the only one when nIn == 1) and its length
 	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
-	int32_t sbs0 = forced ? ga_col_load_sbs<LANES>(mem, cx.slabOff + cs) : (inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff);
+	int32_t sbs0 = inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff;
 	const uint32_t eBegin = g.inOff[node], eEnd = g.inOff[node + 1];
 	for (uint32_t e = eBegin; e < eEnd; e++)
 	{
@@ -817,7 +817,6 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 			const uint32_t ulen = GA_HN(cx.nodeOff + cu, 3);
 			curCol = GA_HN(cx.nodeOff + cu, 1) + ulen - 1;
 			if (nIn == 0) firstInLen = ulen;
-			if (!forced)
 			{
 				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + curCol) + 1;
 				if (v < sbs0) sbs0 = v;
@@ -826,7 +825,6 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		if (pu >= 0)
 		{
 			prevCol = GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1;
-			if (!forced)
 			{
 				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)prevCol * LANES]) + 1;
 				if (v < sbs0) sbs0 = v;
@@ -842,7 +840,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	c0.VP = 0; c0.VN = 0; c0.sbs = 0; c0.scoreEnd = 0;
 	// A node whose only band in-neighbour is in this slice starts with a plain word step from that neighbour's last column:
 	// it gets traceback masks and a link like any inner column (the walk then crosses the node border on the fast path)
-	const bool single = !forced && nIn == 1 && inCur[0] != 0xffffffffu;
+	const bool single = nIn == 1 && inCur[0] != 0xffffffffu;
 	uint64_t H0 = 0, D00 = 0;
 	uint32_t flags0 = 0;
 	if (nIn > 0)
@@ -924,7 +922,7 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	else
 	{
 		// source node (GraphAligner.h:1317-1347,1475-1488); a band node always has a band predecessor or is kept
-		if (!inPrev) { st.status = GA_ERR_INTERNAL; return false; }
+		if (!inPrev) { st.status = GA_ERR_INTERNAL; return; }
 		int32_t ps = ga_tiny_score(oldTiny0);
 		uint64_t mismatch = 1;
 		if (cx.firstSlice)
@@ -938,13 +936,8 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		c0.sbs = ps;
 	}
 #ifdef GA_HOST_DEBUG
-	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return false; }
+	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return; }
 #endif
-	if (forced && !first)
-	{
-		GaCol old = ga_col_load<LANES>(mem, cx.slabOff + cs);
-		if (old.VP == c0.VP && old.VN == c0.VN) return false;   // nothing upstream changed
-	}
 	GA_TLAP(st, 12);
 	{
 		const uint32_t prevCol0 = (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs : GA_NO_COL;
@@ -961,11 +954,10 @@ GA_DEV bool ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		// 4-bit set of graph bases that equal the read character just above the slice (exact compare,
 		// GraphAligner.h:1540); on the first slice the flag is "node is in the previous band" instead
 		const uint32_t prevMask = cx.firstSlice ? (inPrev ? 15u : 0u) : ((1u << cx.prevCharCode) & 15u);
-		if (inPrev) nodeMin = ga_node_columns<LANES, true>(g, mem, cx, wStart, len, cs, pcs, prevMask, forced, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
-		else nodeMin = ga_node_columns<LANES, false>(g, mem, cx, wStart, len, cs, pcs, prevMask, forced, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
+		if (inPrev) nodeMin = ga_node_columns<LANES, true>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
+		else nodeMin = ga_node_columns<LANES, false>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
 	}
 	GA_HN(cx.nodeOff + slot, 2) = (uint32_t)nodeMin;
-	return true;
 }
 
 
@@ -1483,7 +1475,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	while (done < ready)
 	{
 		uint32_t slot = mem.order[(size_t)(done++) * LANES];
-		ga_calc_node<LANES>(g, caps, mem, st, cx, slot, false, true);
+		ga_calc_node<LANES>(g, caps, mem, st, cx, slot);
 		GA_TLAP(st, 3);
 		if (st.status != GA_OK) return false;
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
@@ -1547,7 +1539,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			{
 				if (!(mem.cmpOf[(size_t)firstSlot * LANES] & 0x40000000u))
 				{
-					ga_calc_node<LANES>(g, caps, mem, st, cx, firstSlot, false, true);
+					ga_calc_node<LANES>(g, caps, mem, st, cx, firstSlot);
 					if (st.status != GA_OK) return false;
 				}
 				const int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + firstSlot, 2);
