@@ -12,7 +12,8 @@
 // Known limits (stated, not hidden): bands >= 200 000 bp (the reference's calculateSliceAlternate /
 // BacktraceOverride, GraphAligner.h:2148-2329,167-354) and the -B ramp redo (GraphAligner.h:2648-2719) are
 // not restated; inside a cyclic band component the reference's per-node minimum and tie order depend on
-// its work-list schedule (confirmedRows, GraphAligner.h:1355-1416,2364-2420), here the fix point is used.
+// its work-list schedule (confirmedRows, GraphAligner.h:1355-1416,2364-2420), here the fix point is used - the two
+// fixtures that pin that schedule (tests/golden/cyclic_*) are checked against oracle/_ref/ref_align only.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
