@@ -471,6 +471,9 @@ StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& strea
 	sb->B = rampBandwidth;
 	sb->hostParts = parts;
 	sb->hostPartsBytes = partsBytes;
+	// the big transfer first: sorting and the layout below run while it is in flight
+	ctx->bParts.ensure(partsBytes + 64);
+	if (partsBytes) GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, parts, partsBytes, cudaMemcpyHostToDevice, ctx->stream));
 	const size_t n = streams.size();
 	// longest streams first: the 32 streams of a warp iterate as long as the longest of them
 	sb->perm.resize(n);
@@ -564,7 +567,6 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	}
 	if (sb->smemScratch && ubktSize > GA_SMEM_UBKT) throw std::logic_error("unordered_map bucket schedule does not fit the shared-memory scratch");
 	ubktSize = std::max(ubktSize, caps.maxNodes);
-	ctx->bParts.ensure(sb->hostPartsBytes + 64);
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
 	ctx->bOut.ensure(n * sizeof(ga_stream_out));
 	ctx->bWd.ensure(nWarps * sizeof(WarpDesc));
@@ -603,7 +605,6 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
 	sb->sp.runs = (uint32_t*)ctx->bRuns.ptr;
-	GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, sb->hostParts, sb->hostPartsBytes, cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(ctx->bPeqOff.ptr, peqOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
