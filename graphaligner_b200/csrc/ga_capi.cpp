@@ -461,7 +461,12 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 size_t ga_results_count(const ga_results* r) { return r->reads.size(); }
 const ga_read_result* ga_results_reads(const ga_results* r) { return r->reads.data(); }
 const ga_mapping* ga_results_mappings(const ga_results* r) { return r->mappings.data(); }
-void ga_results_free(ga_results* r) { delete r; }
+void ga_results_free(ga_results* r)
+{
+	StageTimer tm;
+	delete r;
+	tm.lap("results: free");
+}
 
 static void materializeTrace(const ga_results* r, size_t i, std::vector<AlignmentResult::TraceItem>& items)
 {

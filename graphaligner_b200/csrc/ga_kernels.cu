@@ -265,7 +265,8 @@ struct DeviceCtx
 			cap = 0;
 		}
 	};
-	Pinned pinParts, pinOuts, pinArena;
+	Pinned pinParts, pinOuts, pinArena, pinSmall;
+	size_t budgetBytes = 0;    // device bytes a batch may use (FreeDeviceBytes), 0 = not queried yet
 };
 
 struct StagedBatch
@@ -372,6 +373,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	ctx->pinParts.release();
 	ctx->pinOuts.release();
 	ctx->pinArena.release();
+	ctx->pinSmall.release();
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -439,6 +441,7 @@ void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
 	ctx->view.outAdj = uploadVec(ctx, ctx->gOutAdj, graph.OutAdj());
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->hasGraph = true;
+	ctx->budgetBytes = 0;
 }
 
 static uint32_t nextPow2(uint32_t v)
@@ -605,10 +608,18 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
 	sb->sp.runs = (uint32_t*)ctx->bRuns.ptr;
-	GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, sb->sorted.data(), n * sizeof(ga_stream_in), cudaMemcpyHostToDevice, ctx->stream));
-	GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, wds.data(), nWarps * sizeof(WarpDesc), cudaMemcpyHostToDevice, ctx->stream));
-	GA_CUDA(cudaMemcpyAsync(ctx->bPeqOff.ptr, peqOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-	GA_CUDA(cudaStreamSynchronize(ctx->stream));   // wds / peqOff are locals
+	// the small tables go through pinned staging so that nothing here waits for the parts upload still in flight
+	{
+		const size_t bIn = n * sizeof(ga_stream_in), bWd = nWarps * sizeof(WarpDesc), bPo = n * sizeof(uint64_t);
+		const size_t oWd = (bIn + 255) / 256 * 256, oPo = oWd + (bWd + 255) / 256 * 256;
+		uint8_t* pin = (uint8_t*)ctx->pinSmall.ensure(oPo + bPo);
+		memcpy(pin, sb->sorted.data(), bIn);
+		memcpy(pin + oWd, wds.data(), bWd);
+		memcpy(pin + oPo, peqOff.data(), bPo);
+		GA_CUDA(cudaMemcpyAsync(ctx->bIn.ptr, pin, bIn, cudaMemcpyHostToDevice, ctx->stream));
+		GA_CUDA(cudaMemcpyAsync(ctx->bWd.ptr, pin + oWd, bWd, cudaMemcpyHostToDevice, ctx->stream));
+		GA_CUDA(cudaMemcpyAsync(ctx->bPeqOff.ptr, pin + oPo, bPo, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	if (stats) stats->h2dBytes += sb->hostPartsBytes + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc) + n * sizeof(uint64_t);
 }
 
@@ -824,12 +835,18 @@ size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
 size_t FreeDeviceBytes(DeviceCtx* ctx)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
-	size_t freeB = 0, totalB = 0;
+	// cudaMemGetInfo costs 1 - 40 ms per call on a busy box.  Free memory plus the context's own grow-only pools is what a
+	// batch may use, and that sum does not change when the pools grow: it is queried once per uploaded graph.
+	size_t freeB = ctx->budgetBytes;
+	if (freeB == 0)
+	{
+	size_t totalB = 0;
 	GA_CUDA(cudaMemGetInfo(&freeB, &totalB));
-	// the context's grow-only pools are reusable, so count them as available
 	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq,
 		&ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena };
 	for (Buffer* b : all) freeB += b->cap;
+	ctx->budgetBytes = freeB;
+	}
 	if (const char* e = getenv("GA_MEM_BUDGET_MB")) freeB = std::min<size_t>(freeB, (size_t)atoll(e) << 20);   // testing: force batch splitting
 	return freeB;
 }
