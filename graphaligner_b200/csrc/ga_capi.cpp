@@ -276,9 +276,11 @@ static ga_staged* stageOn(ga_ctx* ctx, ga::DeviceCtx* dev, const ga_batch* batch
 		st->dev = dev;
 		fillStaged(st, batch);
 		tm.lap("stage: marshal reads");
-		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads, [dev](size_t bytes) { return ga::AllocPinnedParts(dev, bytes); }));
+		uint8_t* pinned = nullptr;
+		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads, [dev, &pinned](size_t bytes) { pinned = ga::AllocPinnedParts(dev, bytes); return pinned; },
+			[dev, &pinned](size_t off, size_t bytes) { ga::UploadPartsRange(dev, pinned, off, bytes); }));
 		tm.lap("stage: plan + build parts");
-		st->device = ga::StageAndUpload(dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats);
+		st->device = ga::StageAndUpload(dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats, true);
 		tm.lap("stage: layout + H2D");
 	});
 	if (rc != 0)

@@ -27,7 +27,11 @@ size_t GraphBytesOnDevice(DeviceCtx* ctx);
 double MeasureInt32Peak(DeviceCtx* ctx);
 
 // plans the per-warp memory layout and copies parts + stream descriptors to the device.  `parts` must outlive the batch.
-StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+// partsOnDevice: the parts were already uploaded range by range (UploadPartsRange) while they were built
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats,
+	bool partsOnDevice = false);
+// asynchronous upload of parts[offset, offset + bytes) (parts = the buffer AllocPinnedParts returned) to the same offset on the device
+void UploadPartsRange(DeviceCtx* ctx, const uint8_t* parts, size_t offset, size_t bytes);
 // pinned host memory for a batch's padded parts (grow-only, owned by the context, reused by the next batch)
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes);
 // sizing helpers for splitting a batch that would not fit the device in one launch

@@ -286,7 +286,8 @@ static char complementOf(char c)
 	}
 }
 
-BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts)
+BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts,
+	const std::function<void(size_t, size_t)>& partsReady)
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
@@ -381,7 +382,17 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 		ownedParts.resize(top + 64);
 		parts = ownedParts.data();
 	}
-	ParallelFor(jobs.size(), [&](size_t k) {
+	// jobs lie back to back in the parts buffer: a few groups of consecutive jobs, each handed over when it is complete
+	const size_t groups = partsReady ? std::min<size_t>(4, std::max<size_t>(1, jobs.size() / 64)) : 1;
+	size_t groupBegin = 0;
+	for (size_t gi = 0; gi < groups; gi++)
+	{
+	size_t groupEnd = groupBegin;
+	const size_t targetBytes = top * (gi + 1) / groups;
+	while (groupEnd < jobs.size() && (gi + 1 == groups || streams[groupEnd].seqOff + streams[groupEnd].partLen <= targetBytes)) groupEnd++;
+	const size_t first = groupBegin;
+	ParallelFor(groupEnd - groupBegin, [&](size_t kk) {
+		const size_t k = first + kk;
 		const Job& job = jobs[k];
 		const ga_stream_in& in = streams[k];
 		const ReadInput& r = reads[job.read];
@@ -400,6 +411,13 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 		}
 		memset(dst + real, 'N', in.partLen - real);
 	});
+	if (partsReady && groupEnd > groupBegin)
+	{
+		const size_t off = streams[groupBegin].seqOff;
+		partsReady(off, streams[groupEnd - 1].seqOff + streams[groupEnd - 1].partLen - off);
+	}
+	groupBegin = groupEnd;
+	}
 }
 
 namespace

@@ -181,7 +181,10 @@ class BatchPlan
 public:
 	// allocParts(bytes) may hand out pinned host memory for the padded parts (it must stay valid until the batch has
 	// been uploaded); with no allocator the plan owns the storage
-	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts = nullptr);
+	// allocParts: where the parts are built (pinned memory of a device context); partsReady(offset, bytes): called as soon as a
+	// contiguous range of them is complete, so that its upload overlaps the building of the rest
+	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts = nullptr,
+		const std::function<void(size_t, size_t)>& partsReady = nullptr);
 	std::vector<ga_stream_in> streams;
 	uint8_t* parts = nullptr;       // padded parts of all streams, back to back
 	size_t partsBytes = 0;

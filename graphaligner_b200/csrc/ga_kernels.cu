@@ -465,7 +465,8 @@ static ga_caps defaultCaps(int b, int B, int scale)
 	return c;
 }
 
-StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats)
+StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats,
+	bool partsOnDevice = false)
 {
 	if (!ctx->hasGraph) throw std::logic_error("StageStreams: no graph uploaded to this device");
 	GA_CUDA(cudaSetDevice(ctx->device));
@@ -475,8 +476,11 @@ StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& strea
 	sb->hostParts = parts;
 	sb->hostPartsBytes = partsBytes;
 	// the big transfer first: sorting and the layout below run while it is in flight
-	ctx->bParts.ensure(partsBytes + 64);
-	if (partsBytes) GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, parts, partsBytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (!partsOnDevice)
+	{
+		ctx->bParts.ensure(partsBytes + 64);
+		if (partsBytes) GA_CUDA(cudaMemcpyAsync(ctx->bParts.ptr, parts, partsBytes, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	const size_t n = streams.size();
 	// longest streams first: the 32 streams of a warp iterate as long as the longest of them
 	sb->perm.resize(n);
@@ -854,7 +858,15 @@ size_t FreeDeviceBytes(DeviceCtx* ctx)
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
+	ctx->bParts.ensure(bytes + 64);   // its device twin, so that ranges can be uploaded while the rest is built
 	return (uint8_t*)ctx->pinParts.ensure(bytes);
+}
+
+void UploadPartsRange(DeviceCtx* ctx, const uint8_t* parts, size_t offset, size_t bytes)
+{
+	if (bytes == 0) return;
+	GA_CUDA(cudaSetDevice(ctx->device));
+	GA_CUDA(cudaMemcpyAsync((uint8_t*)ctx->bParts.ptr + offset, parts + offset, bytes, cudaMemcpyHostToDevice, ctx->stream));
 }
 
 void FreeStaged(DeviceCtx* ctx, StagedBatch* sb)
@@ -864,9 +876,9 @@ void FreeStaged(DeviceCtx* ctx, StagedBatch* sb)
 }
 
 // exposed for ga_device users: layout + upload happen at stage time
-StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int b, int B, BatchStats* stats)
+StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int b, int B, BatchStats* stats, bool partsOnDevice)
 {
-	StagedBatch* sb = StageStreams(ctx, streams, parts, partsBytes, b, B, stats);
+	StagedBatch* sb = StageStreams(ctx, streams, parts, partsBytes, b, B, stats, partsOnDevice);
 	try
 	{
 		layoutAndUpload(ctx, sb, stats);
