@@ -34,7 +34,9 @@ EXPORTS = ["ga_create", "ga_destroy", "ga_last_error", "ga_global_error", "ga_gr
            "ga_graph_free", "ga_graph_node_count", "ga_graph_size_bp", "ga_graph_edge_count", "ga_graph_upload", "ga_align_batch",
            "ga_stage_batch", "ga_run_staged", "ga_sync", "ga_finish_staged", "ga_staged_free", "ga_cuda_stream", "ga_results_count",
            "ga_results_reads", "ga_results_mappings", "ga_results_read_trace", "ga_results_free", "ga_results_trace_hash", "ga_get_stats",
-           "ga_reset_stats", "ga_measure_int32_peak"]
+           "ga_reset_stats", "ga_measure_int32_peak", "ga_pipeline_create", "ga_pipeline_destroy", "ga_pipeline_last_error", "ga_pipeline_depth",
+           "ga_pipeline_context", "ga_pipeline_graph_upload", "ga_pipeline_submit", "ga_pipeline_next", "ga_pipeline_in_flight",
+           "ga_pipeline_get_stats", "ga_pipeline_reset_stats"]
 
 _lib = None
 
@@ -59,6 +61,10 @@ def load_library():
         "ga_finish_staged": (vp, [vp, vp]), "ga_staged_free": (None, [vp, vp]), "ga_cuda_stream": (vp, [vp]), "ga_results_count": (sz, [vp]),
         "ga_results_reads": (vp, [vp]), "ga_results_mappings": (vp, [vp]), "ga_results_read_trace": (sz, [vp, sz, vp, sz]), "ga_results_free": (None, [vp]),
         "ga_results_trace_hash": (u64, [vp, sz]), "ga_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_reset_stats": (C.c_int, [vp]), "ga_measure_int32_peak": (C.c_double, [vp]),
+        "ga_pipeline_create": (vp, [C.c_int, C.c_int]), "ga_pipeline_destroy": (None, [vp]), "ga_pipeline_last_error": (C.c_char_p, [vp]),
+        "ga_pipeline_depth": (C.c_int, [vp]), "ga_pipeline_context": (vp, [vp, C.c_int]), "ga_pipeline_graph_upload": (C.c_int, [vp, vp]),
+        "ga_pipeline_submit": (C.c_int, [vp, C.POINTER(GaBatch)]), "ga_pipeline_next": (vp, [vp]), "ga_pipeline_in_flight": (C.c_int, [vp]),
+        "ga_pipeline_get_stats": (C.c_int, [vp, C.POINTER(GaStats)]), "ga_pipeline_reset_stats": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -272,6 +278,69 @@ class Aligner:
         if getattr(self, "ctx", None):
             self._lib.ga_destroy(self.ctx)
             self.ctx = None
+
+    def __del__(self):
+        self.close()
+
+
+class Pipeline:
+    """A stream of batches through `depth` contexts of one GPU (ga_pipeline_*): while one batch's kernel runs, the host
+    stages the next and assembles the previous.  Results come back in submission order."""
+
+    def __init__(self, graph, device=0, depth=2):
+        self._lib = load_library()
+        self.handle = self._lib.ga_pipeline_create(int(device), int(depth))
+        if not self.handle:
+            raise RuntimeError("ga_pipeline_create failed: " + self._lib.ga_global_error().decode())
+        self.graph = graph
+        self.depth = int(depth)
+        self._pending = []   # (packed, names) of the batches in flight, oldest first
+        if self._lib.ga_pipeline_graph_upload(self.handle, graph.handle) != 0:
+            raise RuntimeError("ga_pipeline_graph_upload failed: " + self.last_error())
+
+    def last_error(self):
+        return self._lib.ga_pipeline_last_error(self.handle).decode()
+
+    def in_flight(self):
+        return int(self._lib.ga_pipeline_in_flight(self.handle))
+
+    def submit(self, reads, b=10, B=0):
+        packed = reads if isinstance(reads, PackedReads) else PackedReads(reads, b, B)
+        rc = self._lib.ga_pipeline_submit(self.handle, C.byref(packed.struct))
+        if rc != 0:
+            raise RuntimeError("ga_pipeline_submit failed (%d): %s" % (rc, self.last_error()))
+        self._pending.append((packed, None if isinstance(reads, PackedReads) else [r[0] for r in reads]))
+
+    def next(self):
+        h = self._lib.ga_pipeline_next(self.handle)
+        if not self._pending:
+            raise RuntimeError("ga_pipeline_next failed: " + self.last_error())
+        packed, names = self._pending.pop(0)
+        if not h:
+            raise RuntimeError("ga_pipeline_next failed: " + self.last_error())
+        return Results(self._lib, h, names, keepalive=packed)
+
+    def align_all(self, batches, b=10, B=0):
+        """Generator: aligns an iterable of batches, at most `depth` in flight, yielding their Results in order."""
+        for batch in batches:
+            if self.in_flight() == self.depth:
+                yield self.next()
+            self.submit(batch, b, B)
+        while self.in_flight():
+            yield self.next()
+
+    def stats(self):
+        s = GaStats()
+        self._lib.ga_pipeline_get_stats(self.handle, C.byref(s))
+        return {n: int(getattr(s, n)) for n, _ in GaStats._fields_}
+
+    def reset_stats(self):
+        self._lib.ga_pipeline_reset_stats(self.handle)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.ga_pipeline_destroy(self.handle)
+            self.handle = None
 
     def __del__(self):
         self.close()

@@ -2,14 +2,17 @@
 #include "../../include/graphaligner_b200.h"
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include "alignment_graph.h"
 #include "bigraph_to_digraph.h"
@@ -27,6 +30,7 @@ struct ga_ctx
 	const ga_graph* graph = nullptr;
 	std::string error;
 	ga::BatchStats stats;
+	double budgetShare = 1.0;   // share of the device's free memory a batch of this context may plan with (ga_pipeline: 1 / depth)
 };
 
 struct ga_results
@@ -408,7 +412,7 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 	StageTimer tmAll;
 	int rc = guarded(ctx, [&]() {
 		if (!ctx->graph) throw std::logic_error("ga_align_batch: no graph uploaded");
-		const size_t budget = (size_t)(ga::FreeDeviceBytes(ctx->dev) * 0.8);
+		const size_t budget = (size_t)(ga::FreeDeviceBytes(ctx->dev) * 0.8 * ctx->budgetShare);
 		const int bw = std::max(batch->initial_bandwidth, batch->ramp_bandwidth);
 		size_t used = 0;
 		cuts.push_back(0);
@@ -567,6 +571,184 @@ double ga_measure_int32_peak(ga_ctx* ctx)
 int ga_reset_stats(ga_ctx* ctx)
 {
 	ctx->stats = ga::BatchStats();
+	return 0;
+}
+
+// ---- a stream of batches through `depth` contexts of one GPU -------------------------------------------------------
+// The reference keeps its cores busy with N worker threads popping reads from one stack (Aligner.cpp:107-117,285-298).
+// Here the unit is a batch and the resource is the GPU: while the kernel of batch i runs, the host plans, pads and
+// uploads batch i+1 and assembles batch i-1.  Each lane = one context (own stream, device pools, pinned staging) driven
+// by one host thread; batches go to the lanes round robin and come back in submission order.
+struct ga_pipeline
+{
+	struct Lane
+	{
+		ga_ctx* ctx = nullptr;
+		std::thread worker;
+		ga_batch batch;
+		ga_results* result = nullptr;
+		bool busy = false;    // a batch was submitted and its result not taken yet
+		bool done = false;    // ... and the worker has finished it
+		std::string error;
+	};
+	std::vector<std::unique_ptr<Lane>> lanes;
+	std::mutex m;
+	std::condition_variable cv;
+	uint64_t submitted = 0, taken = 0;
+	bool stop = false;
+	std::string error;
+};
+
+static void pipelineWorker(ga_pipeline* p, ga_pipeline::Lane* lane)
+{
+	std::unique_lock<std::mutex> lock(p->m);
+	while (true)
+	{
+		p->cv.wait(lock, [&]() { return p->stop || (lane->busy && !lane->done); });
+		if (p->stop) return;
+		lock.unlock();
+		ga_results* r = ga_align_batch(lane->ctx, &lane->batch);
+		lock.lock();
+		lane->result = r;
+		if (!r) lane->error = lane->ctx->error;
+		lane->done = true;
+		p->cv.notify_all();
+	}
+}
+
+ga_pipeline* ga_pipeline_create(int device, int depth)
+{
+	if (depth < 1 || depth > 8)
+	{
+		g_globalError = "ga_pipeline_create: depth must be 1..8";
+		return nullptr;
+	}
+	ga_pipeline* p = new ga_pipeline();
+	for (int i = 0; i < depth; i++)
+	{
+		ga_ctx* ctx = ga_create(device);
+		if (!ctx)
+		{
+			for (auto& l : p->lanes) ga_destroy(l->ctx);
+			delete p;
+			return nullptr;
+		}
+		ctx->budgetShare = 1.0 / depth;
+		p->lanes.emplace_back(new ga_pipeline::Lane());
+		p->lanes.back()->ctx = ctx;
+	}
+	for (auto& l : p->lanes) l->worker = std::thread(pipelineWorker, p, l.get());
+	return p;
+}
+
+void ga_pipeline_destroy(ga_pipeline* p)
+{
+	if (!p) return;
+	{
+		std::lock_guard<std::mutex> lock(p->m);
+		p->stop = true;
+	}
+	p->cv.notify_all();
+	for (auto& l : p->lanes)
+	{
+		if (l->worker.joinable()) l->worker.join();
+		if (l->result) ga_results_free(l->result);
+		ga_destroy(l->ctx);
+	}
+	delete p;
+}
+
+const char* ga_pipeline_last_error(const ga_pipeline* p) { return p ? p->error.c_str() : ""; }
+int ga_pipeline_depth(const ga_pipeline* p) { return p ? (int)p->lanes.size() : 0; }
+ga_ctx* ga_pipeline_context(ga_pipeline* p, int lane) { return (p && lane >= 0 && (size_t)lane < p->lanes.size()) ? p->lanes[lane]->ctx : nullptr; }
+
+int ga_pipeline_graph_upload(ga_pipeline* p, const ga_graph* g)
+{
+	std::lock_guard<std::mutex> lock(p->m);
+	if (p->submitted != p->taken)
+	{
+		p->error = "ga_pipeline_graph_upload: batches in flight";
+		return -1;
+	}
+	for (auto& l : p->lanes)
+	{
+		if (ga_graph_upload(l->ctx, g) != 0)
+		{
+			p->error = l->ctx->error;
+			return -1;
+		}
+	}
+	return 0;
+}
+
+int ga_pipeline_submit(ga_pipeline* p, const ga_batch* batch)
+{
+	std::lock_guard<std::mutex> lock(p->m);
+	ga_pipeline::Lane& lane = *p->lanes[p->submitted % p->lanes.size()];
+	if (lane.busy)
+	{
+		p->error = "ga_pipeline_submit: pipeline full, take a result with ga_pipeline_next first";
+		return -2;
+	}
+	lane.batch = *batch;
+	lane.result = nullptr;
+	lane.error.clear();
+	lane.done = false;
+	lane.busy = true;
+	p->submitted++;
+	p->cv.notify_all();
+	return 0;
+}
+
+ga_results* ga_pipeline_next(ga_pipeline* p)
+{
+	std::unique_lock<std::mutex> lock(p->m);
+	if (p->taken == p->submitted)
+	{
+		p->error = "ga_pipeline_next: nothing in flight";
+		return nullptr;
+	}
+	ga_pipeline::Lane& lane = *p->lanes[p->taken % p->lanes.size()];
+	p->cv.wait(lock, [&]() { return lane.done; });
+	ga_results* r = lane.result;
+	if (!r) p->error = lane.error;
+	lane.result = nullptr;
+	lane.busy = false;
+	lane.done = false;
+	p->taken++;
+	return r;
+}
+
+int ga_pipeline_in_flight(const ga_pipeline* p) { return p ? (int)(p->submitted - p->taken) : 0; }
+
+int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out)
+{
+	std::lock_guard<std::mutex> lock(p->m);
+	memset(out, 0, sizeof(*out));
+	for (auto& l : p->lanes)
+	{
+		ga_stats s;
+		ga_get_stats(l->ctx, &s);
+		out->streams += s.streams;
+		out->word_columns += s.word_columns;
+		out->retries += s.retries;
+		out->h2d_bytes += s.h2d_bytes;
+		out->d2h_bytes += s.d2h_bytes;
+		out->launches += s.launches;
+		out->graph_bytes += s.graph_bytes;
+	}
+	return 0;
+}
+
+int ga_pipeline_reset_stats(ga_pipeline* p)
+{
+	std::lock_guard<std::mutex> lock(p->m);
+	if (p->submitted != p->taken)
+	{
+		p->error = "ga_pipeline_reset_stats: batches in flight";
+		return -1;
+	}
+	for (auto& l : p->lanes) ga_reset_stats(l->ctx);
 	return 0;
 }
 

@@ -281,6 +281,12 @@ def config3(scale=1.0, seed=2):
     return g, dict(n_reads=max(1, int(100_000 * scale)), read_len=10_000, b=10, seed_offsets=(0, 5000, -300), decoys=1)
 
 
+def config4(scale=1.0, seed=4):
+    """configs[3]: human-scale GFA graph (GFA semantics, 0-bp edge overlap), 1M reads of 15 kbp sharded over the GPUs."""
+    g = make_graph(seed, int(3_000_000_000 * scale), chop=32, snp_every=1000, bubble_every=5000, indel_frac=0.3)
+    return g, dict(n_reads=max(1, int(1_000_000 * scale)), read_len=15_000, b=10, gfa_overlap=0)
+
+
 def config5(scale=1.0, seed=5):
     g = make_graph(seed, int(100_000_000 * scale), chop=32, bubble_every=100, indel_frac=0.2, tangle_every=1_000_000)
     return g, dict(n_reads=max(1, int(2_000 * scale)), read_len=50_000, b=10)

@@ -152,6 +152,25 @@ int ga_reset_stats(ga_ctx* ctx);
  * the integer-ALU roofline fraction.  Returns 0 on failure. */
 double ga_measure_int32_peak(ga_ctx* ctx);
 
+/* ---- a stream of batches: `depth` contexts of one GPU, one host thread each ---------------------------------
+ * Replaces the reference's worker threads popping reads from a shared stack (Aligner.cpp:107-117,285-298): the unit
+ * is a batch, and while batch i's kernel runs the host stages batch i+1 and assembles batch i-1.  Batches are served
+ * round robin and results come back in submission order.  At most `depth` batches may be in flight: ga_pipeline_submit
+ * returns -2 (and does nothing) when the pipeline is full.  The buffers behind a submitted batch must stay valid until
+ * its results have been freed.  All calls on one pipeline come from one thread; the pipeline owns its worker threads. */
+typedef struct ga_pipeline ga_pipeline;
+ga_pipeline* ga_pipeline_create(int device, int depth);          /* depth 1..8 (2 = double buffering); NULL on failure */
+void ga_pipeline_destroy(ga_pipeline* p);
+const char* ga_pipeline_last_error(const ga_pipeline* p);
+int ga_pipeline_depth(const ga_pipeline* p);
+ga_ctx* ga_pipeline_context(ga_pipeline* p, int lane);           /* the lane's context (stats, stream); not for aligning */
+int ga_pipeline_graph_upload(ga_pipeline* p, const ga_graph* g); /* one replica per lane's context */
+int ga_pipeline_submit(ga_pipeline* p, const ga_batch* batch);   /* asynchronous; 0, -2 = full */
+ga_results* ga_pipeline_next(ga_pipeline* p);                    /* oldest submitted batch's results (blocks); NULL on error */
+int ga_pipeline_in_flight(const ga_pipeline* p);
+int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out);        /* summed over the lanes */
+int ga_pipeline_reset_stats(ga_pipeline* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,14 +56,15 @@ def test_cli_validation_messages():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["smallexample", "bubbles_multiseed", "gfa"])
-def test_cli_end_to_end(tmp_path, golden_dir, name):
+@pytest.mark.parametrize("name,batch_bp", [("smallexample", None), ("bubbles_multiseed", None), ("gfa", None), ("bubbles_multiseed", 5000)])
+def test_cli_end_to_end(tmp_path, golden_dir, name, batch_bp):
+    # batch_bp: the driver streams the read set through two contexts in batches of about that many read bases
     case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
     expected = {e["name"]: e for e in load_expected(os.path.join(golden_dir, name + ".expected"))}
     graph_path, fastq, seeds = vgio.write_case_files(case, str(tmp_path / "c"))
     out = str(tmp_path / "out.gam")
     r = subprocess.run([ALIGNER, "-g", graph_path, "-f", fastq, "-s", seeds, "-a", out, "-t", "2", "-b", str(case.b)] + (["-B", str(case.B)] if case.B else []),
-                       capture_output=True, text=True, cwd=str(tmp_path))
+                       capture_output=True, text=True, cwd=str(tmp_path), env=dict(os.environ, **({"GA_BATCH_BP": str(batch_bp)} if batch_bp else {})))
     assert r.returncode == 0, r.stderr[-500:]
     alns = vgio.load_gam(out)
     ok = [e for e in expected.values() if not e["failed"]]

@@ -45,3 +45,28 @@ def test_config5_ultralong_reads_band_sweep(api, tmp_path, band):
     g = synth.make_graph(5, 1_000_000, chop=32, bubble_every=100, indel_frac=0.2, tangle_every=100_000)
     case = synth.make_case(5, g, 16, 50_000, b=band, errors=(0.05, 0.05, 0.05))
     _check(api, tmp_path, case, "config 5, band %d" % band)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_config4_gfa_graph_sharded_reads(api, tmp_path, world):
+    # configs[3] scaled: a GFA graph loaded from its file (GfaGraph + BigraphToDigraph semantics), 15 kbp reads (235 slices),
+    # the read set sharded the way the multi-GPU driver shards it (contiguous by index, graph replicated: one context and
+    # one upload per shard); the concatenation of the shards' results must equal the reference's run over the whole set
+    from graphaligner_b200 import multi_gpu
+    from graphaligner_b200.tools import vgio
+    g, kw = synth.config4(scale=1.0 / 3000)
+    case = synth.make_case(4, g, 96, kw["read_len"], b=kw["b"], errors=(0.05, 0.05, 0.05))
+    case.gfa_overlap = kw["gfa_overlap"]
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=os.cpu_count() or 4)
+    graph_path, _, _ = vgio.write_case_files(case, str(tmp_path / "c4"))
+    got = []
+    for lo, hi in multi_gpu.shard_bounds(len(case.reads), world):
+        aligner = api.Aligner(api.Graph.load(graph_path))
+        res = aligner.align(case.reads[lo:hi], case.b, case.B)
+        got.extend(res.as_dicts())
+        res.free()
+        aligner.close()
+    assert sum(1 for x in got if not x["failed"]) >= len(got) * 0.9
+    assert_same(got, expected, "config 4, %d shards" % world)

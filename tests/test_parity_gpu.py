@@ -149,3 +149,39 @@ def test_cyclic_graphs_against_reference_run_here(api, tmp_path, seed, kw, rl, b
     assert any(x["flags"] & 8 for x in d), "no read met a cyclic band: the case does not test what it says"
     assert_same(d, expected, "seed %d" % seed)
     aligner.close()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_pipeline_of_batches_matches_golden(api, golden_dir, depth):
+    # ga_pipeline_*: a read set cut into small batches and streamed through `depth` contexts comes back in submission
+    # order and equals the reference's output for the whole set (batches of uneven size, more batches than lanes)
+    case = gacase.read_case(os.path.join(golden_dir, "bubbles_multiseed.gacase"))
+    expected = load_expected(os.path.join(golden_dir, "bubbles_multiseed.expected"))
+    n = len(case.reads)
+    cuts = sorted(set([0, 1, n // 5, n // 2, n // 2 + 1, n - 2, n]))
+    batches = [case.reads[lo:hi] for lo, hi in zip(cuts[:-1], cuts[1:])]
+    pipe = api.Pipeline(api.Graph.from_case(case), depth=depth)
+    got = []
+    for res in pipe.align_all(batches, case.b, case.B):
+        got.extend(res.as_dicts())
+        res.free()
+    assert_same(got, expected, "pipeline depth %d" % depth)
+    assert pipe.stats()["streams"] > 0
+    pipe.close()
+
+
+def test_pipeline_full_and_empty_are_reported(api, golden_dir):
+    case = gacase.read_case(os.path.join(golden_dir, "dag_snp.gacase"))
+    pipe = api.Pipeline(api.Graph.from_case(case), depth=2)
+    with pytest.raises(RuntimeError, match="nothing in flight"):
+        pipe.next()
+    packed = api.PackedReads(case.reads, case.b, case.B)
+    pipe.submit(packed)
+    pipe.submit(packed)
+    with pytest.raises(RuntimeError, match="pipeline full"):
+        pipe.submit(packed)
+    a = pipe.next().as_dicts()
+    b = pipe.next().as_dicts()
+    assert [x["score"] for x in a] == [x["score"] for x in b]
+    assert pipe.in_flight() == 0
+    pipe.close()
