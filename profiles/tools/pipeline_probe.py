@@ -16,7 +16,8 @@ case = synth.make_case(1000, g, kw["n_reads"], kw["read_len"], b=kw["b"])
 graph = api.Graph.from_case(case)
 packed = api.PackedReads(case.reads, 10, 0)
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-for n_ctx in (1, 2, 3):
+DEPTHS = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 2, 3]
+for n_ctx in DEPTHS:
     als = [api.Aligner(graph) for _ in range(n_ctx)]
     for al in als:
         for _ in range(2):
@@ -35,6 +36,6 @@ for n_ctx in (1, 2, 3):
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
-    print("contexts %d: %.1f ms per batch (%d batches)" % (n_ctx, dt / (K * n_ctx) * 1e3, K * n_ctx), flush=True)
+    print("S=%s contexts %d: %.1f ms per batch (%d batches)" % (os.environ.get("GA_STREAMS_PER_WARP", "auto"), n_ctx, dt / (K * n_ctx) * 1e3, K * n_ctx), flush=True)
     for al in als:
         al.close()
