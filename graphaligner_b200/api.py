@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgraphaligner_b200.so")
+# GA_LIB: another build of the same library (A/B measurements of kernel variants); there is still no fallback
+LIB_PATH = os.environ.get("GA_LIB") or os.path.join(_HERE, "libgraphaligner_b200.so")
 
 
 class GaBatch(C.Structure):
