@@ -161,6 +161,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # stdout carries the JSON line and nothing else: library chatter on fd 1 (NCCL prints its version there) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     # host worker threads per rank: the ranks of one box share its cores
     os.environ.setdefault("GA_HOST_THREADS", str(max(1, cores // max(1, world))))
     import torch
@@ -287,7 +291,8 @@ def main():
                                         "sample": "first %d reads of the workload, reference AlignOneWay (-O3 -DNDEBUG), %d threads" % (sample, cores)}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "bp/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/ref_align unavailable"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -4,7 +4,7 @@ import subprocess
 
 import pytest
 
-from graphaligner_b200.tools import gacase, vgio
+from graphaligner_b200.tools import gacase, synth, vgio
 from helpers import ROOT, load_expected
 
 ALIGNER = os.path.join(ROOT, "graphaligner_b200", "bin", "Aligner")
@@ -85,3 +85,56 @@ def test_cli_end_to_end(tmp_path, golden_dir, name, batch_bp):
     first = ok[0]["name"]
     assert os.path.exists(str(tmp_path / ("alignment_0_%s.gam" % first))) and os.path.exists(str(tmp_path / ("trace_0_%s.trace" % first)))
     assert "read %s score %d" % (first, ok[0]["score"]) in r.stdout
+
+
+def test_evaluation_tools_roundtrip(tmp_path):
+    # SimulateReads / PickSeedHits / CompareAlignments equivalents over the GAM codec, no GPU involved:
+    # the truth compared with itself is all good matches; dropping a read or swapping its path makes it a bad match
+    from graphaligner_b200.tools import evaltools
+    g = synth.make_graph(21, 20000, chop=32, bubble_every=200)
+    graph_path = str(tmp_path / "g.vg")
+    vgio.write_stream(graph_path, [vgio.encode_graph(g.nodes, g.edges)])
+    truth, fastq, seeds = str(tmp_path / "truth.gam"), str(tmp_path / "reads.fastq"), str(tmp_path / "seeds.gam")
+    assert evaltools.main(["evaltools", "simulate", graph_path, truth, fastq, "12", "1500", "0.05", "0.05", seeds, "0.05"]) == 0
+    reads = vgio.load_fastq(fastq)
+    t = vgio.load_gam(truth)
+    assert len(reads) == 12 and [a["name"] for a in t] == [n for n, _ in reads]
+    assert all(len(a["sequence"]) == 1500 and len(a["path"]) >= 1500 // 33 for a in t)
+    # pickseeds: duplicates and surplus hits are dropped, ids <= 1 ignored, output grouped by sorted name
+    extra = str(tmp_path / "extra.gam")
+    first = t[0]["name"]
+    vgio.write_stream(extra, [vgio.encode_seed(first, 1, 5, False), vgio.encode_seed(first, 77, 9, False), vgio.encode_seed(first, 78, 9, True),
+                              vgio.encode_seed(first, 77, 9, True)])
+    picked = str(tmp_path / "picked.gam")
+    assert evaltools.main(["evaltools", "pickseeds", picked, "2", seeds, seeds, extra]) == 0
+    p = vgio.load_gam(picked)
+    assert [a["name"] for a in p] == sorted([n for n, _ in reads] + [first])
+    mine = [a for a in p if a["name"] == first]
+    assert len(mine) == 2 and mine[1]["path"][0]["position"]["node_id"] == 77 and mine[1]["query_position"] == 9
+    import io
+    out = io.StringIO()
+    assert evaltools.compare_alignments(truth, truth, graph_path, out) == (12, 0)
+    assert "good matches: 12" in out.getvalue()
+    # a prediction on other nodes is a bad match; a missing one too
+    other = g.nodes[-1][0]
+    bad = [evaltools.encode_alignment(t[0]["name"], t[0]["sequence"], [(other, 0, False)], score=3)]
+    bad += [evaltools.encode_alignment(a["name"], a["sequence"], [(m["position"]["node_id"], 0, m["position"]["is_reverse"]) for m in a["path"]]) for a in t[2:]]
+    pred = str(tmp_path / "pred.gam")
+    vgio.write_stream(pred, bad)
+    assert evaltools.compare_alignments(truth, pred, graph_path, io.StringIO()) == (10, 2)
+
+
+@pytest.mark.gpu
+def test_simulate_align_compare_end_to_end(tmp_path):
+    # the reference's evaluation loop: SimulateReads -> Aligner -> CompareAlignments; every simulated read must land on its
+    # true path (identity >= 0.7, CompareAlignments.cpp:83)
+    from graphaligner_b200.tools import evaltools
+    g = synth.make_graph(22, 60000, chop=32, bubble_every=300)
+    graph_path = str(tmp_path / "g.vg")
+    vgio.write_stream(graph_path, [vgio.encode_graph(g.nodes, g.edges)])
+    truth, fastq, seeds, out = (str(tmp_path / n) for n in ("truth.gam", "reads.fastq", "seeds.gam", "out.gam"))
+    assert evaltools.main(["evaltools", "simulate", graph_path, truth, fastq, "40", "3000", "0.05", "0.05", seeds, "0.05"]) == 0
+    r = subprocess.run([ALIGNER, "-g", graph_path, "-f", fastq, "-s", seeds, "-a", out, "-t", "2", "-b", "10"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-500:]
+    good, bad = evaltools.compare_alignments(truth, out, graph_path, open(os.devnull, "w"))
+    assert good >= 38 and good + bad == 40
