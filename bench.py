@@ -245,8 +245,13 @@ def main():
     # step still pads and uploads its reads from host memory and brings its results back to the host; step i+1's
     # host work runs while step i's kernel does.  This is the throughput number (`e2e.value`).
     pipe = api.Pipeline(graph, device=local_rank, depth=PIPELINE_DEPTH)
-    for r in pipe.align_all([packed] * max(PIPELINE_DEPTH, args.warmup)):
+    # warm-up: every lane's grow-only device pools reach their size, and the results are held until the end so that the
+    # process-wide pools of pinned / pageable result blocks hold more blocks than can be alive at once in the timed loop
+    # (a miss there is a cudaHostAlloc of ~120 MB: 40-60 ms in the middle of a 5-step measurement)
+    held = list(pipe.align_all([packed] * max(2 * PIPELINE_DEPTH, args.warmup)))
+    for r in held:
         r.free()
+    del held
     pipe.reset_stats()
     barrier()
     t0 = time.perf_counter()

@@ -86,6 +86,7 @@ std::vector<AlignmentResult> AlignReads(const AlignmentGraph& graph, const std::
 	std::atomic<size_t> nextBatch(0);
 	std::exception_ptr error;
 	std::mutex errorMutex;
+	std::mutex gpuTurn;   // the two lanes take turns on the device; each one's planning and assembly run under the other's kernel
 	auto lane = [&](int laneIndex) {
 		try
 		{
@@ -96,7 +97,7 @@ std::vector<AlignmentResult> AlignReads(const AlignmentGraph& graph, const std::
 				const size_t k = nextBatch.fetch_add(1);
 				if (k >= nBatches) break;
 				std::vector<ga::ReadInput> part(inputs.begin() + cuts[k], inputs.begin() + cuts[k + 1]);
-				std::vector<AlignmentResult> got = ga::AlignBatch(e->ctx, graph, part, initialBandwidth, rampBandwidth, nullptr);
+				std::vector<AlignmentResult> got = ga::AlignBatch(e->ctx, graph, part, initialBandwidth, rampBandwidth, nullptr, &gpuTurn);
 				for (size_t i = 0; i < got.size(); i++) results[cuts[k] + i] = std::move(got[i]);
 			}
 		}

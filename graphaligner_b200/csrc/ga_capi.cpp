@@ -31,6 +31,9 @@ struct ga_ctx
 	std::string error;
 	ga::BatchStats stats;
 	double budgetShare = 1.0;   // share of the device's free memory a batch of this context may plan with (ga_pipeline: 1 / depth)
+	// ga_pipeline: the contexts of one GPU take turns on the kernel.  Two alignment kernels in flight at once share the SMs and
+	// finish together, which puts the lanes in phase (both on the host, then both on the GPU) and loses the overlap.
+	std::mutex* gpuTurn = nullptr;
 };
 
 struct ga_results
@@ -405,6 +408,18 @@ static ga_batch subBatch(const ga_batch* batch, size_t first, size_t last)
 	return sub;
 }
 
+// kernels, then D2H + assembly; inside a pipeline the kernel part runs under the GPU's turn lock (the staging before and
+// the D2H and host work after overlap with the other lanes' kernels)
+static ga_results* runAndFinish(ga_ctx* ctx, ga_staged* st)
+{
+	if (!ctx->gpuTurn) return ga_run_staged(ctx, st) == 0 ? ga_finish_staged(ctx, st) : nullptr;
+	{
+		std::lock_guard<std::mutex> turn(*ctx->gpuTurn);
+		if (ga_run_staged(ctx, st) != 0 || ga_sync(ctx) != 0) return nullptr;
+	}
+	return ga_finish_staged(ctx, st);
+}
+
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 {
 	// split the batch when its DP history would not fit the device (the history is ~64 B per band column and slice)
@@ -444,8 +459,7 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 		// latencies, not a share of the GPU - so nothing is gained.)
 		ga_staged* st = ga_stage_batch(ctx, batch);
 		if (!st) return nullptr;
-		ga_results* res = nullptr;
-		if (ga_run_staged(ctx, st) == 0) res = ga_finish_staged(ctx, st);
+		ga_results* res = runAndFinish(ctx, st);
 		ga_staged_free(ctx, st);
 		return res;
 	}
@@ -453,8 +467,7 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 	{
 		ga_batch sub = subBatch(batch, cuts[c], cuts[c + 1]);
 		ga_staged* st = ga_stage_batch(ctx, &sub);
-		ga_results* part = nullptr;
-		if (st && ga_run_staged(ctx, st) == 0) part = ga_finish_staged(ctx, st);
+		ga_results* part = st ? runAndFinish(ctx, st) : nullptr;
 		if (st) ga_staged_free(ctx, st);
 		if (!part) return fail();
 		parts.push_back(part);
@@ -593,6 +606,7 @@ struct ga_pipeline
 	};
 	std::vector<std::unique_ptr<Lane>> lanes;
 	std::mutex m;
+	std::mutex gpuTurn;   // see ga_ctx::gpuTurn
 	std::condition_variable cv;
 	uint64_t submitted = 0, taken = 0;
 	bool stop = false;
@@ -634,6 +648,7 @@ ga_pipeline* ga_pipeline_create(int device, int depth)
 			return nullptr;
 		}
 		ctx->budgetShare = 1.0 / depth;
+		if (depth > 1) ctx->gpuTurn = &p->gpuTurn;
 		p->lanes.emplace_back(new ga_pipeline::Lane());
 		p->lanes.back()->ctx = ctx;
 	}

@@ -801,13 +801,19 @@ void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const R
 	if (!fw.empty()) traceInfoInner(graph, read, fw, items);
 }
 
-std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats)
+std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats,
+	std::mutex* gpuTurn)
 {
 	if (!graph.Finalized()) throw std::logic_error("AlignBatch: graph not finalized");
 	BatchPlan plan(graph, reads);
 	RawBuffer<ga_stream_out> outs;
 	RawBuffer<uint32_t> arena;
-	ExecuteStreams(ctx, plan.streams, plan.parts, plan.partsBytes, initialBandwidth, rampBandwidth, outs, arena, stats);
+	{
+		// several contexts of one GPU take turns on the device part; planning and assembly overlap with the other's kernel
+		std::unique_lock<std::mutex> turn;
+		if (gpuTurn) turn = std::unique_lock<std::mutex>(*gpuTurn);
+		ExecuteStreams(ctx, plan.streams, plan.parts, plan.partsBytes, initialBandwidth, rampBandwidth, outs, arena, stats);
+	}
 	std::vector<AlignmentResult> results(reads.size());
 	ParallelFor(reads.size(), [&](size_t i) {
 		if (reads[i].nSeeds == 0)

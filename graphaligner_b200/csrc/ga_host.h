@@ -8,6 +8,7 @@
 #include <memory>
 #include <string>
 #include <tuple>
+#include <mutex>
 #include <vector>
 #include "alignment_graph.h"
 #include "ga_types.h"
@@ -246,7 +247,8 @@ void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, co
 	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats);
 
 // C++ batch entry: full AlignmentResults including trace items (the C ABI materialises those lazily instead)
-std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats);
+std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats,
+	std::mutex* gpuTurn = nullptr);
 
 // runs f(i) for i in [0,n) on HostThreads() workers
 void ParallelFor(size_t n, const std::function<void(size_t)>& f);

@@ -12,6 +12,7 @@
 #include <string>
 #include <unordered_map>
 #include <mutex>
+#include <chrono>
 #include <vector>
 #include "ga_core.cuh"
 #include "ga_device.h"
@@ -750,9 +751,18 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	// D2H through pinned staging, then a parallel copy into the caller's buffers
 	ga_stream_out* pinOuts = (ga_stream_out*)ctx->pinOuts.ensure(n * sizeof(ga_stream_out) + sizeof(unsigned long long));
 	unsigned long long* pinTop = (unsigned long long*)(pinOuts + n);
+	const bool timing = getenv("GA_TIMING") != nullptr;
+	auto tLast = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!timing) return;
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[ga timing]   d2h: %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tLast).count());
+		tLast = now;
+	};
 	GA_CUDA(cudaMemcpyAsync(pinOuts, ctx->bOut.ptr, n * sizeof(ga_stream_out), cudaMemcpyDeviceToHost, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(pinTop, ctx->bArenaTop.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	lap("stream records");
 	unsigned long long top = *pinTop;
 	if (top > sb->arenaCap) top = sb->arenaCap;
 	// the trace arena lands in a pinned block that the results then own (recycled through a process-wide pool): no
@@ -762,10 +772,12 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		size_t cap = 0;
 		uint32_t* pin = (uint32_t*)pinnedAcquire(top * sizeof(uint32_t) + 16, cap);
 		arena.adopt(pin, (size_t)top, cap, pinnedRelease);
+		lap("pinned block");
 		GA_CUDA(cudaMemcpyAsync(pin, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	lap("trace arena");
 #ifdef GA_PHASE_TIMING
 	{
 		static const char* names[16] = { "slice start: lock-step wait", "in-degrees", "node start: store + rest", "word-step loop", "successors", "slice end: minima, HMM, headers, wait", "traceback", "trace start",
