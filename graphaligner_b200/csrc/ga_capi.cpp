@@ -648,7 +648,7 @@ ga_pipeline* ga_pipeline_create(int device, int depth)
 			return nullptr;
 		}
 		ctx->budgetShare = 1.0 / depth;
-		if (depth > 1) ctx->gpuTurn = &p->gpuTurn;
+		if (depth > 1 && !getenv("GA_PIPELINE_FREE_RUN")) ctx->gpuTurn = &p->gpuTurn;   // env: A/B measurements without the turn lock
 		p->lanes.emplace_back(new ga_pipeline::Lane());
 		p->lanes.back()->ctx = ctx;
 	}
