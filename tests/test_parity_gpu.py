@@ -185,3 +185,22 @@ def test_pipeline_full_and_empty_are_reported(api, golden_dir):
     assert [x["score"] for x in a] == [x["score"] for x in b]
     assert pipe.in_flight() == 0
     pipe.close()
+
+
+def test_pipeline_degenerate_batches_and_split(api, golden_dir, monkeypatch):
+    # empty batches, failing reads and batches that each lane must split into several launches (half of a 12 MB budget
+    # per lane), mixed in one stream: order and results as for single calls
+    case = gacase.read_case(os.path.join(golden_dir, "bubbles_multiseed.gacase"))
+    expected = load_expected(os.path.join(golden_dir, "bubbles_multiseed.expected"))
+    monkeypatch.setenv("GA_MEM_BUDGET_MB", "12")
+    name, seq, seeds = case.reads[0]
+    bad = [("noseeds", seq, []), ("badnode", seq, [(999999, 0, False)]), ("ok", seq, seeds)]
+    pipe = api.Pipeline(api.Graph.from_case(case), depth=2)
+    out = [r.as_dicts() for r in pipe.align_all([case.reads, [], bad, case.reads, []], case.b, case.B)]
+    assert [len(x) for x in out] == [len(case.reads), 0, 3, len(case.reads), 0]
+    assert_same(out[0], expected, "pipeline, split batch 0")
+    assert_same(out[3], expected, "pipeline, split batch 3")
+    assert [x["failed"] for x in out[2]] == [1, 1, 0]
+    assert out[2][2]["score"] == expected[0]["score"]
+    assert pipe.stats()["launches"] >= 8
+    pipe.close()
