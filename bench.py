@@ -8,8 +8,9 @@ synthetic 5 Mbp linear-ish graph (32-bp nodes, one SNP bubble per 1000 bp), 10 0
 
 A step = one pass of the hot path over one batch (all reads of the rank).  `value` is aligned bp/s with the
 inputs already resident in HBM (kernel only, CUDA events on the launching stream); `e2e` is the same metric
-through ga_align_batch with host buffers (read splitting, H2D, kernel, D2H, result assembly inside the timed
-region).  Reads are sharded across ranks with the graph replicated; no data-path collective (weak scaling:
+through the C ABI with host buffers (read splitting, H2D, kernel, D2H, result assembly inside the timed region):
+`e2e.value` streams the K batches through ga_pipeline_* (two contexts per GPU, fill and drain inside the timed region),
+`e2e.single_call_ms` is one blocking ga_align_batch per step.  Reads are sharded across ranks with the graph replicated; no data-path collective (weak scaling:
 every rank aligns its own 10 000 reads).  Prints ONE JSON line on rank 0.
 """
 import argparse
