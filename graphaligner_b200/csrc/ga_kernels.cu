@@ -466,6 +466,17 @@ static ga_caps defaultCaps(int b, int B, int scale)
 	return c;
 }
 
+// Whole-node banding: a band holds the kept nodes and their successors, so on a graph of long nodes (unchopped unitigs) a
+// slice spans a few node lengths whatever the bandwidth - up to the reference's 200 000-bp switch to its alternate method.
+// The capacities start at the scale that holds three average nodes instead of climbing there through overflow re-runs.
+static int initialCapScale(const DeviceCtx* ctx, int b, int B)
+{
+	const double need = std::min<double>((double)GA_ALT_CUTOFF + 1024.0, 3.0 * ctx->avgNodeLen + 512.0);
+	int scale = 1;
+	while (scale < 1024 && (double)defaultCaps(b, B, scale).maxCols < need) scale *= 4;
+	return scale;
+}
+
 StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats,
 	bool partsOnDevice = false)
 {
@@ -473,6 +484,7 @@ StagedBatch* StageStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& strea
 	GA_CUDA(cudaSetDevice(ctx->device));
 	StagedBatch* sb = new StagedBatch();
 	sb->b = initialBandwidth;
+	sb->capScale = initialCapScale(ctx, initialBandwidth, rampBandwidth);
 	sb->B = rampBandwidth;
 	sb->hostParts = parts;
 	sb->hostPartsBytes = partsBytes;
@@ -801,7 +813,7 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	{
 		if (isOverflow(outs.data()[i].status)) again.push_back((uint32_t)i);
 	}
-	if (!again.empty() && sb->capScale < 64)
+	if (!again.empty() && sb->capScale < 1024)   // 1024: capacities beyond the 200 000-column switch to the alternate method
 	{
 		std::vector<uint32_t> inv(n);
 		for (size_t i = 0; i < n; i++) inv[sb->perm[i]] = (uint32_t)i;
@@ -843,7 +855,7 @@ size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
 {
 	// dominant terms of layoutAndUpload per stream: column history + fixed scratch + trace buffers
 	const double avgNodeLen = std::max(1.0, ctx->avgNodeLen);
-	const double colsGuess = 2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32;
+	const double colsGuess = (2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32) * initialCapScale(ctx, bandwidth, 0);
 	const double slices = (double)((partLen + 63) / 64);
 	return (size_t)(slices * colsGuess * GA_COL_Q * sizeof(uint4) * 1.15 + 96.0 * 1024 + partLen * 12.0);
 }

@@ -70,3 +70,43 @@ def test_config4_gfa_graph_sharded_reads(api, tmp_path, world):
         aligner.close()
     assert sum(1 for x in got if not x["failed"]) >= len(got) * 0.9
     assert_same(got, expected, "config 4, %d shards" % world)
+
+
+@pytest.mark.parametrize("chop", [20_000, 99_000])
+def test_long_nodes_below_the_alternate_cutoff(api, tmp_path, chop):
+    # unchopped unitig-like nodes: whole-node banding puts 2 nodes = up to 198 000 columns into every slice, just under the
+    # reference's 200 000-bp switch to calculateSliceAlternate (GraphAlignerCommon.h:10); still bit-exact
+    g = synth.make_graph(31, 700_000, chop=chop)
+    case = synth.make_case(31, g, 4, 600, b=10, errors=(0.03, 0.03, 0.03))
+    _check(api, tmp_path, case, "long nodes %d" % chop)
+
+
+def _crossing_case(node_len):
+    # two long nodes B -> C and a read made of the last 300 bp of B and the first 300 bp of C, seeded on B: the forward
+    # pass walks from B into C, so the band is both nodes
+    import numpy as np
+    rng = np.random.default_rng(5)
+    b_seq, c_seq = ("".join("ACGT"[i] for i in rng.integers(0, 4, node_len)) for _ in range(2))
+    return gacase.Case([(2, b_seq), (3, c_seq)], [(2, False, 3, False)], [("cross", b_seq[-300:] + c_seq[:300], [(2, 0, False)])], 10, 0)
+
+
+def test_band_just_below_the_alternate_cutoff(api, tmp_path):
+    # 2 x 99 000 columns in one band: the widest band the bit-parallel path ever sees (GraphAligner.h:2483)
+    _check(api, tmp_path, _crossing_case(99_000), "band of 198 000 columns")
+
+
+def test_alternate_method_band_is_a_per_read_failure(api):
+    # 2 x 101 000 columns: the reference switches to calculateSliceAlternate - and at this commit segfaults there in both
+    # build flavours (oracle/_ref/ref_align and ref_align_stock, probed on exactly this case), so there is nothing to
+    # compare with.  Here the read comes back failed with GA_FLAG_STREAM_ERROR and the context stays usable.
+    case = _crossing_case(101_000)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    res = aligner.align(case.reads, case.b, case.B)
+    d = res.as_dicts()
+    assert d[0]["failed"] == 1 and d[0]["flags"] & 1
+    res.free()
+    # (a read inside B does the same: the seed node starts at score 0 everywhere, so B's last column is within reach and C joins
+    # the band of the second slice.)  The failure is per read, not per context: the next batch is served as usual
+    d = aligner.align(case.reads * 2, case.b, case.B).as_dicts()
+    assert [x["failed"] for x in d] == [1, 1] and all(x["flags"] & 1 for x in d)
+    aligner.close()
