@@ -1,7 +1,10 @@
 """Differential fuzzer (test infrastructure): random graphs and reads (tools.synth), the UNMODIFIED reference hot path
 (oracle/_ref/ref_align) as the checker, the CUDA path through the C ABI as the subject.
 
-    python -m graphaligner_b200.tools.fuzz FIRST_SEED COUNT [--keep DIR]
+    python -m graphaligner_b200.tools.fuzz FIRST_SEED COUNT [--keep DIR] [--long-nodes]
+
+--long-nodes: node lengths 300 .. 30 000 bp on backbones of 60 .. 400 kbp (whole-node banding then puts up to ~10^5 columns
+into a slice: launch capacities scaled up front, overflow re-runs, the general scratch layout).
 
 Needs a GPU and the oracle built (python __graft_entry__.py).  Prints one line per differing case and a summary; cases the
 reference itself crashes on (it segfaults on some cyclic inputs with tiny bands) are counted separately."""
@@ -21,11 +24,17 @@ REF = os.path.join(ROOT, "oracle", "_ref", "ref_align")
 KEYS = ("failed", "score", "start", "end", "qpos", "nmap", "ntrace", "th")
 
 
+LONG_NODES = False
+
+
 def make_case(it):
     rng = np.random.default_rng(it)
     kind = it % 6
     L = int(rng.integers(2000, 20000))
     chop = int(rng.choice([4, 8, 16, 32, 64, 100]))
+    if LONG_NODES:
+        L = int(rng.integers(60000, 400000))
+        chop = int(rng.choice([300, 1000, 3000, 10000, 30000]))
     kw = dict(chop=chop)
     if kind == 0:
         kw.update(snp_every=int(rng.integers(20, 1000)))
@@ -50,6 +59,8 @@ def make_case(it):
 
 
 def main():
+    global LONG_NODES
+    LONG_NODES = "--long-nodes" in sys.argv
     first, count = int(sys.argv[1]), int(sys.argv[2])
     keep = sys.argv[sys.argv.index("--keep") + 1] if "--keep" in sys.argv else None
     from graphaligner_b200 import api
