@@ -204,3 +204,50 @@ def test_pipeline_degenerate_batches_and_split(api, golden_dir, monkeypatch):
     assert out[2][2]["score"] == expected[0]["score"]
     assert pipe.stats()["launches"] >= 8
     pipe.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,rate", [(201, 0.05), (202, 0.4)])
+def test_iupac_and_lower_case_reads(api, tmp_path, seed, rate):
+    # ambiguity codes and lower-case letters in the reads: IUPAC matching inside a slice (GraphAligner.h:2039-2110), exact
+    # compare on the row above a slice (:1503,1540), ReverseComplement of the backward part (CommonUtils.cpp:60-136)
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    g = synth.make_graph(seed, 8000, chop=32, bubble_every=80, inversion_every=700)
+    case = synth.make_case(seed, g, 16, 700, b=10, seed_offsets=(0, 350), errors=(0.03, 0.03, 0.03))
+    codes = "RYSWKMBDHVNryswkmbdhvn"
+    reads = []
+    for name, seq, seeds in case.reads:
+        s = list(seq)
+        for i in range(len(s)):
+            if rng.random() < rate:
+                s[i] = codes[int(rng.integers(0, len(codes)))] if rng.random() < 0.7 else s[i].lower()
+        reads.append((name, "".join(s), seeds))
+    case.reads = reads
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    assert_same(aligner.align(case.reads, case.b, case.B).as_dicts(), expected, "iupac %g" % rate)
+    aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+def test_reads_shorter_than_one_slice(api, tmp_path):
+    # 1 .. 70 bp: a single 64-row slice of mostly padding; seeds on the first, a middle and the last base
+    import numpy as np
+    rng = np.random.default_rng(203)
+    g = synth.make_graph(203, 3000, chop=16, bubble_every=60)
+    reads = []
+    for k, ln in enumerate([1, 2, 3, 7, 31, 32, 33, 63, 64, 65, 70]):
+        read, real, walk, mp = synth.simulate_read(rng, g, max(2, ln), 0.03, 0.03, 0.03)
+        read = read[:ln]
+        for off in sorted(set([0, len(read) // 2, len(read) - 1])):
+            reads.append(("r%d_%d" % (k, off), read, synth.seeds_for(walk, mp, len(read), [min(off, len(mp) - 1)])))
+    case = gacase.Case(list(g.nodes), list(g.edges), reads, 5, 0)
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    assert_same(aligner.align(case.reads, case.b, case.B).as_dicts(), expected, "tiny reads")
+    aligner.close()
