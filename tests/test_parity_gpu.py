@@ -251,3 +251,19 @@ def test_reads_shorter_than_one_slice(api, tmp_path):
     aligner = api.Aligner(api.Graph.from_case(case))
     assert_same(aligner.align(case.reads, case.b, case.B).as_dicts(), expected, "tiny reads")
     aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("overlap", [1, 3, 5])
+def test_gfa_edge_overlap(api, tmp_path, overlap):
+    # GFA with a k-bp edge overlap: every node loses its last k bases (BigraphToDigraph.cpp:58-67) and the backward part of
+    # a split read is extended by DBGOverlap (GraphAligner.h:2991-2992); mid-read seeds exercise the latter
+    g = synth.make_graph(210 + overlap, 10000, chop=16)
+    case = synth.make_case(210 + overlap, g, 12, 600, b=10, seed_offsets=(0, 200, -60), errors=(0.02, 0.02, 0.02))
+    case.gfa_overlap = overlap
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=4)
+    aligner = api.Aligner(api.Graph.from_case(case))
+    assert_same(aligner.align(case.reads, case.b, case.B).as_dicts(), expected, "gfa overlap %d" % overlap)
+    aligner.close()
