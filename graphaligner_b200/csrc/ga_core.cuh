@@ -73,7 +73,7 @@ struct GaHmmTables
 	double startCorrect, startFalse;
 };
 
-#ifndef __CUDACC__
+#if !defined(__CUDACC__) && !defined(GA_HOSTSIM)
 struct uint4 { uint32_t x, y, z, w; };
 #endif
 

@@ -60,6 +60,7 @@ struct ScratchPtrs
 __constant__ GaHmmTables c_hmm;
 __constant__ GaUmapSchedule c_sched;
 
+#ifndef GA_HOSTSIM
 // Match masks for every 64-row slice of every stream: one block per stream, one thread per slice, 64 bytes in, 32 bytes out.
 __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq)
 {
@@ -76,6 +77,7 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 		dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
 	}
 }
+#endif
 
 // shared-memory scratch per stream in small-band mode
 #define GA_SMEM_NODES 16u
@@ -86,6 +88,7 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 
 // S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
 // less divergence; big batches run with S = 32 for full lane utilisation.
+#ifndef GA_HOSTSIM
 template <int S>
 __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
 	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, uint32_t smemScratch,
@@ -196,6 +199,90 @@ __global__ void ga_int32_peak_kernel(uint32_t* sink, int iters)
 	}
 	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) sink[0] = a0;
 }
+#endif
+
+
+#ifdef GA_HOSTSIM
+// ---- CPU emulation of the launches (test infrastructure, see oracle/hostsim/cuda_runtime.h): one stream per "warp" ----
+static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, const uint8_t* parts, uint32_t nStreams, uint4* peq)
+{
+	for (uint32_t stream = 0; stream < nStreams; stream++)
+	{
+		const uint32_t nslices = streams[stream].partLen / 64;
+		const uint8_t* base = parts + streams[stream].seqOff;
+		for (uint32_t sl = 0; sl < nslices; sl++)
+		{
+			uint64_t A, C, G, T;
+			ga_peq_words(base + (size_t)sl * 64, A, C, G, T);
+			uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
+			dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
+			dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
+		}
+	}
+}
+
+static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* warpDescs, const ga_stream_in* streams, const uint8_t* parts, uint32_t nStreams,
+	int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* outs, uint32_t* arena, unsigned long long* arenaTop, unsigned long long arenaCap)
+{
+	const int S = 1;
+	std::vector<uint64_t> eqTab(4);
+	for (uint32_t stream = 0; stream < nStreams; stream++)
+	{
+		const size_t w = stream;
+		const WarpDesc wd = warpDescs[w];
+		ga_caps wc = caps;
+		wc.maxSlices = wd.maxSlices;
+		wc.histNodes = wd.histNodes;
+		wc.warpCols = sp.colPoolCap;
+		wc.maxMoves = wd.maxMoves;
+		wc.maxPathNodes = wd.maxPathNodes;
+		wc.maxRuns = wd.maxRuns;
+		GaLaneMem mem;
+		mem.tiny[0] = sp.tiny + (w * 3 + 0) * caps.maxCols * S;
+		mem.tiny[1] = sp.tiny + (w * 3 + 1) * caps.maxCols * S;
+		mem.conf = sp.tiny + (w * 3 + 2) * caps.maxCols * S;
+		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S;
+		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S;
+		mem.heap = sp.heap + w * caps.maxQueue * S;
+		mem.indeg = sp.nodeTmp + (w * 10 + 0) * caps.maxNodes * S;
+		mem.order = sp.nodeTmp + (w * 10 + 1) * caps.maxNodes * S;
+		mem.unext = sp.nodeTmp + (w * 10 + 2) * caps.maxNodes * S;
+		mem.uorder = sp.nodeTmp + (w * 10 + 3) * caps.maxNodes * S;
+		mem.nWlo = sp.nodeTmp + (w * 10 + 4) * caps.maxNodes * S;
+		mem.nWhi = sp.nodeTmp + (w * 10 + 5) * caps.maxNodes * S;
+		mem.nPcs = sp.nodeTmp + (w * 10 + 6) * caps.maxNodes * S;
+		mem.cmpOf = sp.nodeTmp + (w * 10 + 7) * caps.maxNodes * S;
+		mem.emit = sp.nodeTmp + (w * 10 + 8) * caps.maxNodes * S;
+		mem.wl = sp.nodeTmp + (w * 10 + 9) * caps.maxNodes * S;
+		mem.ubkt = sp.ubkt + w * sp.ubktSize * S;
+		mem.hdr = sp.hdr + wd.hdrBase;
+		mem.histNode = sp.histNode + wd.hnBase;
+		mem.col = sp.col;
+		mem.colPoolTop = sp.colPoolTop;
+		mem.moves = sp.moves + wd.movesBase;
+		mem.pathNodes = sp.pathNodes + wd.pathBase;
+		mem.runs = sp.runs + wd.runsBase;
+		mem.peq = sp.peq + sp.peqOff[stream];
+		mem.eqTab = eqTab.data();
+		ga_stream_out* out = outs + stream;
+		ga_run_stream<1>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, out);
+		uint32_t moveWords = (out->nMoves + 15) / 16;
+		uint32_t runWords = out->nRuns * GA_RUN_WORDS;
+		uint32_t words = moveWords + out->nPathNodes + runWords;
+		unsigned long long off = *arenaTop;
+		*arenaTop += words;
+		out->traceOff = off;
+		if (off + words > arenaCap)
+		{
+			if (out->status == GA_OK) out->status = GA_ERR_TRACE_OVERFLOW;
+			continue;
+		}
+		for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * S];
+		for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * S];
+		for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + out->nPathNodes + i] = mem.runs[(size_t)i * S];
+	}
+}
+#endif
 
 // ---- device buffer pool -----------------------------------------------------------------------------------------
 struct Buffer
@@ -358,7 +445,12 @@ DeviceCtx* CreateDevice(int device)
 		GA_CUDA(cudaGetDeviceProperties(&prop, device));
 		ctx->smCount = prop.multiProcessorCount;
 		int blocks = 0;
+#ifndef GA_HOSTSIM
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, ga_align_kernel<4>, 64, 0) == cudaSuccess && blocks > 0) ctx->warpsPerSm = blocks * 2;
+#else
+		(void)blocks;
+		ctx->forceS = 1;   // the emulation runs one stream per "warp"
+#endif
 	}
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
 	return ctx;
@@ -403,7 +495,9 @@ double MeasureInt32Peak(DeviceCtx* ctx)
 	for (int rep = 0; rep < 5; rep++)
 	{
 		GA_CUDA(cudaEventRecord(e0, ctx->stream));
+#ifndef GA_HOSTSIM
 		ga_int32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->bArenaTop.ptr, iters);
+#endif
 		GA_CUDA(cudaEventRecord(e1, ctx->stream));
 		GA_CUDA(cudaEventSynchronize(e1));
 		float ms = 0;
@@ -640,6 +734,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	if (stats) stats->h2dBytes += sb->hostPartsBytes + n * sizeof(ga_stream_in) + nWarps * sizeof(WarpDesc) + n * sizeof(uint64_t);
 }
 
+#ifndef GA_HOSTSIM
 template <int S>
 static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 {
@@ -651,6 +746,7 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, sb->smemScratch ? 1u : 0u, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
 		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
+#endif
 
 int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 {
@@ -661,6 +757,11 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	GA_CUDA(cudaMemsetAsync(ctx->bHash.ptr, 0, sb->nWarps * 2 * (size_t)sb->caps.hashSize * sb->S * sizeof(uint64_t), ctx->stream));
 	GA_CUDA(cudaMemsetAsync(ctx->bArenaTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
 	GA_CUDA(cudaMemsetAsync(ctx->bColTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
+#ifdef GA_HOSTSIM
+	hostsim_peq((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
+	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
+		(ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+#else
 	{
 		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
 		GA_CUDA(cudaGetLastError());
@@ -675,6 +776,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		case 1: launchAlign<1>(ctx, sb); break;
 		default: throw std::logic_error("unsupported streams-per-warp");
 	}
+#endif
 	GA_CUDA(cudaGetLastError());
 	sb->launches += 2;
 	return 2;
