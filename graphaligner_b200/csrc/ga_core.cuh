@@ -15,9 +15,10 @@
 //   slice driver / stop rule  getSqrtSlices, removeWronglyAlignedEnd        GraphAligner.h:2554-2856
 //   correctness HMM           AlignmentCorrectnessEstimationState::NextState AlignmentCorrectnessEstimation.cpp:71-89
 //   traceback + tie-breaks    getTraceFromTable*, pickBacktracePredecessor  GraphAligner.h:493-591,894-1021
-// What is deliberately different: no confirmedRows bookkeeping (acyclic band components are final after one
-// topological pass; cyclic components are iterated to the unique min-plus fix point), no sqrt checkpointing
-// (the full VP/VN history stays in HBM, so traceback never recomputes), no graph-sized scratch.
+// What is deliberately different: no confirmedRows bookkeeping on acyclic band components (final after one
+// topological pass; cyclic components replay the reference's work list), no sqrt checkpointing (the column history
+// - VP, VN and the row -1 score, 20 bytes per column - stays in HBM, so the traceback never recomputes a slice),
+// no graph-sized scratch.  The traceback is a kernel of its own (ga_trace.cuh): this file is the forward pass.
 #ifndef GA_CORE_CUH
 #define GA_CORE_CUH
 #include <stdint.h>
@@ -33,9 +34,6 @@
 #define GA_WARP_ANY(x) __any_sync(0xffffffffu, (x))
 // one allocation per warp from a global bump pointer; every lane gets the same offset
 #define GA_POOL_ALLOC(ptr, n) __shfl_sync(0xffffffffu, ((threadIdx.x & 31) == 0) ? atomicAdd((ptr), (unsigned long long)(n)) : 0ull, 0)
-// traceback-mask quarters of the column history: written once, read once much later by the traceback -> keep them out of
-// L1 (st.global.cg), which the per-slice scratch (node tables, hash windows, tiny arrays) and the value quarters need
-#define GA_ST_HIST(ptr, v) __stcg((ptr), (v))
 #else
 #define GA_DEV inline
 #define GA_DEV_NOINLINE inline
@@ -44,7 +42,6 @@
 #define GA_WARP_MAX(x) (x)
 #define GA_WARP_ANY(x) (x)
 #define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
-#define GA_ST_HIST(ptr, v) (*(ptr) = (v))
 #endif
 
 // -DGA_PHASE_TIMING: per-stream cycle counters per phase (profiling builds only: GA_EXTRA_FLAGS in build.py; the sums are
@@ -80,7 +77,7 @@ struct uint4 { uint32_t x, y, z, w; };
 // per-lane memory; every pointer is already offset by the lane, element i lives at p[i * LANES]
 struct GaLaneMem
 {
-	uint32_t* tiny[2];   // frozen end state per band column, current / previous slice
+	void* tiny[2];       // frozen end state per band column, current / previous slice (ga_tiny_ld / ga_tiny_st)
 	uint64_t* hash[2];   // node -> band slot, (node << 32 | stamp << 16 | slot)
 	uint64_t* heap;
 	uint32_t* indeg;
@@ -94,13 +91,13 @@ struct GaLaneMem
 	uint32_t* conf;      //   per band column: confirmedRows (rows | partial << 8), GraphAligner.h:1355-1416
 	uint32_t* hdr;
 	uint32_t* histNode;
+	uint32_t* hnRing;    // small-band mode: node lists of the current and the previous slice (GA_HN)
+	uint64_t* lastVV;    // small-band mode: {VP, VN} and the row -1 score of the last column of every band node evaluated
+	uint32_t* lastS;     //   in this slice (what the first column of a successor starts from)
 	uint64_t* eqTab;     // four match words of the current slice, [base][lane] (shared memory on the device)
-	uint4* col;          // column history pool (shared by all warps), four 16-byte quarters per column:
-	                     // {VP, VN} {sbs, scoreEnd, linkNode, linkCol} {H, D0} {EQ, flags, prevCol}   (H, D0, EQ: traceback masks, see ga_node_columns)
+	uint4* colVV;        // column history pool (shared by all warps): {VP, VN} per column, [column][lane]
+	uint32_t* colS;      //   and the row -1 score with the traceback's flags (GA_CF_*), [column][lane]
 	unsigned long long* colPoolTop;   // bump pointer of the pool, in columns (x LANES lanes)
-	uint32_t* moves;
-	uint32_t* pathNodes;
-	uint32_t* runs;      // GA_RUN_WORDS words per run
 	uint32_t* ubkt;      // unordered_map emulation: bucket -> "before" node
 	uint32_t* unext;     // unordered_map emulation: forward list links
 	uint32_t* uorder;    // iteration order of the previous slice's node map
@@ -108,7 +105,13 @@ struct GaLaneMem
 };
 
 #define GA_HDR(s, f) mem.hdr[(size_t)((s) * GA_HDR_WORDS + (f)) * LANES]
-#define GA_HN(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
+// Node lists of the slices (node history).  GA_HNG = the history in global memory.  GA_HN = the same entry as the forward
+// pass sees it: in small-band mode the lists of the current and the previous slice (adjacent in the history, at most
+// GA_SMEM_NODES entries each) live in a shared-memory ring of GA_HN_RING entries indexed by the entry number, and a slice's
+// list is copied to the history when the slice is kept (ga_run_stream).
+#define GA_HN_RING 32u
+#define GA_HNG(i, f) mem.histNode[(size_t)((i) * GA_HN_WORDS + (f)) * LANES]
+#define GA_HN(i, f) (*(SMALL ? &mem.hnRing[(size_t)((((i) & (GA_HN_RING - 1u)) * GA_HN_WORDS) + (f)) * LANES] : &GA_HNG(i, f)))
 #define GA_NOT_IN_PREV 0xffffffffu
 
 struct GaCol
@@ -117,102 +120,49 @@ struct GaCol
 	int32_t sbs, scoreEnd;
 };
 
-#define GA_COL_Q 4u   /* 16-byte quarters per column record */
+// Column history record: {VP, VN} (16 bytes) + one word = row -1 score (29 bits) | flags.  The end score is not stored:
+// scoreEnd = sbs + popcount(VP) - popcount(VN) (reference invariant, GraphAligner.h:1421).
+//   GA_CF_PLAIN  the column is a plain word step (ga_next_col, no min-merge) from its left neighbour in the node, so the
+//                traceback may decide its steps from the step's own bit masks (ga_trace.cuh) instead of cell values
+//   GA_CF_LINK   first column of a node: a plain word step from the last column of the node's ONLY band in-neighbour, and
+//                that column is the one stored right before this one in the slice's slab
+//   GA_CF_EQ0    bit 0 of the match word as the step used it (the band-edge rules and a negative horizontal entry change it)
+#define GA_CF_PLAIN 0x80000000u
+#define GA_CF_EQ0 0x40000000u
+#define GA_CF_LINK 0x20000000u
+#define GA_CF_SCORE_MASK 0x1fffffffu
 
-// stores a column without traceback masks (node starts, merged columns, resets): flags = 0 sends the traceback
-// through the exact general path for this column
-// prevCol = pool index of the same graph column in the slice above (GA_NO_COL if the node is not in that band): the
-// traceback crosses slice borders through it without searching
-#define GA_NO_COL 0xffffffffu
 template <int LANES>
-GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint32_t prevCol)
+GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint32_t flags)
 {
-	uint4 a, b, z;
+	uint4 a;
 	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
-	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
-	z.x = z.y = z.z = 0; z.w = prevCol;
-	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
-	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
-	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 3) * LANES], z);
-}
-
-// values only: the record's flags / prevCol quarter stays as ga_force_block wrote it
-template <int LANES>
-GA_DEV void ga_col_store_values(const GaLaneMem& mem, uint32_t col, const GaCol& c)
-{
-	uint4 a, b;
-	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
-	b.x = (uint32_t)c.sbs; b.y = (uint32_t)c.scoreEnd; b.z = 0; b.w = 0;
-	mem.col[(size_t)(col * GA_COL_Q) * LANES] = a;
-	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
-}
-
-// first column of a node that is a plain word step from its single in-neighbour's last column: masks as for any other
-// column (flags bit 0) plus the link to that neighbour (flags bit 1): its node index and the pool index of its last column
-template <int LANES>
-GA_DEV void ga_col_store_linked(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint64_t H, uint64_t D0, uint64_t EQ, uint32_t flags, uint32_t linkNode, uint32_t linkCol, uint32_t prevCol)
-{
-	uint4 ra, rb, rc, rd;
-	ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
-	rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = linkNode; rb.w = linkCol;
-	rc.x = (uint32_t)H; rc.y = (uint32_t)(H >> 32); rc.z = (uint32_t)D0; rc.w = (uint32_t)(D0 >> 32);
-	rd.x = (uint32_t)EQ; rd.y = (uint32_t)(EQ >> 32); rd.z = flags; rd.w = prevCol;
-	mem.col[(size_t)(col * GA_COL_Q) * LANES] = ra;
-	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = rb;
-	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 2) * LANES], rc);
-	GA_ST_HIST(&mem.col[(size_t)(col * GA_COL_Q + 3) * LANES], rd);
+	mem.colVV[(size_t)col * LANES] = a;
+	mem.colS[(size_t)col * LANES] = (uint32_t)c.sbs | flags;
 }
 
 template <int LANES>
 GA_DEV GaCol ga_col_load(const GaLaneMem& mem, uint32_t col)
 {
-	uint4 a = mem.col[(size_t)(col * GA_COL_Q) * LANES];
-	uint4 b = mem.col[(size_t)(col * GA_COL_Q + 1) * LANES];
+	uint4 a = mem.colVV[(size_t)col * LANES];
 	GaCol c;
 	c.VP = (uint64_t)a.x | ((uint64_t)a.y << 32);
 	c.VN = (uint64_t)a.z | ((uint64_t)a.w << 32);
-	c.sbs = (int32_t)b.x;
-	c.scoreEnd = (int32_t)b.y;
+	c.sbs = (int32_t)(mem.colS[(size_t)col * LANES] & GA_CF_SCORE_MASK);
+	c.scoreEnd = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
 	return c;
 }
 
 template <int LANES>
 GA_DEV int32_t ga_col_load_sbs(const GaLaneMem& mem, uint32_t col)
 {
-	return (int32_t)mem.col[(size_t)(col * GA_COL_Q + 1) * LANES].x;
+	return (int32_t)(mem.colS[(size_t)col * LANES] & GA_CF_SCORE_MASK);
 }
 
 template <int LANES>
 GA_DEV void ga_col_store_sbs(const GaLaneMem& mem, uint32_t col, int32_t sbs)
 {
-	uint4 b;
-	b.x = (uint32_t)sbs; b.y = 0; b.z = 0; b.w = 0;
-	mem.col[(size_t)(col * GA_COL_Q + 1) * LANES] = b;
-}
-
-// The traceback is a chain of dependent loads into a history far larger than L2.  Whole nodes are requested into L2
-// when the walk enters them, and the next few columns are pulled into L1 just ahead of the walk.
-template <int LANES>
-GA_DEV void ga_col_prefetch_l2(const GaLaneMem& mem, uint32_t col)
-{
-#ifdef __CUDACC__
-	asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 2) * LANES));
-	// with up to 4 lanes the two mask quarters of a column share a 128-byte line
-	if (LANES > 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
-#else
-	(void)mem; (void)col;
-#endif
-}
-
-template <int LANES>
-GA_DEV void ga_col_prefetch_l1(const GaLaneMem& mem, uint32_t col)
-{
-#ifdef __CUDACC__
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 2) * LANES));
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(mem.col + (size_t)(col * GA_COL_Q + 3) * LANES));
-#else
-	(void)mem; (void)col;
-#endif
+	mem.colS[(size_t)col * LANES] = (uint32_t)sbs;
 }
 
 // tiny = frozen end state of a column, cf. reference TinySlice (NodeSlice.h:26-31):
@@ -225,19 +175,45 @@ GA_DEV int32_t ga_tiny_score(uint32_t t) { return (int32_t)(t >> 3); }
 // value of row 62 of the frozen column = scoreEnd - VP63 + VN63 (GraphAligner.h:1368)
 GA_DEV int32_t ga_tiny_row62(uint32_t t) { return (int32_t)(t >> 3) - (int32_t)(t & 1) + (int32_t)((t >> 1) & 1); }
 
+// The tiny arrays are 32-bit words in global memory in the general layout.  In small-band mode (SMALL) they live in shared
+// memory as 16-bit words: the three flags and the low 13 bits of the score, which is rebuilt against a reference score that
+// is known to be at most GA_TINY_SPAN below it (the minimum of the previous slice: no end score of this or the previous
+// slice is lower).  A stream whose scores spread further leaves small-band mode (ga_node_columns).
+#define GA_TINY_SPAN 8000
+template <int LANES, bool SMALL>
+GA_DEV uint32_t ga_tiny_ld(const void* base, uint32_t idx, int32_t ref)
+{
+	if (SMALL)
+	{
+		const uint32_t t = ((const uint16_t*)base)[(size_t)idx * LANES];
+		const uint32_t score = (uint32_t)ref + (((t >> 3) - (uint32_t)ref) & 0x1fffu);
+		return (score << 3) | (t & 7u);
+	}
+	return ((const uint32_t*)base)[(size_t)idx * LANES];
+}
+template <int LANES, bool SMALL>
+GA_DEV void ga_tiny_st(void* base, uint32_t idx, uint32_t t)
+{
+	if (SMALL) ((uint16_t*)base)[(size_t)idx * LANES] = (uint16_t)t;
+	else ((uint32_t*)base)[(size_t)idx * LANES] = t;
+}
+#define GA_TP(x) ga_tiny_ld<LANES, SMALL>(cx.tinyPrev, (x), cx.tinyRef)
+#define GA_TC(x) ga_tiny_ld<LANES, SMALL>(cx.tinyCur, (x), cx.tinyRef)
+#define GA_TC_ST(x, v) ga_tiny_st<LANES, SMALL>(cx.tinyCur, (x), (v))
+
 GA_DEV uint32_t ga_base(const ga_graph_view& g, uint64_t w)
 {
 	return (g.seq2[w >> 4] >> ((uint32_t)(w & 15) * 2)) & 3u;
 }
 
 // Myers word step without the confirmedRows bookkeeping (GraphAligner.h:1349-1399).
-// H = rows where this column is one above its left neighbour (horizontal delta +1), D0 = rows whose diagonal delta is 0.
 // topScore = end score of this column in the previous slice (or INT_MAX): the reference takes the word step from
 // the left neighbour and then min-merges the result with the vertical ramp from topScore when the step's row -1 score
 // is larger (GraphAligner.h:1541-1546).  That minimum IS the word step whose row -1 score is topScore - same
 // recurrence, lower entry value - so whenever topScore - L.sbs is a legal horizontal delta (-1 or 0) the step is taken
-// with it directly, which also keeps H and D0 exact for the traceback.  needMerge reports the rare other case.
-GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftInside, bool diagInside, bool previousEq, int32_t upleftRow62, int32_t topScore, uint64_t& H, uint64_t& D0, bool& needMerge)
+// with it directly, and the column stays a plain word step for the traceback.  needMerge reports the rare other case.
+// eq0 = bit 0 of the match word as the horizontal part of the step used it (the traceback re-derives the step's masks).
+GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftInside, bool diagInside, bool previousEq, int32_t upleftRow62, int32_t topScore, uint32_t& eq0, bool& needMerge)
 {
 	GaCol r;
 	if (!leftSbE || !diagInside) Eq &= ~(uint64_t)1;
@@ -256,11 +232,10 @@ GA_DEV GaCol ga_next_col(uint64_t Eq, const GaCol& L, bool leftSbE, bool upleftI
 	int32_t hin = sbs - L.sbs;
 	uint64_t Xv = Eq | L.VN;
 	if (hin < 0) Eq |= 1;
+	eq0 = (uint32_t)Eq & 1u;
 	uint64_t Xh = (((Eq & L.VP) + L.VP) ^ L.VP) | Eq;
 	uint64_t Ph = L.VN | ~(Xh | L.VP);
 	uint64_t Mh = L.VP & Xh;
-	H = Ph;
-	D0 = Xh | L.VN;
 	r.scoreEnd = L.scoreEnd + (int32_t)(Ph >> 63) - (int32_t)(Mh >> 63);
 	Ph <<= 1;
 	Mh <<= 1;
@@ -448,7 +423,7 @@ struct GaUmapSchedule
 #define GA_UNIL 0xffffffffu
 
 // keys: GA_HN(keyOff + i, 0), i in [0,n).  Writes the element indices in iteration order to mem.uorder.
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV void ga_umap_order(const GaUmapSchedule& sch, const GaLaneMem& mem, uint32_t keyOff, uint32_t n)
 {
 	uint32_t bktCount = 1;
@@ -577,7 +552,7 @@ GA_DEV uint32_t ga_exact_code(uint8_t c)
 // node history at nodeOff (in the reference's band order), fills hashCur and the per-node scratch records.
 // Returns the number of band nodes.
 // ------------------------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, uint64_t* hashCur, uint32_t& maskCur, uint32_t& stampCur, uint32_t& gen,
 	uint32_t nodeOff, uint32_t& nc, uint32_t& ncols, uint32_t node, uint64_t wStart, uint32_t len, uint32_t pcs)
 {
@@ -606,9 +581,9 @@ GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLan
 	return true;
 }
 
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaUmapSchedule& sch, const GaLaneMem& mem, GaStreamState& st, int bandwidth,
-	uint32_t pNodeOff, uint32_t pNodes, const uint32_t* tinyPrev, const uint64_t* hashPrev, uint32_t maskPrev, uint32_t stampPrev, uint64_t* hashCur, uint32_t& maskCur, uint32_t& stampCur, uint32_t& gen,
+	uint32_t pNodeOff, uint32_t pNodes, const void* tinyPrev, const uint64_t* hashPrev, uint32_t maskPrev, uint32_t stampPrev, uint64_t* hashCur, uint32_t& maskCur, uint32_t& stampCur, uint32_t& gen,
 	uint32_t nodeOff, uint32_t& ncolsOut)
 {
 	const int32_t expand = bandwidth + 64;
@@ -617,7 +592,7 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 	uint32_t heapN = 0;
 	// the reference walks the previous slice's unordered_map (GraphAligner.h:1117)
 	GA_TLAP(st, 0);
-	ga_umap_order<LANES>(sch, mem, pNodeOff, pNodes);
+	ga_umap_order<LANES, SMALL>(sch, mem, pNodeOff, pNodes);
 	GA_TLAP(st, 8);
 	for (uint32_t it = 0; it < pNodes; it++)
 	{
@@ -627,8 +602,8 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		uint32_t node = GA_HN(pNodeOff + i, 0);
 		uint32_t pcs = GA_HN(pNodeOff + i, 1);
 		uint32_t len = GA_HN(pNodeOff + i, 3);
-		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, g.nodeStart[node], len, pcs)) return -1;
-		int32_t endscore = ga_tiny_score(tinyPrev[(size_t)(pcs + len - 1) * LANES]);
+		if (!ga_band_add<LANES, SMALL>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, g.nodeStart[node], len, pcs)) return -1;
+		int32_t endscore = ga_tiny_score(ga_tiny_ld<LANES, SMALL>(tinyPrev, pcs + len - 1, st.prevMin));
 		if (endscore > st.prevMin + expand) continue;
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
@@ -650,7 +625,7 @@ GA_DEV int ga_select_band(const ga_graph_view& g, const ga_caps& caps, const GaU
 		// not kept, but it may still sit in the previous band (its minimum was outside the bandwidth)
 		int pslot = ga_hash_find<LANES>(hashPrev, maskPrev, stampPrev, node);
 		uint32_t pcs = pslot >= 0 ? GA_HN(pNodeOff + pslot, 1) : GA_NOT_IN_PREV;
-		if (!ga_band_add<LANES>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, wStart, len, pcs)) return -1;
+		if (!ga_band_add<LANES, SMALL>(g, caps, mem, st, hashCur, maskCur, stampCur, gen, nodeOff, nc, ncols, node, wStart, len, pcs)) return -1;
 		for (uint32_t e = g.outOff[node], eEnd = g.outOff[node + 1]; e < eEnd; e++)
 		{
 			if (heapN >= caps.maxQueue) { st.status = GA_ERR_QUEUE_OVERFLOW; return -1; }
@@ -671,8 +646,9 @@ struct GaSliceCtx
 	uint32_t slabOff;             // this slice's first column in the warp slab
 	uint32_t pSlabOff;            // the previous slice's (unused when !hasPrevSlab: slice 0 follows the initial slice)
 	bool hasPrevSlab;
-	uint32_t* tinyCur;
-	const uint32_t* tinyPrev;
+	void* tinyCur;
+	const void* tinyPrev;
+	int32_t tinyRef;              // reference score of the 16-bit tiny encoding (the previous slice's minimum)
 	uint64_t* hashCur;
 	const uint64_t* hashPrev;
 	uint32_t stampCur, stampPrev;
@@ -686,13 +662,13 @@ struct GaSliceCtx
 // Columns 1..len-1 of a node: the serial Myers chain (GraphAligner.h:1532-1570).  INPREV = the node is also in
 // the previous slice's band (then every column may be min-merged with the vertical ramp from the previous slice).
 // Returns the minimum scoreEnd over the node.
-template <int LANES, bool INPREV>
+template <int LANES, bool SMALL, bool INPREV>
 GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, const GaSliceCtx& cx, uint64_t wStart, uint32_t len, uint32_t cs, uint32_t pcs,
-	uint32_t prevMask, GaCol L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin)
+	uint32_t prevMask, GaCol& L, bool LsbE, uint32_t oldTinyLeft, uint32_t oldTinyNext, int32_t nodeMin, bool& spanOverflow)
 {
-	uint4* colPtr = mem.col + (size_t)((cx.slabOff + cs + 1) * GA_COL_Q) * LANES;
-	uint32_t* tinyPtr = cx.tinyCur + (size_t)(cs + 1) * LANES;
-	const uint32_t* prevPtr = cx.tinyPrev + (size_t)(pcs + 2) * LANES;   // next column to prefetch
+	uint4* vvPtr = mem.colVV + (size_t)(cx.slabOff + cs + 1) * LANES;
+	uint32_t* sPtr = mem.colS + (size_t)(cx.slabOff + cs + 1) * LANES;
+	int32_t nodeMax = L.scoreEnd;
 	const uint64_t w = wStart + 1;
 	const uint32_t* seqPtr = g.seq2 + (w >> 4) + 1;
 	uint32_t seqWord = g.seq2[w >> 4];
@@ -706,29 +682,27 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		if (shift == 32) { seqWord = *seqPtr++; shift = 0; }
 		// match mask of this column's base from the slice's table (shared memory: the address depends only on the base)
 		const uint64_t Eq = cx.eqTab[(size_t)base * LANES];
-		const uint64_t EqTrue = Eq;   // IUPAC match mask of this column's base, untouched by the band-edge rules
 		const bool previousEq = ((prevMask >> base) & 1u) != 0;
 		GaCol c;
 		bool sbE = false;
-		uint64_t H, D0;
-		uint32_t flags = 1;   // traceback masks valid: this column is a plain word step from its left neighbour
+		uint32_t eq0;
+		uint32_t flags = GA_CF_PLAIN;   // the column is a plain word step from its left neighbour
 		if (INPREV)
 		{
 			const uint32_t oldTiny = oldTinyNext;
 			// software prefetch of the next column's previous-slice state (address known, value independent of this step)
-			if (k + 1 < len) oldTinyNext = *prevPtr;
-			prevPtr += LANES;
+			if (k + 1 < len) oldTinyNext = GA_TP(pcs + k + 1);
 			const int32_t oldScore = ga_tiny_score(oldTiny);
 			// row -1 score = min(left + 1, previous slice's end score); the flag says the latter attains it
 			sbE = oldScore <= L.sbs + 1;
 			bool needMerge;
-			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), oldScore, H, D0, needMerge);
+			c = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), oldScore, eq0, needMerge);
 			if (needMerge) { ga_vertical_merge(c, oldScore); flags = 0; }
 #ifdef GA_HOST_DEBUG
 			{
 				// the shortcut must equal the reference's step-then-merge bit for bit
-				uint64_t h2, d2; bool m2;
-				GaCol ref = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), 0x7fffffff, h2, d2, m2);
+				uint32_t e2; bool m2;
+				GaCol ref = ga_next_col(Eq, L, LsbE, sbE, LsbE, previousEq, ga_tiny_row62(oldTinyLeft), 0x7fffffff, e2, m2);
 				if (ref.sbs > oldScore) ga_vertical_merge(ref, oldScore);
 				if (ref.VP != c.VP || ref.VN != c.VN || ref.sbs != c.sbs || ref.scoreEnd != c.scoreEnd) { fprintf(stderr, "vertical-merge shortcut mismatch\n"); abort(); }
 			}
@@ -738,48 +712,31 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		else
 		{
 			bool needMerge;
-			c = ga_next_col(Eq, L, LsbE, false, LsbE, previousEq, 0, 0x7fffffff, H, D0, needMerge);
+			c = ga_next_col(Eq, L, LsbE, false, LsbE, previousEq, 0, 0x7fffffff, eq0, needMerge);
 		}
-#ifdef GA_HOST_DEBUG
-		if (flags)
-		{
-			// the masks must agree with the cell values for every row >= 1 (row 0 is never taken from them)
-			for (int r = 1; r < 64; r++)
-			{
-				int32_t here = ga_col_value(c.VP, c.VN, c.sbs, r), lft = ga_col_value(L.VP, L.VN, L.sbs, r), diag = ga_col_value(L.VP, L.VN, L.sbs, r - 1);
-				if ((((H >> r) & 1) != 0) != (here - lft == 1) || (((D0 >> r) & 1) != 0) != (here == diag)) { fprintf(stderr, "traceback mask mismatch row %d\n", r); abort(); }
-			}
-		}
-#endif
-		uint4 ra, rb, rc, rd;
+		uint4 ra;
 		ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
-		rb.x = (uint32_t)c.sbs; rb.y = (uint32_t)c.scoreEnd; rb.z = 0; rb.w = 0;
-		rc.x = (uint32_t)H; rc.y = (uint32_t)(H >> 32); rc.z = (uint32_t)D0; rc.w = (uint32_t)(D0 >> 32);
-		rd.x = (uint32_t)EqTrue; rd.y = (uint32_t)(EqTrue >> 32); rd.z = flags; rd.w = (INPREV && cx.hasPrevSlab) ? cx.pSlabOff + pcs + k : GA_NO_COL;
-		colPtr[0] = ra;
-		colPtr[LANES] = rb;
-		GA_ST_HIST(colPtr + 2 * LANES, rc);
-		GA_ST_HIST(colPtr + 3 * LANES, rd);
-		colPtr += GA_COL_Q * LANES;
-		*tinyPtr = ga_tiny_pack(c, sbE);
-		tinyPtr += LANES;
+		*vvPtr = ra;
+		*sPtr = (uint32_t)c.sbs | flags | (eq0 ? GA_CF_EQ0 : 0u);
+		vvPtr += LANES;
+		sPtr += LANES;
+		GA_TC_ST(cs + k, ga_tiny_pack(c, sbE));
 		if (c.scoreEnd < nodeMin) nodeMin = c.scoreEnd;
+		if (SMALL && c.scoreEnd > nodeMax) nodeMax = c.scoreEnd;
 		L = c;
 		LsbE = sbE;
 	}
+	// the 16-bit tiny encoding holds scores up to GA_TINY_SPAN above the reference: beyond that the stream leaves small-band mode
+	if (SMALL && nodeMax - cx.tinyRef > GA_TINY_SPAN) spanOverflow = true;
 	return nodeMin;
 }
 
 #define GA_MAX_CACHED_IN 6
-#ifndef GA_TRACE_PREFETCH
-#define GA_TRACE_PREFETCH 64      /* columns requested into L2 on entering a node (measured: ~1.5 % faster than none) */
-#endif
-#define GA_TRACE_NEAR 4u        /* columns kept ahead in L1 */
 
 // Evaluate one band node whose band predecessors are final (the acyclic part of a band, in topological order): first column
 // from its in-neighbours (or as a source), the rest by the word step.  Members of cyclic components go through
 // ga_ex_calc_node instead.
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot)
 {
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
@@ -794,14 +751,13 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	uint32_t base = (seqWord >> ((uint32_t)(wStart & 15) * 2)) & 3u;
 	uint64_t Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
 	bool previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
-	const uint32_t oldTiny0 = inPrev ? cx.tinyPrev[(size_t)pcs * LANES] : 0;
-	uint32_t oldTinyNext = (inPrev && len > 1) ? cx.tinyPrev[(size_t)(pcs + 1) * LANES] : 0;
+	const uint32_t oldTiny0 = inPrev ? GA_TP(pcs) : 0;
+	uint32_t oldTinyNext = (inPrev && len > 1) ? GA_TP(pcs + 1) : 0;
 
 	// in-neighbours that are in the current or the previous band: column index of their last column in the
 	// current slab / in the previous tiny array (0xffffffff = absent)
-	uint32_t inCur[GA_MAX_CACHED_IN], inPrevCol[GA_MAX_CACHED_IN];
+	uint32_t inCur[GA_MAX_CACHED_IN], inPrevCol[GA_MAX_CACHED_IN], inSlot[GA_MAX_CACHED_IN];
 	uint32_t nIn = 0;
-	uint32_t firstIn = 0, firstInLen = 1;   // the first band in-neighbour (the only one when nIn == 1) and its length
 	// row -1 score of the first column and its "exists" flag (forceComponentZeroRow, GraphAligner.h:1916-1989)
 	int32_t sbs0 = inPrev ? ga_tiny_score(oldTiny0) : 0x7fffffff;
 	const uint32_t eBegin = g.inOff[node], eEnd = g.inOff[node + 1];
@@ -816,9 +772,9 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		{
 			const uint32_t ulen = GA_HN(cx.nodeOff + cu, 3);
 			curCol = GA_HN(cx.nodeOff + cu, 1) + ulen - 1;
-			if (nIn == 0) firstInLen = ulen;
 			{
-				int32_t v = ga_col_load_sbs<LANES>(mem, cx.slabOff + curCol) + 1;
+				// small-band mode keeps the last column of every evaluated band node in shared memory
+				int32_t v = (SMALL ? (int32_t)mem.lastS[(size_t)cu * LANES] : ga_col_load_sbs<LANES>(mem, cx.slabOff + curCol)) + 1;
 				if (v < sbs0) sbs0 = v;
 			}
 		}
@@ -826,12 +782,11 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		{
 			prevCol = GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1;
 			{
-				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)prevCol * LANES]) + 1;
+				int32_t v = ga_tiny_score(GA_TP(prevCol)) + 1;
 				if (v < sbs0) sbs0 = v;
 			}
 		}
-		if (nIn < GA_MAX_CACHED_IN) { inCur[nIn] = curCol; inPrevCol[nIn] = prevCol; }
-		if (nIn == 0) firstIn = u;
+		if (nIn < GA_MAX_CACHED_IN) { inCur[nIn] = curCol; inPrevCol[nIn] = prevCol; inSlot[nIn] = (uint32_t)cu; }
 		nIn++;
 	}
 	GA_TLAP(st, 11);
@@ -841,19 +796,19 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	// A node whose only band in-neighbour is in this slice starts with a plain word step from that neighbour's last column:
 	// it gets traceback masks and a link like any inner column (the walk then crosses the node border on the fast path)
 	const bool single = nIn == 1 && inCur[0] != 0xffffffffu;
-	uint64_t H0 = 0, D00 = 0;
 	uint32_t flags0 = 0;
 	if (nIn > 0)
 	{
 		uint32_t k = 0;
 		for (uint32_t e = eBegin; e < eEnd; e++)
 		{
-			uint32_t curCol, prevCol;
+			uint32_t curCol, prevCol, curSlot;
 			if (nIn <= GA_MAX_CACHED_IN)
 			{
 				if (k >= nIn) break;
 				curCol = inCur[k];
 				prevCol = inPrevCol[k];
+				curSlot = inSlot[k];
 			}
 			else
 			{
@@ -863,17 +818,24 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				int pu = ga_hash_find<LANES>(cx.hashPrev, cx.maskPrev, cx.stampPrev, u);
 				if (cu < 0 && pu < 0) continue;
 				curCol = cu >= 0 ? GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1 : 0xffffffffu;
+				curSlot = (uint32_t)cu;
 				prevCol = pu >= 0 ? GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1 : 0xffffffffu;
 			}
 			bool foundOneUp = prevCol != 0xffffffffu;
-			uint32_t upTiny = foundOneUp ? cx.tinyPrev[(size_t)prevCol * LANES] : 0;
+			uint32_t upTiny = foundOneUp ? GA_TP(prevCol) : 0;
 			GaCol L;
 			bool LsbE;
 			uint64_t EqHere = Eq;
 			if (curCol != 0xffffffffu)
 			{
-				L = ga_col_load<LANES>(mem, cx.slabOff + curCol);
-				uint32_t t = cx.tinyCur[(size_t)curCol * LANES];
+				if (SMALL)
+				{
+					L.VP = mem.lastVV[(size_t)(curSlot * 2) * LANES];
+					L.VN = mem.lastVV[(size_t)(curSlot * 2 + 1) * LANES];
+					L.sbs = (int32_t)mem.lastS[(size_t)curSlot * LANES];
+				}
+				else L = ga_col_load<LANES>(mem, cx.slabOff + curCol);
+				uint32_t t = GA_TC(curCol);
 				L.scoreEnd = ga_tiny_score(t);
 				LsbE = (t & 4u) != 0;
 			}
@@ -888,28 +850,22 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 				LsbE = true;
 				EqHere &= 1;
 			}
-			uint64_t hCand, dCand;
+			uint32_t eq0;
 			bool needMerge;
 			// single: the vertical merge rides on the step as in ga_node_columns (same recurrence, lower entry score)
-			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), (single && inPrev) ? ga_tiny_score(oldTiny0) : 0x7fffffff, hCand, dCand, needMerge);
+			GaCol cand = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), (single && inPrev) ? ga_tiny_score(oldTiny0) : 0x7fffffff, eq0, needMerge);
 			if (single)
 			{
-				H0 = hCand; D00 = dCand; flags0 = 3u | ((firstInLen - 1) << 2);   // bits 2..: the neighbour's last offset
-				if (needMerge) { ga_vertical_merge(cand, ga_tiny_score(oldTiny0)); flags0 = 0; }
+				// the neighbour's last column sits right before this node's first one when the band lists the two back to back:
+				// then the traceback walks across the node border as if the two nodes were one (GA_CF_LINK)
+				if (!needMerge && curCol + 1 == cs) flags0 = GA_CF_LINK | (eq0 ? GA_CF_EQ0 : 0u);
+				if (needMerge) ga_vertical_merge(cand, ga_tiny_score(oldTiny0));
 #ifdef GA_HOST_DEBUG
 				{
-					uint64_t h2, d2; bool m2;
-					GaCol ref = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), 0x7fffffff, h2, d2, m2);
+					uint32_t e2; bool m2;
+					GaCol ref = ga_next_col(EqHere, L, LsbE, sbE0 && foundOneUp, foundOneUp, previousEq, ga_tiny_row62(upTiny), 0x7fffffff, e2, m2);
 					if (inPrev && ref.sbs > ga_tiny_score(oldTiny0)) ga_vertical_merge(ref, ga_tiny_score(oldTiny0));
 					if (ref.VP != cand.VP || ref.VN != cand.VN || ref.sbs != cand.sbs || ref.scoreEnd != cand.scoreEnd) { fprintf(stderr, "node-start shortcut mismatch\n"); abort(); }
-					if (flags0)
-					{
-						for (int r = 1; r < 64; r++)
-						{
-							int32_t here = ga_col_value(cand.VP, cand.VN, cand.sbs, r), lft = ga_col_value(L.VP, L.VN, L.sbs, r), diag = ga_col_value(L.VP, L.VN, L.sbs, r - 1);
-							if ((((H0 >> r) & 1) != 0) != (here - lft == 1) || (((D00 >> r) & 1) != 0) != (here == diag)) { fprintf(stderr, "node-start mask mismatch row %d\n", r); abort(); }
-						}
-					}
 				}
 #endif
 			}
@@ -939,12 +895,8 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 	if (c0.sbs != sbs0) { st.status = GA_ERR_INTERNAL; return; }
 #endif
 	GA_TLAP(st, 12);
-	{
-		const uint32_t prevCol0 = (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs : GA_NO_COL;
-		if (flags0) ga_col_store_linked<LANES>(mem, cx.slabOff + cs, c0, H0, D00, Eq, flags0, firstIn, cx.slabOff + inCur[0], prevCol0);
-		else ga_col_store<LANES>(mem, cx.slabOff + cs, c0, prevCol0);
-	}
-	cx.tinyCur[(size_t)cs * LANES] = ga_tiny_pack(c0, sbE0);
+	ga_col_store<LANES>(mem, cx.slabOff + cs, c0, flags0);
+	GA_TC_ST(cs, ga_tiny_pack(c0, sbE0));
 
 	// ---- columns 1 .. len-1 (GraphAligner.h:1532-1570) ------------------------------------------------------
 	GA_TLAP(st, 2);
@@ -954,10 +906,19 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		// 4-bit set of graph bases that equal the read character just above the slice (exact compare,
 		// GraphAligner.h:1540); on the first slice the flag is "node is in the previous band" instead
 		const uint32_t prevMask = cx.firstSlice ? (inPrev ? 15u : 0u) : ((1u << cx.prevCharCode) & 15u);
-		if (inPrev) nodeMin = ga_node_columns<LANES, true>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
-		else nodeMin = ga_node_columns<LANES, false>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin);
+		bool spanOverflow = false;
+		if (inPrev) nodeMin = ga_node_columns<LANES, SMALL, true>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin, spanOverflow);
+		else nodeMin = ga_node_columns<LANES, SMALL, false>(g, mem, cx, wStart, len, cs, pcs, prevMask, c0, sbE0, oldTiny0, oldTinyNext, nodeMin, spanOverflow);
+		if (spanOverflow) { st.status = GA_ERR_COL_OVERFLOW; return; }
 	}
+	else if (SMALL && c0.scoreEnd - cx.tinyRef > GA_TINY_SPAN) { st.status = GA_ERR_COL_OVERFLOW; return; }
 	GA_HN(cx.nodeOff + slot, 2) = (uint32_t)nodeMin;
+	if (SMALL)
+	{
+		mem.lastVV[(size_t)(slot * 2) * LANES] = c0.VP;
+		mem.lastVV[(size_t)(slot * 2 + 1) * LANES] = c0.VN;
+		mem.lastS[(size_t)slot * LANES] = (uint32_t)c0.sbs;
+	}
 }
 
 
@@ -1130,11 +1091,11 @@ GA_DEV GaExCol ga_ex_merge(GaExCol left, GaExCol right)
 	return result;
 }
 
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV GaExCol ga_ex_load(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col)
 {
 	GaCol c = ga_col_load<LANES>(mem, cx.slabOff + col);
-	uint32_t t = cx.tinyCur[(size_t)col * LANES];
+	uint32_t t = GA_TC(col);
 	uint32_t cf = mem.conf[(size_t)col * LANES];
 	GaExCol e;
 	e.VP = c.VP; e.VN = c.VN; e.sbs = c.sbs; e.scoreEnd = c.scoreEnd;
@@ -1144,19 +1105,19 @@ GA_DEV GaExCol ga_ex_load(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t c
 	return e;
 }
 
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV void ga_ex_store(const GaLaneMem& mem, const GaSliceCtx& cx, uint32_t col, const GaExCol& e)
 {
 	GaCol c;
 	c.VP = e.VP; c.VN = e.VN; c.sbs = e.sbs; c.scoreEnd = e.scoreEnd;
-	ga_col_store_values<LANES>(mem, cx.slabOff + col, c);
-	cx.tinyCur[(size_t)col * LANES] = ga_tiny_pack(c, e.sbE);
+	ga_col_store<LANES>(mem, cx.slabOff + col, c, 0);
+	GA_TC_ST(col, ga_tiny_pack(c, e.sbE));
 	mem.conf[(size_t)col * LANES] = (uint32_t)e.rows | (e.partial ? 0x100u : 0u);
 }
 
 // calculateNode for a member of a cyclic component (GraphAligner.h:1457-1573).  Returns the minimum scoreEnd over the
 // columns this call fully confirmed (INT_MAX if none) and the last such column attaining it.
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t slot, uint32_t& lastMinCol)
 {
 	const uint32_t node = GA_HN(cx.nodeOff + slot, 0);
@@ -1167,7 +1128,7 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 	const bool inPrev = pcs != GA_NOT_IN_PREV;
 	int32_t minScore = 0x7fffffff;
 	lastMinCol = 0xffffffffu;
-	GaExCol cur0 = ga_ex_load<LANES>(mem, cx, cs);
+	GaExCol cur0 = ga_ex_load<LANES, SMALL>(mem, cx, cs);
 	if (cur0.rows == 64) return minScore;
 	const int32_t oldRows0 = cur0.rows;
 	const bool oldPartial0 = cur0.partial;
@@ -1186,9 +1147,9 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 		uint64_t EqHere = Eq;
 		const bool foundOneUp = pu >= 0;
 		uint32_t upTiny = 0;
-		if (foundOneUp) upTiny = cx.tinyPrev[(size_t)(GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1) * LANES];
+		if (foundOneUp) upTiny = GA_TP(GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1);
 		GaExCol previous;
-		if (cu >= 0) previous = ga_ex_load<LANES>(mem, cx, GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1);
+		if (cu >= 0) previous = ga_ex_load<LANES, SMALL>(mem, cx, GA_HN(cx.nodeOff + cu, 1) + GA_HN(cx.nodeOff + cu, 3) - 1);
 		else
 		{
 			const int32_t es = ga_tiny_score(upTiny);
@@ -1199,7 +1160,7 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 		if (!foundOne) { res = here; foundOne = true; }
 		else res = ga_ex_merge(res, here);
 	}
-	uint32_t oldTiny = inPrev ? cx.tinyPrev[(size_t)pcs * LANES] : 0;
+	uint32_t oldTiny = inPrev ? GA_TP(pcs) : 0;
 	if (!foundOne)
 	{
 		// source node downstream of nothing (GraphAligner.h:1317-1347,1475-1488): final at once
@@ -1216,7 +1177,7 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 		mergable.VP = ~(uint64_t)0; mergable.VN = 0; mergable.sbs = ga_tiny_score(oldTiny); mergable.scoreEnd = mergable.sbs + 64; mergable.rows = 64; mergable.partial = false; mergable.sbE = true;
 		res = ga_ex_merge(res, mergable);
 	}
-	ga_ex_store<LANES>(mem, cx, cs, res);
+	ga_ex_store<LANES, SMALL>(mem, cx, cs, res);
 	if (res.rows == 64 && res.scoreEnd < minScore) minScore = res.scoreEnd;
 	if (res.rows == 64 && res.scoreEnd == minScore) lastMinCol = 0;
 	if (ga_conf_eq(res.rows, res.partial, oldRows0, oldPartial0)) return minScore;
@@ -1224,14 +1185,14 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 	uint32_t oldTinyLeft = oldTiny;
 	for (uint32_t k = 1; k < len; k++)
 	{
-		GaExCol c = ga_ex_load<LANES>(mem, cx, cs + k);
+		GaExCol c = ga_ex_load<LANES, SMALL>(mem, cx, cs + k);
 		if (c.rows == 64) return minScore;
 		const int32_t oldRows = c.rows;
 		const bool oldPartial = c.partial;
 		base = ga_base(g, wStart + k);
 		Eq = base == 0 ? cx.BA : base == 1 ? cx.BC : base == 2 ? cx.BG : cx.BT;
 		previousEq = cx.firstSlice ? inPrev : (base == cx.prevCharCode);
-		oldTiny = inPrev ? cx.tinyPrev[(size_t)(pcs + k) * LANES] : 0;
+		oldTiny = inPrev ? GA_TP(pcs + k) : 0;
 		GaExCol n = ga_ex_next(Eq, leftCol, c.sbE, c.sbE, leftCol.sbE, previousEq, ga_tiny_score(oldTinyLeft), oldTinyLeft & 1u, (oldTinyLeft >> 1) & 1u);
 		if (inPrev && n.sbs > ga_tiny_score(oldTiny))
 		{
@@ -1239,7 +1200,7 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 			mergable.VP = ~(uint64_t)0; mergable.VN = 0; mergable.sbs = ga_tiny_score(oldTiny); mergable.scoreEnd = mergable.sbs + 64; mergable.rows = 64; mergable.partial = false; mergable.sbE = true;
 			n = ga_ex_merge(n, mergable);
 		}
-		ga_ex_store<LANES>(mem, cx, cs + k, n);
+		ga_ex_store<LANES, SMALL>(mem, cx, cs + k, n);
 		if (n.rows == 64 && n.scoreEnd < minScore) minScore = n.scoreEnd;
 		if (n.rows == 64 && n.scoreEnd == minScore) lastMinCol = k;
 		if (ga_conf_eq(n.rows, n.partial, oldRows, oldPartial)) return minScore;
@@ -1251,10 +1212,10 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 
 // Row -1 scores for a cyclic block of band nodes (the slots listed in order[from..to)) by shortest paths over
 // the block (forceComponentZeroRow, GraphAligner.h:1903-1995), then reset every column to the all-ones ramp.
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, const GaSliceCtx& cx, uint32_t from, uint32_t to, uint32_t comp)
 {
-	const int32_t INF = 0x3fffffff;
+	const int32_t INF = 0x1fffffff;   // fits the score field of a column record (GA_CF_SCORE_MASK)
 	uint32_t heapN = 0;
 	// the component's members are emit[from..to); cmpOf[slot] == comp tests membership
 	for (uint32_t q = from; q < to; q++)
@@ -1265,7 +1226,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 		uint32_t len = GA_HN(cx.nodeOff + slot, 3);
 		uint32_t pcs = mem.nPcs[(size_t)slot * LANES];
 		bool inPrev = pcs != GA_NOT_IN_PREV;
-		int32_t s0 = inPrev ? ga_tiny_score(cx.tinyPrev[(size_t)pcs * LANES]) : INF;
+		int32_t s0 = inPrev ? ga_tiny_score(GA_TP(pcs)) : INF;
 		for (uint32_t e = g.inOff[node]; e < g.inOff[node + 1]; e++)
 		{
 			uint32_t u = g.inAdj[e];
@@ -1280,7 +1241,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			if (pu >= 0)
 			{
 				uint32_t ucol = GA_HN(cx.pNodeOff + pu, 1) + GA_HN(cx.pNodeOff + pu, 3) - 1;
-				int32_t v = ga_tiny_score(cx.tinyPrev[(size_t)ucol * LANES]) + 1;
+				int32_t v = ga_tiny_score(GA_TP(ucol)) + 1;
 				if (v < s0) s0 = v;
 			}
 		}
@@ -1292,7 +1253,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 				v = v + 1;
 				if (inPrev)
 				{
-					int32_t o = ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]);
+					int32_t o = ga_tiny_score(GA_TP(pcs + k));
 					if (o < v) v = o;
 				}
 			}
@@ -1349,9 +1310,9 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 			c.sbs = ga_col_load_sbs<LANES>(mem, cx.slabOff + cs + k);
 			if (c.sbs >= INF) { st.status = GA_ERR_INTERNAL; return; }
 			c.scoreEnd = c.sbs + 64;
-			bool sbE = inPrev && ga_tiny_score(cx.tinyPrev[(size_t)(pcs + k) * LANES]) == c.sbs;
-			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c, (inPrev && cx.hasPrevSlab) ? cx.pSlabOff + pcs + k : GA_NO_COL);
-			cx.tinyCur[(size_t)(cs + k) * LANES] = ga_tiny_pack(c, sbE);
+			bool sbE = inPrev && ga_tiny_score(GA_TP(pcs + k)) == c.sbs;
+			ga_col_store<LANES>(mem, cx.slabOff + cs + k, c, 0);
+			GA_TC_ST(cs + k, ga_tiny_pack(c, sbE));
 			mem.conf[(size_t)(cs + k) * LANES] = 0;
 		}
 	}
@@ -1363,7 +1324,7 @@ GA_DEV void ga_force_block(const ga_graph_view& g, const ga_caps& caps, const Ga
 // reference's component vector holds them) and cmpOf[slot] with the component number (emission order).  Returns the
 // number of components.  Scratch: indeg = DFS index | on-stack bit, order = low link, uorder = Tarjan stack,
 // unext = call-stack slots, ubkt = call-stack edge cursors.  (The hash table of the slice resolves neighbours.)
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV uint32_t ga_tarjan_components(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, const GaSliceCtx& cx)
 {
 	const uint32_t nNodes = cx.nNodes;
@@ -1440,7 +1401,7 @@ struct GaSliceResult
 // One slice for one stream, after band selection: topological pass (Kahn) over the acyclic part, fix-point
 // sweeps over what is left (cyclic components and everything downstream of them), slice minimum, HMM step.
 // Returns false on error; the slice's minimum and HMM step come back in res (the caller applies the stop / ramp rules).
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaLaneMem& mem, GaStreamState& st, GaSliceCtx& cx, uint32_t ncols, GaSliceResult& res)
 {
 	const uint32_t nc = cx.nNodes;
@@ -1475,7 +1436,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	while (done < ready)
 	{
 		uint32_t slot = mem.order[(size_t)(done++) * LANES];
-		ga_calc_node<LANES>(g, caps, mem, st, cx, slot);
+		ga_calc_node<LANES, SMALL>(g, caps, mem, st, cx, slot);
 		GA_TLAP(st, 3);
 		if (st.status != GA_OK) return false;
 		uint32_t node = GA_HN(cx.nodeOff + slot, 0);
@@ -1503,6 +1464,8 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	}
 	else
 	{
+		// small-band mode covers acyclic bands only: the stream is re-run with the general layout
+		if (SMALL) { st.status = GA_ERR_NODE_OVERFLOW; return false; }
 		// The band holds a cycle.  Components in the reference's order (reverse Tarjan emission = topological); acyclic
 		// ones that Kahn's pass did not reach are evaluated like any other node, cyclic ones replay the reference's
 		// confirmedRows work list.  The slice minimum and its last tied cell are tracked in evaluation order.
@@ -1511,7 +1474,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		for (uint32_t slot = 0; slot < nc; slot++) mem.wl[(size_t)slot * LANES] = 0;
 		for (uint32_t q = 0; q < done; q++) mem.wl[(size_t)mem.order[(size_t)q * LANES] * LANES] = 1;
 		// wl doubles as the "already evaluated" flag array until the work list needs it: copy the flags into cmpOf's top bit
-		const uint32_t nComp = ga_tarjan_components<LANES>(g, caps, mem, cx);
+		const uint32_t nComp = ga_tarjan_components<LANES, SMALL>(g, caps, mem, cx);
 		// columns outside cyclic components are final when a component reads them: confirmedRows = 64
 		for (uint32_t c = 0; c < ncols; c++) mem.conf[(size_t)c * LANES] = 64;
 		for (uint32_t slot = 0; slot < nc; slot++)
@@ -1539,7 +1502,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			{
 				if (!(mem.cmpOf[(size_t)firstSlot * LANES] & 0x40000000u))
 				{
-					ga_calc_node<LANES>(g, caps, mem, st, cx, firstSlot);
+					ga_calc_node<LANES, SMALL>(g, caps, mem, st, cx, firstSlot);
 					if (st.status != GA_OK) return false;
 				}
 				const int32_t nodeMin = (int32_t)GA_HN(cx.nodeOff + firstSlot, 2);
@@ -1549,7 +1512,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 					const uint32_t cs = GA_HN(cx.nodeOff + firstSlot, 1), len = GA_HN(cx.nodeOff + firstSlot, 3);
 					for (uint32_t k = 0; k < len; k++)
 					{
-						if (ga_tiny_score(cx.tinyCur[(size_t)(cs + k) * LANES]) == nodeMin) lastMinCol = k;
+						if (ga_tiny_score(GA_TC(cs + k)) == nodeMin) lastMinCol = k;
 					}
 					minScore = nodeMin;
 					lastMinSlot = firstSlot;
@@ -1558,7 +1521,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 			else
 			{
 				// forceComponentZeroRow, then the UniqueQueue work list (GraphAligner.h:2360-2420, UniqueQueue.h)
-				ga_force_block<LANES>(g, caps, mem, st, cx, compStart, compEnd, ci);
+				ga_force_block<LANES, SMALL>(g, caps, mem, st, cx, compStart, compEnd, ci);
 				if (st.status != GA_OK) return false;
 				uint32_t wlN = 0;
 				const uint32_t INQ = 0x80000000u;
@@ -1576,7 +1539,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 					const uint32_t cs = GA_HN(cx.nodeOff + slot, 1), len = GA_HN(cx.nodeOff + slot, 3);
 					const uint32_t oldEndConf = mem.conf[(size_t)(cs + len - 1) * LANES];
 					uint32_t callLastCol = 0;
-					const int32_t callMin = ga_ex_calc_node<LANES>(g, caps, mem, st, cx, slot, callLastCol);
+					const int32_t callMin = ga_ex_calc_node<LANES, SMALL>(g, caps, mem, st, cx, slot, callLastCol);
 					if (st.status != GA_OK) return false;
 					GA_HN(cx.nodeOff + slot, 2) = (uint32_t)callMin;   // setMinScore: the LAST call's value stays (GraphAligner.h:2375)
 					const uint32_t newEndConf = mem.conf[(size_t)(cs + len - 1) * LANES];
@@ -1615,7 +1578,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		for (uint32_t slot = 0; slot < nc; slot++)
 		{
 			uint32_t cs = GA_HN(cx.nodeOff + slot, 1), len = GA_HN(cx.nodeOff + slot, 3);
-			v.push_back({GA_HN(cx.nodeOff + slot, 0), {(int)GA_HN(cx.nodeOff + slot, 2), ga_tiny_score(cx.tinyCur[(size_t)(cs + len - 1) * LANES])}});
+			v.push_back({GA_HN(cx.nodeOff + slot, 0), {(int)GA_HN(cx.nodeOff + slot, 2), ga_tiny_score(GA_TC(cs + len - 1))}});
 		}
 		std::sort(v.begin(), v.end());
 		fprintf(stderr, "SLICE j=%d min=%d n=%d last=%d\n", (int)cx.s * 64, minScore, (int)nc, lastMinSlot == 0xffffffffu ? -2 : (int)(g.nodeStart[GA_HN(cx.nodeOff + lastMinSlot, 0)] + lastMinCol));
@@ -1637,323 +1600,14 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 	return true;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Traceback over the stored history (getTraceFromTable / pickBacktracePredecessor, GraphAligner.h:493-591,
-// 894-1021).  Emits 2-bit moves and the node crossed into at every node boundary, both in backward order.
-// The walk keeps the current and the left column in registers and carries the current cell's score, so a step
-// inside a node costs one 32-byte column load (prefetched) instead of a chain of lookups.
-// ------------------------------------------------------------------------------------------------------------
 template <int LANES>
 GA_DEV int ga_slice_find(const GaLaneMem& mem, uint32_t nodeOff, uint32_t nNodes, uint32_t node)
 {
 	for (uint32_t i = 0; i < nNodes; i++)
 	{
-		if (GA_HN(nodeOff + i, 0) == node) return (int)i;
+		if (GA_HNG(nodeOff + i, 0) == node) return (int)i;
 	}
 	return -1;
-}
-
-// value of (node, off) at `row` of slice s, or `maxv` when the node is not in that slice's band
-// (getValueOrMax, GraphAligner.h:2008-2017).  s == -1 is the initial slice: seed node = 0, else maxv.
-template <int LANES>
-GA_DEV int32_t ga_hist_value(const GaLaneMem& mem, const GaStreamState& st, int s, uint32_t node, uint32_t off, int row, int32_t maxv)
-{
-	if (s < 0) return node == st.startNode ? 0 : maxv;
-	uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
-	int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
-	if (slot < 0) return maxv;
-	GaCol c = ga_col_load<LANES>(mem, GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1) + off);
-	return ga_col_value(c.VP, c.VN, c.sbs, row);
-}
-
-template <int LANES>
-GA_DEV void ga_traceback(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool doTrace, int nSlices, uint32_t node, uint32_t off,
-	uint32_t& nMovesOut, uint32_t& nPathOut, uint32_t& nRunsOut, uint32_t& nPosOut)
-{
-	// Called by every lane of the warp (doTrace = this lane has a trace to walk).  One loop iteration = one step of
-	// every walking lane, with a warp vote at the loop head: diverged lanes would otherwise serialise their chains of
-	// dependent loads, which is what a traceback is made of.
-	bool walking = doTrace;
-	uint32_t nMoves = 0, nPath = 0, nRuns = 0;
-	// Same-node runs of the trimmed trace, walked backwards.  A run is opened at the first untrimmed position seen on a
-	// node ('last' in read order) and closed when the walk leaves the node; its other end is the position left from.
-	bool runOpen = false;
-	uint32_t runNode = 0, runLastOff = 0, runLastRow = 0;
-	uint32_t skipped = 0;        // positions dropped because their row lies in the trimmed tail
-	uint32_t curWord = 0;
-	int s = nSlices - 1;
-	int row = 63;
-	const int32_t maxv = (int32_t)st.partLen;
-	uint32_t colBase = 0;       // per (slice, node): index of the node's first column in the history pool
-	const uint4* colPtr = nullptr;   // record of the current column
-	bool reload = true;         // slice or node changed without a stored link: re-resolve the base
-	// traceback masks of the current column (valid iff flags & 1): H = rows one above the left neighbour,
-	// D0 = rows with diagonal delta 0, EQ = rows whose read character matches this column's base;
-	// prevCol = the same graph column in the slice above
-	uint64_t mH = 0, mD0 = 0, mEQ = 0;
-	uint32_t flags = 0, prevCol = GA_NO_COL;
-	int32_t here = 0;
-	bool haveHere = false;
-	const uint32_t maxMoves = caps.maxMoves;
-#define GA_TRACE_LOAD_MASKS() \
-	{ \
-		const uint4 q2 = colPtr[2 * LANES], q3 = colPtr[3 * LANES]; \
-		mH = (uint64_t)q2.x | ((uint64_t)q2.y << 32); \
-		mD0 = (uint64_t)q2.z | ((uint64_t)q2.w << 32); \
-		mEQ = (uint64_t)q3.x | ((uint64_t)q3.y << 32); \
-		flags = q3.z; \
-		prevCol = q3.w; \
-	}
-	// the history is far larger than L2: on entering a node request the rest of its columns, so that one HBM round
-	// trip is paid per node and slice instead of per step
-#if GA_TRACE_PREFETCH > 0
-#define GA_TRACE_PREFETCH_NODE() for (uint32_t t = 1; t <= off && t <= GA_TRACE_PREFETCH; t++) ga_col_prefetch_l2<LANES>(mem, colBase + off - t);
-#else
-#define GA_TRACE_PREFETCH_NODE()
-#endif
-	while (GA_WARP_ANY(walking))
-	{
-		if (!walking) continue;
-		if (reload)
-		{
-#ifdef GA_HOST_DEBUG
-			g_dbgReload++;
-#endif
-			uint32_t nodeOff = GA_HDR(s, 2), nNodes = GA_HDR(s, 3);
-			int slot = ga_slice_find<LANES>(mem, nodeOff, nNodes, node);
-			if (slot < 0) { st.status = GA_ERR_TRACE; walking = false; continue; }
-			colBase = GA_HDR(s, 0) + GA_HN(nodeOff + slot, 1);
-			colPtr = mem.col + (size_t)((colBase + off) * GA_COL_Q) * LANES;
-			GA_TRACE_PREFETCH_NODE();
-			if (!haveHere)
-			{
-				GaCol c = ga_col_load<LANES>(mem, colBase + off);
-				here = ga_col_value(c.VP, c.VN, c.sbs, row);
-				haveHere = true;
-			}
-			GA_TRACE_LOAD_MASKS();
-			reload = false;
-		}
-		if (!runOpen)
-		{
-			// still inside the trimmed tail, or a run was just closed: open one at the first untrimmed position
-			const uint32_t j = (uint32_t)s * 64u + (uint32_t)row;
-			if (j < st.trimRows) { runOpen = true; runNode = node; runLastOff = off; runLastRow = j; }
-			else skipped++;
-		}
-		// ---- fast step: inside the node, inside the slice, on a word-step column (nine steps in ten).  The three
-		// candidates of pickBacktracePredecessor reduce to three bit tests, taken in the reference's order: horizontal,
-		// diagonal, vertical.  Nothing here can fail or change node / slice / run.
-		if (runOpen && off > 0 && row > 0 && (flags & 1u) && nMoves < maxMoves)
-		{
-#ifdef GA_HOST_DEBUG
-			g_dbgFast++;
-#endif
-			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
-			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
-			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
-			// diagonal delta = 1 - D0 must equal the mismatch cost 1 - EQ
-			const uint32_t mv = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
-			here = here - 1 + (int32_t)((mv == GA_MOVE_D) ? d0 : 0u);
-			curWord |= mv << ((nMoves & 15) * 2);
-			nMoves++;
-			if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
-			if (mv != GA_MOVE_V)
-			{
-				off--;
-				colPtr -= GA_COL_Q * LANES;
-				GA_TRACE_LOAD_MASKS();
-			}
-			row -= (mv != GA_MOVE_H) ? 1 : 0;
-			continue;
-		}
-		// ---- link step: first column of a node whose only band in-neighbour is in this slice.  The column is a word step
-		// from that neighbour's last column, so the same three bit tests apply (in-neighbour horizontal, in-neighbour
-		// diagonal, vertical: GraphAligner.h:501-533 with one neighbour); the record holds where the neighbour's column is.
-		// here < maxv: an in-neighbour outside the band reads as maxv in the reference and must not be able to match.
-		if (runOpen && off == 0 && row > 0 && (flags & 2u) && here < maxv && nMoves < maxMoves && nPath < caps.maxPathNodes && nRuns < caps.maxRuns)
-		{
-#ifdef GA_HOST_DEBUG
-			g_dbgLink++;
-#endif
-			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
-			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
-			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
-			const uint32_t mv = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
-			here = here - 1 + (int32_t)((mv == GA_MOVE_D) ? d0 : 0u);
-			curWord |= mv << ((nMoves & 15) * 2);
-			nMoves++;
-			if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
-			if (mv != GA_MOVE_V)
-			{
-				// leaving the node: close the run on the position we stand on, cross into the neighbour
-				uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
-				r[0] = runNode; r[LANES] = 0; r[2 * LANES] = runLastOff; r[3 * LANES] = (uint32_t)s * 64u + (uint32_t)row; r[4 * LANES] = runLastRow;
-				nRuns++;
-				runOpen = false;
-				const uint4 q1 = colPtr[LANES];
-				node = q1.z;
-				off = flags >> 2;
-				colBase = q1.w - off;
-				colPtr = mem.col + (size_t)(q1.w * GA_COL_Q) * LANES;
-				mem.pathNodes[(size_t)nPath * LANES] = node;
-				nPath++;
-				GA_TRACE_PREFETCH_NODE();
-				GA_TRACE_LOAD_MASKS();
-			}
-			row -= (mv != GA_MOVE_H) ? 1 : 0;
-			continue;
-		}
-#ifdef GA_HOST_DEBUG
-		g_dbgOuter++;
-		if (!(off > 0 && row > 0 && (flags & 1u))) { g_dbgGeneral++; if (off == 0) g_dbgNodeStart++; else if (row == 0) g_dbgRow0++; else g_dbgMerged++; }
-#endif
-		uint32_t move = 4;
-		uint32_t nnode = node, noff = off;
-		int32_t nhere = 0;
-		uint32_t upCol = GA_NO_COL;   // where the walk lands in the slice above, when the stored index tells
-		if (off > 0 && row > 0 && (flags & 1u))
-		{
-			// the fast step's tests, outside an open run (trimmed tail) or at a capacity limit
-			const uint32_t hbit = (uint32_t)(mH >> row) & 1u;
-			const uint32_t d0 = (uint32_t)(mD0 >> row) & 1u;
-			const uint32_t eq = (uint32_t)(mEQ >> row) & 1u;
-			move = hbit ? (uint32_t)GA_MOVE_H : (d0 == eq ? (uint32_t)GA_MOVE_D : (uint32_t)GA_MOVE_V);
-			nhere = here - 1 + (int32_t)((move == GA_MOVE_D) ? d0 : 0u);
-			noff = off - (move != GA_MOVE_V ? 1u : 0u);
-		}
-		else
-		{
-			// general path (node starts, slice borders, merged columns): evaluate the candidates from the stored columns
-			const GaCol cur = ga_col_load<LANES>(mem, colBase + off);
-			const uint64_t w = g.nodeStart[node] + off;
-			const uint32_t base = ga_base(g, w);
-			const uint4 pq = mem.peq[(size_t)s * 2 + (base >> 1)];
-			const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
-			const int32_t match = (int32_t)((eqWord >> row) & 1);
-			const int32_t diagWant = here - 1 + match;
-			const bool firstRow = s == 0 && row == 0;
-			if (firstRow && node == st.startNode && (here == 0 || here == 1))
-			{
-				move = GA_MOVE_END;   // GraphAligner.h:500
-			}
-			else if (off > 0)
-			{
-				const GaCol left = ga_col_load<LANES>(mem, colBase + off - 1);
-				const int32_t hs = ga_col_value(left.VP, left.VN, left.sbs, row);
-				int32_t ds, us;
-				if (row > 0)
-				{
-					ds = hs - (int32_t)((left.VP >> row) & 1) + (int32_t)((left.VN >> row) & 1);
-					us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
-				}
-				else if (s == 0)
-				{
-					ds = us = node == st.startNode ? 0 : maxv;   // the initial slice: seed node all zero
-				}
-				else if (prevCol == GA_NO_COL)
-				{
-					ds = us = maxv;
-				}
-				else
-				{
-					// scoreEnd = row 63 of the slice above; a node's columns are contiguous there too
-					ds = (int32_t)mem.col[(size_t)((prevCol - 1) * GA_COL_Q + 1) * LANES].y;
-					us = (int32_t)mem.col[(size_t)(prevCol * GA_COL_Q + 1) * LANES].y;
-				}
-				if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; nhere = hs; }
-				else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; nhere = ds; if (row == 0 && s > 0 && prevCol != GA_NO_COL) upCol = prevCol - 1; }
-				else if (us == here - 1) { move = GA_MOVE_V; nhere = us; if (row == 0 && s > 0) upCol = prevCol; }
-			}
-			else
-			{
-				// first column of a node: in-neighbours in inNeighbors order, horizontal before diagonal (GraphAligner.h:501-533)
-				for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
-				{
-					uint32_t u = g.inAdj[e];
-					uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-					int32_t hs = ga_hist_value<LANES>(mem, st, s, u, uoff, row, maxv);
-					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
-					int32_t ds = row == 0 ? ga_hist_value<LANES>(mem, st, s - 1, u, uoff, 63, maxv) : ga_hist_value<LANES>(mem, st, s, u, uoff, row - 1, maxv);
-					if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
-				}
-				if (move == 4)
-				{
-					int32_t us;
-					if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
-					else if (s == 0) us = node == st.startNode ? 0 : maxv;
-					else if (prevCol == GA_NO_COL) us = maxv;
-					else us = (int32_t)mem.col[(size_t)(prevCol * GA_COL_Q + 1) * LANES].y;
-					if (us == here - 1) { move = GA_MOVE_V; nhere = us; if (row == 0 && s > 0) upCol = prevCol; }
-				}
-			}
-			// any step into row -1 ends the trace; that last position is popped again (GraphAligner.h:949-951)
-			if (firstRow && (move == GA_MOVE_D || move == GA_MOVE_V)) move = GA_MOVE_END;
-#ifdef GA_HOST_DEBUG
-			if (move == 4) fprintf(stderr, "trace fail at node %u off %u s %d row %d here %d\n", node, off, s, row, here);
-#endif
-			if (move == 4) { st.status = GA_ERR_TRACE; walking = false; continue; }   // reference: assert(false); std::abort()
-		}
-		if (nMoves >= maxMoves) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
-		curWord |= move << ((nMoves & 15) * 2);
-		nMoves++;
-		if ((nMoves & 15) == 0) { mem.moves[(size_t)((nMoves >> 4) - 1) * LANES] = curWord; curWord = 0; }
-		// leaving the node (or ending): close the open run; its first position is the one we stand on
-		if (runOpen && (move == GA_MOVE_END || nnode != node))
-		{
-			if (nRuns >= caps.maxRuns) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
-			uint32_t* r = mem.runs + (size_t)(nRuns * GA_RUN_WORDS) * LANES;
-			r[0] = runNode; r[LANES] = off; r[2 * LANES] = runLastOff; r[3 * LANES] = (uint32_t)s * 64u + (uint32_t)row; r[4 * LANES] = runLastRow;
-			nRuns++;
-			runOpen = false;
-		}
-		if (move == GA_MOVE_END) { walking = false; continue; }
-		here = nhere;
-		if (move != GA_MOVE_V)
-		{
-			if (off == 0)
-			{
-				if (nPath >= caps.maxPathNodes) { st.status = GA_ERR_TRACE_OVERFLOW; walking = false; continue; }
-				mem.pathNodes[(size_t)nPath * LANES] = nnode;
-				nPath++;
-				reload = true;
-			}
-			else if (row > 0 || move == GA_MOVE_H)
-			{
-				colPtr -= GA_COL_Q * LANES;
-				GA_TRACE_LOAD_MASKS();
-			}
-		}
-		if (move != GA_MOVE_H)
-		{
-			row--;
-			if (row < 0)
-			{
-				row = 63;
-				s--;
-				if (upCol != GA_NO_COL && !reload)
-				{
-					// same node, slice above: the stored index replaces the search
-					colBase = upCol - noff;
-					colPtr = mem.col + (size_t)(upCol * GA_COL_Q) * LANES;
-					off = noff;
-					GA_TRACE_PREFETCH_NODE();
-					GA_TRACE_LOAD_MASKS();
-				}
-				else reload = true;
-			}
-		}
-		node = nnode;
-		off = noff;
-	}
-#undef GA_TRACE_LOAD_MASKS
-#undef GA_TRACE_PREFETCH_NODE
-	if (doTrace && (nMoves & 15)) mem.moves[(size_t)(nMoves >> 4) * LANES] = curWord;
-	nMovesOut = nMoves;
-	nPathOut = nPath;
-	nRunsOut = nRuns;
-	// positions = the start cell plus one per move except the terminating one, minus the trimmed tail
-	nPosOut = nMoves > skipped ? nMoves - skipped : 0;
 }
 
 // Iterative Tarjan over the band of slice sl in the reference's visiting order (band order, outNeighbors order,
@@ -1975,7 +1629,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 		if (mem.indeg[(size_t)root * LANES] != 0) continue;
 		uint32_t depth = 0;
 		mem.unext[0] = root;
-		mem.ubkt[0] = g.outOff[GA_HN(nodeOff + root, 0)];
+		mem.ubkt[0] = g.outOff[GA_HNG(nodeOff + root, 0)];
 		counter++;
 		mem.indeg[(size_t)root * LANES] = counter | ONSTACK;
 		mem.order[(size_t)root * LANES] = counter;
@@ -1983,7 +1637,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 		while (true)
 		{
 			uint32_t slot = mem.unext[(size_t)depth * LANES];
-			uint32_t node = GA_HN(nodeOff + slot, 0);
+			uint32_t node = GA_HNG(nodeOff + slot, 0);
 			uint32_t e = mem.ubkt[(size_t)depth * LANES];
 			if (e < g.outOff[node + 1])
 			{
@@ -1995,7 +1649,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 				{
 					depth++;
 					mem.unext[(size_t)depth * LANES] = (uint32_t)nb;
-					mem.ubkt[(size_t)depth * LANES] = g.outOff[GA_HN(nodeOff + nb, 0)];
+					mem.ubkt[(size_t)depth * LANES] = g.outOff[GA_HNG(nodeOff + nb, 0)];
 					counter++;
 					mem.indeg[(size_t)nb * LANES] = counter | ONSTACK;
 					mem.order[(size_t)nb * LANES] = counter;
@@ -2020,7 +1674,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 					mem.indeg[(size_t)back * LANES] &= ~ONSTACK;
 					// within a component the reference evaluates via a LIFO work-list; the root is popped first,
 					// so the earliest-listed member is the best guess for "evaluated last"
-					if (found < 0 && (int32_t)GA_HN(nodeOff + back, 2) == minScore) found = (int)back;
+					if (found < 0 && (int32_t)GA_HNG(nodeOff + back, 2) == minScore) found = (int)back;
 					if (back == slot) break;
 				}
 				if (found >= 0) return found;
@@ -2050,10 +1704,10 @@ GA_DEV void ga_peq_words(const uint8_t* p, uint64_t& BA, uint64_t& BC, uint64_t&
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Whole stream: forward slices (lock step across the warp), end trimming, tie list, traceback.
+// Whole stream, forward part: slices (lock step across the warp), end trimming, tie list, trace start.
 // `active` = this lane holds a stream.  warpColTop is the warp-uniform bump pointer into the column slab.
 // ------------------------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, bool SMALL>
 GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaUmapSchedule& sch, const GaLaneMem& mem, bool active,
 	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* out)
 {
@@ -2092,8 +1746,9 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			GA_HN(0, 1) = 0;
 			GA_HN(0, 2) = 0;
 			GA_HN(0, 3) = len;
+			if (SMALL) { GA_HNG(0, 0) = st.startNode; GA_HNG(0, 1) = 0; GA_HNG(0, 2) = 0; GA_HNG(0, 3) = len; }
 			ga_hash_insert<LANES>(mem.hash[0], ga_hash_window(1, caps.hashSize), 1, st.startNode, 0);
-			for (uint32_t k = 0; k < len; k++) mem.tiny[0][(size_t)k * LANES] = 0;
+			for (uint32_t k = 0; k < len; k++) ga_tiny_st<LANES, SMALL>(mem.tiny[0], k, 0);
 			pNodes = 1;
 			st.histNodeTop = 1;
 		}
@@ -2125,7 +1780,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 				stampCur = ++gen;
 				// slices up to rampUntil run with rampBandwidth; rampUntil starts at 0, so slice 0 always does (GraphAligner.h:2612)
 				int bandwidth = (rampUntil >= s) ? rampBandwidth : initialBandwidth;
-				nc = ga_select_band<LANES>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], maskPrev, stampPrev, mem.hash[tc], maskCur, stampCur, gen, nodeOff, ncols);
+				nc = ga_select_band<LANES, SMALL>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], maskPrev, stampPrev, mem.hash[tc], maskCur, stampCur, gen, nodeOff, ncols);
 				if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 			}
 		}
@@ -2152,6 +1807,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.pSlabOff = s > 0 ? GA_HDR(s - 1, 0) : 0;
 		cx.tinyCur = mem.tiny[tc];
 		cx.tinyPrev = mem.tiny[tp];
+		cx.tinyRef = st.prevMin;
 		cx.hashCur = mem.hash[tc];
 		cx.hashPrev = mem.hash[tp];
 		cx.stampCur = stampCur;
@@ -2163,7 +1819,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		GA_HDR(s, 2) = nodeOff;
 		GA_HDR(s, 3) = (uint32_t)nc;
 		GaSliceResult res;
-		if (!ga_fill_slice<LANES>(g, caps, hmm, mem, st, cx, ncols, res)) { st.done = true; continue; }
+		if (!ga_fill_slice<LANES, SMALL>(g, caps, hmm, mem, st, cx, ncols, res)) { st.done = true; continue; }
 		// remember where a ramp would restart from (GraphAligner.h:2630-2634)
 		if (rampUntil == s - 1 || (rampUntil < s && res.currentlyCorrect && res.falseFromCorrect)) rampRedoIndex = s - 1;
 		if (!res.correctFromCorrect) { st.done = true; continue; }   // GraphAligner.h:2640-2647: stop, slice not recorded
@@ -2185,6 +1841,12 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			pNodeOff = GA_HDR(target, 2);
 			pNodes = GA_HDR(target, 3);
 			st.histNodeTop = nodeOff + (uint32_t)nc;   // abandoned entries are simply left behind
+			if (SMALL)
+			{
+				// the ring holds the target's list again; the next list must land right behind it in the ring
+				for (uint32_t i = 0; i < pNodes; i++) for (uint32_t f = 0; f < GA_HN_WORDS; f++) GA_HN(pNodeOff + i, f) = GA_HNG(pNodeOff + i, f);
+				st.histNodeTop += (pNodeOff + pNodes - st.histNodeTop) & (GA_HN_RING - 1u);
+			}
 			st.slicesPushed = (uint32_t)target + 1;
 			stampPrev = ++gen;
 			maskPrev = ga_hash_window(pNodes, caps.hashSize);
@@ -2197,7 +1859,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 					for (uint32_t k = 0; k < len; k++)
 					{
 						GaCol c = ga_col_load<LANES>(mem, tSlab + cs + k);
-						mem.tiny[tp][(size_t)(cs + k) * LANES] = ga_tiny_pack(c, false);
+						ga_tiny_st<LANES, SMALL>(mem.tiny[tp], cs + k, ga_tiny_pack(c, false));
 					}
 				}
 			}
@@ -2205,6 +1867,10 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			continue;
 		}
 		// the slice is kept
+		if (SMALL)
+		{
+			for (uint32_t i = 0; i < (uint32_t)nc; i++) for (uint32_t f = 0; f < GA_HN_WORDS; f++) GA_HNG(nodeOff + i, f) = GA_HN(nodeOff + i, f);
+		}
 		st.hmmC = res.hmmC;
 		st.hmmF = res.hmmF;
 		st.prevMin = res.minScore;
@@ -2271,10 +1937,10 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			uint32_t nTies = 0;
 			for (uint32_t slot = 0; slot < nNodes; slot++)
 			{
-				if ((int32_t)GA_HN(nodeOff + slot, 2) != minScore) continue;
-				uint32_t node = GA_HN(nodeOff + slot, 0);
-				uint32_t cs = GA_HN(nodeOff + slot, 1);
-				uint32_t len = GA_HN(nodeOff + slot, 3);
+				if ((int32_t)GA_HNG(nodeOff + slot, 2) != minScore) continue;
+				uint32_t node = GA_HNG(nodeOff + slot, 0);
+				uint32_t cs = GA_HNG(nodeOff + slot, 1);
+				uint32_t len = GA_HNG(nodeOff + slot, 3);
 				for (uint32_t k = 0; k < len; k++)
 				{
 					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
@@ -2290,9 +1956,9 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			if (endSlot < 0) out->status = GA_ERR_INTERNAL;
 			else
 			{
-				endNode = GA_HN(nodeOff + endSlot, 0);
-				uint32_t cs = GA_HN(nodeOff + endSlot, 1);
-				uint32_t len = GA_HN(nodeOff + endSlot, 3);
+				endNode = GA_HNG(nodeOff + endSlot, 0);
+				uint32_t cs = GA_HNG(nodeOff + endSlot, 1);
+				uint32_t len = GA_HNG(nodeOff + endSlot, 3);
 				if (recSlot != 0xffffffffu) endOff = GA_HDR(sl, 11);
 				else
 				{
@@ -2311,21 +1977,12 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			}
 		}
 	}
-	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
 	GA_TLAP(st, 7);
-	ga_traceback<LANES>(g, caps, mem, st, doTrace, n, endNode, endOff, nMoves, nPath, nRuns, nPos);
-	GA_TLAP(st, 6);
 #ifdef GA_PHASE_TIMING
 	if (active) for (int i = 0; i < 16; i++) out->phase[i] = st.phase[i];
 #endif
-	if (doTrace)
-	{
-		out->nMoves = nMoves;
-		out->nPathNodes = nPath;
-		out->nRuns = nRuns;
-		out->nPositions = nPos;
-		out->status = st.status;
-	}
+	// the traceback kernel (ga_trace.cuh) walks every stream that has a trace start
+	if (active) out->traceOff = doTrace ? 1 : 0;
 }
 
 #endif

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <vector>
 #include "ga_core.cuh"
+#include "ga_trace.cuh"
 #include "ga_device.h"
 
 namespace ga
@@ -46,7 +47,8 @@ struct ScratchPtrs
 	uint32_t* ubkt;     // [warp][ubktSize][S]
 	uint32_t* hdr;
 	uint32_t* histNode;
-	uint4* col;         // [warp slab][2][S]
+	uint4* colVV;       // column history pool: {VP, VN} [column][S]
+	uint32_t* colS;     //   row -1 score | flags [column][S]
 	uint32_t* moves;
 	uint32_t* pathNodes;
 	uint32_t* runs;
@@ -84,15 +86,74 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 #define GA_SMEM_HASH 32u
 #define GA_SMEM_HEAP 32u
 #define GA_SMEM_UBKT 32u
-#define GA_SMEM_WORDS64 (2 * GA_SMEM_HASH + GA_SMEM_HEAP + (7 * GA_SMEM_NODES + GA_SMEM_UBKT) / 2)
+#define GA_SMEM_COLS 256u
+#define GA_SMEM_WORDS64 (2 * GA_SMEM_HASH + GA_SMEM_HEAP + 2 * GA_SMEM_NODES + (8 * GA_SMEM_NODES + GA_SMEM_UBKT + GA_HN_RING * GA_HN_WORDS) / 2 + (2 * GA_SMEM_COLS) / 4)
+
+// Per-lane pointers of one stream (lane ml of `warp`, S streams per warp).  In small-band mode (host: caps.maxNodes =
+// GA_SMEM_NODES, hashSize = GA_SMEM_HASH, maxQueue = GA_SMEM_HEAP, maxCols = GA_SMEM_COLS) everything that is written and
+// read back within a slice or by the next one lives in the warp's shared-memory block `ws` (GA_SMEM_WORDS64 x S words):
+// a global store invalidates its L1 line, so in global memory every such read-after-write is an L2 round trip on the
+// stream's critical path.  eqTab = the warp's four match words, [base][lane].
+static __host__ __device__ inline void setupLaneMem(GaLaneMem& mem, const ScratchPtrs& sp, const WarpDesc& wd, const ga_caps& caps, size_t w, uint32_t ml, uint32_t S, bool small,
+	unsigned long long* ws, uint64_t* eqTab)
+{
+	mem.conf = sp.tiny + (w * 3 + 2) * caps.maxCols * S + ml;
+	mem.cmpOf = sp.nodeTmp + (w * 10 + 7) * caps.maxNodes * S + ml;
+	mem.emit = sp.nodeTmp + (w * 10 + 8) * caps.maxNodes * S + ml;
+	mem.wl = sp.nodeTmp + (w * 10 + 9) * caps.maxNodes * S + ml;
+	mem.hdr = sp.hdr + wd.hdrBase + ml;
+	mem.histNode = sp.histNode + wd.hnBase + ml;
+	mem.colVV = sp.colVV + ml;
+	mem.colS = sp.colS + ml;
+	mem.colPoolTop = sp.colPoolTop;
+	mem.eqTab = eqTab + ml;
+	mem.hnRing = nullptr;
+	mem.lastVV = nullptr;
+	mem.lastS = nullptr;
+	if (!small)
+	{
+		mem.tiny[0] = sp.tiny + (w * 3 + 0) * caps.maxCols * S + ml;
+		mem.tiny[1] = sp.tiny + (w * 3 + 1) * caps.maxCols * S + ml;
+		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S + ml;
+		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S + ml;
+		mem.heap = sp.heap + w * caps.maxQueue * S + ml;
+		mem.indeg = sp.nodeTmp + (w * 10 + 0) * caps.maxNodes * S + ml;
+		mem.order = sp.nodeTmp + (w * 10 + 1) * caps.maxNodes * S + ml;
+		mem.unext = sp.nodeTmp + (w * 10 + 2) * caps.maxNodes * S + ml;
+		mem.uorder = sp.nodeTmp + (w * 10 + 3) * caps.maxNodes * S + ml;
+		mem.nWlo = sp.nodeTmp + (w * 10 + 4) * caps.maxNodes * S + ml;
+		mem.nWhi = sp.nodeTmp + (w * 10 + 5) * caps.maxNodes * S + ml;
+		mem.nPcs = sp.nodeTmp + (w * 10 + 6) * caps.maxNodes * S + ml;
+		mem.ubkt = sp.ubkt + w * sp.ubktSize * S + ml;
+		return;
+	}
+	mem.hash[0] = (uint64_t*)ws + ml;
+	mem.hash[1] = (uint64_t*)ws + GA_SMEM_HASH * S + ml;
+	mem.heap = (uint64_t*)ws + 2 * GA_SMEM_HASH * S + ml;
+	mem.lastVV = (uint64_t*)ws + (2 * GA_SMEM_HASH + GA_SMEM_HEAP) * S + ml;
+	uint32_t* base32 = (uint32_t*)(ws + (2 * GA_SMEM_HASH + GA_SMEM_HEAP + 2 * GA_SMEM_NODES) * S);
+	mem.indeg = base32 + 0 * GA_SMEM_NODES * S + ml;
+	mem.order = base32 + 1 * GA_SMEM_NODES * S + ml;
+	mem.unext = base32 + 2 * GA_SMEM_NODES * S + ml;
+	mem.uorder = base32 + 3 * GA_SMEM_NODES * S + ml;
+	mem.nWlo = base32 + 4 * GA_SMEM_NODES * S + ml;
+	mem.nWhi = base32 + 5 * GA_SMEM_NODES * S + ml;
+	mem.nPcs = base32 + 6 * GA_SMEM_NODES * S + ml;
+	mem.lastS = base32 + 7 * GA_SMEM_NODES * S + ml;
+	mem.ubkt = base32 + 8 * GA_SMEM_NODES * S + ml;
+	mem.hnRing = base32 + (8 * GA_SMEM_NODES + GA_SMEM_UBKT) * S + ml;
+	uint16_t* base16 = (uint16_t*)(base32 + (8 * GA_SMEM_NODES + GA_SMEM_UBKT + GA_HN_RING * GA_HN_WORDS) * S);
+	mem.tiny[0] = base16 + ml;
+	mem.tiny[1] = base16 + GA_SMEM_COLS * S + ml;
+}
 
 // S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
 // less divergence; big batches run with S = 32 for full lane utilisation.
 #ifndef GA_HOSTSIM
-template <int S>
-__global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
-	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, uint32_t smemScratch,
-	ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
+template <int S, bool SMALL>
+__global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
+	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
+	ga_stream_out* __restrict__ outs)
 {
 	extern __shared__ __align__(16) unsigned long long gaShared[];
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,78 +168,89 @@ __global__ void __launch_bounds__(64, 10) ga_align_kernel(ga_graph_view g, ga_ca
 	wc.maxSlices = wd.maxSlices;
 	wc.histNodes = wd.histNodes;
 	wc.warpCols = sp.colPoolCap;
-	wc.maxMoves = wd.maxMoves;
-	wc.maxPathNodes = wd.maxPathNodes;
-	wc.maxRuns = wd.maxRuns;
 	GaLaneMem mem;
+	// shared memory: four match words per stream [warp in block][base][lane], then (small-band mode) the warps' scratch blocks
+	uint64_t* eqTab = (uint64_t*)gaShared + (size_t)(threadIdx.x >> 5) * (4 * S);
+	unsigned long long* ws = gaShared + (size_t)(blockDim.x >> 5) * (4 * S) + (size_t)(threadIdx.x >> 5) * (GA_SMEM_WORDS64 * S);
+	if (SMALL)
 	{
-		size_t w = warp;
-		mem.tiny[0] = sp.tiny + (w * 3 + 0) * caps.maxCols * S + ml;
-		mem.tiny[1] = sp.tiny + (w * 3 + 1) * caps.maxCols * S + ml;
-		mem.conf = sp.tiny + (w * 3 + 2) * caps.maxCols * S + ml;
-		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S + ml;
-		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S + ml;
-		mem.heap = sp.heap + w * caps.maxQueue * S + ml;
-		mem.indeg = sp.nodeTmp + (w * 10 + 0) * caps.maxNodes * S + ml;
-		mem.order = sp.nodeTmp + (w * 10 + 1) * caps.maxNodes * S + ml;
-		mem.unext = sp.nodeTmp + (w * 10 + 2) * caps.maxNodes * S + ml;
-		mem.uorder = sp.nodeTmp + (w * 10 + 3) * caps.maxNodes * S + ml;
-		mem.nWlo = sp.nodeTmp + (w * 10 + 4) * caps.maxNodes * S + ml;
-		mem.nWhi = sp.nodeTmp + (w * 10 + 5) * caps.maxNodes * S + ml;
-		mem.nPcs = sp.nodeTmp + (w * 10 + 6) * caps.maxNodes * S + ml;
-		mem.cmpOf = sp.nodeTmp + (w * 10 + 7) * caps.maxNodes * S + ml;
-		mem.emit = sp.nodeTmp + (w * 10 + 8) * caps.maxNodes * S + ml;
-		mem.wl = sp.nodeTmp + (w * 10 + 9) * caps.maxNodes * S + ml;
-		mem.ubkt = sp.ubkt + w * sp.ubktSize * S + ml;
-		mem.hdr = sp.hdr + wd.hdrBase + ml;
-		mem.histNode = sp.histNode + wd.hnBase + ml;
-		mem.col = sp.col + ml;
-		mem.colPoolTop = sp.colPoolTop;
-		mem.moves = sp.moves + wd.movesBase + ml;
-		mem.pathNodes = sp.pathNodes + wd.pathBase + ml;
-		mem.runs = sp.runs + wd.runsBase + ml;
-		mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
-		// every launch: four match words per stream, [warp in block][base][lane]
-		mem.eqTab = (uint64_t*)gaShared + (size_t)(threadIdx.x >> 5) * (4 * S) + ml;
-		if (smemScratch)
+		for (uint32_t i = lane; i < (2 * GA_SMEM_HASH) * S; i += 32) ws[i] = 0;   // the stamped tables start empty
+		__syncwarp();
+	}
+	setupLaneMem(mem, sp, wd, caps, warp, ml, S, SMALL, ws, eqTab);
+	mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
+	ga_stream_out* out = active ? outs + stream : nullptr;
+	ga_run_stream<S, SMALL>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
+}
+#endif
+
+// Pointers of one stream's trace inputs and temporary outputs (the forward launch's layout: [..][S] interleaved per warp)
+static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, const WarpDesc& wd, uint32_t stream, uint32_t S)
+{
+	const uint32_t fl = stream % S;
+	GaTraceMem tm;
+	tm.S = S;
+	tm.hdr = sp.hdr + wd.hdrBase + fl;
+	tm.histNode = sp.histNode + wd.hnBase + fl;
+	tm.colVV = sp.colVV + fl;
+	tm.colS = sp.colS + fl;
+	tm.peq = sp.peq + sp.peqOff[stream];
+	tm.moves = sp.moves + wd.movesBase + fl;
+	tm.pathNodes = sp.pathNodes + wd.pathBase + fl;
+	tm.runs = sp.runs + wd.runsBase + fl;
+	tm.maxMoves = wd.maxMoves;
+	tm.maxPathNodes = wd.maxPathNodes;
+	tm.maxRuns = wd.maxRuns;
+	return tm;
+}
+
+#ifndef GA_HOSTSIM
+// Traceback: G lanes per stream (ga_trace.cuh), 32 / G streams per warp.  Runs after the forward kernel on the same stream.
+#define GA_TRACE_THREADS 128
+template <int G>
+__global__ void __launch_bounds__(GA_TRACE_THREADS) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
+	uint32_t nStreams, uint32_t S, ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
+{
+	__shared__ GaTraceWindow<G> wins[GA_TRACE_THREADS / G];
+	const uint32_t group = threadIdx.x / G;
+	const uint32_t gl = threadIdx.x & (G - 1);
+	const uint32_t stream = blockIdx.x * (GA_TRACE_THREADS / G) + group;
+	if (stream >= nStreams) return;
+	const uint32_t groupMask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31u) / G * G));
+	ga_stream_out* out = outs + stream;
+	const bool doTrace = out->traceOff != 0 && out->status == GA_OK;
+	__syncwarp(groupMask);   // everybody has read traceOff before the leader overwrites it
+	GaTraceWindow<G>& win = wins[group];
+	const WarpDesc wd = warpDescs[stream / S];
+	const GaTraceMem tm = traceMemOf(sp, wd, stream, S);
+	int32_t status = GA_OK;
+	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+	if (doTrace) ga_trace_stream<G>(g, tm, win, groupMask, streams[stream], out->nSlices, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
+	// compact this stream's trace record into the arena
+	const uint32_t moveWords = (nMoves + 15) / 16;
+	const uint32_t runWords = nRuns * GA_RUN_WORDS;
+	const uint32_t words = moveWords + nPath + runWords;
+	__syncwarp(groupMask);
+	if (gl == 0)
+	{
+		const unsigned long long off = atomicAdd(arenaTop, (unsigned long long)words);
+		win.peq[0] = off;
+		out->traceOff = off;
+		if (doTrace)
 		{
-			// Small-band mode (host: caps.maxNodes = GA_SMEM_NODES, hashSize = GA_SMEM_HASH, maxQueue = GA_SMEM_HEAP): the per-slice
-			// scratch that is written and read back within a slice lives in shared memory.  A global store invalidates its L1
-			// line, so in global memory every such read-after-write is an L2 round trip on the stream's critical path.
-			unsigned long long* base64 = gaShared + (size_t)(blockDim.x >> 5) * (4 * S) + (size_t)(threadIdx.x >> 5) * (GA_SMEM_WORDS64 * S);
-			for (uint32_t i = lane; i < (2 * GA_SMEM_HASH) * S; i += 32) base64[i] = 0;   // the stamped tables start empty
-			__syncwarp();
-			mem.hash[0] = (uint64_t*)base64 + ml;
-			mem.hash[1] = (uint64_t*)base64 + GA_SMEM_HASH * S + ml;
-			mem.heap = (uint64_t*)base64 + 2 * GA_SMEM_HASH * S + ml;
-			uint32_t* base32 = (uint32_t*)(base64 + (2 * GA_SMEM_HASH + GA_SMEM_HEAP) * S);
-			mem.indeg = base32 + 0 * GA_SMEM_NODES * S + ml;
-			mem.order = base32 + 1 * GA_SMEM_NODES * S + ml;
-			mem.unext = base32 + 2 * GA_SMEM_NODES * S + ml;
-			mem.uorder = base32 + 3 * GA_SMEM_NODES * S + ml;
-			mem.nWlo = base32 + 4 * GA_SMEM_NODES * S + ml;
-			mem.nWhi = base32 + 5 * GA_SMEM_NODES * S + ml;
-			mem.nPcs = base32 + 6 * GA_SMEM_NODES * S + ml;
-			mem.ubkt = base32 + 7 * GA_SMEM_NODES * S + ml;
+			out->nMoves = nMoves;
+			out->nPathNodes = nPath;
+			out->nRuns = nRuns;
+			out->nPositions = nPos;
+			out->status = off + words > arenaCap && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
 		}
 	}
-	ga_stream_out* out = active ? outs + stream : nullptr;
-	ga_run_stream<S>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
-	if (!active) return;
-	// compact this stream's trace record into the arena
-	uint32_t moveWords = (out->nMoves + 15) / 16;
-	uint32_t runWords = out->nRuns * GA_RUN_WORDS;
-	uint32_t words = moveWords + out->nPathNodes + runWords;
-	unsigned long long off = atomicAdd(arenaTop, (unsigned long long)words);
-	out->traceOff = off;
-	if (off + words > arenaCap)
-	{
-		if (out->status == GA_OK) out->status = GA_ERR_TRACE_OVERFLOW;
-		return;
-	}
-	for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * S];
-	for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * S];
-	for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + out->nPathNodes + i] = mem.runs[(size_t)i * S];
+	__syncwarp(groupMask);
+	const unsigned long long off = win.peq[0];
+	if (off + words > arenaCap) return;
+	for (uint32_t i = gl; i < moveWords; i += G) arena[off + i] = tm.moves[(size_t)i * S];
+	for (uint32_t i = gl; i < nPath; i += G) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
+	for (uint32_t i = gl; i < runWords; i += G) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
 }
 
 // INT32 roofline probe: 8 independent dependency chains per thread of alternating LOP3 / IADD3, no memory traffic.
@@ -222,10 +294,11 @@ static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, con
 }
 
 static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* warpDescs, const ga_stream_in* streams, const uint8_t* parts, uint32_t nStreams,
-	int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* outs, uint32_t* arena, unsigned long long* arenaTop, unsigned long long arenaCap)
+	int initialBandwidth, int rampBandwidth, uint32_t debugFlags, bool small, ga_stream_out* outs, uint32_t* arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
 	const int S = 1;
 	std::vector<uint64_t> eqTab(4);
+	std::vector<unsigned long long> ws(GA_SMEM_WORDS64);
 	for (uint32_t stream = 0; stream < nStreams; stream++)
 	{
 		const size_t w = stream;
@@ -234,52 +307,43 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		wc.maxSlices = wd.maxSlices;
 		wc.histNodes = wd.histNodes;
 		wc.warpCols = sp.colPoolCap;
-		wc.maxMoves = wd.maxMoves;
-		wc.maxPathNodes = wd.maxPathNodes;
-		wc.maxRuns = wd.maxRuns;
 		GaLaneMem mem;
-		mem.tiny[0] = sp.tiny + (w * 3 + 0) * caps.maxCols * S;
-		mem.tiny[1] = sp.tiny + (w * 3 + 1) * caps.maxCols * S;
-		mem.conf = sp.tiny + (w * 3 + 2) * caps.maxCols * S;
-		mem.hash[0] = sp.hash + (w * 2 + 0) * caps.hashSize * S;
-		mem.hash[1] = sp.hash + (w * 2 + 1) * caps.hashSize * S;
-		mem.heap = sp.heap + w * caps.maxQueue * S;
-		mem.indeg = sp.nodeTmp + (w * 10 + 0) * caps.maxNodes * S;
-		mem.order = sp.nodeTmp + (w * 10 + 1) * caps.maxNodes * S;
-		mem.unext = sp.nodeTmp + (w * 10 + 2) * caps.maxNodes * S;
-		mem.uorder = sp.nodeTmp + (w * 10 + 3) * caps.maxNodes * S;
-		mem.nWlo = sp.nodeTmp + (w * 10 + 4) * caps.maxNodes * S;
-		mem.nWhi = sp.nodeTmp + (w * 10 + 5) * caps.maxNodes * S;
-		mem.nPcs = sp.nodeTmp + (w * 10 + 6) * caps.maxNodes * S;
-		mem.cmpOf = sp.nodeTmp + (w * 10 + 7) * caps.maxNodes * S;
-		mem.emit = sp.nodeTmp + (w * 10 + 8) * caps.maxNodes * S;
-		mem.wl = sp.nodeTmp + (w * 10 + 9) * caps.maxNodes * S;
-		mem.ubkt = sp.ubkt + w * sp.ubktSize * S;
-		mem.hdr = sp.hdr + wd.hdrBase;
-		mem.histNode = sp.histNode + wd.hnBase;
-		mem.col = sp.col;
-		mem.colPoolTop = sp.colPoolTop;
-		mem.moves = sp.moves + wd.movesBase;
-		mem.pathNodes = sp.pathNodes + wd.pathBase;
-		mem.runs = sp.runs + wd.runsBase;
+		std::fill(ws.begin(), ws.end(), 0ull);
+		setupLaneMem(mem, sp, wd, caps, w, 0, S, small, ws.data(), eqTab.data());
 		mem.peq = sp.peq + sp.peqOff[stream];
-		mem.eqTab = eqTab.data();
+		if (small) ga_run_stream<1, true>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+		else ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+	}
+	// the traceback "launch": the same group code with its lanes as a loop
+	const int G = 8;
+	for (uint32_t stream = 0; stream < nStreams; stream++)
+	{
 		ga_stream_out* out = outs + stream;
-		ga_run_stream<1>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, out);
-		uint32_t moveWords = (out->nMoves + 15) / 16;
-		uint32_t runWords = out->nRuns * GA_RUN_WORDS;
-		uint32_t words = moveWords + out->nPathNodes + runWords;
-		unsigned long long off = *arenaTop;
+		const bool doTrace = out->traceOff != 0 && out->status == GA_OK;
+		const WarpDesc wd = warpDescs[stream / S];
+		const GaTraceMem tm = traceMemOf(sp, wd, stream, S);
+		GaTraceWindow<G> win;
+		int32_t status = GA_OK;
+		uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
+		if (doTrace) ga_trace_stream<G>(g, tm, win, 0, streams[stream], out->nSlices, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
+		const uint32_t moveWords = (nMoves + 15) / 16;
+		const uint32_t runWords = nRuns * GA_RUN_WORDS;
+		const uint32_t words = moveWords + nPath + runWords;
+		const unsigned long long off = *arenaTop;
 		*arenaTop += words;
 		out->traceOff = off;
-		if (off + words > arenaCap)
+		if (doTrace)
 		{
-			if (out->status == GA_OK) out->status = GA_ERR_TRACE_OVERFLOW;
-			continue;
+			out->nMoves = nMoves;
+			out->nPathNodes = nPath;
+			out->nRuns = nRuns;
+			out->nPositions = nPos;
+			out->status = off + words > arenaCap && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
 		}
-		for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = mem.moves[(size_t)i * S];
-		for (uint32_t i = 0; i < out->nPathNodes; i++) arena[off + moveWords + i] = mem.pathNodes[(size_t)i * S];
-		for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + out->nPathNodes + i] = mem.runs[(size_t)i * S];
+		if (off + words > arenaCap) continue;
+		for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = tm.moves[(size_t)i * S];
+		for (uint32_t i = 0; i < nPath; i++) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
+		for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
 	}
 }
 #endif
@@ -323,11 +387,12 @@ struct DeviceCtx
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bCol, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bColVV, bColS, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
+	int traceGroup = 8;        // GA_TRACE_GROUP env: lanes per stream in the traceback kernel (4, 8, 16, 32)
 	int smCount = 148;
 	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
@@ -440,13 +505,14 @@ DeviceCtx* CreateDevice(int device)
 	ctx->sched = probeUmapSchedule(70000);
 	if (const char* f = getenv("GA_DEBUG_FLAGS")) ctx->debugFlags = (uint32_t)atoi(f);
 	if (const char* f = getenv("GA_STREAMS_PER_WARP")) ctx->forceS = atoi(f);
+	if (const char* f = getenv("GA_TRACE_GROUP")) ctx->traceGroup = atoi(f);
 	{
 		cudaDeviceProp prop;
 		GA_CUDA(cudaGetDeviceProperties(&prop, device));
 		ctx->smCount = prop.multiProcessorCount;
 		int blocks = 0;
 #ifndef GA_HOSTSIM
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, ga_align_kernel<4>, 64, 0) == cudaSuccess && blocks > 0) ctx->warpsPerSm = blocks * 2;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, ga_forward_kernel<4, false>, 64, 0) == cudaSuccess && blocks > 0) ctx->warpsPerSm = blocks * 2;
 #else
 		(void)blocks;
 		ctx->forceS = 1;   // the emulation runs one stream per "warp"
@@ -461,7 +527,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
 	for (Buffer* b : all) b->release();
 	ctx->pinParts.release();
 	ctx->pinOuts.release();
@@ -622,12 +688,13 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		// small-band mode: few streams per warp (shared memory per SM) and a graph whose bands hold a handful of nodes; a stream
 		// that outgrows the fixed capacities reports an overflow and is re-run with the general layout (capScale > 1)
 		const double bandNodes = 2.0 * (std::max(sb->b, sb->B) + 64) / std::max(1.0, ctx->avgNodeLen) + 2;
-		sb->smemScratch = scale == 1 && sb->S <= 4 && bandNodes <= 10 && getenv("GA_NO_SMEM") == nullptr;
+		sb->smemScratch = scale == 1 && bandNodes <= 10 && getenv("GA_NO_SMEM") == nullptr;
 		if (sb->smemScratch)
 		{
 			caps.maxNodes = GA_SMEM_NODES;
 			caps.hashSize = GA_SMEM_HASH;
 			caps.maxQueue = GA_SMEM_HEAP;
+			caps.maxCols = GA_SMEM_COLS;
 		}
 	}
 	const size_t nWarps = (n + S - 1) / S;
@@ -694,7 +761,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	colTop += caps.maxCols;
 	if (colTop >= 0xffffffffull) throw std::runtime_error("batch too large for one launch: column-history pool would exceed 2^32 columns; split the batch");
 	sb->colPoolCap = colTop;
-	ctx->bCol.ensure(colTop * GA_COL_Q * S * sizeof(uint4));
+	ctx->bColVV.ensure(colTop * S * sizeof(uint4));
+	ctx->bColS.ensure(colTop * S * sizeof(uint32_t));
 	ctx->bColTop.ensure(sizeof(unsigned long long));
 	ctx->bPeq.ensure(std::max<uint64_t>(peqTop, 1) * sizeof(uint4));
 	ctx->bPeqOff.ensure(n * sizeof(uint64_t));
@@ -711,7 +779,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.ubktSize = ubktSize;
 	sb->sp.hdr = (uint32_t*)ctx->bHdr.ptr;
 	sb->sp.histNode = (uint32_t*)ctx->bHn.ptr;
-	sb->sp.col = (uint4*)ctx->bCol.ptr;
+	sb->sp.colVV = (uint4*)ctx->bColVV.ptr;
+	sb->sp.colS = (uint32_t*)ctx->bColS.ptr;
 	sb->sp.colPoolTop = (unsigned long long*)ctx->bColTop.ptr;
 	sb->sp.colPoolCap = colTop;
 	sb->sp.peq = (const uint4*)ctx->bPeq.ptr;
@@ -739,12 +808,32 @@ template <int S>
 static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
-	const int threads = 64;
+	// small-band mode: one warp per block, so that the shared-memory blocks of the warps pack an SM without remainder
+	const int threads = sb->smemScratch ? 32 : 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
 	const size_t smemBytes = (size_t)(threads / 32) * (4 + (sb->smemScratch ? GA_SMEM_WORDS64 : 0)) * S * sizeof(unsigned long long);
-	ga_align_kernel<S><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, sb->smemScratch ? 1u : 0u, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr,
-		(unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+	if (sb->smemScratch)
+	{
+		static bool attr = false;
+		if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_forward_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+		ga_forward_kernel<S, true><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+			(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+	}
+	else
+	{
+		ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+			(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+	}
+}
+
+template <int G>
+static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
+{
+	const size_t n = sb->sorted.size();
+	const unsigned perBlock = GA_TRACE_THREADS / G;
+	const unsigned blocks = (unsigned)((n + perBlock - 1) / perBlock);
+	ga_trace_kernel<G><<<blocks, GA_TRACE_THREADS, 0, ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n, (uint32_t)sb->S,
+		(ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 #endif
 
@@ -760,12 +849,17 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 #ifdef GA_HOSTSIM
 	hostsim_peq((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
 	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
-		(ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+		sb->smemScratch, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 #else
+	// GA_KERNEL_TIMING: device time of each kernel of the launch sequence on stderr (tuning; serialises the stream)
+	static const bool kernelTiming = getenv("GA_KERNEL_TIMING") != nullptr;
+	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	if (kernelTiming) { for (auto& e : ev) GA_CUDA(cudaEventCreate(&e)); GA_CUDA(cudaEventRecord(ev[0], ctx->stream)); }
 	{
 		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
 		GA_CUDA(cudaGetLastError());
 	}
+	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[1], ctx->stream));
 	switch (sb->S)
 	{
 		case 32: launchAlign<32>(ctx, sb); break;
@@ -776,10 +870,30 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		case 1: launchAlign<1>(ctx, sb); break;
 		default: throw std::logic_error("unsupported streams-per-warp");
 	}
+	GA_CUDA(cudaGetLastError());
+	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[2], ctx->stream));
+	switch (ctx->traceGroup)
+	{
+		case 32: launchTrace<32>(ctx, sb); break;
+		case 16: launchTrace<16>(ctx, sb); break;
+		case 4: launchTrace<4>(ctx, sb); break;
+		default: launchTrace<8>(ctx, sb); break;
+	}
+	if (kernelTiming)
+	{
+		GA_CUDA(cudaEventRecord(ev[3], ctx->stream));
+		GA_CUDA(cudaEventSynchronize(ev[3]));
+		float a = 0, b = 0, c = 0;
+		cudaEventElapsedTime(&a, ev[0], ev[1]);
+		cudaEventElapsedTime(&b, ev[1], ev[2]);
+		cudaEventElapsedTime(&c, ev[2], ev[3]);
+		fprintf(stderr, "[ga kernels] streams %zu S %d G %d: peq %.3f ms, forward %.3f ms, trace %.3f ms\n", n, sb->S, ctx->traceGroup, a, b, c);
+		for (auto& e : ev) cudaEventDestroy(e);
+	}
 #endif
 	GA_CUDA(cudaGetLastError());
-	sb->launches += 2;
-	return 2;
+	sb->launches += 3;
+	return 3;
 }
 
 static bool isOverflow(int32_t status)
@@ -959,7 +1073,7 @@ size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
 	const double avgNodeLen = std::max(1.0, ctx->avgNodeLen);
 	const double colsGuess = (2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32) * initialCapScale(ctx, bandwidth, 0);
 	const double slices = (double)((partLen + 63) / 64);
-	return (size_t)(slices * colsGuess * GA_COL_Q * sizeof(uint4) * 1.15 + 96.0 * 1024 + partLen * 12.0);
+	return (size_t)(slices * colsGuess * (sizeof(uint4) + sizeof(uint32_t)) * 1.15 + 96.0 * 1024 + partLen * 12.0);
 }
 
 size_t FreeDeviceBytes(DeviceCtx* ctx)
@@ -972,7 +1086,7 @@ size_t FreeDeviceBytes(DeviceCtx* ctx)
 	{
 	size_t totalB = 0;
 	GA_CUDA(cudaMemGetInfo(&freeB, &totalB));
-	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bCol, &ctx->bPeq,
+	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq,
 		&ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena };
 	for (Buffer* b : all) freeB += b->cap;
 	ctx->budgetBytes = freeB;
