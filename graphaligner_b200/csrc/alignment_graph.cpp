@@ -200,5 +200,7 @@ ga_graph_view AlignmentGraph::View() const
 	v.inAdj = inAdj.data();
 	v.outOff = outOff.data();
 	v.outAdj = outAdj.data();
+	v.nodeRec = nullptr;
+	v.seqChunks = nullptr;
 	return v;
 }

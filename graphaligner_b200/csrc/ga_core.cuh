@@ -32,6 +32,7 @@
 #define GA_CTZ(x) (__ffsll((long long)(x)) - 1)
 #define GA_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
 #define GA_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#define GA_SYNCWARP() __syncwarp()
 // one allocation per warp from a global bump pointer; every lane gets the same offset
 #define GA_POOL_ALLOC(ptr, n) __shfl_sync(0xffffffffu, ((threadIdx.x & 31) == 0) ? atomicAdd((ptr), (unsigned long long)(n)) : 0ull, 0)
 #else
@@ -41,6 +42,7 @@
 #define GA_CTZ(x) __builtin_ctzll(x)
 #define GA_WARP_MAX(x) (x)
 #define GA_WARP_ANY(x) (x)
+#define GA_SYNCWARP()
 #define GA_POOL_ALLOC(ptr, n) ((*(ptr) += (n)) - (n))
 #endif
 
@@ -269,23 +271,29 @@ GA_DEV void ga_vertical_merge(GaCol& c, int32_t top)
 
 // exact element-wise minimum of two columns (values of WordSlice::mergeTwoSlices, WordSlice.h:361-421).
 // A 1-Lipschitz column has a unique (sbs,VP,VN) form, so any exact minimum is bit-identical to the reference's.
+// The difference d = A - B only changes at rows where the two columns' vertical deltas differ; everywhere else the
+// minimum's delta is the common delta whichever column is lower.  So the result starts as A with those rows cleared, and
+// only the differing rows (a handful for the columns that meet at a node start) are walked, d carried along.
 GA_DEV_NOINLINE GaCol ga_merge_cols(const GaCol& A, const GaCol& B)
 {
 	GaCol r;
 	r.sbs = A.sbs < B.sbs ? A.sbs : B.sbs;
 	r.scoreEnd = A.scoreEnd < B.scoreEnd ? A.scoreEnd : B.scoreEnd;
 	int32_t d = A.sbs - B.sbs;
-	uint64_t VP = 0, VN = 0;
-	for (int row = 0; row < 64; row++)
+	uint64_t diff = (A.VP ^ B.VP) | (A.VN ^ B.VN);
+	uint64_t VP = A.VP & ~diff, VN = A.VN & ~diff;
+	while (diff)
 	{
-		int32_t da = (int32_t)((A.VP >> row) & 1) - (int32_t)((A.VN >> row) & 1);
-		int32_t db = (int32_t)((B.VP >> row) & 1) - (int32_t)((B.VN >> row) & 1);
-		int32_t dn = d + da - db;
+		const uint64_t bit = diff & (0 - diff);
+		diff ^= bit;
+		const int32_t da = ((A.VP & bit) ? 1 : 0) - ((A.VN & bit) ? 1 : 0);
+		const int32_t db = ((B.VP & bit) ? 1 : 0) - ((B.VN & bit) ? 1 : 0);
+		const int32_t dn = d + da - db;
 		int32_t delta;
 		if (d <= 0) delta = (dn <= 0) ? da : da - dn;
 		else delta = (dn > 0) ? db : db + dn;
-		if (delta > 0) VP |= (uint64_t)1 << row;
-		else if (delta < 0) VN |= (uint64_t)1 << row;
+		if (delta > 0) VP |= bit;
+		else if (delta < 0) VN |= bit;
 		d = dn;
 	}
 	r.VP = VP;
@@ -1688,6 +1696,109 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 	return -1;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// End of a stream's forward pass: end trimming (removeWronglyAlignedEnd), the tied minimum cells of the last retained
+// slice and the cell the traceback starts from.  Reads the slice headers, node lists and columns from the history in
+// global memory; scratch: indeg, order, uorder, unext, ubkt (one entry per band node of a slice).
+// ------------------------------------------------------------------------------------------------------------
+template <int LANES>
+GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool active, uint32_t slicesRun, uint32_t debugFlags, ga_stream_out* out)
+{
+	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------
+	bool doTrace = false;
+	int n = 0;
+	uint32_t endNode = 0, endOff = 0;
+	if (active)
+	{
+		out->nSlicesRun = (int32_t)slicesRun;
+		out->wordColumns = st.wordColumns;
+		out->cyclicSlices = st.cyclicSlices;
+		out->nMoves = 0;
+		out->nPathNodes = 0;
+		out->nRuns = 0;
+		out->nPositions = 0;
+		out->nTies = 0;
+		out->nSlices = 0;
+		out->score = 0;
+		out->endNode = 0;
+		out->endOff = 0;
+		out->status = st.status;
+	}
+	if (active && st.status == GA_OK)
+	{
+		// removeWronglyAlignedEnd (GraphAligner.h:2554-2569)
+		n = (int)st.slicesPushed;
+		if (n > 0)
+		{
+			bool currentlyCorrect = (GA_HDR(n - 1, 5) & 1u) != 0;
+			while (!currentlyCorrect)
+			{
+				n--;
+				if (n == 0) break;
+				currentlyCorrect = (GA_HDR(n - 1, 5) & 2u) != 0;   // FalseFromCorrect of the new last slice, as the reference reads it
+			}
+		}
+		out->nSlices = n;
+		if (n == 0) out->status = GA_EMPTY;
+		else
+		{
+			// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
+			// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
+			// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
+			const int sl = n - 1;
+			const int32_t minScore = (int32_t)GA_HDR(sl, 4);
+			const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
+			uint32_t nTies = 0;
+			for (uint32_t slot = 0; slot < nNodes; slot++)
+			{
+				if ((int32_t)GA_HNG(nodeOff + slot, 2) != minScore) continue;
+				uint32_t node = GA_HNG(nodeOff + slot, 0);
+				uint32_t cs = GA_HNG(nodeOff + slot, 1);
+				uint32_t len = GA_HNG(nodeOff + slot, 3);
+				for (uint32_t k = 0; k < len; k++)
+				{
+					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+					int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
+					if (v != minScore) continue;
+					if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
+					nTies++;
+				}
+			}
+			// a slice with a cyclic component recorded its last minimum cell while replaying the reference's schedule
+			const uint32_t recSlot = GA_HDR(sl, 10);
+			int endSlot = recSlot != 0xffffffffu ? (int)recSlot : (nTies > 0 ? ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore) : -1);
+			if (endSlot < 0) out->status = GA_ERR_INTERNAL;
+			else
+			{
+				endNode = GA_HNG(nodeOff + endSlot, 0);
+				uint32_t cs = GA_HNG(nodeOff + endSlot, 1);
+				uint32_t len = GA_HNG(nodeOff + endSlot, 3);
+				if (recSlot != 0xffffffffu) endOff = GA_HDR(sl, 11);
+				else
+				{
+					for (uint32_t k = 0; k < len; k++)
+					{
+						GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
+						int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
+						if (v == minScore) endOff = k;
+					}
+				}
+				out->nTies = nTies;
+				out->score = minScore;
+				out->endNode = endNode;
+				out->endOff = endOff;
+				doTrace = !(debugFlags & 1u);
+			}
+		}
+	}
+	GA_TLAP(st, 7);
+#ifdef GA_PHASE_TIMING
+	if (active) for (int i = 0; i < 16; i++) out->phase[i] = st.phase[i];
+#endif
+	// the traceback kernel (ga_trace.cuh) walks every stream that has a trace start
+	if (active) out->traceOff = doTrace ? 1 : 0;
+}
+
 // Match masks of 64 read characters: bit i of {A,C,G,T} word = characterMatch(read[i], base) with IUPAC codes
 // (GraphAligner.h:2338-2351).  Used by the Peq pre-pass kernel.
 GA_DEV void ga_peq_words(const uint8_t* p, uint64_t& BA, uint64_t& BC, uint64_t& BG, uint64_t& BT)
@@ -1890,99 +2001,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		maskPrev = maskCur;
 		ls = s + 1;
 	}
-	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------
-	bool doTrace = false;
-	int n = 0;
-	uint32_t endNode = 0, endOff = 0;
-	if (active)
-	{
-		out->nSlicesRun = (int32_t)slicesRun;
-		out->wordColumns = st.wordColumns;
-		out->cyclicSlices = st.cyclicSlices;
-		out->nMoves = 0;
-		out->nPathNodes = 0;
-		out->nRuns = 0;
-		out->nPositions = 0;
-		out->nTies = 0;
-		out->nSlices = 0;
-		out->score = 0;
-		out->endNode = 0;
-		out->endOff = 0;
-		out->status = st.status;
-	}
-	if (active && st.status == GA_OK)
-	{
-		// removeWronglyAlignedEnd (GraphAligner.h:2554-2569)
-		n = (int)st.slicesPushed;
-		if (n > 0)
-		{
-			bool currentlyCorrect = (GA_HDR(n - 1, 5) & 1u) != 0;
-			while (!currentlyCorrect)
-			{
-				n--;
-				if (n == 0) break;
-				currentlyCorrect = (GA_HDR(n - 1, 5) & 2u) != 0;   // FalseFromCorrect of the new last slice, as the reference reads it
-			}
-		}
-		out->nSlices = n;
-		if (n == 0) out->status = GA_EMPTY;
-		else
-		{
-			// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
-			// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
-			// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
-			const int sl = n - 1;
-			const int32_t minScore = (int32_t)GA_HDR(sl, 4);
-			const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
-			uint32_t nTies = 0;
-			for (uint32_t slot = 0; slot < nNodes; slot++)
-			{
-				if ((int32_t)GA_HNG(nodeOff + slot, 2) != minScore) continue;
-				uint32_t node = GA_HNG(nodeOff + slot, 0);
-				uint32_t cs = GA_HNG(nodeOff + slot, 1);
-				uint32_t len = GA_HNG(nodeOff + slot, 3);
-				for (uint32_t k = 0; k < len; k++)
-				{
-					GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
-					int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
-					if (v != minScore) continue;
-					if (nTies < GA_MAX_TIES) { out->tieNode[nTies] = node; out->tieOff[nTies] = k; }
-					nTies++;
-				}
-			}
-			// a slice with a cyclic component recorded its last minimum cell while replaying the reference's schedule
-			const uint32_t recSlot = GA_HDR(sl, 10);
-			int endSlot = recSlot != 0xffffffffu ? (int)recSlot : (nTies > 0 ? ga_first_emitted_min_node<LANES>(g, caps, mem, sl, minScore) : -1);
-			if (endSlot < 0) out->status = GA_ERR_INTERNAL;
-			else
-			{
-				endNode = GA_HNG(nodeOff + endSlot, 0);
-				uint32_t cs = GA_HNG(nodeOff + endSlot, 1);
-				uint32_t len = GA_HNG(nodeOff + endSlot, 3);
-				if (recSlot != 0xffffffffu) endOff = GA_HDR(sl, 11);
-				else
-				{
-					for (uint32_t k = 0; k < len; k++)
-					{
-						GaCol c = ga_col_load<LANES>(mem, slabOff + cs + k);
-						int32_t v = c.sbs + (int32_t)GA_POPC(c.VP) - (int32_t)GA_POPC(c.VN);
-						if (v == minScore) endOff = k;
-					}
-				}
-				out->nTies = nTies;
-				out->score = minScore;
-				out->endNode = endNode;
-				out->endOff = endOff;
-				doTrace = !(debugFlags & 1u);
-			}
-		}
-	}
-	GA_TLAP(st, 7);
-#ifdef GA_PHASE_TIMING
-	if (active) for (int i = 0; i < 16; i++) out->phase[i] = st.phase[i];
-#endif
-	// the traceback kernel (ga_trace.cuh) walks every stream that has a trace start
-	if (active) out->traceOff = doTrace ? 1 : 0;
+	ga_finish_stream<LANES>(g, caps, mem, st, active, slicesRun, debugFlags, out);
 }
 
 #endif

@@ -16,6 +16,7 @@
 #include <vector>
 #include "ga_core.cuh"
 #include "ga_trace.cuh"
+#include "ga_fast.cuh"
 #include "ga_device.h"
 
 namespace ga
@@ -54,6 +55,7 @@ struct ScratchPtrs
 	uint32_t* runs;
 	const uint4* peq;   // [stream][slice][2]
 	const uint64_t* peqOff;  // per stream: first uint4 of its masks
+	uint32_t* peqAux;        // per stream and slice (index peqOff / 2 + slice): exact code of the read character above the slice | IUPAC mask of the first character << 4
 	unsigned long long* colPoolTop;
 	uint64_t colPoolCap;
 	uint32_t ubktSize;
@@ -64,12 +66,14 @@ __constant__ GaUmapSchedule c_sched;
 
 #ifndef GA_HOSTSIM
 // Match masks for every 64-row slice of every stream: one block per stream, one thread per slice, 64 bytes in, 32 bytes out.
-__global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq)
+__global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq,
+	uint32_t* __restrict__ peqAux)
 {
 	const uint32_t stream = blockIdx.x;
 	if (stream >= nStreams) return;
 	const uint32_t nslices = streams[stream].partLen / 64;
 	const uint8_t* base = parts + streams[stream].seqOff;
+	const uint32_t firstMask = nslices ? ga_iupac_mask(base[0]) : 0;
 	for (uint32_t sl = threadIdx.x; sl < nslices; sl += blockDim.x)
 	{
 		uint64_t A, C, G, T;
@@ -77,6 +81,7 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 		uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
 		dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
 		dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
+		peqAux[peqOff[stream] / 2 + sl] = (sl > 0 ? ga_exact_code(base[(size_t)sl * 64 - 1]) : 4u) | (firstMask << 4);
 	}
 }
 #endif
@@ -184,6 +189,44 @@ __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_
 }
 #endif
 
+#ifndef GA_HOSTSIM
+// Small-band forward kernel (ga_fast.cuh): one warp per block, S streams per warp, the warp's state in its block's shared memory
+template <int S>
+__global__ void __launch_bounds__(32) ga_fast_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
+	const ga_stream_in* __restrict__ streams, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* __restrict__ outs)
+{
+	extern __shared__ __align__(16) unsigned long long gaShared[];
+	GaFastShared<S>& sh = *reinterpret_cast<GaFastShared<S>*>(gaShared);
+	const uint32_t warp = blockIdx.x;
+	const uint32_t lane = threadIdx.x;
+	const uint32_t stream = warp * S + lane;
+	const bool active = lane < S && stream < nStreams;
+	const uint32_t ml = lane < S ? lane : 0;      // idle lanes alias lane 0's addresses but never touch memory
+	const WarpDesc wd = warpDescs[warp];
+	ga_caps wc = caps;
+	wc.maxSlices = wd.maxSlices;
+	wc.histNodes = wd.histNodes;
+	wc.warpCols = sp.colPoolCap;
+	const GaFastLane<S> fl(sh, ml);
+	GaLaneMem mem;
+	memset(&mem, 0, sizeof(mem));
+	mem.hdr = sp.hdr + wd.hdrBase + ml;
+	mem.histNode = sp.histNode + wd.hnBase + ml;
+	mem.colVV = sp.colVV + ml;
+	mem.colS = sp.colS + ml;
+	mem.colPoolTop = sp.colPoolTop;
+	mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
+	// scratch of ga_finish_stream (Tarjan over the last slice's band): the selection scratch and the queue
+	mem.indeg = fl.scratch();
+	mem.order = fl.scratch() + 16 * S;
+	mem.uorder = fl.scratch() + 32 * S;
+	mem.unext = fl.scratch() + 48 * S;
+	mem.ubkt = (uint32_t*)&sh.heap[0][0] + ml;
+	ga_fast_stream<S>(g, wc, c_hmm, c_sched, mem, fl, active, active ? streams + stream : nullptr, active ? sp.peqAux + sp.peqOff[stream] / 2 : nullptr, initialBandwidth, rampBandwidth,
+		debugFlags, active ? outs + stream : nullptr);
+}
+#endif
+
 // Pointers of one stream's trace inputs and temporary outputs (the forward launch's layout: [..][S] interleaved per warp)
 static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, const WarpDesc& wd, uint32_t stream, uint32_t S)
 {
@@ -276,7 +319,7 @@ __global__ void ga_int32_peak_kernel(uint32_t* sink, int iters)
 
 #ifdef GA_HOSTSIM
 // ---- CPU emulation of the launches (test infrastructure, see oracle/hostsim/cuda_runtime.h): one stream per "warp" ----
-static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, const uint8_t* parts, uint32_t nStreams, uint4* peq)
+static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, const uint8_t* parts, uint32_t nStreams, uint4* peq, uint32_t* peqAux)
 {
 	for (uint32_t stream = 0; stream < nStreams; stream++)
 	{
@@ -289,6 +332,7 @@ static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, con
 			uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
 			dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
 			dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
+			peqAux[peqOff[stream] / 2 + sl] = (sl > 0 ? ga_exact_code(base[(size_t)sl * 64 - 1]) : 4u) | (ga_iupac_mask(base[0]) << 4);
 		}
 	}
 }
@@ -308,11 +352,30 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		wc.histNodes = wd.histNodes;
 		wc.warpCols = sp.colPoolCap;
 		GaLaneMem mem;
+		if (small)
+		{
+			// the small-band kernel body with one lane
+			static GaFastShared<1> sh;
+			const GaFastLane<1> fl(sh, 0);
+			memset(&mem, 0, sizeof(mem));
+			mem.hdr = sp.hdr + wd.hdrBase;
+			mem.histNode = sp.histNode + wd.hnBase;
+			mem.colVV = sp.colVV;
+			mem.colS = sp.colS;
+			mem.colPoolTop = sp.colPoolTop;
+			mem.peq = sp.peq + sp.peqOff[stream];
+			mem.indeg = fl.scratch();
+			mem.order = fl.scratch() + 16;
+			mem.uorder = fl.scratch() + 32;
+			mem.unext = fl.scratch() + 48;
+			mem.ubkt = (uint32_t*)&sh.heap[0][0];
+			ga_fast_stream<1>(g, wc, c_hmm, c_sched, mem, fl, true, streams + stream, sp.peqAux + sp.peqOff[stream] / 2, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+			continue;
+		}
 		std::fill(ws.begin(), ws.end(), 0ull);
-		setupLaneMem(mem, sp, wd, caps, w, 0, S, small, ws.data(), eqTab.data());
+		setupLaneMem(mem, sp, wd, caps, w, 0, S, false, ws.data(), eqTab.data());
 		mem.peq = sp.peq + sp.peqOff[stream];
-		if (small) ga_run_stream<1, true>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
-		else ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
 	}
 	// the traceback "launch": the same group code with its lanes as a loop
 	const int G = 8;
@@ -382,17 +445,17 @@ struct DeviceCtx
 	cudaStream_t stream = nullptr;
 	std::string lastError;
 	// graph
-	Buffer gNodeStart, gSeq, gInOff, gInAdj, gOutOff, gOutAdj;
+	Buffer gNodeStart, gSeq, gInOff, gInAdj, gOutOff, gOutAdj, gNodeRec, gChunks;
 	ga_graph_view view;
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bColVV, bColS, bPeq, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bColVV, bColS, bPeq, bPeqAux, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
-	int traceGroup = 8;        // GA_TRACE_GROUP env: lanes per stream in the traceback kernel (4, 8, 16, 32)
+	int traceGroup = 8;        // GA_TRACE_GROUP env: lanes per stream in the traceback kernel (8, 16, 32)
 	int smCount = 148;
 	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
@@ -526,8 +589,8 @@ void DestroyDevice(DeviceCtx* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
+	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->gNodeRec, &ctx->gChunks, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqAux, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
 	for (Buffer* b : all) b->release();
 	ctx->pinParts.release();
 	ctx->pinOuts.release();
@@ -600,6 +663,40 @@ void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
 	ctx->view.inAdj = uploadVec(ctx, ctx->gInAdj, graph.InAdj());
 	ctx->view.outOff = uploadVec(ctx, ctx->gOutOff, graph.OutOff());
 	ctx->view.outAdj = uploadVec(ctx, ctx->gOutAdj, graph.OutAdj());
+	{
+		// fixed-width node records and chunked sequence for the small-band forward kernel (ga_types.h)
+		const size_t n = graph.NodeSize();
+		const std::vector<uint64_t>& ns = graph.NodeStarts();
+		const std::vector<uint32_t>& seq2 = graph.Seq2();
+		std::vector<ga_node_rec> recs(n);
+		uint64_t chunkTop = 0;
+		for (size_t i = 0; i < n; i++) { recs[i].seqChunk = (uint32_t)chunkTop; chunkTop += (ns[i + 1] - ns[i] + 63) / 64; }
+		if (chunkTop >= 0xffffffffull) throw std::runtime_error("graph too large for 32-bit sequence chunk indices");
+		std::vector<uint32_t> chunks((size_t)chunkTop * 4 + 4, 0);
+		ParallelFor(n, [&](size_t i) {
+			ga_node_rec& r = recs[i];
+			const uint64_t len = ns[i + 1] - ns[i];
+			const uint32_t inDeg = graph.InOff()[i + 1] - graph.InOff()[i], outDeg = graph.OutOff()[i + 1] - graph.OutOff()[i];
+			r.lenDeg = (uint32_t)std::min<uint64_t>(len, 0xffffffu) | (std::min(inDeg, 15u) << 24) | (std::min(outDeg, 15u) << 28);
+			r.inOff = graph.InOff()[i];
+			r.outOff = graph.OutOff()[i];
+			for (uint32_t k = 0; k < 2; k++)
+			{
+				r.in[k] = k < inDeg ? graph.InAdj()[r.inOff + k] : 0xffffffffu;
+				r.out[k] = k < outDeg ? graph.OutAdj()[r.outOff + k] : 0xffffffffu;
+			}
+			uint32_t* dst = chunks.data() + (size_t)r.seqChunk * 4;
+			for (uint64_t k = 0; k < len; k++)
+			{
+				const uint64_t w = ns[i] + k;
+				const uint32_t base = (seq2[w >> 4] >> ((uint32_t)(w & 15) * 2)) & 3u;
+				dst[k >> 4] |= base << ((uint32_t)(k & 15) * 2);
+			}
+		});
+		ctx->view.nodeRec = uploadVec(ctx, ctx->gNodeRec, recs);
+		ctx->view.seqChunks = uploadVec(ctx, ctx->gChunks, chunks);
+		GA_CUDA(cudaStreamSynchronize(ctx->stream));   // the vectors go out of scope
+	}
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->hasGraph = true;
 	ctx->budgetBytes = 0;
@@ -682,21 +779,16 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	const int scale = sb->capScale;
 	sb->caps = defaultCaps(sb->b, sb->B, scale);
 	ga_caps& caps = sb->caps;
-	sb->S = pickStreamsPerWarp(ctx, n);
-	const size_t S = (size_t)sb->S;
 	{
-		// small-band mode: few streams per warp (shared memory per SM) and a graph whose bands hold a handful of nodes; a stream
-		// that outgrows the fixed capacities reports an overflow and is re-run with the general layout (capScale > 1)
+		// small-band kernel (ga_fast.cuh): a graph whose bands hold a handful of nodes, fixed bandwidth; a stream that outgrows
+		// the kernel's limits reports an overflow and is re-run by the general kernel (capScale > 1)
 		const double bandNodes = 2.0 * (std::max(sb->b, sb->B) + 64) / std::max(1.0, ctx->avgNodeLen) + 2;
-		sb->smemScratch = scale == 1 && bandNodes <= 10 && getenv("GA_NO_SMEM") == nullptr;
-		if (sb->smemScratch)
-		{
-			caps.maxNodes = GA_SMEM_NODES;
-			caps.hashSize = GA_SMEM_HASH;
-			caps.maxQueue = GA_SMEM_HEAP;
-			caps.maxCols = GA_SMEM_COLS;
-		}
+		// no -B ramp: a redo needs the general kernel's history rewind (slice 0 still runs with B, as in the reference)
+		sb->smemScratch = scale == 1 && bandNodes <= 10 && sb->B <= sb->b && getenv("GA_NO_SMEM") == nullptr;
 	}
+	// streams per warp.  Small-band kernel: 16, i.e. five warps of state per SM in shared memory; general kernel: see pickStreamsPerWarp
+	sb->S = sb->smemScratch ? (ctx->forceS > 0 ? ctx->forceS : 16) : pickStreamsPerWarp(ctx, n);
+	const size_t S = (size_t)sb->S;
 	const size_t nWarps = (n + S - 1) / S;
 	sb->nWarps = nWarps;
 	const int bw = std::max(sb->b, sb->B);
@@ -746,7 +838,14 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		ubktSize = ctx->sched.buckets[i];
 		if (ctx->sched.buckets[i] >= caps.maxNodes) break;
 	}
-	if (sb->smemScratch && ubktSize > GA_SMEM_UBKT) throw std::logic_error("unordered_map bucket schedule does not fit the shared-memory scratch");
+	if (sb->smemScratch)
+	{
+		// the small-band kernel's unordered_map emulation has 32 buckets for up to GAF_NODES keys
+		for (uint32_t i = 0; i < ctx->sched.n; i++)
+		{
+			if (ctx->sched.threshold[i] <= GAF_NODES && ctx->sched.buckets[i] > 32) throw std::logic_error("unordered_map bucket schedule does not fit the small-band kernel's scratch");
+		}
+	}
 	ubktSize = std::max(ubktSize, caps.maxNodes);
 	ctx->bIn.ensure(n * sizeof(ga_stream_in));
 	ctx->bOut.ensure(n * sizeof(ga_stream_out));
@@ -765,6 +864,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	ctx->bColS.ensure(colTop * S * sizeof(uint32_t));
 	ctx->bColTop.ensure(sizeof(unsigned long long));
 	ctx->bPeq.ensure(std::max<uint64_t>(peqTop, 1) * sizeof(uint4));
+	ctx->bPeqAux.ensure(std::max<uint64_t>(peqTop / 2, 1) * sizeof(uint32_t));
 	ctx->bPeqOff.ensure(n * sizeof(uint64_t));
 	ctx->bMoves.ensure(movesTop * sizeof(uint32_t));
 	ctx->bPath.ensure(pathTop * sizeof(uint32_t));
@@ -784,6 +884,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 	sb->sp.colPoolTop = (unsigned long long*)ctx->bColTop.ptr;
 	sb->sp.colPoolCap = colTop;
 	sb->sp.peq = (const uint4*)ctx->bPeq.ptr;
+	sb->sp.peqAux = (uint32_t*)ctx->bPeqAux.ptr;
 	sb->sp.peqOff = (const uint64_t*)ctx->bPeqOff.ptr;
 	sb->sp.moves = (uint32_t*)ctx->bMoves.ptr;
 	sb->sp.pathNodes = (uint32_t*)ctx->bPath.ptr;
@@ -808,22 +909,20 @@ template <int S>
 static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
-	// small-band mode: one warp per block, so that the shared-memory blocks of the warps pack an SM without remainder
-	const int threads = sb->smemScratch ? 32 : 64;
-	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
-	const size_t smemBytes = (size_t)(threads / 32) * (4 + (sb->smemScratch ? GA_SMEM_WORDS64 : 0)) * S * sizeof(unsigned long long);
 	if (sb->smemScratch)
 	{
+		// small-band kernel: one warp per block, the warp's state in dynamic shared memory
 		static bool attr = false;
-		if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_forward_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-		ga_forward_kernel<S, true><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-			(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_fast_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaFastShared<S>))); attr = true; }
+		ga_fast_kernel<S><<<(unsigned)sb->nWarps, 32, sizeof(GaFastShared<S>), ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+			(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		return;
 	}
-	else
-	{
-		ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-			(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
-	}
+	const int threads = 64;
+	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
+	const size_t smemBytes = (size_t)(threads / 32) * 4 * S * sizeof(unsigned long long);
+	ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
 }
 
 template <int G>
@@ -847,7 +946,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	GA_CUDA(cudaMemsetAsync(ctx->bArenaTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
 	GA_CUDA(cudaMemsetAsync(ctx->bColTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
 #ifdef GA_HOSTSIM
-	hostsim_peq((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
+	hostsim_peq((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr, (uint32_t*)ctx->bPeqAux.ptr);
 	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
 		sb->smemScratch, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 #else
@@ -856,7 +955,8 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	if (kernelTiming) { for (auto& e : ev) GA_CUDA(cudaEventCreate(&e)); GA_CUDA(cudaEventRecord(ev[0], ctx->stream)); }
 	{
-		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr);
+		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr,
+			(uint32_t*)ctx->bPeqAux.ptr);
 		GA_CUDA(cudaGetLastError());
 	}
 	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[1], ctx->stream));
@@ -876,7 +976,6 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	{
 		case 32: launchTrace<32>(ctx, sb); break;
 		case 16: launchTrace<16>(ctx, sb); break;
-		case 4: launchTrace<4>(ctx, sb); break;
 		default: launchTrace<8>(ctx, sb); break;
 	}
 	if (kernelTiming)
@@ -1086,7 +1185,7 @@ size_t FreeDeviceBytes(DeviceCtx* ctx)
 	{
 	size_t totalB = 0;
 	GA_CUDA(cudaMemGetInfo(&freeB, &totalB));
-	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq,
+	Buffer* all[] = { &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash, &ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqAux,
 		&ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena };
 	for (Buffer* b : all) freeB += b->cap;
 	ctx->budgetBytes = freeB;

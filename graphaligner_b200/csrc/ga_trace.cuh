@@ -32,24 +32,30 @@ struct GaTraceMem
 };
 
 // per group, in shared memory on the device
+#define GA_TR_WIN 32        /* columns per window */
+#define GA_TR_NODES 32      /* band nodes of the current slice kept in shared memory (larger bands are searched in global memory) */
 template <int G>
 struct GaTraceWindow
 {
-	uint64_t VP[G], VN[G];       // window load: the columns themselves (lane i holds column top - i) ...
-	uint64_t H[G], D0[G], EQ[G]; // ... and the masks of the word step that produced them
-	uint32_t sw[G];              // score word (score | flags); 0xffffffff = no such column
-	uint32_t ok[G];              // bit 0: H/D0 valid against the left neighbour in the node, bit 1: against the linked neighbour
-	uint64_t peq[4];             // match words of the slice the window belongs to
+	uint64_t VP[GA_TR_WIN], VN[GA_TR_WIN];         // window load: the columns themselves (entry i = column top - i) ...
+	uint64_t H[GA_TR_WIN], D0[GA_TR_WIN], EQ[GA_TR_WIN];   // ... and the masks of the word step that produced them
+	uint32_t sw[GA_TR_WIN];                        // score word (score | flags); 0xffffffff = no such column
+	uint32_t ok[GA_TR_WIN];                        // bit 0: H/D0 valid against the left neighbour in the node, bit 1: against the linked neighbour
+	uint64_t peq[4];                               // match words of the current slice
+	uint64_t nodeW[GA_TR_NODES];                   // current slice's band: first base of each node in the graph sequence,
+	uint32_t nodeId[GA_TR_NODES], nodeCs[GA_TR_NODES], nodeLen[GA_TR_NODES];   // node, first column in the slab, length
 };
 
 #ifdef __CUDACC__
 #define GA_TR_LANES(gl) if (const int gl = (int)(threadIdx.x & (G - 1)); true)
 #define GA_TR_SYNC() __syncwarp(groupMask)
 #define GA_TR_LEADER ((threadIdx.x & (G - 1)) == 0)
+#define GA_TR_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
 #else
 #define GA_TR_LANES(gl) for (int gl = 0; gl < G; gl++)
 #define GA_TR_SYNC()
 #define GA_TR_LEADER true
+#define GA_TR_PREFETCH(p) (void)(p)
 #endif
 
 #define GA_TR_HDR(s, f) tm.hdr[(size_t)((size_t)(s) * GA_HDR_WORDS + (f)) * tm.S]
@@ -118,14 +124,17 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 	const int32_t maxv = (int32_t)in.partLen;
 	const uint32_t startNode = in.startNode;
 	const uint32_t trimRows = in.trimRows;
+	// the slice the walk is in: header and (bands of up to GA_TR_NODES nodes) its node list in shared memory
+	int loadedSlice = -1;
+	uint32_t sNodeOff = 0, sNodes = 0, sSlab = 0;
+	bool sCached = false;
 	uint32_t slot = 0;           // band slot of `node` in slice s
 	uint32_t colBase = 0;        // index of the node's first column in the history pool
-	uint32_t sNodeOff = 0;       // slice s: first entry of its node list
+	uint64_t nodeW = 0;          // first base of the node in the graph sequence
 	bool reload = true;          // slice or node changed: re-resolve slot and colBase
 	int32_t here = 0;
 	bool haveHere = false;
 	int winTop = -1;             // offset (in the node) of the window's newest column; -1 = no window
-	int winSlice = -1;           // slice whose match words the window holds
 	const uint32_t maxMoves = tm.maxMoves;
 	const bool leader = GA_TR_LEADER;
 #define GA_TR_EMIT(mv) \
@@ -138,12 +147,52 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 	{
 		if (reload)
 		{
-			sNodeOff = GA_TR_HDR(s, 2);
-			const uint32_t nNodes = GA_TR_HDR(s, 3);
-			const int found = ga_tr_find(tm, sNodeOff, nNodes, node);
+			if (loadedSlice != s)
+			{
+				// ---- entering a slice: its header, match words and node list; the next slice's are requested into L2 ----
+				sSlab = GA_TR_HDR(s, 0);
+				sNodeOff = GA_TR_HDR(s, 2);
+				sNodes = GA_TR_HDR(s, 3);
+				sCached = sNodes <= GA_TR_NODES;
+				GA_TR_SYNC();   // everybody is done with the old slice's tables
+				GA_TR_LANES(gl)
+				{
+					if (gl < 2)
+					{
+						const uint4 q = tm.peq[(size_t)s * 2 + gl];
+						win.peq[gl * 2] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+						win.peq[gl * 2 + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+					}
+					if (sCached)
+					{
+						for (uint32_t i = (uint32_t)gl; i < sNodes; i += G)
+						{
+							const uint32_t nd = GA_TR_HN(sNodeOff + i, 0);
+							win.nodeId[i] = nd;
+							win.nodeCs[i] = GA_TR_HN(sNodeOff + i, 1);
+							win.nodeLen[i] = GA_TR_HN(sNodeOff + i, 3);
+							win.nodeW[i] = g.nodeStart[nd];
+						}
+					}
+					if (s > 0 && gl == 0)
+					{
+						GA_TR_PREFETCH(&GA_TR_HDR(s - 1, 0));
+						GA_TR_PREFETCH(tm.peq + (size_t)(s - 1) * 2);
+					}
+				}
+				GA_TR_SYNC();
+				loadedSlice = s;
+			}
+			int found = -1;
+			if (sCached)
+			{
+				for (uint32_t i = 0; i < sNodes; i++) if (win.nodeId[i] == node) { found = (int)i; break; }
+			}
+			else found = ga_tr_find(tm, sNodeOff, sNodes, node);
 			if (found < 0) { status = GA_ERR_TRACE; break; }
 			slot = (uint32_t)found;
-			colBase = GA_TR_HDR(s, 0) + GA_TR_HN(sNodeOff + slot, 1);
+			if (sCached) { colBase = sSlab + win.nodeCs[slot]; nodeW = win.nodeW[slot]; }
+			else { colBase = sSlab + GA_TR_HN(sNodeOff + slot, 1); nodeW = g.nodeStart[node]; }
 			if (!haveHere)
 			{
 				const GaTrCol c = ga_tr_col(tm, colBase + off);
@@ -164,85 +213,81 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 		int wi = 0;
 		if (runOpen && row > 0 && nMoves < maxMoves)
 		{
-			// ---- window: the G columns ending at `off`, their masks re-derived by the lanes in parallel ----------------
-			if (winTop < 0 || (int)off > winTop || winTop - (int)off >= G)
+			// ---- window: the GA_TR_WIN columns ending at `off`, their masks re-derived by the lanes in parallel ----------
+			if (winTop < 0 || (int)off > winTop || winTop - (int)off >= GA_TR_WIN)
 			{
 				GA_TR_SYNC();   // everybody is done reading the old window
-				if (winSlice != s)
-				{
-					GA_TR_LANES(gl)
-					{
-						if (gl < 2)
-						{
-							const uint4 q = tm.peq[(size_t)s * 2 + gl];
-							win.peq[gl * 2] = (uint64_t)q.x | ((uint64_t)q.y << 32);
-							win.peq[gl * 2 + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
-						}
-					}
-					winSlice = s;
-				}
 				winTop = (int)off;
-				const uint64_t wStart = g.nodeStart[node];
 				GA_TR_LANES(gl)
 				{
-					const int c = winTop - gl;
-					uint32_t sw = 0xffffffffu;
-					uint64_t vp = 0, vn = 0;
-					// column -1 = the column stored right before the node's first one (GA_CF_LINK says when that means something)
-					if (c >= 0 || (c == -1 && colBase > 0))
+#pragma unroll
+					for (int r = 0; r < GA_TR_WIN / G; r++)
 					{
-						const uint32_t idx = (uint32_t)((int)colBase + c);
-						const uint4 a = tm.colVV[(size_t)idx * tm.S];
-						vp = (uint64_t)a.x | ((uint64_t)a.y << 32);
-						vn = (uint64_t)a.z | ((uint64_t)a.w << 32);
-						sw = tm.colS[(size_t)idx * tm.S];
+						const int i = r * G + gl;
+						const int c = winTop - i;
+						uint32_t sw = 0xffffffffu;
+						uint64_t vp = 0, vn = 0;
+						// column -1 = the column stored right before the node's first one (GA_CF_LINK says when that means something)
+						if (c >= 0 || (c == -1 && colBase > 0))
+						{
+							const uint32_t idx = (uint32_t)((int)colBase + c);
+							const uint4 a = tm.colVV[(size_t)idx * tm.S];
+							vp = (uint64_t)a.x | ((uint64_t)a.y << 32);
+							vn = (uint64_t)a.z | ((uint64_t)a.w << 32);
+							sw = tm.colS[(size_t)idx * tm.S];
+						}
+						win.VP[i] = vp;
+						win.VN[i] = vn;
+						win.sw[i] = sw;
 					}
-					win.VP[gl] = vp;
-					win.VN[gl] = vn;
-					win.sw[gl] = sw;
 				}
 				GA_TR_SYNC();
 				GA_TR_LANES(gl)
 				{
-					const int c = winTop - gl;
-					uint32_t ok = 0;
-					uint64_t H = 0, D0 = 0, EQ = 0;
-					const uint32_t sw = win.sw[gl];
-					if (c >= 0 && sw != 0xffffffffu && (sw & (c > 0 ? GA_CF_PLAIN : GA_CF_LINK)))
+#pragma unroll
+					for (int r = 0; r < GA_TR_WIN / G; r++)
 					{
-						// the left neighbour: the next lane's column, or one more load for the last lane
-						uint64_t lvp, lvn;
-						bool haveLeft = true;
-						if (gl + 1 < G)
+						const int i = r * G + gl;
+						const int c = winTop - i;
+						uint32_t ok = 0;
+						uint64_t H = 0, D0 = 0, EQ = 0;
+						const uint32_t sw = win.sw[i];
+						if (c >= 0 && sw != 0xffffffffu && (sw & (c > 0 ? GA_CF_PLAIN : GA_CF_LINK)))
 						{
-							lvp = win.VP[gl + 1];
-							lvn = win.VN[gl + 1];
-							haveLeft = win.sw[gl + 1] != 0xffffffffu;
+							// the left neighbour: the next entry of the window, or one more load for the last entry
+							uint64_t lvp, lvn;
+							bool haveLeft = true;
+							if (i + 1 < GA_TR_WIN)
+							{
+								lvp = win.VP[i + 1];
+								lvn = win.VN[i + 1];
+								haveLeft = win.sw[i + 1] != 0xffffffffu;
+							}
+							else
+							{
+								const uint32_t idx = (uint32_t)((int)colBase + c - 1);
+								const uint4 a = tm.colVV[(size_t)idx * tm.S];
+								lvp = (uint64_t)a.x | ((uint64_t)a.y << 32);
+								lvn = (uint64_t)a.z | ((uint64_t)a.w << 32);
+							}
+							if (haveLeft)
+							{
+								const uint64_t w = nodeW + (uint64_t)c;
+								const uint32_t base = (g.seq2[w >> 4] >> ((uint32_t)(w & 15) * 2)) & 3u;
+								EQ = win.peq[base];
+								// the horizontal half of ga_next_col with the match bit of row 0 as the forward pass used it
+								const uint64_t Eq = (EQ & ~(uint64_t)1) | ((sw & GA_CF_EQ0) ? 1u : 0u);
+								const uint64_t Xh = (((Eq & lvp) + lvp) ^ lvp) | Eq;
+								H = lvn | ~(Xh | lvp);
+								D0 = Xh | lvn;
+								ok = c > 0 ? 1u : 2u;
+							}
 						}
-						else
-						{
-							const uint32_t idx = (uint32_t)((int)colBase + c - 1);
-							const uint4 a = tm.colVV[(size_t)idx * tm.S];
-							lvp = (uint64_t)a.x | ((uint64_t)a.y << 32);
-							lvn = (uint64_t)a.z | ((uint64_t)a.w << 32);
-						}
-						if (haveLeft)
-						{
-							const uint64_t w = wStart + (uint64_t)c;
-							const uint32_t base = (g.seq2[w >> 4] >> ((uint32_t)(w & 15) * 2)) & 3u;
-							EQ = win.peq[base];
-							// the horizontal half of ga_next_col with the match bit of row 0 as the forward pass used it
-							const uint64_t Eq = (EQ & ~(uint64_t)1) | ((sw & GA_CF_EQ0) ? 1u : 0u);
-							const uint64_t Xh = (((Eq & lvp) + lvp) ^ lvp) | Eq;
-							H = lvn | ~(Xh | lvp);
-							D0 = Xh | lvn;
-							ok = c > 0 ? 1u : 2u;
-						}
+						win.H[i] = H;
+						win.D0[i] = D0;
+						win.EQ[i] = EQ;
+						win.ok[i] = ok;
 					}
-					win.H[gl] = H;
-					win.D0[gl] = D0;
-					win.EQ[gl] = EQ;
-					win.ok[gl] = ok;
 				}
 				GA_TR_SYNC();
 			}
@@ -288,8 +333,9 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 				nRuns++;
 				runOpen = false;
 				slot--;
-				node = GA_TR_HN(sNodeOff + slot, 0);
-				const uint32_t len = GA_TR_HN(sNodeOff + slot, 3);
+				uint32_t len;
+				if (sCached) { node = win.nodeId[slot]; len = win.nodeLen[slot]; nodeW = win.nodeW[slot]; }
+				else { node = GA_TR_HN(sNodeOff + slot, 0); len = GA_TR_HN(sNodeOff + slot, 3); nodeW = g.nodeStart[node]; }
 				off = len - 1;
 				colBase -= len;
 				if (leader) tm.pathNodes[(size_t)nPath * tm.S] = node;
@@ -306,11 +352,9 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 		int32_t nhere = 0;
 		{
 			const GaTrCol cur = ga_tr_col(tm, colBase + off);
-			const uint64_t w = g.nodeStart[node] + off;
+			const uint64_t w = nodeW + off;
 			const uint32_t base = ga_base(g, w);
-			const uint4 pq = tm.peq[(size_t)s * 2 + (base >> 1)];
-			const uint64_t eqWord = (base & 1u) ? ((uint64_t)pq.z | ((uint64_t)pq.w << 32)) : ((uint64_t)pq.x | ((uint64_t)pq.y << 32));
-			const int32_t match = (int32_t)((eqWord >> row) & 1);
+			const int32_t match = (int32_t)((win.peq[base] >> row) & 1);
 			const int32_t diagWant = here - 1 + match;
 			const bool firstRow = s == 0 && row == 0;
 			if (firstRow && node == startNode && (here == 0 || here == 1))
@@ -354,10 +398,27 @@ GA_DEV void ga_trace_stream(const ga_graph_view& g, const GaTraceMem& tm, GaTrac
 				for (uint32_t e = g.inOff[node], eEnd = g.inOff[node + 1]; e < eEnd; e++)
 				{
 					const uint32_t u = g.inAdj[e];
-					const uint32_t uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
-					const int32_t hs = ga_tr_value(tm, startNode, s, u, uoff, row, maxv);
+					// the neighbour's last column in this slice: from the shared-memory node list when there is one
+					int uslot = -1;
+					uint32_t uoff;
+					if (sCached)
+					{
+						for (uint32_t i = 0; i < sNodes; i++) if (win.nodeId[i] == u) { uslot = (int)i; break; }
+						uoff = uslot >= 0 ? win.nodeLen[uslot] - 1 : (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+					}
+					else
+					{
+						uslot = ga_tr_find(tm, sNodeOff, sNodes, u);
+						uoff = (uint32_t)(g.nodeStart[u + 1] - g.nodeStart[u]) - 1;
+					}
+					GaTrCol uc;
+					uc.VP = uc.VN = 0; uc.sbs = 0;
+					if (uslot >= 0) uc = ga_tr_col(tm, sSlab + (sCached ? win.nodeCs[uslot] : GA_TR_HN(sNodeOff + uslot, 1)) + uoff);
+					const int32_t hs = uslot >= 0 ? ga_col_value(uc.VP, uc.VN, uc.sbs, row) : maxv;
 					if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; nhere = hs; break; }
-					const int32_t ds = row == 0 ? ga_tr_value(tm, startNode, s - 1, u, uoff, 63, maxv) : ga_tr_value(tm, startNode, s, u, uoff, row - 1, maxv);
+					int32_t ds;
+					if (row == 0) ds = ga_tr_value(tm, startNode, s - 1, u, uoff, 63, maxv);
+					else ds = uslot >= 0 ? ga_col_value(uc.VP, uc.VN, uc.sbs, row - 1) : maxv;
 					if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; nhere = ds; break; }
 				}
 				if (move == 4)

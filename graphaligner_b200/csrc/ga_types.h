@@ -19,7 +19,27 @@ typedef struct ga_graph_view
 	const uint32_t* inAdj;
 	const uint32_t* outOff;
 	const uint32_t* outAdj;
+	/* The same graph as fixed-width node records for the small-band forward kernel (ga_fast.cuh): one 32-byte record per
+	 * node (two 128-bit loads of one sector) and the node sequences as 16-byte chunks of 64 two-bit bases, every node starting
+	 * on a chunk (one 128-bit load per 64 columns).  Built by the device layer at upload; NULL on the host side. */
+	const struct ga_node_rec* nodeRec;
+	const uint32_t* seqChunks;    /* 4 words per chunk */
 } ga_graph_view;
+
+/* len and degrees: len | min(inDeg, 15) << 24 | min(outDeg, 15) << 28.  in[] / out[]: the first two neighbours in the
+ * reference's insertion order (0xffffffff = none); longer lists continue in inAdj / outAdj at inOff / outOff. */
+typedef struct ga_node_rec
+{
+	uint32_t seqChunk;
+	uint32_t lenDeg;
+	uint32_t inOff;
+	uint32_t outOff;
+	uint32_t in[2];
+	uint32_t out[2];
+} ga_node_rec;
+#define GA_REC_LEN(r) ((r) & 0xffffffu)
+#define GA_REC_INDEG(r) (((r) >> 24) & 15u)
+#define GA_REC_OUTDEG(r) ((r) >> 28)
 
 // One DP stream = one direction of one (read, seed) pair: the padded read part aligned forward from a
 // start node (reference getSplitAlignment, GraphAligner.h:2969-3024).
