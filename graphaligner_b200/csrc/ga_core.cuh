@@ -58,7 +58,7 @@
 
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
 #define GA_HDR_WORDS 12u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles), last minimum cell (slot, column)
-#define GA_HN_WORDS 4u          // node, colStart, nodeMin, len
+#define GA_HN_WORDS 5u          // node, colStart, nodeMin, len, first sequence chunk (ga_node_rec::seqChunk)
 
 #ifdef GA_HOST_DEBUG
 static unsigned long long g_dbgFast = 0, g_dbgOuter = 0, g_dbgGeneral = 0, g_dbgNodeStart = 0, g_dbgRow0 = 0, g_dbgMerged = 0, g_dbgReload = 0, g_dbgLink = 0;
@@ -579,6 +579,7 @@ GA_DEV bool ga_band_add(const ga_graph_view& g, const ga_caps& caps, const GaLan
 	GA_HN(nodeOff + nc, 0) = node;
 	GA_HN(nodeOff + nc, 1) = ncols;
 	GA_HN(nodeOff + nc, 3) = len;
+	GA_HN(nodeOff + nc, 4) = g.nodeRec[node].seqChunk;
 	mem.nWlo[(size_t)nc * LANES] = (uint32_t)wStart;
 	mem.nWhi[(size_t)nc * LANES] = (uint32_t)(wStart >> 32);
 	mem.nPcs[(size_t)nc * LANES] = pcs;
@@ -1857,7 +1858,8 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			GA_HN(0, 1) = 0;
 			GA_HN(0, 2) = 0;
 			GA_HN(0, 3) = len;
-			if (SMALL) { GA_HNG(0, 0) = st.startNode; GA_HNG(0, 1) = 0; GA_HNG(0, 2) = 0; GA_HNG(0, 3) = len; }
+			GA_HN(0, 4) = g.nodeRec[st.startNode].seqChunk;
+			if (SMALL) { GA_HNG(0, 0) = st.startNode; GA_HNG(0, 1) = 0; GA_HNG(0, 2) = 0; GA_HNG(0, 3) = len; GA_HNG(0, 4) = GA_HN(0, 4); }
 			ga_hash_insert<LANES>(mem.hash[0], ga_hash_window(1, caps.hashSize), 1, st.startNode, 0);
 			for (uint32_t k = 0; k < len; k++) ga_tiny_st<LANES, SMALL>(mem.tiny[0], k, 0);
 			pNodes = 1;

@@ -377,6 +377,15 @@ GA_DEV bool gaf_resolve(const ga_graph_view& g, const GaFastLane<S>& fl, GaStrea
 		}
 	}
 	if (ready != nc) { st.status = GA_ERR_NODE_OVERFLOW; return false; }   // a cycle: the general kernel replays the reference's work list
+	// the nodes' columns lie in the slice's slab (and in the tiny array) in evaluation order: a chain of nodes is then one
+	// contiguous run of columns, which the traceback walks without looking anything up (GA_CF_LINK)
+	uint32_t col = 0;
+	for (uint32_t d = 0; d < nc; d++)
+	{
+		const uint32_t slot = order[(size_t)d * S];
+		fl.sh.csPcs[tc][slot][fl.lane] = (fl.sh.csPcs[tc][slot][fl.lane] & 0xffff0000u) | col;
+		col += GA_REC_LEN(fl.sh.lenDeg[tc][slot][fl.lane]);
+	}
 	return true;
 }
 
@@ -427,7 +436,7 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 		{
 			fl.sh.nodeMin[0][0][fl.lane] = 0;
 			for (uint32_t k = 0; k < len; k++) fl.sh.tiny[0][k][fl.lane] = 0;
-			GA_HNG(0, 0) = st.startNode; GA_HNG(0, 1) = 0; GA_HNG(0, 2) = 0; GA_HNG(0, 3) = len;
+			GA_HNG(0, 0) = st.startNode; GA_HNG(0, 1) = 0; GA_HNG(0, 2) = 0; GA_HNG(0, 3) = len; GA_HNG(0, 4) = r.seqChunk;
 			pNodes = 1;
 			st.histNodeTop = 1;
 		}
@@ -770,6 +779,7 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 			GA_HNG(nodeOff + i, 1) = fl.sh.csPcs[tc][i][fl.lane] & 0xffffu;
 			GA_HNG(nodeOff + i, 2) = (uint32_t)fl.sh.nodeMin[tc][i][fl.lane];
 			GA_HNG(nodeOff + i, 3) = GA_REC_LEN(fl.sh.lenDeg[tc][i][fl.lane]);
+			GA_HNG(nodeOff + i, 4) = fl.sh.chunk[tc][i][fl.lane];
 		}
 		st.hmmC = hmmC;
 		st.hmmF = hmmF;

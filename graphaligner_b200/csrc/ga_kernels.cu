@@ -248,36 +248,33 @@ static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, c
 }
 
 #ifndef GA_HOSTSIM
-// Traceback: G lanes per stream (ga_trace.cuh), 32 / G streams per warp.  Runs after the forward kernel on the same stream.
-#define GA_TRACE_THREADS 128
-template <int G>
-__global__ void __launch_bounds__(GA_TRACE_THREADS) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
+// Traceback (ga_trace.cuh): one lane per stream, one warp per block, the lanes' column windows and slice tables in the
+// block's shared memory.  Runs after the forward kernel on the same stream.
+__global__ void __launch_bounds__(32) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
 	uint32_t nStreams, uint32_t S, ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
-	__shared__ GaTraceWindow<G> wins[GA_TRACE_THREADS / G];
-	const uint32_t group = threadIdx.x / G;
-	const uint32_t gl = threadIdx.x & (G - 1);
-	const uint32_t stream = blockIdx.x * (GA_TRACE_THREADS / G) + group;
-	if (stream >= nStreams) return;
-	const uint32_t groupMask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31u) / G * G));
-	ga_stream_out* out = outs + stream;
-	const bool doTrace = out->traceOff != 0 && out->status == GA_OK;
-	__syncwarp(groupMask);   // everybody has read traceOff before the leader overwrites it
-	GaTraceWindow<G>& win = wins[group];
-	const WarpDesc wd = warpDescs[stream / S];
-	const GaTraceMem tm = traceMemOf(sp, wd, stream, S);
+	extern __shared__ __align__(16) unsigned long long gaShared[];
+	GaTraceShared<32>& sh = *reinterpret_cast<GaTraceShared<32>*>(gaShared);
+	const uint32_t lane = threadIdx.x;
+	const uint32_t stream = blockIdx.x * 32 + lane;
+	const bool have = stream < nStreams;
+	ga_stream_out* out = have ? outs + stream : nullptr;
+	const bool doTrace = have && out->traceOff != 0 && out->status == GA_OK;
+	GaTraceMem tm;
+	memset(&tm, 0, sizeof(tm));
+	tm.S = S;
+	if (have) tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
 	int32_t status = GA_OK;
 	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-	if (doTrace) ga_trace_stream<G>(g, tm, win, groupMask, streams[stream], out->nSlices, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
-	// compact this stream's trace record into the arena
+	ga_trace_warp<32>(g, tm, sh, lane, doTrace, have ? streams + stream : nullptr, doTrace ? out->nSlices : 0, doTrace ? out->endNode : 0, doTrace ? out->endOff : 0, status, nMoves, nPath, nRuns, nPos);
+	// compact the streams' trace records into the arena: the warp copies one stream's record at a time, 32 words per step
 	const uint32_t moveWords = (nMoves + 15) / 16;
 	const uint32_t runWords = nRuns * GA_RUN_WORDS;
-	const uint32_t words = moveWords + nPath + runWords;
-	__syncwarp(groupMask);
-	if (gl == 0)
+	const uint32_t words = have ? moveWords + nPath + runWords : 0;
+	const unsigned long long off = words ? atomicAdd(arenaTop, (unsigned long long)words) : 0ull;
+	const bool fits = off + words <= arenaCap;
+	if (have)
 	{
-		const unsigned long long off = atomicAdd(arenaTop, (unsigned long long)words);
-		win.peq[0] = off;
 		out->traceOff = off;
 		if (doTrace)
 		{
@@ -285,17 +282,26 @@ __global__ void __launch_bounds__(GA_TRACE_THREADS) ga_trace_kernel(ga_graph_vie
 			out->nPathNodes = nPath;
 			out->nRuns = nRuns;
 			out->nPositions = nPos;
-			out->status = off + words > arenaCap && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
+			out->status = !fits && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
 		}
 	}
-	__syncwarp(groupMask);
-	const unsigned long long off = win.peq[0];
-	if (off + words > arenaCap) return;
-	for (uint32_t i = gl; i < moveWords; i += G) arena[off + i] = tm.moves[(size_t)i * S];
-	for (uint32_t i = gl; i < nPath; i += G) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
-	for (uint32_t i = gl; i < runWords; i += G) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
+	for (int r = 0; r < 32; r++)
+	{
+		const uint32_t w = __shfl_sync(0xffffffffu, (fits && words) ? words : 0u, r);
+		if (w == 0) continue;
+		const uint32_t mw = __shfl_sync(0xffffffffu, moveWords, r), np = __shfl_sync(0xffffffffu, nPath, r), rw = __shfl_sync(0xffffffffu, runWords, r);
+		const unsigned long long o = __shfl_sync(0xffffffffu, off, r);
+		const uint32_t* pm = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.moves, r);
+		const uint32_t* pp = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.pathNodes, r);
+		const uint32_t* pr = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.runs, r);
+		for (uint32_t i = lane; i < mw; i += 32) arena[o + i] = pm[(size_t)i * S];
+		for (uint32_t i = lane; i < np; i += 32) arena[o + mw + i] = pp[(size_t)i * S];
+		for (uint32_t i = lane; i < rw; i += 32) arena[o + mw + np + i] = pr[(size_t)i * S];
+	}
 }
+#endif
 
+#ifndef GA_HOSTSIM
 // INT32 roofline probe: 8 independent dependency chains per thread of alternating LOP3 / IADD3, no memory traffic.
 // Its rate is the denominator of the integer-ALU roofline fraction.
 __global__ void ga_int32_peak_kernel(uint32_t* sink, int iters)
@@ -315,7 +321,6 @@ __global__ void ga_int32_peak_kernel(uint32_t* sink, int iters)
 	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) sink[0] = a0;
 }
 #endif
-
 
 #ifdef GA_HOSTSIM
 // ---- CPU emulation of the launches (test infrastructure, see oracle/hostsim/cuda_runtime.h): one stream per "warp" ----
@@ -377,18 +382,17 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		mem.peq = sp.peq + sp.peqOff[stream];
 		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
 	}
-	// the traceback "launch": the same group code with its lanes as a loop
-	const int G = 8;
+	// the traceback "launch": the same lane code, one lane per "warp"
 	for (uint32_t stream = 0; stream < nStreams; stream++)
 	{
 		ga_stream_out* out = outs + stream;
 		const bool doTrace = out->traceOff != 0 && out->status == GA_OK;
 		const WarpDesc wd = warpDescs[stream / S];
 		const GaTraceMem tm = traceMemOf(sp, wd, stream, S);
-		GaTraceWindow<G> win;
+		static GaTraceShared<1> sh;
 		int32_t status = GA_OK;
 		uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-		if (doTrace) ga_trace_stream<G>(g, tm, win, 0, streams[stream], out->nSlices, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
+		ga_trace_warp<1>(g, tm, sh, 0, doTrace, streams + stream, doTrace ? out->nSlices : 0, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
 		const uint32_t moveWords = (nMoves + 15) / 16;
 		const uint32_t runWords = nRuns * GA_RUN_WORDS;
 		const uint32_t words = moveWords + nPath + runWords;
@@ -455,7 +459,6 @@ struct DeviceCtx
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
-	int traceGroup = 8;        // GA_TRACE_GROUP env: lanes per stream in the traceback kernel (8, 16, 32)
 	int smCount = 148;
 	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
@@ -568,7 +571,6 @@ DeviceCtx* CreateDevice(int device)
 	ctx->sched = probeUmapSchedule(70000);
 	if (const char* f = getenv("GA_DEBUG_FLAGS")) ctx->debugFlags = (uint32_t)atoi(f);
 	if (const char* f = getenv("GA_STREAMS_PER_WARP")) ctx->forceS = atoi(f);
-	if (const char* f = getenv("GA_TRACE_GROUP")) ctx->traceGroup = atoi(f);
 	{
 		cudaDeviceProp prop;
 		GA_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -925,13 +927,12 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
 }
 
-template <int G>
 static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
-	const unsigned perBlock = GA_TRACE_THREADS / G;
-	const unsigned blocks = (unsigned)((n + perBlock - 1) / perBlock);
-	ga_trace_kernel<G><<<blocks, GA_TRACE_THREADS, 0, ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n, (uint32_t)sb->S,
+	static bool attr = false;
+	if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<32>))); attr = true; }
+	ga_trace_kernel<<<(unsigned)((n + 31) / 32), 32, sizeof(GaTraceShared<32>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n, (uint32_t)sb->S,
 		(ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 #endif
@@ -972,12 +973,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	}
 	GA_CUDA(cudaGetLastError());
 	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[2], ctx->stream));
-	switch (ctx->traceGroup)
-	{
-		case 32: launchTrace<32>(ctx, sb); break;
-		case 16: launchTrace<16>(ctx, sb); break;
-		default: launchTrace<8>(ctx, sb); break;
-	}
+	launchTrace(ctx, sb);
 	if (kernelTiming)
 	{
 		GA_CUDA(cudaEventRecord(ev[3], ctx->stream));
@@ -986,7 +982,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		cudaEventElapsedTime(&a, ev[0], ev[1]);
 		cudaEventElapsedTime(&b, ev[1], ev[2]);
 		cudaEventElapsedTime(&c, ev[2], ev[3]);
-		fprintf(stderr, "[ga kernels] streams %zu S %d G %d: peq %.3f ms, forward %.3f ms, trace %.3f ms\n", n, sb->S, ctx->traceGroup, a, b, c);
+		fprintf(stderr, "[ga kernels] streams %zu S %d: peq %.3f ms, forward %.3f ms, trace %.3f ms\n", n, sb->S, a, b, c);
 		for (auto& e : ev) cudaEventDestroy(e);
 	}
 #endif
