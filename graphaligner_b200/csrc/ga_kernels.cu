@@ -248,26 +248,29 @@ static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, c
 }
 
 #ifndef GA_HOSTSIM
-// Traceback (ga_trace.cuh): one lane per stream, one warp per block, the lanes' column windows and slice tables in the
-// block's shared memory.  Runs after the forward kernel on the same stream.
+// Traceback (ga_trace.cuh): one warp per block walks T streams (lane per stream, all 32 lanes fetch the windows), the
+// windows and slice tables in the block's shared memory.  Runs after the forward kernel on the same stream.
+template <int T, int P>
 __global__ void __launch_bounds__(32) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
 	uint32_t nStreams, uint32_t S, ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
 	extern __shared__ __align__(16) unsigned long long gaShared[];
-	GaTraceShared<32>& sh = *reinterpret_cast<GaTraceShared<32>*>(gaShared);
+	GaTraceShared<T, P>& sh = *reinterpret_cast<GaTraceShared<T, P>*>(gaShared);
 	const uint32_t lane = threadIdx.x;
-	const uint32_t stream = blockIdx.x * 32 + lane;
-	const bool have = stream < nStreams;
+	const uint32_t stream = blockIdx.x * T + lane;
+	const bool have = lane < T && stream < nStreams;
 	ga_stream_out* out = have ? outs + stream : nullptr;
 	const bool doTrace = have && out->traceOff != 0 && out->status == GA_OK;
-	GaTraceMem tm;
-	memset(&tm, 0, sizeof(tm));
-	tm.S = S;
-	if (have) tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
-	int32_t status = GA_OK;
-	uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-	ga_trace_warp<32>(g, tm, sh, lane, doTrace, have ? streams + stream : nullptr, doTrace ? out->nSlices : 0, doTrace ? out->endNode : 0, doTrace ? out->endOff : 0, status, nMoves, nPath, nRuns, nPos);
+	GaTraceLane L;
+	memset(&L.tm, 0, sizeof(L.tm));
+	L.tm.S = S;
+	L.in = have ? streams + stream : streams;
+	if (have) L.tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
+	ga_trace_init(L, doTrace, doTrace ? out->nSlices : 0, doTrace ? out->endNode : 0, doTrace ? out->endOff : 0, doTrace ? out->score : 0);
+	ga_trace_warp<T, P>(g, sh, lane, &L, S);
 	// compact the streams' trace records into the arena: the warp copies one stream's record at a time, 32 words per step
+	const GaTraceMem& tm = L.tm;
+	const uint32_t nMoves = L.t.nMoves, nPath = L.t.nPath, nRuns = L.t.nRuns;
 	const uint32_t moveWords = (nMoves + 15) / 16;
 	const uint32_t runWords = nRuns * GA_RUN_WORDS;
 	const uint32_t words = have ? moveWords + nPath + runWords : 0;
@@ -281,11 +284,11 @@ __global__ void __launch_bounds__(32) ga_trace_kernel(ga_graph_view g, ScratchPt
 			out->nMoves = nMoves;
 			out->nPathNodes = nPath;
 			out->nRuns = nRuns;
-			out->nPositions = nPos;
-			out->status = !fits && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
+			out->nPositions = ga_trace_positions(L.t);
+			out->status = !fits && L.t.status == GA_OK ? GA_ERR_TRACE_OVERFLOW : L.t.status;
 		}
 	}
-	for (int r = 0; r < 32; r++)
+	for (int r = 0; r < T; r++)
 	{
 		const uint32_t w = __shfl_sync(0xffffffffu, (fits && words) ? words : 0u, r);
 		if (w == 0) continue;
@@ -382,35 +385,52 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		mem.peq = sp.peq + sp.peqOff[stream];
 		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
 	}
-	// the traceback "launch": the same lane code, one lane per "warp"
-	for (uint32_t stream = 0; stream < nStreams; stream++)
+	// the traceback "launch": the same warp code with its lanes as loops, HT streams per "warp"
+	const int HT = 4, HP = 1;
+	for (uint32_t first = 0; first < nStreams; first += HT)
 	{
-		ga_stream_out* out = outs + stream;
-		const bool doTrace = out->traceOff != 0 && out->status == GA_OK;
-		const WarpDesc wd = warpDescs[stream / S];
-		const GaTraceMem tm = traceMemOf(sp, wd, stream, S);
-		static GaTraceShared<1> sh;
-		int32_t status = GA_OK;
-		uint32_t nMoves = 0, nPath = 0, nRuns = 0, nPos = 0;
-		ga_trace_warp<1>(g, tm, sh, 0, doTrace, streams + stream, doTrace ? out->nSlices : 0, out->endNode, out->endOff, status, nMoves, nPath, nRuns, nPos);
-		const uint32_t moveWords = (nMoves + 15) / 16;
-		const uint32_t runWords = nRuns * GA_RUN_WORDS;
-		const uint32_t words = moveWords + nPath + runWords;
-		const unsigned long long off = *arenaTop;
-		*arenaTop += words;
-		out->traceOff = off;
-		if (doTrace)
+		static GaTraceShared<HT, HP> sh;
+		GaTraceLane lanes[HT];
+		bool doTrace[HT];
+		for (int l = 0; l < HT; l++)
 		{
-			out->nMoves = nMoves;
-			out->nPathNodes = nPath;
-			out->nRuns = nRuns;
-			out->nPositions = nPos;
-			out->status = off + words > arenaCap && status == GA_OK ? GA_ERR_TRACE_OVERFLOW : status;
+			const uint32_t stream = first + l;
+			const bool have = stream < nStreams;
+			ga_stream_out* out = have ? outs + stream : nullptr;
+			doTrace[l] = have && out->traceOff != 0 && out->status == GA_OK;
+			memset(&lanes[l].tm, 0, sizeof(GaTraceMem));
+			lanes[l].tm.S = S;
+			lanes[l].in = have ? streams + stream : streams;
+			if (have) lanes[l].tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
+			ga_trace_init(lanes[l], doTrace[l], doTrace[l] ? out->nSlices : 0, doTrace[l] ? out->endNode : 0, doTrace[l] ? out->endOff : 0, doTrace[l] ? out->score : 0);
 		}
-		if (off + words > arenaCap) continue;
-		for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = tm.moves[(size_t)i * S];
-		for (uint32_t i = 0; i < nPath; i++) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
-		for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
+		ga_trace_warp<HT, HP>(g, sh, 0, lanes, S);
+		for (int l = 0; l < HT; l++)
+		{
+			const uint32_t stream = first + l;
+			if (stream >= nStreams) break;
+			ga_stream_out* out = outs + stream;
+			const GaTraceMem& tm = lanes[l].tm;
+			const uint32_t nMoves = lanes[l].t.nMoves, nPath = lanes[l].t.nPath, nRuns = lanes[l].t.nRuns;
+			const uint32_t moveWords = (nMoves + 15) / 16;
+			const uint32_t runWords = nRuns * GA_RUN_WORDS;
+			const uint32_t words = moveWords + nPath + runWords;
+			const unsigned long long off = *arenaTop;
+			*arenaTop += words;
+			out->traceOff = off;
+			if (doTrace[l])
+			{
+				out->nMoves = nMoves;
+				out->nPathNodes = nPath;
+				out->nRuns = nRuns;
+				out->nPositions = ga_trace_positions(lanes[l].t);
+				out->status = off + words > arenaCap && lanes[l].t.status == GA_OK ? GA_ERR_TRACE_OVERFLOW : lanes[l].t.status;
+			}
+			if (off + words > arenaCap) continue;
+			for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = tm.moves[(size_t)i * S];
+			for (uint32_t i = 0; i < nPath; i++) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
+			for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
+		}
 	}
 }
 #endif
@@ -459,6 +479,7 @@ struct DeviceCtx
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
+	int traceT = 0, traceP = 2; // GA_TRACE_T / GA_TRACE_P env: streams per warp / 32-column passes per window of the traceback kernel (tuning)
 	int smCount = 148;
 	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
@@ -571,6 +592,8 @@ DeviceCtx* CreateDevice(int device)
 	ctx->sched = probeUmapSchedule(70000);
 	if (const char* f = getenv("GA_DEBUG_FLAGS")) ctx->debugFlags = (uint32_t)atoi(f);
 	if (const char* f = getenv("GA_STREAMS_PER_WARP")) ctx->forceS = atoi(f);
+	if (const char* f = getenv("GA_TRACE_T")) ctx->traceT = atoi(f);
+	if (const char* f = getenv("GA_TRACE_P")) ctx->traceP = atoi(f);
 	{
 		cudaDeviceProp prop;
 		GA_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -927,13 +950,30 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
 }
 
-static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
+template <int T, int P>
+static void launchTraceTP(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
 	static bool attr = false;
-	if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<32>))); attr = true; }
-	ga_trace_kernel<<<(unsigned)((n + 31) / 32), 32, sizeof(GaTraceShared<32>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n, (uint32_t)sb->S,
-		(ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+	if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<T, P>))); attr = true; }
+	ga_trace_kernel<T, P><<<(unsigned)((n + T - 1) / T), 32, sizeof(GaTraceShared<T, P>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n,
+		(uint32_t)sb->S, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
+}
+
+static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
+{
+	// streams per warp: few, so that a batch is many warps (the walk is latency-bound); more once every SM has its share
+	const size_t n = sb->sorted.size();
+	int T = ctx->traceT;
+	if (T == 0) T = n <= (size_t)ctx->smCount * 8 * 8 ? 8 : (n <= (size_t)ctx->smCount * 8 * 16 ? 16 : 32);
+	const int P = ctx->traceP;
+	if (T == 8 && P == 1) launchTraceTP<8, 1>(ctx, sb);
+	else if (T == 8) launchTraceTP<8, 2>(ctx, sb);
+	else if (T == 16 && P == 1) launchTraceTP<16, 1>(ctx, sb);
+	else if (T == 16) launchTraceTP<16, 2>(ctx, sb);
+	else if (T == 4) launchTraceTP<4, 2>(ctx, sb);
+	else if (P == 1) launchTraceTP<32, 1>(ctx, sb);
+	else launchTraceTP<32, 2>(ctx, sb);
 }
 #endif
 
