@@ -31,7 +31,7 @@ BAND = 10
 # algorithmic work per forward word update (64 cells), DESIGN.md "Roofline":
 BYTES_PER_WORD_COLUMN = 72.25    # 0.25 bases + 4 previous-slice end state in + 4 end state out + 64-byte history record (VP, VN, scores, traceback masks)
 LANE_OPS_PER_WORD_COLUMN = 50.0
-PIPELINE_DEPTH = 2               # contexts per GPU in the end-to-end arm (ga_pipeline_*)
+PIPELINE_DEPTH = int(os.environ.get("GA_PIPELINE_DEPTH", "2"))
 
 
 def load_traffic():

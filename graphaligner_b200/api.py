@@ -20,8 +20,7 @@ class GaBatch(C.Structure):
 READ_RESULT = np.dtype([("failed", "<i4"), ("score", "<i4"), ("alignment_start", "<u8"), ("alignment_end", "<u8"),
                         ("query_position", "<i4"), ("flags", "<u4"), ("mapping_offset", "<u8"), ("n_mappings", "<u8"),
                         ("reserved", "<u8"), ("n_trace", "<u8"), ("word_columns", "<u8")])
-MAPPING = np.dtype([("node_id", "<i8"), ("offset", "<i8"), ("rank", "<i8"), ("is_reverse", "<i4"), ("from_length", "<i4"),
-                    ("to_length", "<i4"), ("reserved", "<u4"), ("read_start", "<u8")])
+MAPPING = np.dtype([("node_id", "<i8"), ("offset", "<u4"), ("rank", "<u4"), ("from_length", "<i4"), ("to_length", "<i4"), ("read_start", "<u4"), ("is_reverse", "<u4")])
 TRACE_ITEM = np.dtype([("node_id", "<i4"), ("offset", "<u4"), ("readpos", "<u8"), ("reverse", "u1"), ("type", "u1"),
                        ("graph_char", "S1"), ("read_char", "S1"), ("reserved", "<u4")])
 

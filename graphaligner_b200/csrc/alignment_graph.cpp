@@ -132,6 +132,13 @@ void AlignmentGraph::Finalize(int wordSize)
 	{
 		if (inOff[i + 1] - inOff[i] >= 2) special++;
 	}
+	reverseNode.assign(n, 0xffffffffu);
+	for (size_t i = 0; i < n; i++)
+	{
+		const int id = nodeIDs[i];
+		auto found = nodeLookup.find(id % 2 == 1 ? (id / 2) * 2 : (id / 2) * 2 + 1);
+		if (found != nodeLookup.end()) reverseNode[i] = found->second;
+	}
 	// same graph statistics on stderr as the reference (AlignmentGraph.cpp:125-138)
 	std::cerr << n << " nodes" << std::endl;
 	std::cerr << totalBp << "bp" << std::endl;
@@ -154,7 +161,8 @@ bool AlignmentGraph::HasNode(int digraphNodeId) const
 
 size_t AlignmentGraph::GetReverseNode(size_t nodeIndex) const
 {
-	// AlignmentGraph.cpp:199-214
+	// AlignmentGraph.cpp:199-214; the finalized graph answers from a table (one lookup per run of every trace)
+	if (finalized && reverseNode[nodeIndex] != 0xffffffffu) return reverseNode[nodeIndex];
 	int id = nodeIDs[nodeIndex];
 	int bigraphNodeId = id / 2;
 	return Lookup(id % 2 == 1 ? bigraphNodeId * 2 : bigraphNodeId * 2 + 1);

@@ -58,6 +58,7 @@ private:
 	std::vector<uint64_t> nodeStart;   // while building: one entry per node; Finalize appends the total
 	std::vector<int> nodeIDs;
 	std::vector<uint8_t> reverse;
+	std::vector<uint32_t> reverseNode;   // index of the node on the other strand (0xffffffff: none), built by Finalize
 	std::vector<uint32_t> seq2;
 	uint64_t totalBp;
 	std::unordered_map<int, uint32_t> nodeLookup;

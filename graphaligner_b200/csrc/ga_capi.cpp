@@ -233,13 +233,15 @@ static void fillStaged(ga_staged* st, const ga_batch* batch)
 	st->B = batch->ramp_bandwidth;
 }
 
-static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as)
+// the reads' records and, straight from the device's run records into their final place, the mappings
+static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as, const AlignmentGraph& graph, const std::vector<ga::ReadInput>& reads, const ga_stream_out* outs,
+	const uint32_t* arena)
 {
 	const size_t n = as.size();
 	out->reads.resize(n);
 	out->lazy.resize(n);
 	std::vector<uint64_t> mapOff(n + 1, 0);
-	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].mappings.size());
+	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].nMappings);
 	out->mappings.resize(mapOff[n]);
 	ga::ParallelFor(n, [&](size_t i) {
 		const ga::ReadAssembly& a = as[i];
@@ -255,22 +257,10 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 		o.alignment_start = a.alignmentStart;
 		o.alignment_end = a.alignmentEnd;
 		o.query_position = a.queryPosition;
-		o.n_mappings = a.mappings.size();
+		o.n_mappings = a.nMappings;
 		o.n_trace = a.nTraceItems;
 		ga_mapping* dst = out->mappings.data() + mapOff[i];
-		for (auto& m : a.mappings)
-		{
-			ga_mapping gm;
-			memset(&gm, 0, sizeof(gm));
-			gm.node_id = m.node_id;
-			gm.offset = m.offset;
-			gm.rank = m.rank;
-			gm.is_reverse = m.is_reverse ? 1 : 0;
-			gm.from_length = m.from_length;
-			gm.to_length = m.to_length;
-			gm.read_start = m.read_start;
-			*dst++ = gm;
-		}
+		ga::WriteMappings(graph, reads[i], a, outs, arena, dst);
 	});
 }
 
@@ -288,6 +278,7 @@ static ga_staged* stageOn(ga_ctx* ctx, ga::DeviceCtx* dev, const ga_batch* batch
 			[dev, &pinned](size_t off, size_t bytes) { ga::UploadPartsRange(dev, pinned, off, bytes); }));
 		tm.lap("stage: plan + build parts");
 		st->device = ga::StageAndUpload(dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats, true);
+		ga::SetReadRanges(dev, st->device, st->plan->readOff);
 		tm.lap("stage: layout + H2D");
 	});
 	if (rc != 0)
@@ -317,19 +308,19 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 		StageTimer tm;
 		res->chunks.emplace_back(new ga_results::Chunk());
 		ga_results::Chunk& ch = *res->chunks.back();
-		ga::FinishStaged(st->dev, st->device, ch.outs, ch.arena, &ctx->stats);
+		ga::FinishStaged(st->dev, st->device, ch.outs, ch.arena, &ctx->stats, &st->plan->badChar);
 		tm.lap("finish: wait kernel + D2H");
 		const AlignmentGraph& graph = ctx->graph->graph;
 		const size_t n = st->reads.size();
 		std::vector<ga::ReadAssembly> as(n);
 		ga::ParallelFor(n, [&](size_t i) {
 			if (st->reads[i].nSeeds == 0) return;   // stays failed: "has no seed hits" (Aligner.cpp:131-138)
-			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, ch.outs.data(), ch.arena.data());
+			as[i] = ga::AssembleRead(graph, st->reads[i], *st->plan, (uint32_t)i, ch.outs.data(), ch.arena.data(), false);
 		});
 		tm.lap("finish: assemble reads");
 		ctx->stats.streams += st->plan->streams.size();
 		for (size_t i = 0; i < ch.outs.size(); i++) ctx->stats.wordColumns += ch.outs.data()[i].wordColumns;
-		packResults(res, as);
+		packResults(res, as, graph, st->reads, ch.outs.data(), ch.arena.data());
 		res->graph = &graph;
 		res->inputs = st->reads;
 		ch.streams = st->plan->streams;

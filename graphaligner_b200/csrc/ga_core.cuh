@@ -497,7 +497,7 @@ GA_DEV void ga_umap_order(const GaUmapSchedule& sch, const GaLaneMem& mem, uint3
 struct GaStreamState
 {
 	// stream constants
-	const uint8_t* seq;
+	const uint32_t* aux;   // per slice: exact code of the read character above the slice | IUPAC mask of the part's first character << 4 (ga_peq_kernel)
 	uint32_t partLen;
 	uint32_t nslices;
 	uint32_t startNode;
@@ -892,7 +892,7 @@ GA_DEV void ga_calc_node(const ga_graph_view& g, const ga_caps& caps, const GaLa
 		uint64_t mismatch = 1;
 		if (cx.firstSlice)
 		{
-			uint32_t m = ga_iupac_mask(st.seq[0]);
+			uint32_t m = st.aux[0] >> 4;
 			mismatch = ((m >> base) & 1u) ? 0 : 1;
 		}
 		c0.VP = (~(uint64_t)1) | mismatch;
@@ -1176,7 +1176,7 @@ GA_DEV int32_t ga_ex_calc_node(const ga_graph_view& g, const ga_caps& caps, cons
 		if (!inPrev) { st.status = GA_ERR_INTERNAL; return minScore; }
 		const int32_t ps = ga_tiny_score(oldTiny);
 		uint64_t mismatch = 1;
-		if (cx.firstSlice) mismatch = ((ga_iupac_mask(st.seq[0]) >> base) & 1u) ? 0 : 1;
+		if (cx.firstSlice) mismatch = (((st.aux[0] >> 4) >> base) & 1u) ? 0 : 1;
 		res.VP = (~(uint64_t)1) | mismatch; res.VN = 0; res.scoreEnd = ps + 63 + (int32_t)mismatch; res.sbs = ps;
 		res.rows = 64; res.partial = false; res.sbE = true;
 	}
@@ -1423,7 +1423,7 @@ GA_DEV bool ga_fill_slice(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.BT = (uint64_t)b.z | ((uint64_t)b.w << 32);
 		cx.eqTab = mem.eqTab;
 		cx.eqTab[0] = cx.BA; cx.eqTab[LANES] = cx.BC; cx.eqTab[2 * LANES] = cx.BG; cx.eqTab[3 * LANES] = cx.BT;
-		cx.prevCharCode = cx.s > 0 ? ga_exact_code(st.seq[(size_t)cx.s * 64 - 1]) : 4;
+		cx.prevCharCode = cx.s > 0 ? (st.aux[cx.s] & 7u) : 4;
 		cx.firstSlice = cx.s == 0;
 	}
 	GA_TLAP(st, 13);
@@ -1800,19 +1800,55 @@ GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const 
 	if (active) out->traceOff = doTrace ? 1 : 0;
 }
 
-// Match masks of 64 read characters: bit i of {A,C,G,T} word = characterMatch(read[i], base) with IUPAC codes
-// (GraphAligner.h:2338-2351).  Used by the Peq pre-pass kernel.
-GA_DEV void ga_peq_words(const uint8_t* p, uint64_t& BA, uint64_t& BC, uint64_t& BG, uint64_t& BT)
+// The parts of a read are never materialised: a stream names its source range in the batch's raw read bytes
+// (ga_stream_in::seqOff, srcInfo) and the Peq pre-pass reads the characters from there - forwards for the part after the
+// seed, backwards and complemented for the part before it (getSplitAlignment, GraphAligner.h:2969-3024 with
+// CommonUtils::ReverseComplement), 'N' beyond the real length (the padding to a multiple of 64 rows).
+// Character i of the part as (IUPAC match mask, exact code): the mask of a complemented character is the mask with A<->T and
+// C<->G exchanged (bit reversal of the 4-bit set); the exact code (GraphAligner.h:1540 compares characters, so only the
+// upper-case letters the graph holds can be equal) of a complemented character is always that of an upper-case letter.
+GA_DEV void ga_part_char(const uint8_t* raw, const ga_stream_in& in, uint32_t i, uint32_t& mask, uint32_t& code)
+{
+	const uint32_t real = in.srcInfo & 0x7fffffffu;
+	if (i >= real) { mask = 15; code = 4; return; }
+	if (in.srcInfo & 0x80000000u)
+	{
+		const uint8_t c = raw[in.seqOff - i];
+		const uint32_t m = ga_iupac_mask(c);
+		mask = ((m & 1u) << 3) | ((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 8u) >> 3);
+		code = mask == 1 ? 0u : (mask == 2 ? 1u : (mask == 4 ? 2u : (mask == 8 ? 3u : 4u)));
+	}
+	else
+	{
+		const uint8_t c = raw[in.seqOff + i];
+		mask = ga_iupac_mask(c);
+		code = ga_exact_code(c);
+	}
+}
+
+// Match masks of the 64 read characters of slice sl: bit i of {A,C,G,T} word = characterMatch(read[i], base) with IUPAC
+// codes (GraphAligner.h:2338-2351).  Used by the Peq pre-pass kernel.
+GA_DEV void ga_peq_words(const uint8_t* raw, const ga_stream_in& in, uint32_t sl, uint64_t& BA, uint64_t& BC, uint64_t& BG, uint64_t& BT)
 {
 	BA = BC = BG = BT = 0;
-	for (int i = 0; i < 64; i++)
+	for (uint32_t i = 0; i < 64; i++)
 	{
-		uint32_t m = ga_iupac_mask(p[i]);
+		uint32_t m, code;
+		ga_part_char(raw, in, sl * 64 + i, m, code);
 		BA |= (uint64_t)(m & 1u) << i;
 		BC |= (uint64_t)((m >> 1) & 1u) << i;
 		BG |= (uint64_t)((m >> 2) & 1u) << i;
 		BT |= (uint64_t)((m >> 3) & 1u) << i;
 	}
+}
+
+// the per-slice word of the Peq pre-pass next to the match masks (GaStreamState::aux)
+GA_DEV uint32_t ga_peq_aux(const uint8_t* raw, const ga_stream_in& in, uint32_t sl)
+{
+	uint32_t m0, c0, mp = 0, cp = 4;
+	ga_part_char(raw, in, 0, m0, c0);
+	if (sl > 0) ga_part_char(raw, in, sl * 64 - 1, mp, cp);
+	return cp | (m0 << 4);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1821,12 +1857,12 @@ GA_DEV void ga_peq_words(const uint8_t* p, uint64_t& BA, uint64_t& BC, uint64_t&
 // ------------------------------------------------------------------------------------------------------------
 template <int LANES, bool SMALL>
 GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaUmapSchedule& sch, const GaLaneMem& mem, bool active,
-	const ga_stream_in* in, const uint8_t* parts, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* out)
+	const ga_stream_in* in, const uint32_t* peqAux, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* out)
 {
 	GaStreamState st;
 	st.status = GA_OK;
 	st.done = !active;
-	st.seq = active ? parts + in->seqOff : nullptr;
+	st.aux = active ? peqAux : nullptr;
 	st.partLen = active ? in->partLen : 0;
 	st.nslices = st.partLen / 64;
 	st.startNode = active ? in->startNode : 0;

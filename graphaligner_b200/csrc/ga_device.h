@@ -26,10 +26,13 @@ size_t GraphBytesOnDevice(DeviceCtx* ctx);
 // INT32 lane-ops per second of a dependency-free LOP3/IADD3 kernel on this device (roofline denominator)
 double MeasureInt32Peak(DeviceCtx* ctx);
 
-// plans the per-warp memory layout and copies parts + stream descriptors to the device.  `parts` must outlive the batch.
-// partsOnDevice: the parts were already uploaded range by range (UploadPartsRange) while they were built
+// plans the per-warp memory layout and copies the reads' bytes (`parts`) + stream descriptors to the device.  `parts` must
+// outlive the batch.  partsOnDevice: they were already uploaded range by range (UploadPartsRange) while they were staged
 StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth, BatchStats* stats,
 	bool partsOnDevice = false);
+// where each read lies in `parts` (n + 1 offsets): the batch's run then also checks every read for characters the reference
+// aborts on; FinishStaged hands the flags back through `badChar` (one byte per read)
+void SetReadRanges(DeviceCtx* ctx, StagedBatch* batch, const std::vector<uint64_t>& readOff);
 // asynchronous upload of parts[offset, offset + bytes) (parts = the buffer AllocPinnedParts returned) to the same offset on the device
 void UploadPartsRange(DeviceCtx* ctx, const uint8_t* parts, size_t offset, size_t bytes);
 // pinned host memory for a batch's padded parts (grow-only, owned by the context, reused by the next batch)
@@ -40,7 +43,7 @@ size_t FreeDeviceBytes(DeviceCtx* ctx);
 // launches the alignment kernel(s) on the context's stream (asynchronous); returns number of launches
 int RunStaged(DeviceCtx* ctx, StagedBatch* batch);
 // waits, copies results back, re-runs streams that overflowed their scratch with larger capacities
-void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats);
+void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar = nullptr);
 void FreeStaged(DeviceCtx* ctx, StagedBatch* batch);
 void* DeviceStream(DeviceCtx* ctx);   // cudaStream_t
 void SyncDevice(DeviceCtx* ctx);

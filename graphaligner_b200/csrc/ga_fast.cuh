@@ -405,7 +405,7 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 	GaStreamState st;
 	st.status = GA_OK;
 	st.done = !active;
-	st.seq = nullptr;
+	st.aux = nullptr;
 	st.partLen = active ? in->partLen : 0;
 	st.nslices = st.partLen / 64;
 	st.startNode = active ? in->startNode : 0;

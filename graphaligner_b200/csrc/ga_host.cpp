@@ -1,4 +1,5 @@
 #include "ga_host.h"
+#include "../../include/graphaligner_b200.h"
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -291,31 +292,15 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
-	// 256-entry tables: validity (the reference aborts on anything outside its IUPAC switch) and complement
-	static const struct Tables
-	{
-		uint8_t valid[256];
-		uint8_t comp[256];
-		Tables()
-		{
-			for (int c = 0; c < 256; c++)
-			{
-				valid[c] = ValidReadChar((char)c) ? 1 : 0;
-				comp[c] = (uint8_t)complementOf((char)c);
-			}
-		}
-	} tables;
-	ParallelFor(n, [&](size_t i) {
-		const uint8_t* p = (const uint8_t*)reads[i].seq;
-		const size_t len = reads[i].seqLen;
-		uint8_t ok = 1;
-		for (size_t k = 0; k < len; k++) ok &= tables.valid[p[k]];
-		badChar[i] = ok ? 0 : 1;
-	});
-	struct Job { uint32_t read; uint32_t backward; size_t pos; };
-	std::vector<Job> jobs;
-	firstSeedOfRead.reserve(n + 1);
+	// the reads' bytes go to the device as they are, back to back; a stream names its source range in them and the
+	// device reads the (reverse-complemented, padded) part from there.  Which reads hold a character the reference
+	// aborts on is found out on the device as well (badChar is filled in when the results come back).
+	readOff.resize(n + 1);
 	size_t top = 0;
+	for (size_t ri = 0; ri < n; ri++) { readOff[ri] = top; top += reads[ri].seqLen; }
+	readOff[n] = top;
+	partsBytes = top;
+	firstSeedOfRead.reserve(n + 1);
 	const size_t overlap = (size_t)graph.DBGOverlap;
 	for (size_t ri = 0; ri < n; ri++)
 	{
@@ -333,7 +318,7 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 			int nodeId = std::get<0>(hit);
 			size_t pos = std::get<1>(hit);
 			bool backwards = std::get<2>(hit);
-			if (badChar[ri] || !graph.HasNode(nodeId * 2) || !graph.HasNode(nodeId * 2 + 1) || pos >= len || pos + overlap > len)
+			if (!graph.HasNode(nodeId * 2) || !graph.HasNode(nodeId * 2 + 1) || pos >= len || pos + overlap > len)
 			{
 				sp.invalid = true;
 				seeds.push_back(sp);
@@ -348,75 +333,53 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 				size_t partLen = pos + overlap;
 				ga_stream_in in;
 				in.startNode = (uint32_t)backwardNode;
-				in.seqOff = top;
+				in.seqOff = readOff[ri] + partLen - 1;
 				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
 				in.trimRows = (uint32_t)pos;                       // GraphAligner.h:3086-3089
-				in.reserved = 0;
-				top += in.partLen;
+				in.srcInfo = (uint32_t)partLen | 0x80000000u;
 				sp.bwStream = (int64_t)streams.size();
 				streams.push_back(in);
-				jobs.push_back(Job { (uint32_t)ri, 1, pos });
 			}
 			if (pos < len - 1)
 			{
 				size_t partLen = len - pos;
 				ga_stream_in in;
 				in.startNode = (uint32_t)forwardNode;
-				in.seqOff = top;
+				in.seqOff = readOff[ri] + pos;
 				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
 				in.trimRows = (uint32_t)(len - pos - overlap);     // GraphAligner.h:3063-3066
-				in.reserved = 0;
-				top += in.partLen;
+				in.srcInfo = (uint32_t)partLen;
 				sp.fwStream = (int64_t)streams.size();
 				streams.push_back(in);
-				jobs.push_back(Job { (uint32_t)ri, 0, pos });
 			}
 			seeds.push_back(sp);
 		}
 	}
 	firstSeedOfRead.push_back((uint32_t)seeds.size());
-	partsBytes = top;
 	if (allocParts) parts = allocParts(top + 64);
 	else
 	{
 		ownedParts.resize(top + 64);
 		parts = ownedParts.data();
 	}
-	// jobs lie back to back in the parts buffer: a few groups of consecutive jobs, each handed over when it is complete
-	const size_t groups = partsReady ? std::min<size_t>(4, std::max<size_t>(1, jobs.size() / 64)) : 1;
+	// the copy into the (pinned) staging buffer: a few groups of consecutive reads, each handed over when it is complete
+	const size_t groups = partsReady ? std::min<size_t>(4, std::max<size_t>(1, n / 64)) : 1;
 	size_t groupBegin = 0;
 	for (size_t gi = 0; gi < groups; gi++)
 	{
-	size_t groupEnd = groupBegin;
-	const size_t targetBytes = top * (gi + 1) / groups;
-	while (groupEnd < jobs.size() && (gi + 1 == groups || streams[groupEnd].seqOff + streams[groupEnd].partLen <= targetBytes)) groupEnd++;
-	const size_t first = groupBegin;
-	ParallelFor(groupEnd - groupBegin, [&](size_t kk) {
-		const size_t k = first + kk;
-		const Job& job = jobs[k];
-		const ga_stream_in& in = streams[k];
-		const ReadInput& r = reads[job.read];
-		uint8_t* dst = parts + in.seqOff;
-		size_t real;
-		if (job.backward)
+		size_t groupEnd = groupBegin;
+		const size_t targetBytes = top * (gi + 1) / groups;
+		while (groupEnd < n && (gi + 1 == groups || readOff[groupEnd + 1] <= targetBytes)) groupEnd++;
+		// pieces of at most 1 MiB so that a few long reads still spread over the workers
+		struct Piece { size_t off, bytes; const char* src; };
+		std::vector<Piece> pieces;
+		for (size_t ri = groupBegin; ri < groupEnd; ri++)
 		{
-			real = job.pos + overlap;
-			const uint8_t* src = (const uint8_t*)r.seq;
-			for (size_t i = 0; i < real; i++) dst[i] = tables.comp[src[real - 1 - i]];
+			for (size_t o = 0; o < reads[ri].seqLen; o += (size_t)1 << 20) pieces.push_back(Piece { readOff[ri] + o, std::min<size_t>((size_t)1 << 20, reads[ri].seqLen - o), reads[ri].seq + o });
 		}
-		else
-		{
-			real = r.seqLen - job.pos;
-			memcpy(dst, r.seq + job.pos, real);
-		}
-		memset(dst + real, 'N', in.partLen - real);
-	});
-	if (partsReady && groupEnd > groupBegin)
-	{
-		const size_t off = streams[groupBegin].seqOff;
-		partsReady(off, streams[groupEnd - 1].seqOff + streams[groupEnd - 1].partLen - off);
-	}
-	groupBegin = groupEnd;
+		ParallelFor(pieces.size(), [&](size_t k) { memcpy(parts + pieces[k].off, pieces[k].src, pieces[k].bytes); });
+		if (partsReady && groupEnd > groupBegin && readOff[groupEnd] > readOff[groupBegin]) partsReady(readOff[groupBegin], readOff[groupEnd] - readOff[groupBegin]);
+		groupBegin = groupEnd;
 	}
 }
 
@@ -447,20 +410,6 @@ bool charMatch(char readChar, char graphChar)
 	}
 }
 
-
-// same-node runs of one stream's trimmed trace, in forward (ascending row) order
-void decodeRuns(const ga_stream_out& out, const uint32_t* arena, std::vector<TraceRun>& runs)
-{
-	runs.clear();
-	if (out.status != GA_OK || out.nSlices <= 0) return;
-	const uint32_t* rec = arena + out.traceOff + (out.nMoves + 15) / 16 + out.nPathNodes;
-	runs.resize(out.nRuns);
-	for (uint32_t k = 0; k < out.nRuns; k++)
-	{
-		const uint32_t* r = rec + (size_t)(out.nRuns - 1 - k) * GA_RUN_WORDS;
-		runs[k] = TraceRun { r[0], r[1], r[2], (size_t)r[3], (size_t)r[4] };
-	}
-}
 
 // every position of one stream's trimmed trace in forward order (only needed for TraceItems)
 void decodePositions(const AlignmentGraph& graph, const ga_stream_in& in, const ga_stream_out& out, const uint32_t* arena, std::vector<MatrixPos>& t)
@@ -498,87 +447,12 @@ void decodePositions(const AlignmentGraph& graph, const ga_stream_in& in, const 
 	std::reverse(t.begin(), t.end());
 }
 
-// reverseTrace (GraphAligner.h:3026-3037) on runs: order reversed, positions mapped to the other strand,
-// rows mirrored around `end`
-void reverseRuns(const AlignmentGraph& graph, std::vector<TraceRun>& runs, size_t end)
-{
-	std::reverse(runs.begin(), runs.end());
-	for (auto& r : runs)
-	{
-		size_t other = graph.GetReverseNode(r.node);
-		uint32_t len = (uint32_t)graph.NodeLength(other);
-		TraceRun n;
-		n.node = (uint32_t)other;
-		n.firstOff = len - 1 - r.lastOff;
-		n.lastOff = len - 1 - r.firstOff;
-		n.firstJ = end - r.lastJ;
-		n.lastJ = end - r.firstJ;
-		r = n;
-	}
-}
-
 AlignmentResult emptyAlignment()
 {
 	AlignmentResult r;
 	r.alignment.score = std::numeric_limits<int32_t>::max();
 	r.alignmentFailed = true;
 	return r;
-}
-
-// traceToAlignment, GraphAligner.h:782-847, from runs: one Mapping per run with exactly one Edit; non-final
-// mappings get from_length = end - start + 1, the final one end - start; only the first mapping has an offset.
-// Returns false for a failed (empty) direction.
-bool runsToMappings(const AlignmentGraph& graph, const ReadInput& read, const std::vector<TraceRun>& runs, std::vector<FlatMapping>& out)
-{
-	out.clear();
-	if (runs.empty()) return false;
-	size_t k = 0;
-	while (runs[k].node == graph.DummyNodeStart())
-	{
-		k++;
-		if (k == runs.size()) return false;
-	}
-	if (runs[k].node == graph.DummyNodeEnd()) return false;
-	size_t last = k;
-	while (last + 1 < runs.size() && runs[last + 1].node != graph.DummyNodeEnd()) last++;
-	out.resize(last - k + 1);
-	size_t beforeJ = runs[k].firstJ;
-	for (size_t i = k; i <= last; i++)
-	{
-		FlatMapping& m = out[i - k];
-		m.rank = (int64_t)(i - k);
-		m.node_id = graph.NodeID(runs[i].node);
-		m.is_reverse = graph.Reverse(runs[i].node);
-		m.offset = i == k ? runs[i].firstOff : 0;
-		m.from_length = (int32_t)(runs[i].lastOff - runs[i].firstOff) + (i == last ? 0 : 1);
-		m.to_length = (int32_t)(runs[i].lastJ - beforeJ);
-		m.read_start = runs[i].firstJ;
-		if (runs[i].firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");   // what sequence.substr would do
-		beforeJ = runs[i].lastJ;
-	}
-	return true;
-}
-
-// mergeAlignments, GraphAligner.h:648-688, on flat mappings: bw first, then fw without its first mapping when both
-// meet on the same node
-void mergeMappings(const AlignmentGraph& graph, bool firstOk, std::vector<FlatMapping>& first, int32_t firstScore, bool secondOk, std::vector<FlatMapping>& second,
-	int32_t secondScore, std::vector<FlatMapping>& out, int32_t& score)
-{
-	if (!firstOk) { out.swap(second); score = secondScore; return; }
-	if (!secondOk) { out.swap(first); score = firstScore; return; }
-	if (first.empty()) { out.swap(second); score = secondScore; return; }
-	if (second.empty()) { out.swap(first); score = firstScore; return; }
-	score = firstScore + secondScore;
-	const FlatMapping& firstEnd = first.back();
-	const FlatMapping& secondStart = second.front();
-	size_t firstEndNode = graph.Lookup((int)firstEnd.node_id);
-	size_t secondStartNode = graph.Lookup((int)secondStart.node_id);
-	size_t start = 0;
-	if (firstEnd.node_id == secondStart.node_id && firstEnd.is_reverse == secondStart.is_reverse) start = 1;
-	else if (graph.HasOutNeighbor(firstEndNode, secondStartNode)) start = 0;
-	// else: the reference only logs "Piecewise alignments can't be merged!" and appends everything
-	out.swap(first);
-	out.insert(out.end(), second.begin() + start, second.end());
 }
 
 // getTraceInfoInner, GraphAligner.h:718-780
@@ -611,8 +485,92 @@ void traceInfoInner(const AlignmentGraph& graph, const ReadInput& read, const st
 
 }
 
+namespace
+{
+
+// The same-node runs of one stream's trace in the orientation the read is reported in, straight from the device's record
+// (backward order, GA_RUN_WORDS words each), without a copy:
+//   forward part   run i = record n-1-i, rows shifted by `shift` (getPiecewiseTracesFromSplit, GraphAligner.h:3090-3093)
+//   backward part  reverseTrace (GraphAligner.h:3026-3037): order reversed, positions mapped to the other strand, rows
+//                  mirrored around `end` - so run i = record i
+struct RunView
+{
+	const AlignmentGraph* graph = nullptr;
+	const uint32_t* rec = nullptr;
+	size_t n = 0;
+	bool backward = false;
+	size_t end = 0, shift = 0;
+	uint32_t node(size_t i) const
+	{
+		if (!backward) return rec[(n - 1 - i) * GA_RUN_WORDS];
+		return (uint32_t)graph->GetReverseNode(rec[i * GA_RUN_WORDS]);
+	}
+	TraceRun get(size_t i) const
+	{
+		if (!backward)
+		{
+			const uint32_t* r = rec + (n - 1 - i) * GA_RUN_WORDS;
+			return TraceRun { r[0], r[1], r[2], (size_t)r[3] + shift, (size_t)r[4] + shift };
+		}
+		const uint32_t* r = rec + i * GA_RUN_WORDS;
+		const size_t other = graph->GetReverseNode(r[0]);
+		const uint32_t len = (uint32_t)graph->NodeLength(other);
+		return TraceRun { (uint32_t)other, len - 1 - r[2], len - 1 - r[1], end - (size_t)r[4], end - (size_t)r[3] };
+	}
+};
+
+RunView viewOf(const AlignmentGraph& graph, const ga_stream_out& out, const uint32_t* arena, bool backward, size_t end, size_t shift)
+{
+	RunView v;
+	v.graph = &graph;
+	v.backward = backward;
+	v.end = end;
+	v.shift = shift;
+	if (out.status != GA_OK || out.nSlices <= 0) return v;
+	v.rec = arena + out.traceOff + (out.nMoves + 15) / 16 + out.nPathNodes;
+	v.n = out.nRuns;
+	return v;
+}
+
+// traceToAlignment, GraphAligner.h:782-847, from runs: one Mapping per run with exactly one Edit; the runs on the dummy
+// nodes at either end are dropped.  Returns false for a failed (empty) direction, else the range [k, last] of runs kept.
+bool mappingRange(const AlignmentGraph& graph, const RunView& v, size_t& k, size_t& last)
+{
+	if (v.n == 0) return false;
+	k = 0;
+	while (v.node(k) == graph.DummyNodeStart())
+	{
+		k++;
+		if (k == v.n) return false;
+	}
+	if (v.node(k) == graph.DummyNodeEnd()) return false;
+	last = k;
+	while (last + 1 < v.n && v.node(last + 1) != graph.DummyNodeEnd()) last++;
+	return true;
+}
+
+// mapping i (k <= i <= last) of a direction: non-final mappings get from_length = end - start + 1, the final one
+// end - start; only the first mapping has an offset
+FlatMapping mappingOf(const AlignmentGraph& graph, const ReadInput& read, const RunView& v, size_t k, size_t last, size_t i, size_t& beforeJ)
+{
+	const TraceRun r = v.get(i);
+	FlatMapping m;
+	m.rank = (int64_t)(i - k);
+	m.node_id = graph.NodeID(r.node);
+	m.is_reverse = graph.Reverse(r.node);
+	m.offset = i == k ? r.firstOff : 0;
+	m.from_length = (int32_t)(r.lastOff - r.firstOff) + (i == last ? 0 : 1);
+	m.to_length = (int32_t)(r.lastJ - beforeJ);
+	m.read_start = r.firstJ;
+	if (r.firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");   // what sequence.substr would do
+	beforeJ = r.lastJ;
+	return m;
+}
+
+}
+
 ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const ga_stream_out* outs, const uint32_t* arena)
+	const ga_stream_out* outs, const uint32_t* arena, bool materialize)
 {
 	ReadAssembly as;
 	uint32_t first = plan.firstSeedOfRead[readIndex], last = plan.firstSeedOfRead[readIndex + 1];
@@ -622,9 +580,15 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		if (sp.fwStream >= 0) as.wordColumns += outs[sp.fwStream].wordColumns;
 		if (sp.bwStream >= 0) as.wordColumns += outs[sp.bwStream].wordColumns;
 	}
+	// reference: abort on a character outside its IUPAC switch, before any seed is looked at
+	if (plan.badChar[readIndex] && last > first)
+	{
+		as.flags |= FLAG_BAD_CHAR;
+		return as;
+	}
 	std::vector<std::tuple<size_t, size_t, size_t>> tried;
 	bool hasAlignment = false;
-	std::vector<TraceRun> fw, bw, bestFw, bestBw;
+	RunView bestFw, bestBw;
 	int32_t bestFwScore = 0, bestBwScore = 0;
 	size_t bestEstimated = 0, bestSeedPos = 0, bestFwN = 0, bestBwN = 0;
 	for (uint32_t k = first; k < last; k++)
@@ -633,8 +597,8 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		const SeedHit& hit = read.seeds[sp.seed];
 		if (sp.invalid)
 		{
-			// reference: nodeLookup.at / substr throw std::out_of_range (GraphAligner.h:423), or abort on a bad character
-			as.flags |= plan.badChar[readIndex] ? FLAG_BAD_CHAR : FLAG_BAD_SEED;
+			// reference: nodeLookup.at / substr throw std::out_of_range (GraphAligner.h:423)
+			as.flags |= FLAG_BAD_SEED;
 			return as;
 		}
 		size_t nodeIndex = graph.Lookup(std::get<0>(hit) * 2);
@@ -650,21 +614,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		bool streamError = false, shifted = false;
 		size_t fwSlices = 0, bwSlices = 0, fwN = 0, bwN = 0;
 		int32_t fwScore = 0, bwScore = 0;
-		fw.clear();
-		bw.clear();
-		if (sp.fwStream >= 0)
-		{
-			const ga_stream_out& o = outs[sp.fwStream];
-			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
-			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
-			if (o.status == GA_OK && o.nSlices > 0)
-			{
-				fwSlices = (size_t)o.nSlices;
-				fwScore = o.score;
-				fwN = o.nPositions;
-				decodeRuns(o, arena, fw);
-			}
-		}
+		RunView fw, bw;
 		if (sp.bwStream >= 0)
 		{
 			const ga_stream_out& o = outs[sp.bwStream];
@@ -675,11 +625,22 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 				bwSlices = (size_t)o.nSlices;
 				bwScore = o.score;
 				bwN = o.nPositions;
-				decodeRuns(o, arena, bw);
-				reverseRuns(graph, bw, splitIndex - 1);
+				bw = viewOf(graph, o, arena, true, splitIndex - 1, 0);
 				// the forward rows are shifted only inside this branch in the reference (GraphAligner.h:3090-3093)
-				for (auto& r : fw) { r.firstJ += splitIndex; r.lastJ += splitIndex; }
 				shifted = true;
+			}
+		}
+		if (sp.fwStream >= 0)
+		{
+			const ga_stream_out& o = outs[sp.fwStream];
+			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
+			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.status == GA_OK && o.nSlices > 0)
+			{
+				fwSlices = (size_t)o.nSlices;
+				fwScore = o.score;
+				fwN = o.nPositions;
+				fw = viewOf(graph, o, arena, false, 0, shifted ? splitIndex : 0);
 			}
 		}
 		if (streamError)
@@ -691,14 +652,14 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		// addAlignmentNodes, GraphAligner.h:594-634
 		if (k + 1 < last)   // only a later seed of this read ever looks at them
 		{
-			tried.reserve(tried.size() + fw.size() + bw.size());
-			for (auto& r : fw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
-			for (auto& r : bw) tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node);
+			tried.reserve(tried.size() + fw.n + bw.n);
+			for (size_t i = 0; i < fw.n; i++) { const TraceRun r = fw.get(i); tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node); }
+			for (size_t i = 0; i < bw.n; i++) { const TraceRun r = bw.get(i); tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node); }
 		}
 		if (!hasAlignment || estimated > bestEstimated)
 		{
-			bestFw.swap(fw);
-			bestBw.swap(bw);
+			bestFw = fw;
+			bestBw = bw;
 			bestFwScore = fwScore;
 			bestBwScore = bwScore;
 			bestFwN = fwN;
@@ -708,23 +669,93 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			hasAlignment = true;
 			as.fwStream = fwN > 0 ? sp.fwStream : -1;
 			as.bwStream = bwN > 0 ? sp.bwStream : -1;
+			as.mapFwStream = fw.n > 0 ? sp.fwStream : -1;
+			as.mapBwStream = bw.n > 0 ? sp.bwStream : -1;
 			as.splitIndex = splitIndex;
 			as.fwShifted = shifted;
 		}
 	}
 	if (!hasAlignment) return as;
-	std::vector<FlatMapping> fwMap, bwMap;
-	bool fwOk = runsToMappings(graph, read, bestFw, fwMap);
-	bool bwOk = runsToMappings(graph, read, bestBw, bwMap);
+	size_t fk = 0, fl = 0, bk = 0, bl = 0;
+	const bool fwOk = mappingRange(graph, bestFw, fk, fl);
+	const bool bwOk = mappingRange(graph, bestBw, bk, bl);
 	if (!fwOk && !bwOk) return as;
-	mergeMappings(graph, bwOk, bwMap, bestBwScore, fwOk, fwMap, bestFwScore, as.mappings, as.score);
-	size_t lastAligned = !bestBw.empty() ? bestBw[0].firstJ : bestSeedPos;
+	// mergeAlignments, GraphAligner.h:648-688: bw first, then fw without its first mapping when both meet on the same node
+	// (otherwise the reference checks the edge and, failing that, only logs "Piecewise alignments can't be merged!")
+	size_t start = 0;
+	if (fwOk && bwOk)
+	{
+		as.score = bestBwScore + bestFwScore;
+		const uint32_t a = bestBw.node(bl), b2 = bestFw.node(fk);
+		if (graph.NodeID(a) == graph.NodeID(b2) && graph.Reverse(a) == graph.Reverse(b2)) start = 1;
+	}
+	else as.score = bwOk ? bestBwScore : bestFwScore;
+	as.mapBwFirst = bk;
+	as.mapBwCount = bwOk ? bl - bk + 1 : 0;
+	as.mapFwFirst = fk;
+	as.mapFwCount = fwOk ? fl - fk + 1 : 0;
+	as.mapFwSkip = start;
+	as.nMappings = as.mapBwCount + as.mapFwCount - start;
+	size_t lastAligned = bestBw.n > 0 ? bestBw.get(0).firstJ : bestSeedPos;
 	as.queryPosition = (int32_t)lastAligned;
 	as.alignmentStart = lastAligned;
 	as.alignmentEnd = lastAligned + bestEstimated;
 	as.nTraceItems = (bestBwN > 0 ? bestBwN - 1 : 0) + ((bestBwN > 0 && bestFwN > 0) ? 1 : 0) + (bestFwN > 0 ? bestFwN - 1 : 0);
 	as.failed = false;
+	if (materialize)
+	{
+		as.mappings.resize(as.nMappings);
+		EmitMappings(graph, read, as, outs, arena, [&](size_t i, const FlatMapping& m) { as.mappings[i] = m; });
+	}
 	return as;
+}
+
+namespace
+{
+template <typename Sink>
+void emitMappingsTo(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, const Sink& sink)
+{
+	if (as.failed) return;
+	size_t idx = 0;
+	if (as.mapBwCount)
+	{
+		const RunView v = viewOf(graph, outs[as.mapBwStream], arena, true, as.splitIndex - 1, 0);
+		const size_t k = as.mapBwFirst, last = k + as.mapBwCount - 1;
+		size_t beforeJ = v.get(k).firstJ;
+		for (size_t i = k; i <= last; i++) sink(idx++, mappingOf(graph, read, v, k, last, i, beforeJ));
+	}
+	if (as.mapFwCount)
+	{
+		const RunView v = viewOf(graph, outs[as.mapFwStream], arena, false, 0, as.fwShifted ? as.splitIndex : 0);
+		const size_t k = as.mapFwFirst, last = k + as.mapFwCount - 1;
+		size_t beforeJ = v.get(k).firstJ;
+		for (size_t i = k; i <= last; i++)
+		{
+			const FlatMapping m = mappingOf(graph, read, v, k, last, i, beforeJ);
+			if (i - k >= as.mapFwSkip) sink(idx++, m);
+		}
+	}
+}
+}
+
+void EmitMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena,
+	const std::function<void(size_t, const FlatMapping&)>& sink)
+{
+	emitMappingsTo(graph, read, as, outs, arena, sink);
+}
+
+void WriteMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, ::ga_mapping* dst)
+{
+	emitMappingsTo(graph, read, as, outs, arena, [dst](size_t k, const FlatMapping& m) {
+		::ga_mapping& gm = dst[k];
+		gm.node_id = m.node_id;
+		gm.offset = (uint32_t)m.offset;
+		gm.rank = (uint32_t)m.rank;
+		gm.from_length = m.from_length;
+		gm.to_length = m.to_length;
+		gm.read_start = (uint32_t)m.read_start;
+		gm.is_reverse = m.is_reverse ? 1u : 0u;
+	});
 }
 
 AlignmentResult ToAlignmentResult(const ReadInput& read, const ReadAssembly& as, bool keepSequences)
@@ -812,7 +843,7 @@ std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& gr
 		// several contexts of one GPU take turns on the device part; planning and assembly overlap with the other's kernel
 		std::unique_lock<std::mutex> turn;
 		if (gpuTurn) turn = std::unique_lock<std::mutex>(*gpuTurn);
-		ExecuteStreams(ctx, plan.streams, plan.parts, plan.partsBytes, initialBandwidth, rampBandwidth, outs, arena, stats);
+		ExecuteStreams(ctx, plan.streams, plan.parts, plan.partsBytes, plan.readOff, initialBandwidth, rampBandwidth, outs, arena, plan.badChar, stats);
 	}
 	std::vector<AlignmentResult> results(reads.size());
 	ParallelFor(reads.size(), [&](size_t i) {

@@ -83,6 +83,8 @@ public:
 	uint32_t flags = 0;
 };
 
+struct ga_mapping;   // include/graphaligner_b200.h
+
 namespace ga
 {
 
@@ -176,7 +178,7 @@ std::string ReverseComplement(const std::string& s);
 bool ValidReadChar(char c);
 unsigned HostThreads();   // worker threads for the host-side passes (GA_HOST_THREADS or hardware_concurrency)
 
-// Plans the streams of a batch (two per seed: backward part, forward part) and writes the padded parts.
+// Plans the streams of a batch (two per seed: backward part, forward part) and stages the reads' bytes for the upload.
 class BatchPlan
 {
 public:
@@ -187,8 +189,9 @@ public:
 	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts = nullptr,
 		const std::function<void(size_t, size_t)>& partsReady = nullptr);
 	std::vector<ga_stream_in> streams;
-	uint8_t* parts = nullptr;       // padded parts of all streams, back to back
+	uint8_t* parts = nullptr;       // the reads' bytes, back to back (the streams' parts are ranges of them, ga_stream_in::seqOff / srcInfo)
 	size_t partsBytes = 0;
+	std::vector<uint64_t> readOff;  // size reads+1: where each read lies in `parts`
 	RawBuffer<uint8_t> ownedParts;
 	struct SeedPlan
 	{
@@ -200,7 +203,7 @@ public:
 	};
 	std::vector<SeedPlan> seeds;
 	std::vector<uint32_t> firstSeedOfRead;   // size reads+1
-	std::vector<uint8_t> badChar;            // per read
+	std::vector<uint8_t> badChar;            // per read: holds a character the reference aborts on (found on the device, valid once the results are back)
 };
 
 // What the seeded AlignOneWay decided for one read (GraphAligner.h:408-491): enough to build the
@@ -229,22 +232,33 @@ struct ReadAssembly
 	int32_t score = 0x7fffffff;
 	int32_t queryPosition = 0;
 	size_t alignmentStart = 0, alignmentEnd = 0;
+	// the path: mappings [mapBwFirst, +mapBwCount) of the backward stream's runs, then those of the forward stream without
+	// its first mapFwSkip (mergeAlignments); EmitMappings writes them out, `mappings` holds them only when asked for
+	int64_t mapFwStream = -1, mapBwStream = -1;
+	size_t mapBwFirst = 0, mapBwCount = 0, mapFwFirst = 0, mapFwCount = 0, mapFwSkip = 0;
+	size_t nMappings = 0;
 	std::vector<FlatMapping> mappings;
 };
 
 // the reference-shaped AlignmentResult (vg::Alignment with names / sequences / edits) of an assembled read
 AlignmentResult ToAlignmentResult(const ReadInput& read, const ReadAssembly& as, bool keepSequences);
 
+// materialize = false: the mappings are only counted (nMappings); EmitMappings produces them later, straight into their
+// final place
 ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, const BatchPlan& plan, uint32_t readIndex,
-	const ga_stream_out* outs, const uint32_t* arena);
+	const ga_stream_out* outs, const uint32_t* arena, bool materialize = true);
+void EmitMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena,
+	const std::function<void(size_t, const FlatMapping&)>& sink);
+// the same, as the C ABI's records (include/graphaligner_b200.h), into dst[0 .. nMappings)
+void WriteMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, ::ga_mapping* dst);
 
 // AlignmentResult::trace of an assembled read (getTraceInfo, GraphAligner.h:690-780), decoded from the device's move record
 void BuildTraceItems(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_in* streams,
 	const ga_stream_out* outs, const uint32_t* arena, std::vector<AlignmentResult::TraceItem>& items);
 
 // Implemented by the CUDA translation unit: runs all streams on the device behind ctx.
-void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth,
-	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats);
+void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, const std::vector<uint64_t>& readOff, int initialBandwidth, int rampBandwidth,
+	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, std::vector<uint8_t>& badChar, BatchStats* stats);
 
 // C++ batch entry: full AlignmentResults including trace items (the C ABI materialises those lazily instead)
 std::vector<AlignmentResult> AlignBatch(DeviceCtx* ctx, const AlignmentGraph& graph, const std::vector<ReadInput>& reads, int initialBandwidth, int rampBandwidth, BatchStats* stats,

@@ -71,18 +71,30 @@ __global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const ui
 {
 	const uint32_t stream = blockIdx.x;
 	if (stream >= nStreams) return;
-	const uint32_t nslices = streams[stream].partLen / 64;
-	const uint8_t* base = parts + streams[stream].seqOff;
-	const uint32_t firstMask = nslices ? ga_iupac_mask(base[0]) : 0;
+	const ga_stream_in in = streams[stream];
+	const uint32_t nslices = in.partLen / 64;
 	for (uint32_t sl = threadIdx.x; sl < nslices; sl += blockDim.x)
 	{
 		uint64_t A, C, G, T;
-		ga_peq_words(base + (size_t)sl * 64, A, C, G, T);
+		ga_peq_words(parts, in, sl, A, C, G, T);
 		uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
 		dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
 		dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
-		peqAux[peqOff[stream] / 2 + sl] = (sl > 0 ? ga_exact_code(base[(size_t)sl * 64 - 1]) : 4u) | (firstMask << 4);
+		peqAux[peqOff[stream] / 2 + sl] = ga_peq_aux(parts, in, sl);
 	}
+}
+
+// Reads the reference aborts on (a character outside its IUPAC switch, GraphAligner.h:2039-2110): one block per read
+__global__ void ga_validate_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ readOff, uint32_t nReads, uint32_t* __restrict__ bad)
+{
+	const uint32_t read = blockIdx.x;
+	if (read >= nReads) return;
+	const uint8_t* p = raw + readOff[read];
+	const uint64_t len = readOff[read + 1] - readOff[read];
+	uint32_t any = 0;
+	for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) any |= ga_iupac_mask(p[i]) == 0 ? 1u : 0u;
+	any = __syncthreads_or((int)any);
+	if (threadIdx.x == 0) bad[read] = any ? 1u : 0u;
 }
 #endif
 
@@ -157,7 +169,7 @@ static __host__ __device__ inline void setupLaneMem(GaLaneMem& mem, const Scratc
 #ifndef GA_HOSTSIM
 template <int S, bool SMALL>
 __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
-	const ga_stream_in* __restrict__ streams, const uint8_t* __restrict__ parts, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
+	const ga_stream_in* __restrict__ streams, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
 	ga_stream_out* __restrict__ outs)
 {
 	extern __shared__ __align__(16) unsigned long long gaShared[];
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_
 	setupLaneMem(mem, sp, wd, caps, warp, ml, S, SMALL, ws, eqTab);
 	mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
 	ga_stream_out* out = active ? outs + stream : nullptr;
-	ga_run_stream<S, SMALL>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, parts, initialBandwidth, rampBandwidth, debugFlags, out);
+	ga_run_stream<S, SMALL>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, active ? sp.peqAux + sp.peqOff[stream] / 2 : nullptr, initialBandwidth, rampBandwidth, debugFlags, out);
 }
 #endif
 
@@ -331,16 +343,16 @@ static void hostsim_peq(const ga_stream_in* streams, const uint64_t* peqOff, con
 {
 	for (uint32_t stream = 0; stream < nStreams; stream++)
 	{
-		const uint32_t nslices = streams[stream].partLen / 64;
-		const uint8_t* base = parts + streams[stream].seqOff;
+		const ga_stream_in in = streams[stream];
+		const uint32_t nslices = in.partLen / 64;
 		for (uint32_t sl = 0; sl < nslices; sl++)
 		{
 			uint64_t A, C, G, T;
-			ga_peq_words(base + (size_t)sl * 64, A, C, G, T);
+			ga_peq_words(parts, in, sl, A, C, G, T);
 			uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
 			dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
 			dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
-			peqAux[peqOff[stream] / 2 + sl] = (sl > 0 ? ga_exact_code(base[(size_t)sl * 64 - 1]) : 4u) | (ga_iupac_mask(base[0]) << 4);
+			peqAux[peqOff[stream] / 2 + sl] = ga_peq_aux(parts, in, sl);
 		}
 	}
 }
@@ -383,7 +395,7 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		std::fill(ws.begin(), ws.end(), 0ull);
 		setupLaneMem(mem, sp, wd, caps, w, 0, S, false, ws.data(), eqTab.data());
 		mem.peq = sp.peq + sp.peqOff[stream];
-		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, parts, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, sp.peqAux + sp.peqOff[stream] / 2, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
 	}
 	// the traceback "launch": the same warp code with its lanes as loops, HT streams per "warp"
 	const int HT = 4, HP = 1;
@@ -474,12 +486,12 @@ struct DeviceCtx
 	size_t graphBytes = 0;
 	bool hasGraph = false;
 	// batch buffers
-	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bColVV, bColS, bPeq, bPeqAux, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop;
+	Buffer bParts, bIn, bOut, bWd, bTiny, bHash, bHeap, bNodeTmp, bUbkt, bHdr, bHn, bColVV, bColS, bPeq, bPeqAux, bPeqOff, bMoves, bPath, bRuns, bArena, bArenaTop, bColTop, bReadOff, bBad;
 	GaUmapSchedule sched;
 	uint32_t debugFlags = 0;   // GA_DEBUG_FLAGS env: bit0 skip traceback (timing experiments only)
 	double avgNodeLen = 32;    // mean node length of the uploaded graph (sizing heuristics)
 	int forceS = 0;            // GA_STREAMS_PER_WARP env: override the streams-per-warp heuristic (tuning)
-	int traceT = 0, traceP = 2; // GA_TRACE_T / GA_TRACE_P env: streams per warp / 32-column passes per window of the traceback kernel (tuning)
+	int traceT = 0, traceP = 1; // GA_TRACE_T / GA_TRACE_P env: streams per warp / 32-column passes per window of the traceback kernel (tuning)
 	int smCount = 148;
 	int warpsPerSm = 20;       // resident warps of ga_align_kernel per SM (occupancy query)
 	// pinned host staging (grow-only): parts for H2D, stream results + trace arena for D2H
@@ -505,7 +517,7 @@ struct DeviceCtx
 			cap = 0;
 		}
 	};
-	Pinned pinParts, pinOuts, pinArena, pinSmall;
+	Pinned pinParts, pinOuts, pinArena, pinSmall, pinReadOff;
 	size_t budgetBytes = 0;    // device bytes a batch may use (FreeDeviceBytes), 0 = not queried yet
 };
 
@@ -527,6 +539,7 @@ struct StagedBatch
 	bool smemScratch = false;   // small-band mode: per-slice scratch in shared memory
 	size_t peqWords = 0;
 	uint64_t colPoolCap = 0;
+	size_t nReads = 0;     // reads whose characters the run validates (SetReadRanges), 0 = none
 };
 
 static GaHmmTables makeHmmTables()
@@ -615,12 +628,13 @@ void DestroyDevice(DeviceCtx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->gNodeRec, &ctx->gChunks, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
-		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqAux, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop };
+		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqAux, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop, &ctx->bReadOff, &ctx->bBad };
 	for (Buffer* b : all) b->release();
 	ctx->pinParts.release();
 	ctx->pinOuts.release();
 	ctx->pinArena.release();
 	ctx->pinSmall.release();
+	ctx->pinReadOff.release();
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -947,7 +961,7 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
 	const size_t smemBytes = (size_t)(threads / 32) * 4 * S * sizeof(unsigned long long);
 	ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
 }
 
 template <int T, int P>
@@ -965,7 +979,7 @@ static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
 	// streams per warp: few, so that a batch is many warps (the walk is latency-bound); more once every SM has its share
 	const size_t n = sb->sorted.size();
 	int T = ctx->traceT;
-	if (T == 0) T = n <= (size_t)ctx->smCount * 8 * 8 ? 8 : (n <= (size_t)ctx->smCount * 8 * 16 ? 16 : 32);
+	if (T == 0) T = n <= (size_t)ctx->smCount * 16 * 8 ? 8 : (n <= (size_t)ctx->smCount * 16 * 16 ? 16 : 32);
 	const int P = ctx->traceP;
 	if (T == 8 && P == 1) launchTraceTP<8, 1>(ctx, sb);
 	else if (T == 8) launchTraceTP<8, 2>(ctx, sb);
@@ -988,6 +1002,13 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	GA_CUDA(cudaMemsetAsync(ctx->bColTop.ptr, 0, sizeof(unsigned long long), ctx->stream));
 #ifdef GA_HOSTSIM
 	hostsim_peq((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr, (uint32_t*)ctx->bPeqAux.ptr);
+	for (size_t r = 0; r < sb->nReads; r++)
+	{
+		const uint64_t* ro = (const uint64_t*)ctx->bReadOff.ptr;
+		uint32_t any = 0;
+		for (uint64_t i = ro[r]; i < ro[r + 1]; i++) any |= ga_iupac_mask(((const uint8_t*)ctx->bParts.ptr)[i]) == 0 ? 1u : 0u;
+		((uint32_t*)ctx->bBad.ptr)[r] = any;
+	}
 	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
 		sb->smemScratch, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 #else
@@ -998,6 +1019,8 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	{
 		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr,
 			(uint32_t*)ctx->bPeqAux.ptr);
+		GA_CUDA(cudaGetLastError());
+		if (sb->nReads) ga_validate_kernel<<<(unsigned)sb->nReads, 128, 0, ctx->stream>>>((const uint8_t*)ctx->bParts.ptr, (const uint64_t*)ctx->bReadOff.ptr, (uint32_t)sb->nReads, (uint32_t*)ctx->bBad.ptr);
 		GA_CUDA(cudaGetLastError());
 	}
 	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[1], ctx->stream));
@@ -1104,13 +1127,19 @@ void pinnedRelease(void* p, size_t cap)
 }
 }
 
-void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats)
+void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
 	const size_t n = sb->sorted.size();
 	outs.resize(n);
 	arena.clear();
 	if (n == 0) return;
+	uint32_t* pinBad = nullptr;
+	if (badChar && sb->nReads)
+	{
+		pinBad = (uint32_t*)ctx->pinReadOff.ensure((sb->nReads + 1) * sizeof(uint64_t));   // the offsets were uploaded long ago: the staging block is free again
+		GA_CUDA(cudaMemcpyAsync(pinBad, ctx->bBad.ptr, sb->nReads * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	}
 	// D2H through pinned staging, then a parallel copy into the caller's buffers
 	ga_stream_out* pinOuts = (ga_stream_out*)ctx->pinOuts.ensure(n * sizeof(ga_stream_out) + sizeof(unsigned long long));
 	unsigned long long* pinTop = (unsigned long long*)(pinOuts + n);
@@ -1128,6 +1157,11 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	lap("stream records");
 	unsigned long long top = *pinTop;
 	if (top > sb->arenaCap) top = sb->arenaCap;
+	if (pinBad)
+	{
+		badChar->assign(sb->nReads, 0);
+		for (size_t r = 0; r < sb->nReads; r++) (*badChar)[r] = pinBad[r] ? 1 : 0;
+	}
 	// the trace arena lands in a pinned block that the results then own (recycled through a process-wide pool): no
 	// second pass over ~100 MB, no fresh pages to fault in
 	if (top)
@@ -1230,6 +1264,19 @@ size_t FreeDeviceBytes(DeviceCtx* ctx)
 	return freeB;
 }
 
+void SetReadRanges(DeviceCtx* ctx, StagedBatch* sb, const std::vector<uint64_t>& readOff)
+{
+	if (readOff.size() < 2) return;
+	GA_CUDA(cudaSetDevice(ctx->device));
+	const size_t bytes = readOff.size() * sizeof(uint64_t);
+	ctx->bReadOff.ensure(bytes);
+	ctx->bBad.ensure((readOff.size() - 1) * sizeof(uint32_t));
+	void* pin = ctx->pinReadOff.ensure(bytes);
+	memcpy(pin, readOff.data(), bytes);
+	GA_CUDA(cudaMemcpyAsync(ctx->bReadOff.ptr, pin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	sb->nReads = readOff.size() - 1;
+}
+
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
@@ -1266,14 +1313,15 @@ StagedBatch* StageAndUpload(DeviceCtx* ctx, const std::vector<ga_stream_in>& str
 	return sb;
 }
 
-void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, int initialBandwidth, int rampBandwidth,
-	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats)
+void ExecuteStreams(DeviceCtx* ctx, const std::vector<ga_stream_in>& streams, const uint8_t* parts, size_t partsBytes, const std::vector<uint64_t>& readOff, int initialBandwidth, int rampBandwidth,
+	RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, std::vector<uint8_t>& badChar, BatchStats* stats)
 {
 	StagedBatch* sb = StageAndUpload(ctx, streams, parts, partsBytes, initialBandwidth, rampBandwidth, stats);
 	try
 	{
+		SetReadRanges(ctx, sb, readOff);
 		RunStaged(ctx, sb);
-		FinishStaged(ctx, sb, outs, arena, stats);
+		FinishStaged(ctx, sb, outs, arena, stats, &badChar);
 	}
 	catch (...)
 	{

@@ -45,11 +45,11 @@ typedef struct ga_node_rec
 // start node (reference getSplitAlignment, GraphAligner.h:2969-3024).
 typedef struct ga_stream_in
 {
-	uint64_t seqOff;     // byte offset of the padded part in the parts buffer
+	uint64_t seqOff;     // byte offset, in the batch's raw read bytes, of the part's first character (a backward part walks down from it)
 	uint32_t partLen;    // padded length (multiple of 64) = reference sequence.size()
 	uint32_t startNode;  // graph node index whose columns are all 0 in the initial slice
 	uint32_t trimRows;   // trace positions with row >= trimRows are dropped (padding / DBG overlap, GraphAligner.h:3063-3066,3086-3089)
-	uint32_t reserved;
+	uint32_t srcInfo;    // real (unpadded) length of the part | backward << 31 (backward: reverse complement of the read's prefix)
 } ga_stream_in;
 
 enum

@@ -88,16 +88,15 @@ typedef struct ga_read_result
 #define GA_FLAG_BAD_CHAR 4u         /* read character the reference aborts on */
 #define GA_FLAG_CYCLIC 8u           /* a band held a cyclic component */
 
-typedef struct ga_mapping
+typedef struct ga_mapping            /* 32 bytes: a batch of 10 000 x 10 kbp reads on 32-bp nodes returns 3.3 million of them */
 {
 	int64_t node_id;                /* digraph node id (2*id / 2*id+1), as the reference's AlignOneWay returns it */
-	int64_t offset;
-	int64_t rank;
-	int32_t is_reverse;
+	uint32_t offset;
+	uint32_t rank;
 	int32_t from_length;            /* the single Edit of the mapping */
 	int32_t to_length;
-	uint32_t reserved;
-	uint64_t read_start;            /* edit.sequence == read.substr(read_start, to_length) */
+	uint32_t read_start;            /* edit.sequence == read.substr(read_start, to_length) */
+	uint32_t is_reverse;
 } ga_mapping;
 
 typedef struct ga_trace_item        /* AlignmentResult::TraceItem */
