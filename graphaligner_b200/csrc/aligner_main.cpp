@@ -11,6 +11,8 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <atomic>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -81,10 +83,52 @@ static std::string sanitize(std::string name)
 	return name;
 }
 
+// -G: the GPUs to align on: "3", "0,2,5" or "0-7" (not in the reference: its parallelism is -t host threads)
+static std::vector<int> parseDevices(const std::string& arg)
+{
+	std::vector<int> devices;
+	size_t pos = 0;
+	while (pos <= arg.size())
+	{
+		size_t comma = arg.find(',', pos);
+		if (comma == std::string::npos) comma = arg.size();
+		const std::string item = arg.substr(pos, comma - pos);
+		const size_t dash = item.find('-');
+		if (dash != std::string::npos && dash > 0)
+		{
+			const int lo = std::stoi(item.substr(0, dash)), hi = std::stoi(item.substr(dash + 1));
+			for (int d = lo; d <= hi; d++) devices.push_back(d);
+		}
+		else if (!item.empty()) devices.push_back(std::stoi(item));
+		pos = comma + 1;
+	}
+	return devices;
+}
+
+// augmentGraphwithAlignment, Aligner.cpp:24-74: the input graph's nodes, and one edge per pair of consecutive mappings of
+// every alignment (node ids already back to the original ones)
+static void writeAugmentedGraph(const std::string& graphFile, const std::string& outFile, const std::vector<vg::Alignment>& alignments)
+{
+	std::vector<DirectedGraph::BiNode> nodes;
+	std::vector<DirectedGraph::BiEdge> inputEdges, edges;
+	vgcodec::ReadGraphFile(graphFile, nodes, inputEdges);
+	for (auto& a : alignments)
+	{
+		for (size_t i = 0; i + 1 < a.path.mapping.size(); i++)
+		{
+			const auto& from = a.path.mapping[i].position;
+			const auto& to = a.path.mapping[i + 1].position;
+			edges.push_back(DirectedGraph::BiEdge { (int64_t)from.node_id, (int64_t)to.node_id, from.is_reverse, to.is_reverse });
+		}
+	}
+	vgcodec::WriteStreamFile(outFile, { vgcodec::EncodeGraph(nodes, edges) });
+}
+
 int main(int argc, char** argv)
 {
 	std::string graphFile, fastqFile, alignmentFile, auggraphFile, seedFile;
-	int numThreads = 0, initialBandwidth = 0, rampBandwidth = 0, dynamicRowStart = 64, device = 0;
+	int numThreads = 0, initialBandwidth = 0, rampBandwidth = 0, dynamicRowStart = 64;
+	std::vector<int> devices;
 	bool initialFullBand = false;
 	int c;
 	while ((c = getopt(argc, argv, "g:f:a:t:B:A:is:d:MSb:G:")) != -1)
@@ -101,7 +145,7 @@ int main(int argc, char** argv)
 			case 'i': initialFullBand = true; break;
 			case 's': seedFile = optarg; break;
 			case 'd': dynamicRowStart = std::stoi(optarg); break;
-			case 'G': device = std::stoi(optarg); break;
+			case 'G': devices = parseDevices(optarg); break;
 		}
 	}
 	// AlignerMain.cpp:68-96
@@ -160,9 +204,39 @@ int main(int argc, char** argv)
 		results.resize(batch.size());
 		for (auto& r : results) r.alignment.score = std::numeric_limits<int32_t>::max();
 	}
+	else if (getenv("GA_PER_READ"))
+	{
+		// the reference's own structure (Aligner.cpp:107-140,285-298): -t worker threads, each calling the per-read
+		// AlignOneWay; kept for checking the drop-in entry point, the batched call below is what the GPU wants
+		results.resize(batch.size());
+		std::atomic<size_t> next(0);
+		std::vector<std::thread> workers;
+		for (int t = 0; t < numThreads; t++)
+		{
+			workers.emplace_back([&]() {
+				while (true)
+				{
+					const size_t i = next.fetch_add(1);
+					if (i >= batch.size()) break;
+					if (haveSeeds && batch[i].seedHits.empty()) { results[i].alignment.score = std::numeric_limits<int32_t>::max(); continue; }
+					try
+					{
+						results[i] = AlignOneWay(graph, batch[i].name, batch[i].sequence, initialBandwidth, rampBandwidth, (size_t)dynamicRowStart, batch[i].seedHits);
+					}
+					catch (const std::out_of_range&)
+					{
+						results[i] = AlignmentResult();
+						results[i].alignmentFailed = true;
+						results[i].alignment.score = std::numeric_limits<int32_t>::max();
+					}
+				}
+			});
+		}
+		for (auto& w : workers) w.join();
+	}
 	else
 	{
-		results = AlignReads(graph, batch, initialBandwidth, rampBandwidth, device);
+		results = AlignReads(graph, batch, initialBandwidth, rampBandwidth, devices);
 	}
 	std::vector<vg::Alignment> alignments;
 	const int threadnum = 0;
@@ -210,7 +284,12 @@ int main(int argc, char** argv)
 	std::cout << "thread " << threadnum << " finished with " << alignments.size() << " alignments" << std::endl;
 	std::cerr << "final result has " << alignments.size() << " alignments" << std::endl;
 	if (alignmentFile != "") vgcodec::WriteAlignmentFile(alignmentFile, alignments);
-	if (auggraphFile != "") std::cerr << "-A (augmented graph) is not supported by this build" << std::endl;
+	if (auggraphFile != "")
+	{
+		// the reference reads the graph file as a vg graph here whatever its type (Aligner.cpp:317 CommonUtils::LoadVGGraph)
+		if (graphFile.size() >= 3 && graphFile.substr(graphFile.size() - 3) == ".vg") writeAugmentedGraph(graphFile, auggraphFile, alignments);
+		else std::cerr << "-A needs a .vg graph (the reference parses the graph file as vg for the augmented graph)" << std::endl;
+	}
 	ReleaseAlignerEngine(graph);
 	return 0;
 }

@@ -24,6 +24,9 @@ struct AlignerRead
 };
 // the batched form the driver should prefer: one GPU launch for all reads
 std::vector<AlignmentResult> AlignReads(const AlignmentGraph& graph, const std::vector<AlignerRead>& reads, int initialBandwidth, int rampBandwidth, int device = 0);
+// the same over several GPUs of the node (the counterpart of the reference's worker threads, Aligner.cpp:285-306): the read
+// set is cut into batches that the devices pull from one queue; results come back in input order
+std::vector<AlignmentResult> AlignReads(const AlignmentGraph& graph, const std::vector<AlignerRead>& reads, int initialBandwidth, int rampBandwidth, const std::vector<int>& devices);
 // drops the cached engine of a graph (call before destroying the graph)
 void ReleaseAlignerEngine(const AlignmentGraph& graph);
 

@@ -1,4 +1,5 @@
 #include "alignment_graph.h"
+#include <atomic>
 #include <algorithm>
 #include <cstdlib>
 #include <iostream>
@@ -132,6 +133,8 @@ void AlignmentGraph::Finalize(int wordSize)
 	{
 		if (inOff[i + 1] - inOff[i] >= 2) special++;
 	}
+	static std::atomic<uint64_t> nextUid(1);
+	uid = nextUid.fetch_add(1);
 	reverseNode.assign(n, 0xffffffffu);
 	for (size_t i = 0; i < n; i++)
 	{

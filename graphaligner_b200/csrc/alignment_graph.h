@@ -52,6 +52,8 @@ public:
 	const std::vector<uint32_t>& OutAdj() const { return outAdj; }
 
 	int DBGOverlap;
+	// distinguishes graph objects beyond their address (a cached device replica must not outlive its graph's identity)
+	uint64_t Uid() const { return uid; }
 
 private:
 	void pushBase(unsigned code);
@@ -65,6 +67,7 @@ private:
 	std::vector<std::pair<uint32_t, uint32_t>> pendingEdges;   // (from, to) in AddEdgeNodeId order
 	std::vector<uint32_t> inOff, inAdj, outOff, outAdj;
 	bool finalized;
+	uint64_t uid = 0;    // assigned by Finalize
 };
 
 #endif

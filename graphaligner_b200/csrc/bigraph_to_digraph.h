@@ -15,6 +15,7 @@ struct BiNode
 {
 	int64_t id;
 	std::string sequence;
+	std::string name;   // vg Node.name: carried through to the -A augmented graph only
 };
 struct BiEdge
 {

@@ -443,28 +443,45 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 		for (ga_results* p : parts) delete p;
 		return nullptr;
 	};
-	if (cuts.size() <= 2)
+	// A chunk the device cannot hold after all (the estimate is an estimate: long-node graphs, wide bands) is cut in half
+	// and tried again - the results of the other chunks are kept.
+	// (Running two half-batches through two sets of device buffers and streams, to overlap staging and assembly with the
+	// kernel, was measured: each half's kernel takes as long as the whole batch's - a stream's time is a chain of
+	// latencies, not a share of the GPU - so nothing is gained.)
+	auto capacityError = [&]() {
+		const std::string& e = ctx->error;
+		return e.find("out of memory") != std::string::npos || e.find("allocating") != std::string::npos || e.find("batch too large") != std::string::npos;
+	};
+	std::vector<size_t> done(1, 0);   // boundaries of the chunks as they were finally run
+	std::vector<std::pair<size_t, size_t>> todo;
+	for (size_t c = cuts.size() - 1; c-- > 0;) todo.emplace_back(cuts[c], cuts[c + 1]);   // a stack: first chunk on top
+	while (!todo.empty())
 	{
-		// (Running two half-batches through two sets of device buffers and streams, to overlap staging and assembly with the
-		// kernel, was measured: each half's kernel takes as long as the whole batch's - a stream's time is a chain of
-		// latencies, not a share of the GPU - so nothing is gained.)
-		ga_staged* st = ga_stage_batch(ctx, batch);
-		if (!st) return nullptr;
-		ga_results* res = runAndFinish(ctx, st);
-		ga_staged_free(ctx, st);
-		return res;
-	}
-	for (size_t c = 0; c + 1 < cuts.size(); c++)
-	{
-		ga_batch sub = subBatch(batch, cuts[c], cuts[c + 1]);
+		const std::pair<size_t, size_t> range = todo.back();
+		todo.pop_back();
+		ga_batch sub = subBatch(batch, range.first, range.second);
 		ga_staged* st = ga_stage_batch(ctx, &sub);
 		ga_results* part = st ? runAndFinish(ctx, st) : nullptr;
 		if (st) ga_staged_free(ctx, st);
-		if (!part) return fail();
+		if (!part)
+		{
+			if (range.second - range.first < 2 || !capacityError()) return fail();
+			const size_t mid = range.first + (range.second - range.first) / 2;
+			todo.emplace_back(mid, range.second);
+			todo.emplace_back(range.first, mid);
+			continue;
+		}
 		parts.push_back(part);
+		done.push_back(range.second);
+	}
+	if (parts.size() == 1)
+	{
+		ga_results* only = parts[0];
+		parts.clear();
+		return only;
 	}
 	ga_results* all = nullptr;
-	rc = guarded(ctx, [&]() { all = mergeParts(ctx, parts, cuts); });
+	rc = guarded(ctx, [&]() { all = mergeParts(ctx, parts, done); });
 	return rc == 0 ? all : fail();
 }
 

@@ -511,6 +511,7 @@ struct GaStreamState
 	uint32_t slicesPushed;
 	uint64_t wordColumns;
 	uint32_t cyclicSlices;
+	uint32_t rampRedos;
 #ifdef GA_PHASE_TIMING
 	long long tLast;
 	unsigned long long phase[16];  // see the names in FinishStaged
@@ -1714,6 +1715,8 @@ GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const 
 		out->nSlicesRun = (int32_t)slicesRun;
 		out->wordColumns = st.wordColumns;
 		out->cyclicSlices = st.cyclicSlices;
+		out->rampRedos = st.rampRedos;
+		out->reserved = 0;
 		out->nMoves = 0;
 		out->nPathNodes = 0;
 		out->nRuns = 0;
@@ -1874,6 +1877,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 	st.slicesPushed = 0;
 	st.wordColumns = 0;
 	st.cyclicSlices = 0;
+	st.rampRedos = 0;
 #ifdef GA_PHASE_TIMING
 	for (int i = 0; i < 16; i++) st.phase[i] = 0;
 #endif
@@ -1978,6 +1982,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			const int target = rampRedoIndex;
 			rampUntil = s;
 			rampRedoIndex = s;
+			st.rampRedos++;
 			if (target < 0) { st.status = GA_ERR_INTERNAL; st.done = true; continue; }
 			// the previous slice becomes slice `target` again: state from its header, tables rebuilt from the history
 			st.prevMin = (int32_t)GA_HDR(target, 4);

@@ -417,6 +417,7 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 	st.slicesPushed = 0;
 	st.wordColumns = 0;
 	st.cyclicSlices = 0;
+	st.rampRedos = 0;
 #ifdef GA_PHASE_TIMING
 	for (int i = 0; i < 16; i++) st.phase[i] = 0;
 #endif

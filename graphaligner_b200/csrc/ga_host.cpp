@@ -17,6 +17,7 @@ static const uint32_t FLAG_STREAM_ERROR = 1;   // a stream hit a hard limit (see
 static const uint32_t FLAG_BAD_SEED = 2;       // seed node not in graph / position outside read
 static const uint32_t FLAG_BAD_CHAR = 4;       // read holds a character the reference aborts on
 static const uint32_t FLAG_CYCLIC = 8;         // some band held a cyclic component
+static const uint32_t FLAG_RAMP_REDO = 16;     // -B: a stream went back and redid a stretch with the wide band
 
 std::string ReverseComplement(const std::string& str)
 {
@@ -620,6 +621,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			const ga_stream_out& o = outs[sp.bwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
 			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
 			if (o.status == GA_OK && o.nSlices > 0)
 			{
 				bwSlices = (size_t)o.nSlices;
@@ -635,6 +637,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			const ga_stream_out& o = outs[sp.fwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
 			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
 			if (o.status == GA_OK && o.nSlices > 0)
 			{
 				fwSlices = (size_t)o.nSlices;

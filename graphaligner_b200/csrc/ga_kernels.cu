@@ -756,7 +756,7 @@ static ga_caps defaultCaps(int b, int B, int scale)
 	// a band holds the kept nodes (scores within bw of the minimum) plus everything within bw+64 bp downstream
 	uint32_t cols = (uint32_t)(4 * (bw + 64) + 256);
 	c.maxCols = std::max<uint32_t>(1024, cols * 2) * scale;
-	c.maxNodes = std::min<uint32_t>(60000, std::max<uint32_t>(128, c.maxCols / 8) * scale);
+	c.maxNodes = std::min<uint32_t>(60000, std::max<uint32_t>(128, c.maxCols / 8));   // maxCols carries the scale already
 	c.hashSize = nextPow2(c.maxNodes * 2);
 	c.maxQueue = c.maxNodes * 8;
 	return c;
@@ -1238,11 +1238,20 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 
 size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
 {
-	// dominant terms of layoutAndUpload per stream: column history + fixed scratch + trace buffers
+	// what layoutAndUpload allocates per stream, from the same terms: the per-slice scratch of the general layout (sized by
+	// the capacities of the launch, which grow with the graph's node length), the column history, node lists, headers,
+	// match words and the trace buffers
+	const int scale = initialCapScale(ctx, bandwidth, 0);
+	const ga_caps caps = defaultCaps(bandwidth, 0, scale);
 	const double avgNodeLen = std::max(1.0, ctx->avgNodeLen);
-	const double colsGuess = (2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32) * initialCapScale(ctx, bandwidth, 0);
+	const double colsGuess = (2.0 * (bandwidth + 64) + 2.0 * std::min(avgNodeLen, 256.0) + 32) * scale;
+	const double nodesGuess = colsGuess / avgNodeLen * 1.5 + 8;
 	const double slices = (double)((partLen + 63) / 64);
-	return (size_t)(slices * colsGuess * (sizeof(uint4) + sizeof(uint32_t)) * 1.15 + 96.0 * 1024 + partLen * 12.0);
+	const double scratch = 3.0 * caps.maxCols * sizeof(uint32_t) + 2.0 * caps.hashSize * sizeof(uint64_t) + (double)caps.maxQueue * sizeof(uint64_t) + 10.0 * caps.maxNodes * sizeof(uint32_t)
+		+ 2.0 * caps.maxNodes * sizeof(uint32_t);
+	const double history = slices * (colsGuess * (sizeof(uint4) + sizeof(uint32_t)) + nodesGuess * GA_HN_WORDS * sizeof(uint32_t) + GA_HDR_WORDS * sizeof(uint32_t) + 36.0);
+	const double trace = partLen * 1.5 + (partLen * 1.3 / avgNodeLen * 2.0 * scale + 66) * (1 + GA_RUN_WORDS) * sizeof(uint32_t) * 2.0 + 1024;
+	return (size_t)((scratch + history + trace) * 1.15);
 }
 
 size_t FreeDeviceBytes(DeviceCtx* ctx)

@@ -85,6 +85,8 @@ typedef struct ga_stream_out
 	uint64_t traceOff;      // offset (in 32-bit words) of this stream's record in the trace arena
 	uint32_t nTies;         // cells of the last retained slice tied at the minimum (incl. the chosen one)
 	uint32_t cyclicSlices;  // slices whose band held a cyclic component
+	uint32_t rampRedos;     // -B ramp: how often the stream went back and redid a stretch with the wide band (GraphAligner.h:2648-2719)
+	uint32_t reserved;
 	uint32_t tieNode[GA_MAX_TIES];
 	uint32_t tieOff[GA_MAX_TIES];
 #ifdef GA_PHASE_TIMING

@@ -1,5 +1,6 @@
 #include "vg_codec.h"
 #include <zlib.h>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 
@@ -45,8 +46,12 @@ struct Reader
 	{
 		if (wireType == 0) varint();
 		else if (wireType == 2) sub();
-		else if (wireType == 1) p += 8;
-		else if (wireType == 5) p += 4;
+		else if (wireType == 1 || wireType == 5)
+		{
+			const size_t n = wireType == 1 ? 8 : 4;
+			if ((size_t)(end - p) < n) throw std::runtime_error("vg codec: truncated fixed-width field");
+			p += n;
+		}
 		else throw std::runtime_error("vg codec: unsupported wire type");
 	}
 };
@@ -122,8 +127,18 @@ void WriteStreamFile(const std::string& filename, const std::vector<std::string>
 	}
 	gzFile f = gzopen(filename.c_str(), "wb");
 	if (!f) throw std::runtime_error("cannot open " + filename + " for writing");
-	if (!raw.empty()) gzwrite(f, raw.data(), (unsigned)raw.size());
-	gzclose(f);
+	// gzwrite takes an unsigned length: pieces of at most 1 GiB, every result checked
+	const size_t piece = (size_t)1 << 30;
+	for (size_t off = 0; off < raw.size(); off += piece)
+	{
+		const unsigned len = (unsigned)std::min(piece, raw.size() - off);
+		if (gzwrite(f, raw.data() + off, len) != (int)len)
+		{
+			gzclose(f);
+			throw std::runtime_error("short write to " + filename);
+		}
+	}
+	if (gzclose(f) != Z_OK) throw std::runtime_error("cannot finish writing " + filename);
 }
 
 void ReadGraphFile(const std::string& filename, std::vector<DirectedGraph::BiNode>& nodes, std::vector<DirectedGraph::BiEdge>& edges)
@@ -145,6 +160,7 @@ void ReadGraphFile(const std::string& filename, std::vector<DirectedGraph::BiNod
 					uint64_t k2 = n.varint();
 					int f2 = (int)(k2 >> 3), w2 = (int)(k2 & 7);
 					if (f2 == 1 && w2 == 2) node.sequence = n.str();
+					else if (f2 == 2 && w2 == 2) node.name = n.str();
 					else if (f2 == 3 && w2 == 0) node.id = (int64_t)n.varint();
 					else n.skip(w2);
 				}
@@ -178,6 +194,7 @@ std::string EncodeGraph(const std::vector<DirectedGraph::BiNode>& nodes, const s
 	{
 		std::string m;
 		putBytes(m, 1, n.sequence);
+		putBytes(m, 2, n.name);
 		putInt(m, 3, n.id);
 		putBytes(out, 1, m, true);
 	}

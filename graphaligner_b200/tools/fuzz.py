@@ -25,6 +25,7 @@ KEYS = ("failed", "score", "start", "end", "qpos", "nmap", "ntrace", "th")
 
 
 LONG_NODES = False
+RAMP = False
 
 
 def make_case(it):
@@ -54,13 +55,22 @@ def make_case(it):
     b = int(rng.choice([2, 5, 10, 20, 35, 50, 100]))
     offs = [(0,), (0, rl // 2, -50), (rl // 3,), (-1,), (1,)][int(rng.integers(0, 5))]
     err = float(rng.choice([0.0, 0.02, 0.05, 0.1]))
-    case = synth.make_case(it, g, 12, rl, b=b, seed_offsets=offs, decoys=int(rng.integers(0, 2)), errors=(err, err, err), len_jitter=min(rl // 4, 40))
-    return case, dict(kind=kind, rl=rl, b=b, **kw)
+    B = 0
+    if RAMP:
+        # -B ramp: a narrow band that loses noisy reads now and then, a wide backup band (GraphAligner.h:2612-2719)
+        b = int(rng.choice([2, 3, 5, 8]))
+        B = b + int(rng.choice([5, 15, 40]))
+        err = float(rng.choice([0.05, 0.1, 0.15]))
+        rl = int(rng.choice([300, 1000, 3000]))
+    case = synth.make_case(it, g, 12, rl, b=b, B=B, seed_offsets=offs, decoys=int(rng.integers(0, 2)), errors=(err, err, err), len_jitter=min(rl // 4, 40))
+    return case, dict(kind=kind, rl=rl, b=b, B=B, **kw)
 
 
 def main():
-    global LONG_NODES
+    global LONG_NODES, RAMP
     LONG_NODES = "--long-nodes" in sys.argv
+    RAMP = "--ramp" in sys.argv
+    redo_same = redo_differ = redo_crashed = reads_redo = reads_redo_differ = 0
     first, count = int(sys.argv[1]), int(sys.argv[2])
     keep = sys.argv[sys.argv.index("--keep") + 1] if "--keep" in sys.argv else None
     from graphaligner_b200 import api
@@ -74,6 +84,12 @@ def main():
         ref = subprocess.run([REF, path, "--quiet", "--threads", "4"], capture_output=True, text=True)
         if ref.returncode != 0:
             ref_crashed += 1
+            if RAMP:
+                aligner = api.Aligner(api.Graph.from_case(case))
+                res = aligner.align(case.reads, case.b, case.B)
+                redo_crashed += 1 if any(m["flags"] & 16 for m in res.as_dicts()) else 0
+                res.free()
+                aligner.close()
             if not keep:
                 os.remove(path)
             continue
@@ -85,6 +101,17 @@ def main():
                if any(m[k] != e[k] for k in KEYS) or [tuple(x) for x in m["mappings"]] != [tuple(x) for x in e["mappings"]]]
         res.free()
         aligner.close()
+        if RAMP:
+            redo = [m["name"] if "name" in m else i for i, m in enumerate(mine) if m["flags"] & 16]
+            reads_redo += len(redo)
+            reads_redo_differ += sum(1 for i, (m, e) in enumerate(zip(mine, expected)) if (m["flags"] & 16) and e["name"] in bad)
+            if redo:
+                if bad:
+                    redo_differ += 1
+                else:
+                    redo_same += 1
+                    if keep:
+                        print("REDO-IDENTICAL seed %d (%d reads with a redo) %s" % (it, len(redo), desc), flush=True)
         if bad or len(mine) != len(expected):
             differ += 1
             print("DIFF seed %d reads %s %s" % (it, bad[:4], desc), flush=True)
@@ -93,6 +120,9 @@ def main():
             if not keep:
                 os.remove(path)
     print("fuzz %d..%d: identical %d, different %d, reference crashed %d" % (first, first + count - 1, same, differ, ref_crashed), flush=True)
+    if RAMP:
+        print("ramp: cases where a redo fired: identical %d, different %d, reference crashed %d; reads with a redo %d, of them different %d"
+              % (redo_same, redo_differ, redo_crashed, reads_redo, reads_redo_differ), flush=True)
     return 1 if differ else 0
 
 

@@ -87,6 +87,7 @@ typedef struct ga_read_result
 #define GA_FLAG_BAD_SEED 2u         /* seed node not in the graph / position outside the read (reference: std::out_of_range) */
 #define GA_FLAG_BAD_CHAR 4u         /* read character the reference aborts on */
 #define GA_FLAG_CYCLIC 8u           /* a band held a cyclic component */
+#define GA_FLAG_RAMP_REDO 16u       /* -B: a stream went back and redid a stretch with the ramp bandwidth (GraphAligner.h:2648-2719) */
 
 typedef struct ga_mapping            /* 32 bytes: a batch of 10 000 x 10 kbp reads on 32-bp nodes returns 3.3 million of them */
 {

@@ -67,10 +67,19 @@ def cases():
     yield "cyclic_partial_confirm", fuzz_case(11205)
     yield "cyclic_last_call_min", fuzz_case(1605)
     yield "ramp", synth.make_case(18, synth.make_graph(18, 20000, chop=32, bubble_every=100), 8, 2000, b=5, B=30, errors=(0.08, 0.08, 0.08))
+    # -B where the ramp fires: 8 of the 12 reads lose the narrow band somewhere, go back and redo a stretch with the wide one
+    # (GraphAligner.h:2648-2719), and the reference still finishes (it does not on every such input, profiles/r02_ramp_fuzz.txt)
+    from graphaligner_b200.tools import fuzz
+    fuzz.RAMP = True
+    yield "ramp_redo", fuzz.make_case(8)[0]
+    fuzz.RAMP = False
 
 
 def main():
+    only = sys.argv[1:]
     for name, case in cases():
+        if only and name not in only:
+            continue
         path = os.path.join(OUT, name + ".gacase")
         gacase.write_case(case, path)
         res = subprocess.run([REF, path, "--quiet"], capture_output=True, text=True, check=True)

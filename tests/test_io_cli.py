@@ -55,17 +55,51 @@ def test_cli_validation_messages():
     assert "backup bandwidth must be higher than initial bandwidth" in r.stderr
 
 
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,batch_bp", [("smallexample", None), ("bubbles_multiseed", None), ("gfa", None), ("bubbles_multiseed", 5000)])
-def test_cli_end_to_end(tmp_path, golden_dir, name, batch_bp):
-    # batch_bp: the driver streams the read set through two contexts in batches of about that many read bases
+@pytest.mark.parametrize("name,batch_bp,devices", [("smallexample", None, None), ("bubbles_multiseed", None, None), ("gfa", None, None), ("bubbles_multiseed", 5000, None),
+                                                   ("bubbles_multiseed", 5000, "0,0"), ("bubbles_multiseed", None, "0-1"), ("dag_snp", 3000, "0,1"),
+                                                   ("bubbles_multiseed", "per-read", None)])
+def test_cli_end_to_end(tmp_path, golden_dir, name, batch_bp, devices):
+    # batch_bp: the driver streams the read set through two contexts per device in batches of about that many read bases
+    # devices: -G list (the counterpart of the reference's worker threads, Aligner.cpp:285-306); "0,0" runs the batch queue
+    # with four lanes on one GPU, the others need two GPUs
+    # batch_bp "per-read": -t 2 worker threads calling the per-read AlignOneWay concurrently, as the reference's driver does
+    # (Aligner.cpp:107-140)
+    if devices and devices != "0,0" and _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    extra_env = {}
+    if batch_bp == "per-read":
+        extra_env["GA_PER_READ"] = "1"
+    elif batch_bp:
+        extra_env["GA_BATCH_BP"] = str(batch_bp)
     case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
     expected = {e["name"]: e for e in load_expected(os.path.join(golden_dir, name + ".expected"))}
     graph_path, fastq, seeds = vgio.write_case_files(case, str(tmp_path / "c"))
     out = str(tmp_path / "out.gam")
-    r = subprocess.run([ALIGNER, "-g", graph_path, "-f", fastq, "-s", seeds, "-a", out, "-t", "2", "-b", str(case.b)] + (["-B", str(case.B)] if case.B else []),
-                       capture_output=True, text=True, cwd=str(tmp_path), env=dict(os.environ, **({"GA_BATCH_BP": str(batch_bp)} if batch_bp else {})))
+    aug = str(tmp_path / "aug.vg")
+    r = subprocess.run([ALIGNER, "-g", graph_path, "-f", fastq, "-s", seeds, "-a", out, "-t", "2", "-b", str(case.b)] + (["-B", str(case.B)] if case.B else [])
+                       + (["-G", devices] if devices else []) + (["-A", aug] if graph_path.endswith(".vg") else []),
+                       capture_output=True, text=True, cwd=str(tmp_path), env=dict(os.environ, **extra_env))
     assert r.returncode == 0, r.stderr[-500:]
+    if graph_path.endswith(".vg"):
+        # -A (augmentGraphwithAlignment, Aligner.cpp:24-74): the input graph's nodes, one edge per pair of consecutive mappings
+        in_nodes, _ = vgio.load_vg_graph(graph_path)
+        aug_nodes, aug_edges = vgio.load_vg_graph(aug)
+        assert [(n["id"], n["sequence"], n["name"]) for n in aug_nodes] == [(n["id"], n["sequence"], n["name"]) for n in in_nodes]
+        want_edges = []
+        for a in vgio.load_gam(out):
+            p = a["path"]
+            want_edges += [(p[i]["position"]["node_id"], p[i + 1]["position"]["node_id"], bool(p[i]["position"]["is_reverse"]), bool(p[i + 1]["position"]["is_reverse"]))
+                           for i in range(len(p) - 1)]
+        assert [(e["from"], e["to"], e["from_start"], e["to_end"]) for e in aug_edges] == want_edges
     alns = vgio.load_gam(out)
     ok = [e for e in expected.values() if not e["failed"]]
     assert len(alns) == len(ok)

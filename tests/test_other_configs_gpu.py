@@ -110,3 +110,28 @@ def test_alternate_method_band_is_a_per_read_failure(api):
     d = aligner.align(case.reads * 2, case.b, case.B).as_dicts()
     assert [x["failed"] for x in d] == [1, 1] and all(x["flags"] & 1 for x in d)
     aligner.close()
+
+
+def test_many_reads_on_long_node_graph_are_split_not_dropped(api, tmp_path):
+    # 2 kbp unitig-like nodes and a few thousand streams: the per-stream scratch of the general layout grows with the node
+    # length (the band holds whole nodes), so the batch planner has to count it - and when the device is (made) too small for
+    # the batch, the batch is cut into several launches instead of failing as a whole (GA_MEM_BUDGET_MB forces the cut)
+    g = synth.make_graph(33, 400_000, chop=2000, snp_every=500)
+    case = synth.make_case(33, g, 1500, 1000, b=10, errors=(0.04, 0.04, 0.04))
+    path = str(tmp_path / "case.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=os.cpu_count() or 4)
+    for budget in (None, "600"):
+        if budget:
+            os.environ["GA_MEM_BUDGET_MB"] = budget
+        try:
+            aligner = api.Aligner(api.Graph.from_case(case))
+            res = aligner.align(case.reads, case.b, case.B)
+            got = res.as_dicts()
+            assert_same(got, expected, "long-node graph, budget %s" % budget)
+            if budget:
+                assert aligner.stats()["launches"] > 3   # more than one launch sequence
+            res.free()
+            aligner.close()
+        finally:
+            os.environ.pop("GA_MEM_BUDGET_MB", None)

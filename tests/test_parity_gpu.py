@@ -91,10 +91,22 @@ def test_oversized_batch_is_split_into_launches(api, golden_dir, monkeypatch):
     aligner.close()
 
 
+def test_ramp_redo_fixture_fires_the_ramp(api, golden_dir):
+    # the ramp_redo golden (bit-exact in test_golden above) is only worth something if streams really go back and redo a
+    # stretch with the wide band on it: GA_FLAG_RAMP_REDO (16) on most of its reads
+    case = gacase.read_case(os.path.join(golden_dir, "ramp_redo.gacase"))
+    assert case.B > case.b
+    aligner = api.Aligner(api.Graph.from_case(case))
+    d = aligner.align(case.reads, case.b, case.B).as_dicts()
+    assert sum(1 for x in d if x["flags"] & 16) >= 6
+    aligner.close()
+
+
 def test_ramp_bandwidth_runs(api):
     # -B: slice 0 and every redone stretch use the wide band (GraphAligner.h:2612,2648-2719).  The reference's own ramp
-    # path crashes on many inputs (stale sqrt checkpoints), so this checks our invariants rather than bit parity:
-    # every read aligns, and a wide-band rescue can only help the score on average
+    # path keeps a stale sqrt checkpoint across a redo and then crashes or traces through recomputed slices that differ from
+    # its forward pass (measured: profiles/r02_ramp_fuzz.txt), so beyond the goldens (ramp, ramp_redo) this checks invariants:
+    # every read aligns, and a wide-band rescue can only help the coverage
     g = synth.make_graph(301, 40000, chop=32, bubble_every=120, indel_frac=0.5)
     narrow = synth.make_case(301, g, 48, 3000, b=3, B=0, errors=(0.08, 0.08, 0.08))
     ramped = synth.make_case(301, g, 48, 3000, b=3, B=40, errors=(0.08, 0.08, 0.08))
