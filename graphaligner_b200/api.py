@@ -26,7 +26,7 @@ TRACE_ITEM = np.dtype([("node_id", "<i4"), ("offset", "<u4"), ("readpos", "<u8")
 
 
 class GaStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("streams", "word_columns", "retries", "h2d_bytes", "d2h_bytes", "launches", "graph_bytes")]
+    _fields_ = [(n, C.c_uint64) for n in ("streams", "word_columns", "retries", "h2d_bytes", "d2h_bytes", "launches", "graph_bytes", "peq_us", "forward_us", "trace_us")]
 
 
 EXPORTS = ["ga_create", "ga_destroy", "ga_last_error", "ga_global_error", "ga_graph_new", "ga_graph_add_node", "ga_graph_add_edge",

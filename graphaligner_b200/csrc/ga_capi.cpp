@@ -579,6 +579,9 @@ int ga_get_stats(const ga_ctx* ctx, ga_stats* out)
 	out->d2h_bytes = ctx->stats.d2hBytes;
 	out->launches = ctx->stats.launches;
 	out->graph_bytes = ga::GraphBytesOnDevice(ctx->dev);
+	out->peq_us = (uint64_t)(ctx->stats.peqMs * 1000.0);
+	out->forward_us = (uint64_t)(ctx->stats.forwardMs * 1000.0);
+	out->trace_us = (uint64_t)(ctx->stats.traceMs * 1000.0);
 	return 0;
 }
 
@@ -759,6 +762,9 @@ int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out)
 		out->d2h_bytes += s.d2h_bytes;
 		out->launches += s.launches;
 		out->graph_bytes += s.graph_bytes;
+		out->peq_us += s.peq_us;
+		out->forward_us += s.forward_us;
+		out->trace_us += s.trace_us;
 	}
 	return 0;
 }

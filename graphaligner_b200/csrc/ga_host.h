@@ -171,6 +171,7 @@ struct BatchStats
 	uint64_t d2hBytes = 0;
 	uint64_t launches = 0;
 	double kernelMs = 0;
+	double peqMs = 0, forwardMs = 0, traceMs = 0;   // device time per kernel (events on the context's stream)
 };
 
 // Reference reverse complement incl. its IUPAC table and the 'H' fall-through (CommonUtils.cpp:60-136).

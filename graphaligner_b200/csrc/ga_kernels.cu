@@ -519,6 +519,8 @@ struct DeviceCtx
 	};
 	Pinned pinParts, pinOuts, pinArena, pinSmall, pinReadOff;
 	size_t budgetBytes = 0;    // device bytes a batch may use (FreeDeviceBytes), 0 = not queried yet
+	cudaEvent_t evKernel[4] = { nullptr, nullptr, nullptr, nullptr };   // around the three kernels of the last launch sequence
+	bool evRecorded = false;
 };
 
 struct StagedBatch
@@ -620,6 +622,7 @@ DeviceCtx* CreateDevice(int device)
 #endif
 	}
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
+	for (auto& e : ctx->evKernel) GA_CUDA(cudaEventCreate(&e));
 	return ctx;
 }
 
@@ -635,6 +638,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	ctx->pinArena.release();
 	ctx->pinSmall.release();
 	ctx->pinReadOff.release();
+	for (auto& e : ctx->evKernel) if (e) cudaEventDestroy(e);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -1012,10 +1016,8 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
 		sb->smemScratch, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 #else
-	// GA_KERNEL_TIMING: device time of each kernel of the launch sequence on stderr (tuning; serialises the stream)
-	static const bool kernelTiming = getenv("GA_KERNEL_TIMING") != nullptr;
-	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-	if (kernelTiming) { for (auto& e : ev) GA_CUDA(cudaEventCreate(&e)); GA_CUDA(cudaEventRecord(ev[0], ctx->stream)); }
+	// device time of each kernel of the launch sequence: events on the stream (read in FinishStaged; GA_KERNEL_TIMING prints them)
+	GA_CUDA(cudaEventRecord(ctx->evKernel[0], ctx->stream));
 	{
 		ga_peq_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((const ga_stream_in*)ctx->bIn.ptr, (const uint64_t*)ctx->bPeqOff.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, (uint4*)ctx->bPeq.ptr,
 			(uint32_t*)ctx->bPeqAux.ptr);
@@ -1023,7 +1025,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		if (sb->nReads) ga_validate_kernel<<<(unsigned)sb->nReads, 128, 0, ctx->stream>>>((const uint8_t*)ctx->bParts.ptr, (const uint64_t*)ctx->bReadOff.ptr, (uint32_t)sb->nReads, (uint32_t*)ctx->bBad.ptr);
 		GA_CUDA(cudaGetLastError());
 	}
-	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[1], ctx->stream));
+	GA_CUDA(cudaEventRecord(ctx->evKernel[1], ctx->stream));
 	switch (sb->S)
 	{
 		case 32: launchAlign<32>(ctx, sb); break;
@@ -1035,18 +1037,19 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		default: throw std::logic_error("unsupported streams-per-warp");
 	}
 	GA_CUDA(cudaGetLastError());
-	if (kernelTiming) GA_CUDA(cudaEventRecord(ev[2], ctx->stream));
+	GA_CUDA(cudaEventRecord(ctx->evKernel[2], ctx->stream));
 	launchTrace(ctx, sb);
+	GA_CUDA(cudaEventRecord(ctx->evKernel[3], ctx->stream));
+	ctx->evRecorded = true;
+	static const bool kernelTiming = getenv("GA_KERNEL_TIMING") != nullptr;
 	if (kernelTiming)
 	{
-		GA_CUDA(cudaEventRecord(ev[3], ctx->stream));
-		GA_CUDA(cudaEventSynchronize(ev[3]));
+		GA_CUDA(cudaEventSynchronize(ctx->evKernel[3]));
 		float a = 0, b = 0, c = 0;
-		cudaEventElapsedTime(&a, ev[0], ev[1]);
-		cudaEventElapsedTime(&b, ev[1], ev[2]);
-		cudaEventElapsedTime(&c, ev[2], ev[3]);
+		cudaEventElapsedTime(&a, ctx->evKernel[0], ctx->evKernel[1]);
+		cudaEventElapsedTime(&b, ctx->evKernel[1], ctx->evKernel[2]);
+		cudaEventElapsedTime(&c, ctx->evKernel[2], ctx->evKernel[3]);
 		fprintf(stderr, "[ga kernels] streams %zu S %d: peq %.3f ms, forward %.3f ms, trace %.3f ms\n", n, sb->S, a, b, c);
-		for (auto& e : ev) cudaEventDestroy(e);
 	}
 #endif
 	GA_CUDA(cudaGetLastError());
@@ -1155,6 +1158,16 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	GA_CUDA(cudaMemcpyAsync(pinTop, ctx->bArenaTop.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 	lap("stream records");
+	if (stats && ctx->evRecorded)
+	{
+		float a = 0, b = 0, c = 0;
+		if (cudaEventElapsedTime(&a, ctx->evKernel[0], ctx->evKernel[1]) == cudaSuccess && cudaEventElapsedTime(&b, ctx->evKernel[1], ctx->evKernel[2]) == cudaSuccess
+			&& cudaEventElapsedTime(&c, ctx->evKernel[2], ctx->evKernel[3]) == cudaSuccess)
+		{
+			stats->peqMs += a; stats->forwardMs += b; stats->traceMs += c; stats->kernelMs += a + b + c;
+		}
+		ctx->evRecorded = false;
+	}
 	unsigned long long top = *pinTop;
 	if (top > sb->arenaCap) top = sb->arenaCap;
 	if (pinBad)

@@ -145,6 +145,10 @@ typedef struct ga_stats
 	uint64_t d2h_bytes;
 	uint64_t launches;              /* alignment kernel launches */
 	uint64_t graph_bytes;           /* bytes of the graph replica on the device */
+	/* device time of the three kernels of every launch sequence, CUDA events on the context's stream, microseconds */
+	uint64_t peq_us;                /* the match-mask pre-pass and the bad-character check */
+	uint64_t forward_us;            /* the bit-parallel DP (small-band or general forward kernel) */
+	uint64_t trace_us;              /* the traceback */
 } ga_stats;
 int ga_get_stats(const ga_ctx* ctx, ga_stats* out);   /* cumulative since ga_create / ga_reset_stats */
 int ga_reset_stats(ga_ctx* ctx);
