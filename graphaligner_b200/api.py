@@ -184,10 +184,10 @@ class Results:
     def trace_hash(self, i):
         return int(self._lib.ga_results_trace_hash(self.handle, i))
 
-    def as_dicts(self, with_trace=False):
-        """Same shape as gacase.parse_ref_output, for differential tests against the oracle."""
+    def as_dicts(self, with_trace=False, indices=None):
+        """Same shape as gacase.parse_ref_output, for differential tests against the oracle (indices: only these reads)."""
         out = []
-        for i in range(len(self.reads)):
+        for i in (range(len(self.reads)) if indices is None else indices):
             r = self.reads[i]
             failed = int(r["failed"])
             d = {"name": self.names[i] if self.names else str(i), "failed": failed, "asserted": 0,

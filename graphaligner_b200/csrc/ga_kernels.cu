@@ -1053,8 +1053,9 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 	}
 #endif
 	GA_CUDA(cudaGetLastError());
-	sb->launches += 3;
-	return 3;
+	const int launched = sb->nReads ? 4 : 3;   // match masks, bad-character check, forward DP, traceback
+	sb->launches += launched;
+	return launched;
 }
 
 static bool isOverflow(int32_t status)

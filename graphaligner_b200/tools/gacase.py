@@ -81,3 +81,14 @@ def parse_ref_output(text):
                 k, v = kv.split("=")
                 timing[k] = float(v)
     return reads, timing
+
+
+RESULT_KEYS = ("failed", "score", "start", "end", "qpos", "nmap", "ntrace", "th")
+
+
+def same_result(mine, expected):
+    """One read's result dict (Results.as_dicts) against the reference's (parse_ref_output): score, range, query position,
+    every mapping and the fingerprint of every trace item."""
+    if any(mine[k] != expected[k] for k in RESULT_KEYS):
+        return False
+    return [tuple(x) for x in mine["mappings"]] == [tuple(x) for x in expected["mappings"]]

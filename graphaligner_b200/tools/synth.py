@@ -158,6 +158,7 @@ def make_graph(seed, backbone_len, chop=32, snp_every=0, bubble_every=0, indel_f
             pos += len(g.seq[n1])
             next_cyc += cycle_every
             plain(min(chop, max(1, backbone_len - pos)))
+    g.exits = exits
     return g
 
 
@@ -269,6 +270,71 @@ def make_case(seed, graph, n_reads, read_len, b=10, B=0, seed_offsets=(0,), deco
     return Case(list(graph.nodes), list(graph.edges), reads, b, B)
 
 
+_PAR = {}
+
+
+def _par_chunk(args):
+    seed, n, first = args
+    c = make_case(seed, _PAR["graph"], n, **_PAR["kw"])
+    return [("read_%d" % (first + k), s, sd) for k, (_, s, sd) in enumerate(c.reads)]
+
+
+def make_case_parallel(seed, graph, n_reads, read_len, workers=None, chunk=500, read_range=None, **kw):
+    """make_case over `workers` forked processes (the full-size configs hold 10^5 reads; one process simulates ~150 reads/s).
+    Chunk k of `chunk` reads is make_case(seed + 1000003 * (k + 1), ...), so the read set depends on (seed, chunk) only,
+    not on the worker count.  read_range = (lo, hi), multiples of `chunk`: only that part of the read set (a rank's shard)."""
+    import multiprocessing as mp
+    import os
+    workers = workers or os.cpu_count() or 1
+    b, B = kw.pop("b", 10), kw.pop("B", 0)
+    lo, hi = read_range if read_range is not None else (0, n_reads)
+    assert lo % chunk == 0
+    graph.succ()   # built once, inherited by the workers
+    _PAR["graph"] = graph
+    _PAR["kw"] = dict(kw, read_len=read_len, b=b, B=B)
+    jobs = [(seed + 1000003 * (first // chunk + 1), min(chunk, hi - first), first) for first in range(lo, hi, chunk)]
+    if workers <= 1 or len(jobs) <= 1:
+        parts = [_par_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_par_chunk, jobs)
+    _PAR.clear()
+    return Case(list(graph.nodes), list(graph.edges), [r for p_ in parts for r in p_], b, B)
+
+
+def _graph_segment(args):
+    seed, length, kw = args
+    g = make_graph(seed, length, **kw)
+    return g.nodes, g.edges, g.exits
+
+
+def make_graph_parallel(seed, backbone_len, workers=None, segment=2_000_000, **kw):
+    """make_graph built as a chain of independently generated segments of `segment` bp (segment k = make_graph(seed +
+    7919 * k, ...)), joined exit -> entry; the result depends on (seed, segment) only.  For the 100 Mbp configs."""
+    import multiprocessing as mp
+    import os
+    workers = workers or os.cpu_count() or 1
+    lens = [min(segment, backbone_len - o) for o in range(0, backbone_len, segment)]
+    jobs = [(seed + 7919 * k, ln, kw) for k, ln in enumerate(lens)]
+    if workers <= 1 or len(jobs) <= 1:
+        segs = [_graph_segment(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            segs = pool.map(_graph_segment, jobs)
+    g = Graph()
+    exits = []
+    for nodes, edges, seg_exits in segs:
+        off = len(g.nodes)          # ids are 2.. in file order: shift by the nodes already there
+        g.nodes.extend((nid + off, seq) for nid, seq in nodes)
+        for (a, sa) in exits:       # every segment starts with a plain node (id 2, forward)
+            g.edges.append((a, sa == 1, 2 + off, False))
+        g.edges.extend((a + off, fs, b + off, te) for a, fs, b, te in edges)
+        exits = [(a + off, sa) for a, sa in seg_exits]
+    g.seq = dict(g.nodes)
+    g.exits = exits
+    return g
+
+
 # ---- the five BASELINE.json configs, scaled by `scale` for tests (scale=1.0 is full size) -------------
 
 def config2(scale=1.0, seed=1):
@@ -276,17 +342,20 @@ def config2(scale=1.0, seed=1):
     return g, dict(n_reads=max(1, int(10_000 * scale)), read_len=10_000, b=10)
 
 
-def config3(scale=1.0, seed=2):
-    g = make_graph(seed, int(100_000_000 * scale), chop=32, bubble_every=100, indel_frac=0.2, inversion_every=5000)
+def config3(scale=1.0, seed=2, parallel=False):
+    mk = make_graph_parallel if parallel else make_graph
+    g = mk(seed, int(100_000_000 * scale), chop=32, bubble_every=100, indel_frac=0.2, inversion_every=5000)
     return g, dict(n_reads=max(1, int(100_000 * scale)), read_len=10_000, b=10, seed_offsets=(0, 5000, -300), decoys=1)
 
 
-def config4(scale=1.0, seed=4):
+def config4(scale=1.0, seed=4, parallel=False):
     """configs[3]: human-scale GFA graph (GFA semantics, 0-bp edge overlap), 1M reads of 15 kbp sharded over the GPUs."""
-    g = make_graph(seed, int(3_000_000_000 * scale), chop=32, snp_every=1000, bubble_every=5000, indel_frac=0.3)
+    mk = make_graph_parallel if parallel else make_graph
+    g = mk(seed, int(3_000_000_000 * scale), chop=32, snp_every=1000, bubble_every=5000, indel_frac=0.3)
     return g, dict(n_reads=max(1, int(1_000_000 * scale)), read_len=15_000, b=10, gfa_overlap=0)
 
 
-def config5(scale=1.0, seed=5):
-    g = make_graph(seed, int(100_000_000 * scale), chop=32, bubble_every=100, indel_frac=0.2, tangle_every=1_000_000)
+def config5(scale=1.0, seed=5, parallel=False):
+    mk = make_graph_parallel if parallel else make_graph
+    g = mk(seed, int(100_000_000 * scale), chop=32, bubble_every=100, indel_frac=0.2, tangle_every=250_000)
     return g, dict(n_reads=max(1, int(2_000 * scale)), read_len=50_000, b=10)

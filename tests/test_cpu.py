@@ -57,3 +57,26 @@ def test_restatement_oracle_reproduces_golden(golden_dir, name):
     res = subprocess.run([RESTATEMENT, os.path.join(golden_dir, name + ".gacase")], capture_output=True, text=True, check=True)
     got, _ = gacase.parse_ref_output(res.stdout)
     assert_same(got, load_expected(os.path.join(golden_dir, name + ".expected")), name)
+
+
+def test_parallel_generators_make_valid_cases(tmp_path):
+    # bench.py's full-size configs build graph and reads on worker processes (segments joined exit -> entry, chunked read
+    # seeds): the reference must align reads that cross segment borders, and the read set must not depend on the worker count
+    import os
+    import pytest
+    from graphaligner_b200.tools import gacase, synth
+    from helpers import REF_ALIGN, run_reference
+    g = synth.make_graph_parallel(11, 6000, workers=2, segment=1500, chop=32, bubble_every=100, indel_frac=0.2)
+    assert len(g.exits) >= 1 and len(g.nodes) == len(g.seq)
+    a = synth.make_case_parallel(5, g, 24, 3000, workers=2, chunk=8, b=10)
+    b = synth.make_case_parallel(5, g, 24, 3000, workers=1, chunk=8, b=10)
+    assert a.reads == b.reads and [r[0] for r in a.reads] == ["read_%d" % i for i in range(24)]
+    shard = synth.make_case_parallel(5, g, 24, 3000, workers=2, chunk=8, read_range=(8, 16), b=10)
+    assert shard.reads == a.reads[8:16]
+    if not os.path.exists(REF_ALIGN):
+        pytest.skip("oracle/_ref not built")
+    path = str(tmp_path / "par.gacase")
+    gacase.write_case(a, path)
+    expected, _ = run_reference(path, threads=4)
+    assert sum(1 for e in expected if not e["failed"]) >= 22
+    assert all(e["score"] < 0.3 * 3000 for e in expected if not e["failed"])
