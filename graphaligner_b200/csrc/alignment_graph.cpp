@@ -142,6 +142,19 @@ void AlignmentGraph::Finalize(int wordSize)
 		auto found = nodeLookup.find(id % 2 == 1 ? (id / 2) * 2 : (id / 2) * 2 + 1);
 		if (found != nodeLookup.end()) reverseNode[i] = found->second;
 	}
+	// digraph id -> node index as a flat table when the ids are dense (every seed costs several lookups: a hash probe is two
+	// or three cache misses, the table one)
+	{
+		// from the map itself: the two dummy nodes carry id 0 in nodeIDs without being looked up by it
+		int maxId = -1, minId = 0;
+		for (const auto& kv : nodeLookup) { maxId = std::max(maxId, kv.first); minId = std::min(minId, kv.first); }
+		denseLookup.clear();
+		if (minId >= 0 && maxId >= 0 && (size_t)maxId < 4 * n + 1024)
+		{
+			denseLookup.assign((size_t)maxId + 1, 0xffffffffu);
+			for (const auto& kv : nodeLookup) denseLookup[(size_t)kv.first] = kv.second;
+		}
+	}
 	// same graph statistics on stderr as the reference (AlignmentGraph.cpp:125-138)
 	std::cerr << n << " nodes" << std::endl;
 	std::cerr << totalBp << "bp" << std::endl;
@@ -152,6 +165,11 @@ void AlignmentGraph::Finalize(int wordSize)
 
 size_t AlignmentGraph::Lookup(int digraphNodeId) const
 {
+	if (!denseLookup.empty())
+	{
+		if (digraphNodeId < 0 || (size_t)digraphNodeId >= denseLookup.size() || denseLookup[(size_t)digraphNodeId] == 0xffffffffu) throw std::out_of_range("AlignmentGraph: node id not in graph");
+		return denseLookup[(size_t)digraphNodeId];
+	}
 	auto found = nodeLookup.find(digraphNodeId);
 	if (found == nodeLookup.end()) throw std::out_of_range("AlignmentGraph: node id not in graph");
 	return found->second;
@@ -159,6 +177,7 @@ size_t AlignmentGraph::Lookup(int digraphNodeId) const
 
 bool AlignmentGraph::HasNode(int digraphNodeId) const
 {
+	if (!denseLookup.empty()) return digraphNodeId >= 0 && (size_t)digraphNodeId < denseLookup.size() && denseLookup[(size_t)digraphNodeId] != 0xffffffffu;
 	return nodeLookup.count(digraphNodeId) != 0;
 }
 

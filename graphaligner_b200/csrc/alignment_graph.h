@@ -64,6 +64,7 @@ private:
 	std::vector<uint32_t> seq2;
 	uint64_t totalBp;
 	std::unordered_map<int, uint32_t> nodeLookup;
+	std::vector<uint32_t> denseLookup;   // digraph id -> node index (0xffffffff: none) when the ids are dense, built by Finalize; else empty
 	std::vector<std::pair<uint32_t, uint32_t>> pendingEdges;   // (from, to) in AddEdgeNodeId order
 	std::vector<uint32_t> inOff, inAdj, outOff, outAdj;
 	bool finalized;

@@ -23,6 +23,8 @@
 #define GAF_HEAP 32u
 #define GAF_NONE 0xffu
 #define GAF_NOPCS 0xfffu
+#define GAF_ORD_CHAIN 0x100u
+#define GAF_ORD_NOUP 0x200u
 
 // One warp's shared memory: [..][lane] so that the lanes of a warp hit different banks
 template <int S>
@@ -379,12 +381,21 @@ GA_DEV bool gaf_resolve(const ga_graph_view& g, const GaFastLane<S>& fl, GaStrea
 	if (ready != nc) { st.status = GA_ERR_NODE_OVERFLOW; return false; }   // a cycle: the general kernel replays the reference's work list
 	// the nodes' columns lie in the slice's slab (and in the tiny array) in evaluation order: a chain of nodes is then one
 	// contiguous run of columns, which the traceback walks without looking anything up (GA_CF_LINK)
+	// An order entry also says how the node starts: GAF_ORD_CHAIN = its only band in-neighbour is the node evaluated (and
+	// therefore stored) right before it, so its first column is one more word step from that node's last column;
+	// GAF_ORD_NOUP = that neighbour is not in the previous band.
 	uint32_t col = 0;
+	uint32_t prevSlot = GAF_NONE;
 	for (uint32_t d = 0; d < nc; d++)
 	{
 		const uint32_t slot = order[(size_t)d * S];
 		fl.sh.csPcs[tc][slot][fl.lane] = (fl.sh.csPcs[tc][slot][fl.lane] & 0xffff0000u) | col;
 		col += GA_REC_LEN(fl.sh.lenDeg[tc][slot][fl.lane]);
+		const uint32_t ins = inSlots[(size_t)slot * S];
+		const bool two = (ins >> 16) != 0xffffu;
+		const bool chain = !two && (ins & 0xffu) != GAF_NONE && (ins & 0xffu) == prevSlot;
+		order[(size_t)d * S] = slot | (chain ? GAF_ORD_CHAIN : 0u) | (((ins >> 8) & 0xffu) == GAF_NONE ? GAF_ORD_NOUP : 0u);
+		prevSlot = slot;
 	}
 	return true;
 }
@@ -472,6 +483,9 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 		}
 		GA_SYNCWARP();
 		GA_TLAP(st, 0);
+		// the first 32 bases of every band node, into the queue's memory (free until the next selection): they arrive while
+		// the band is resolved, and a node start in the column loop reads shared memory only
+		for (int i = 0; i < nc; i++) ga_cp_async8(&fl.sh.heap[i][fl.lane], (const uint64_t*)g.seqChunks + (size_t)fl.sh.chunk[tc][i][fl.lane] * 2);
 		if (!gaf_resolve<S>(g, fl, st, tc, (uint32_t)nc, run ? pNodes : 0) && run) { st.done = true; run = false; nc = 0; ncols = 0; }
 		GA_SYNCWARP();
 		GA_TLAP(st, 1);
@@ -513,14 +527,12 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 		bool inPrev = false;
 		uint32_t prevMask = 0;
 		uint64_t seqBits = 0;            // the next (up to 32) bases of the node
-		uint4 chunkCur = make_uint4(0, 0, 0, 0);
 		uint32_t chunkIdx = 0;
 		uint64_t VP = 0, VN = 0;         // the left neighbour: the column of the previous iteration
 		int32_t sbsL = 0, endL = 0;
 		uint32_t LsbE = 0;
 		int32_t upScore = INF, upRow62 = 0;   // the up-left neighbour: previous iteration's column in the previous slice (INF = none)
 		uint32_t lastSlot = GAF_NONE;    // slot whose last column is the left neighbour
-		uint32_t linkOk = 0;             // first column of a chain whose neighbour is stored right before it
 		int32_t nodeMin = 0x7fffffff, scoreMax = 0;
 		if (!run) oi = (uint32_t)nc;
 		for (uint32_t it = 0; it < maxc; it++)
@@ -531,7 +543,8 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 			{
 				// ---- next node of the evaluation order ----
 				if (lastSlot != GAF_NONE) fl.sh.nodeMin[tc][lastSlot][fl.lane] = nodeMin;
-				slot = order[(size_t)(oi++) * S];
+				const uint32_t ord = order[(size_t)(oi++) * S];
+				slot = ord & 0xffu;
 				const uint32_t len = GA_REC_LEN(fl.sh.lenDeg[tc][slot][fl.lane]);
 				const uint32_t cp = fl.sh.csPcs[tc][slot][fl.lane];
 				const uint32_t cs = cp & 0xffffu, pcs = cp >> 16;
@@ -540,27 +553,24 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 				topIdx = inPrev ? pcs : 0;
 				prevMask = firstSlice ? (inPrev ? 15u : 0u) : ((1u << prevCharCode) & 15u);
 				chunkIdx = fl.sh.chunk[tc][slot][fl.lane];
-				chunkCur = *((const uint4*)g.seqChunks + chunkIdx);
-				seqBits = (uint64_t)chunkCur.x | ((uint64_t)chunkCur.y << 32);
+				seqBits = fl.sh.heap[slot][fl.lane];
 				k = 0;
 				kLeft = len;
 				nodeMin = 0x7fffffff;
-				const uint32_t ins = inSlots[(size_t)slot * S];
-				const uint32_t cu0 = ins & 0xffu, pu0 = (ins >> 8) & 0xffu, cu1 = (ins >> 16) & 0xffu, pu1 = ins >> 24;
-				const bool two = cu1 != GAF_NONE || pu1 != GAF_NONE;
-				// a chain: the node's only band in-neighbour is the node evaluated just before it - its last column is the left
-				// neighbour in the registers, and its last column of the previous slice (if any) was the previous iteration's
-				// up neighbour: the first column is then one more word step of the loop below
-				if (!two && cu0 != GAF_NONE && cu0 == lastSlot)
+				// a chain (GAF_ORD_CHAIN): the node's only band in-neighbour is the node evaluated just before it - its last column
+				// is the left neighbour in the registers, and its last column of the previous slice (if any) was the previous
+				// iteration's up neighbour: the first column is then one more word step of the loop below, and the column is
+				// stored right after its neighbour's (GA_CF_LINK)
+				if (ord & GAF_ORD_CHAIN)
 				{
 					isFirst = 1;
-					if (pu0 == GAF_NONE) upScore = INF;
-					const uint32_t nbEnd = (fl.sh.csPcs[tc][lastSlot][fl.lane] & 0xffffu) + GA_REC_LEN(fl.sh.lenDeg[tc][lastSlot][fl.lane]);
-					linkOk = nbEnd == cs ? 1u : 0u;
+					if (ord & GAF_ORD_NOUP) upScore = INF;
 				}
 				else
 				{
 					// ---- first column of every other node (GraphAligner.h:1270-1347,1457-1531), cf. ga_calc_node ----
+					const uint32_t ins = inSlots[(size_t)slot * S];
+					const uint32_t cu0 = ins & 0xffu, pu0 = (ins >> 8) & 0xffu, cu1 = (ins >> 16) & 0xffu, pu1 = ins >> 24;
 					const uint32_t base = (uint32_t)seqBits & 3u;
 					const uint64_t Eq = eqTab[(size_t)base * S];
 					const bool previousEq = ((prevMask >> base) & 1u) != 0;
@@ -665,12 +675,8 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 				}
 			}
 			// ---- one column by the word step: columns 1.. of a node (GraphAligner.h:1349-1399,1532-1570) or the first column of a chain ----
-			if ((k & 31u) == 0 && k > 0)
-			{
-				// the next 32 bases: the chunk's upper half, or the next chunk
-				if ((k & 63u) == 0) { chunkCur = *((const uint4*)g.seqChunks + chunkIdx + (k >> 6)); seqBits = (uint64_t)chunkCur.x | ((uint64_t)chunkCur.y << 32); }
-				else seqBits = (uint64_t)chunkCur.z | ((uint64_t)chunkCur.w << 32);
-			}
+			// the next 32 bases of a node longer than that: 8 bytes of its chunks
+			if ((k & 31u) == 0 && k > 0) seqBits = *((const uint64_t*)g.seqChunks + (size_t)chunkIdx * 2 + (k >> 5));
 			const uint32_t base = (uint32_t)seqBits & 3u;
 			seqBits >>= 2;
 			uint64_t Eq = eqTab[(size_t)base * S];
@@ -705,7 +711,7 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 			Mh = (Mh << 1) | (hin < 0 ? 1u : 0u);
 			uint64_t VPn = Mh | ~(Xv | Ph);
 			uint64_t VNn = Ph & Xv;
-			uint32_t flags = isFirst ? (linkOk ? GA_CF_LINK : 0u) : GA_CF_PLAIN;
+			uint32_t flags = isFirst ? GA_CF_LINK : GA_CF_PLAIN;
 			if (needMerge)
 			{
 				GaCol c;

@@ -749,6 +749,34 @@ void EmitMappings(const AlignmentGraph& graph, const ReadInput& read, const Read
 
 void WriteMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, ::ga_mapping* dst)
 {
+	if (as.failed) return;
+	if (!as.mapBwCount && as.mapFwCount && !as.mapFwSkip)
+	{
+		// the common case (a seed at read position 0: forward part only) as one flat loop over the device's run records, last run
+		// first (mappingOf / RunView::get with backward = false written out)
+		const ga_stream_out& out = outs[as.mapFwStream];
+		const size_t n = out.nRuns, shift = as.fwShifted ? as.splitIndex : 0;
+		const uint32_t* rec = arena + out.traceOff + (out.nMoves + 15) / 16 + out.nPathNodes;
+		const size_t k = as.mapFwFirst, count = as.mapFwCount;
+		const uint32_t* r = rec + (n - 1 - k) * GA_RUN_WORDS;
+		size_t beforeJ = (size_t)r[3] + shift;
+		for (size_t i = 0; i < count; i++, r -= GA_RUN_WORDS)
+		{
+			const uint32_t node = r[0];
+			const size_t firstJ = (size_t)r[3] + shift, lastJ = (size_t)r[4] + shift;
+			if (firstJ > read.seqLen) throw std::out_of_range("basic_string::substr");
+			::ga_mapping& gm = dst[i];
+			gm.node_id = graph.NodeID(node);
+			gm.offset = i == 0 ? r[1] : 0;
+			gm.rank = (uint32_t)i;
+			gm.from_length = (int32_t)(r[2] - r[1]) + (i + 1 == count ? 0 : 1);
+			gm.to_length = (int32_t)(lastJ - beforeJ);
+			gm.read_start = (uint32_t)firstJ;
+			gm.is_reverse = graph.Reverse(node) ? 1u : 0u;
+			beforeJ = lastJ;
+		}
+		return;
+	}
 	emitMappingsTo(graph, read, as, outs, arena, [dst](size_t k, const FlatMapping& m) {
 		::ga_mapping& gm = dst[k];
 		gm.node_id = m.node_id;

@@ -3,6 +3,7 @@
 // no CUDA device is usable.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -816,6 +817,22 @@ static int pickStreamsPerWarp(DeviceCtx* ctx, size_t nStreams)
 	return S;
 }
 
+// Small-band kernel: a launch lasts as long as one warp's chain of slices, and a warp that shares its SM sub-partition
+// with a second one is the slower for it.  So: the fewest streams per warp (16..32, not only powers of two - the lane
+// interleave of every buffer is just a stride) that still give every warp a sub-partition of its own; a batch too large
+// for that runs in waves of 16-stream warps, five warps of state per SM.
+static int pickFastStreamsPerWarp(DeviceCtx* ctx, size_t nStreams)
+{
+	if (ctx->forceS > 0) return ctx->forceS;
+	const size_t slots = (size_t)ctx->smCount * 4;
+	static const int candidates[] = { 16, 17, 18, 20, 24, 28, 32 };
+	for (int S : candidates)
+	{
+		if ((nStreams + S - 1) / S <= slots) return S;
+	}
+	return 16;
+}
+
 static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 {
 	const size_t n = sb->sorted.size();
@@ -829,8 +846,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		// no -B ramp: a redo needs the general kernel's history rewind (slice 0 still runs with B, as in the reference)
 		sb->smemScratch = scale == 1 && bandNodes <= 10 && sb->B <= sb->b && getenv("GA_NO_SMEM") == nullptr;
 	}
-	// streams per warp.  Small-band kernel: 16, i.e. five warps of state per SM in shared memory; general kernel: see pickStreamsPerWarp
-	sb->S = sb->smemScratch ? (ctx->forceS > 0 ? ctx->forceS : 16) : pickStreamsPerWarp(ctx, n);
+	sb->S = sb->smemScratch ? pickFastStreamsPerWarp(ctx, n) : pickStreamsPerWarp(ctx, n);
 	const size_t S = (size_t)sb->S;
 	const size_t nWarps = (n + S - 1) / S;
 	sb->nWarps = nWarps;
@@ -948,19 +964,27 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 }
 
 #ifndef GA_HOSTSIM
+// small-band kernel: one warp per block, the warp's state in dynamic shared memory
+template <int S>
+static void launchFast(DeviceCtx* ctx, StagedBatch* sb)
+{
+	const size_t n = sb->sorted.size();
+	// per device: the attribute belongs to the function on the current device
+	static std::atomic<uint64_t> attrDone(0);
+	const uint64_t bit = 1ull << (ctx->device & 63);
+	if (!(attrDone.load() & bit))
+	{
+		GA_CUDA(cudaFuncSetAttribute(ga_fast_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaFastShared<S>)));
+		attrDone.fetch_or(bit);
+	}
+	ga_fast_kernel<S><<<(unsigned)sb->nWarps, 32, sizeof(GaFastShared<S>), ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+}
+
 template <int S>
 static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
-	if (sb->smemScratch)
-	{
-		// small-band kernel: one warp per block, the warp's state in dynamic shared memory
-		static bool attr = false;
-		if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_fast_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaFastShared<S>))); attr = true; }
-		ga_fast_kernel<S><<<(unsigned)sb->nWarps, 32, sizeof(GaFastShared<S>), ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-			(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
-		return;
-	}
 	const int threads = 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
 	const size_t smemBytes = (size_t)(threads / 32) * 4 * S * sizeof(unsigned long long);
@@ -972,20 +996,33 @@ template <int T, int P>
 static void launchTraceTP(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
-	static bool attr = false;
-	if (!attr) { GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<T, P>))); attr = true; }
+	static std::atomic<uint64_t> attrDone(0);   // per device, as in launchFast
+	const uint64_t bit = 1ull << (ctx->device & 63);
+	if (!(attrDone.load() & bit))
+	{
+		GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<T, P>)));
+		attrDone.fetch_or(bit);
+	}
 	ga_trace_kernel<T, P><<<(unsigned)((n + T - 1) / T), 32, sizeof(GaTraceShared<T, P>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n,
 		(uint32_t)sb->S, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 
 static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
 {
-	// streams per warp: few, so that a batch is many warps (the walk is latency-bound); more once every SM has its share
+	// streams per warp: few, so that a batch is many warps (the walk is latency-bound).  Measured on the B200 (168 registers:
+	// 12 warps per SM): 10 000 streams 5.3 ms at T = 6 (one wave), 7.0 at 8, 8.9 at 5 (two waves); 28 000 streams in waves
+	// 13.2 ms at T = 8, 14.8 at 6, 18.1 at 16, 28.3 at 32.
 	const size_t n = sb->sorted.size();
 	int T = ctx->traceT;
-	if (T == 0) T = n <= (size_t)ctx->smCount * 16 * 8 ? 8 : (n <= (size_t)ctx->smCount * 16 * 16 ? 16 : 32);
+	if (T == 0) T = n <= (size_t)ctx->smCount * 12 * 6 ? 6 : 8;
 	const int P = ctx->traceP;
-	if (T == 8 && P == 1) launchTraceTP<8, 1>(ctx, sb);
+	if (T == 6) launchTraceTP<6, 1>(ctx, sb);
+	else if (T == 5) launchTraceTP<5, 1>(ctx, sb);
+	else if (T == 7) launchTraceTP<7, 1>(ctx, sb);
+	else if (T == 4 && P == 1) launchTraceTP<4, 1>(ctx, sb);
+	else if (T == 10) launchTraceTP<10, 1>(ctx, sb);
+	else if (T == 12) launchTraceTP<12, 1>(ctx, sb);
+	else if (T == 8 && P == 1) launchTraceTP<8, 1>(ctx, sb);
 	else if (T == 8) launchTraceTP<8, 2>(ctx, sb);
 	else if (T == 16 && P == 1) launchTraceTP<16, 1>(ctx, sb);
 	else if (T == 16) launchTraceTP<16, 2>(ctx, sb);
@@ -1026,7 +1063,23 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		GA_CUDA(cudaGetLastError());
 	}
 	GA_CUDA(cudaEventRecord(ctx->evKernel[1], ctx->stream));
-	switch (sb->S)
+	if (sb->smemScratch)
+	{
+		switch (sb->S)
+		{
+			case 32: launchFast<32>(ctx, sb); break;
+			case 28: launchFast<28>(ctx, sb); break;
+			case 24: launchFast<24>(ctx, sb); break;
+			case 20: launchFast<20>(ctx, sb); break;
+			case 18: launchFast<18>(ctx, sb); break;
+			case 17: launchFast<17>(ctx, sb); break;
+			case 16: launchFast<16>(ctx, sb); break;
+			case 8: launchFast<8>(ctx, sb); break;
+			case 4: launchFast<4>(ctx, sb); break;
+			default: throw std::logic_error("unsupported streams-per-warp (small-band kernel)");
+		}
+	}
+	else switch (sb->S)
 	{
 		case 32: launchAlign<32>(ctx, sb); break;
 		case 16: launchAlign<16>(ctx, sb); break;
