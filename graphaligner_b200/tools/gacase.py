@@ -69,7 +69,7 @@ def parse_ref_output(text):
             cur = {"name": p[1], "mappings": [], "trace": []}
             for kv in p[2:]:
                 k, v = kv.split("=")
-                cur[k] = int(v, 16) if k == "th" else int(v)
+                cur[k] = int(v, 16) if k in ("th", "mh") else int(v)
             reads.append(cur)
         elif line.startswith("M "):
             cur["mappings"].append(tuple(int(x) for x in line.split()[1:]))
@@ -92,3 +92,32 @@ def same_result(mine, expected):
     if any(mine[k] != expected[k] for k in RESULT_KEYS):
         return False
     return [tuple(x) for x in mine["mappings"]] == [tuple(x) for x in expected["mappings"]]
+
+
+def mapping_checksums(read_records, mappings):
+    """Per read: sum over its mappings m of (m + 1) * mix(m) mod 2^64 - the order-sensitive checksum ref_align --summary
+    prints as mh= (read_records / mappings: the numpy views of api.Results)."""
+    import numpy as np
+    n = len(read_records)
+    out = np.zeros(n, dtype=np.uint64)
+    if len(mappings) == 0:
+        return out
+    with np.errstate(over="ignore"):
+        mix = (mappings["node_id"].astype(np.int64).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+               + mappings["is_reverse"].astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+               + mappings["offset"].astype(np.uint64) * np.uint64(0x165667B19E3779F9)
+               + mappings["from_length"].astype(np.int64).astype(np.uint64) * np.uint64(0x27D4EB2F165667C5)
+               + mappings["to_length"].astype(np.int64).astype(np.uint64) * np.uint64(0x85EBCA77C2B2AE63))
+        off = read_records["mapping_offset"].astype(np.int64)
+        cnt = np.where(read_records["failed"] == 0, read_records["n_mappings"], 0).astype(np.int64)
+        rank = (np.arange(len(mappings), dtype=np.int64) - np.repeat(off, cnt) + 1).astype(np.uint64) if int(cnt.sum()) == len(mappings) else None
+        if rank is None:
+            # mappings of failed reads interleaved (never produced by the library, kept for safety): per-read loop
+            for i in range(n):
+                m = mix[off[i]:off[i] + cnt[i]]
+                out[i] = (m * np.arange(1, len(m) + 1, dtype=np.uint64)).sum(dtype=np.uint64)
+            return out
+        w = mix * rank
+        csum = np.concatenate(([np.uint64(0)], np.cumsum(w, dtype=np.uint64)))
+        out = csum[off + cnt] - csum[off]
+    return out

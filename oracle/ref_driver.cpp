@@ -67,18 +67,20 @@ int main(int argc, char** argv)
 {
 	if (argc < 2)
 	{
-		std::cerr << "usage: ref_align <case.gacase> [--threads T] [--full] [--quiet] [--limit N]" << std::endl;
+		std::cerr << "usage: ref_align <case.gacase> [--threads T] [--full] [--quiet] [--limit N] [--summary]" << std::endl;
 		return 2;
 	}
 	int threads = 1;
 	bool full = false;
 	bool quiet = false;
+	bool summary = false;
 	size_t limit = (size_t)-1;
 	for (int i = 2; i < argc; i++)
 	{
 		if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--full")) full = true;
 		else if (!strcmp(argv[i], "--quiet")) quiet = true;
+		else if (!strcmp(argv[i], "--summary")) summary = true;
 		else if (!strcmp(argv[i], "--limit") && i + 1 < argc) limit = strtoull(argv[++i], nullptr, 10);
 	}
 	std::ifstream in(argv[1]);
@@ -255,6 +257,22 @@ int main(int argc, char** argv)
 		}
 		if (!failed) alignedBp += reads[i].sequence.size();
 		int nmap = failed ? 0 : r.alignment.path().mapping_size();
+		if (summary)
+		{
+			// --summary: the mappings as one order-sensitive checksum instead of a line each (full-size read sets):
+			// mh = sum over mappings m of (m + 1) * mix(m) mod 2^64, see tools/gacase.py mapping_checksums
+			uint64_t mh = 0;
+			for (int m = 0; m < nmap; m++)
+			{
+				const auto& mp = r.alignment.path().mapping(m);
+				const uint64_t mix = (uint64_t)(int64_t)mp.position().node_id() * 0x9E3779B97F4A7C15ull + (uint64_t)(mp.position().is_reverse() ? 1 : 0) * 0xC2B2AE3D27D4EB4Full
+					+ (uint64_t)(int64_t)mp.position().offset() * 0x165667B19E3779F9ull + (uint64_t)(int64_t)(mp.edit_size() > 0 ? mp.edit(0).from_length() : -1) * 0x27D4EB2F165667C5ull
+					+ (uint64_t)(int64_t)(mp.edit_size() > 0 ? mp.edit(0).to_length() : -1) * 0x85EBCA77C2B2AE63ull;
+				mh += (uint64_t)(m + 1) * mix;
+			}
+			printf("READ %s failed=%d asserted=%d score=%d start=%zu end=%zu qpos=%d nmap=%d ntrace=%zu th=%016llx mh=%016llx\n", reads[i].name.c_str(), failed ? 1 : 0, outs[i].asserted ? 1 : 0, failed ? 0 : r.alignment.score(), failed ? (size_t)0 : r.alignmentStart, failed ? (size_t)0 : r.alignmentEnd, failed ? 0 : r.alignment.query_position(), nmap, failed ? (size_t)0 : r.trace.size(), (unsigned long long)(failed ? 0 : h), (unsigned long long)mh);
+			continue;
+		}
 		printf("READ %s failed=%d asserted=%d score=%d start=%zu end=%zu qpos=%d nmap=%d ntrace=%zu th=%016llx\n", reads[i].name.c_str(), failed ? 1 : 0, outs[i].asserted ? 1 : 0, failed ? 0 : r.alignment.score(), failed ? (size_t)0 : r.alignmentStart, failed ? (size_t)0 : r.alignmentEnd, failed ? 0 : r.alignment.query_position(), nmap, failed ? (size_t)0 : r.trace.size(), (unsigned long long)(failed ? 0 : h));
 		for (int m = 0; m < nmap; m++)
 		{

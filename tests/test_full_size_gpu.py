@@ -33,7 +33,7 @@ def test_every_read_aligns_and_invariants_hold(workload):
     r = res.reads
     assert int((r["flags"] & 1).sum()) == 0, "a DP stream hit a hard limit"
     ok = r["failed"] == 0
-    assert ok.mean() > 0.99   # which reads fail is pinned against the reference in test_sample_against_reference
+    assert ok.mean() > 0.99   # WHICH reads fail is pinned against the reference in test_every_read_against_reference
     lens = np.array([len(x[1]) for x in case.reads])
     # alignmentEnd - alignmentStart = 64 * (retained slices), never more than the padded read (GraphAligner.h:486)
     span = (r["alignment_end"] - r["alignment_start"])[ok]
@@ -81,15 +81,31 @@ def test_results_do_not_depend_on_batch_composition(workload, monkeypatch):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
-def test_sample_against_reference(workload, tmp_path):
-    # every 41st read plus every read that failed here: the reference must fail exactly the same reads (a read fails when
-    # the correctness HMM rejects every slice, GraphAligner.h:2554-2569, e.g. a seed placed on the wrong strand of a repeat)
+def test_every_read_against_reference(workload, tmp_path):
+    # ALL reads of the full-size batch through the reference (ref_align --summary: one line per read with the trace fingerprint
+    # and an order-sensitive checksum of the mappings): the set of failed reads must be the reference's set (a read fails when
+    # the correctness HMM rejects every slice, GraphAligner.h:2554-2569, e.g. a seed on the wrong strand of a repeat), and every
+    # other read must agree in score, range, query position, mapping count + checksum and trace-item count + fingerprint
     api, case, aligner, packed, res = workload
-    failed = [int(i) for i in np.nonzero(res.reads["failed"])[0]]
-    idx = sorted(set(range(0, N_READS, 41)) | set(failed))
-    sub = gacase.Case(case.nodes, case.edges, [case.reads[i] for i in idx], 10, 0)
-    path = str(tmp_path / "sample.gacase")
-    gacase.write_case(sub, path)
-    expected, _ = run_reference(path, threads=8)
-    mine = res.as_dicts()
-    assert_same([mine[i] for i in idx], expected, "config-2 sample")
+    path = str(tmp_path / "full.gacase")
+    gacase.write_case(case, path)
+    expected, _ = run_reference(path, threads=os.cpu_count() or 8, extra=["--summary"])
+    assert len(expected) == N_READS
+    r = res.reads
+    ref_failed = sorted(i for i, e in enumerate(expected) if e["failed"])
+    my_failed = sorted(int(i) for i in np.nonzero(r["failed"])[0])
+    assert my_failed == ref_failed, "failed reads differ: here %s, reference %s" % (my_failed[:10], ref_failed[:10])
+    mh = gacase.mapping_checksums(r, res.mappings)
+    ok = [i for i in range(N_READS) if not expected[i]["failed"]]
+    for key, col in (("score", "score"), ("start", "alignment_start"), ("end", "alignment_end"), ("qpos", "query_position"), ("nmap", "n_mappings"), ("ntrace", "n_trace")):
+        mine = r[col][ok].astype(np.int64)
+        ref = np.array([expected[i][key] for i in ok], dtype=np.int64)
+        bad = np.nonzero(mine != ref)[0]
+        assert len(bad) == 0, "%s differs for %d reads, first: read %d here %d reference %d" % (key, len(bad), ok[bad[0]], mine[bad[0]], ref[bad[0]])
+    ref_mh = np.array([expected[i]["mh"] for i in ok], dtype=np.uint64)
+    assert np.array_equal(mh[ok], ref_mh), "mapping checksums differ for %d reads" % int((mh[ok] != ref_mh).sum())
+    # trace fingerprints (materialised per read on the host): every 7th read plus the first and last hundred
+    for i in sorted(set(ok[::7]) | set(ok[:100]) | set(ok[-100:])):
+        assert res.trace_hash(i) == expected[i]["th"], "trace fingerprint of read %d" % i
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "full_size_failed_reads.txt") if os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")) else os.devnull, "w") as f:
+        f.write("config 2, %d reads: failed here %s; failed in the reference %s\n" % (N_READS, my_failed, ref_failed))
