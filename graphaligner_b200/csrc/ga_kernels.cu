@@ -737,9 +737,43 @@ void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
 				dst[k >> 4] |= base << ((uint32_t)(k & 15) * 2);
 			}
 		});
-		ctx->view.nodeRec = uploadVec(ctx, ctx->gNodeRec, recs);
-		ctx->view.seqChunks = uploadVec(ctx, ctx->gChunks, chunks);
+		// one allocation for both, so that one L2 access-policy window covers them
+		const size_t recBytes = (recs.size() * sizeof(ga_node_rec) + 255) / 256 * 256, chunkBytes = chunks.size() * sizeof(uint32_t);
+		ctx->gNodeRec.ensure(recBytes + chunkBytes);
+		GA_CUDA(cudaMemcpyAsync(ctx->gNodeRec.ptr, recs.data(), recs.size() * sizeof(ga_node_rec), cudaMemcpyHostToDevice, ctx->stream));
+		GA_CUDA(cudaMemcpyAsync((uint8_t*)ctx->gNodeRec.ptr + recBytes, chunks.data(), chunkBytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->graphBytes += recBytes + chunkBytes;
+		ctx->view.nodeRec = (const ga_node_rec*)ctx->gNodeRec.ptr;
+		ctx->view.seqChunks = (const uint32_t*)((uint8_t*)ctx->gNodeRec.ptr + recBytes);
 		GA_CUDA(cudaStreamSynchronize(ctx->stream));   // the vectors go out of scope
+#ifndef GA_HOSTSIM
+		// The node records and sequence chunks are what every band selection waits for (a dependent load per node that enters a
+		// band): keep them in L2 across the gigabytes of history a launch streams through it.  Best effort - a device without
+		// a persisting carve-out just runs without the window.
+		{
+			int maxPersist = 0, maxWindow = 0;
+			cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+			cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+			const size_t want = recBytes + chunkBytes;
+			if (maxPersist > 0 && maxWindow > 0 && getenv("GA_NO_L2_WINDOW") == nullptr)
+			{
+				const size_t persist = std::min<size_t>(want, (size_t)maxPersist / 2);   // half of what the device allows: the rest of L2 stays a normal cache
+				const size_t window = std::min<size_t>(want, (size_t)maxWindow);
+				if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess)
+				{
+					cudaStreamAttrValue attr;
+					memset(&attr, 0, sizeof(attr));
+					attr.accessPolicyWindow.base_ptr = ctx->gNodeRec.ptr;
+					attr.accessPolicyWindow.num_bytes = window;
+					attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)window);
+					attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+					attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+					if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+				}
+				else cudaGetLastError();
+			}
+		}
+#endif
 	}
 	GA_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->hasGraph = true;
