@@ -134,30 +134,13 @@ struct GaCol
 #define GA_CF_LINK 0x20000000u
 #define GA_CF_SCORE_MASK 0x1fffffffu
 
-// The column history is written once by the forward pass and read once, much later, by the traceback (gigabytes per
-// launch against 126 MB of L2): streaming stores (evict-first), so that the history does not push the graph's node
-// records and the match words out of L2.
-#if defined(__CUDACC__)
-GA_DEV void ga_st_stream(uint4* p, const uint4& v)
-{
-	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-GA_DEV void ga_st_stream(uint32_t* p, uint32_t v)
-{
-	asm volatile("st.global.cs.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-#else
-GA_DEV void ga_st_stream(uint4* p, const uint4& v) { *p = v; }
-GA_DEV void ga_st_stream(uint32_t* p, uint32_t v) { *p = v; }
-#endif
-
 template <int LANES>
 GA_DEV void ga_col_store(const GaLaneMem& mem, uint32_t col, const GaCol& c, uint32_t flags)
 {
 	uint4 a;
 	a.x = (uint32_t)c.VP; a.y = (uint32_t)(c.VP >> 32); a.z = (uint32_t)c.VN; a.w = (uint32_t)(c.VN >> 32);
-	ga_st_stream(&mem.colVV[(size_t)col * LANES], a);
-	ga_st_stream(&mem.colS[(size_t)col * LANES], (uint32_t)c.sbs | flags);
+	mem.colVV[(size_t)col * LANES] = a;
+	mem.colS[(size_t)col * LANES] = (uint32_t)c.sbs | flags;
 }
 
 template <int LANES>
@@ -743,8 +726,8 @@ GA_DEV int32_t ga_node_columns(const ga_graph_view& g, const GaLaneMem& mem, con
 		}
 		uint4 ra;
 		ra.x = (uint32_t)c.VP; ra.y = (uint32_t)(c.VP >> 32); ra.z = (uint32_t)c.VN; ra.w = (uint32_t)(c.VN >> 32);
-		ga_st_stream(vvPtr, ra);
-		ga_st_stream(sPtr, (uint32_t)c.sbs | flags | (eq0 ? GA_CF_EQ0 : 0u));
+		*vvPtr = ra;
+		*sPtr = (uint32_t)c.sbs | flags | (eq0 ? GA_CF_EQ0 : 0u);
 		vvPtr += LANES;
 		sPtr += LANES;
 		GA_TC_ST(cs + k, ga_tiny_pack(c, sbE));

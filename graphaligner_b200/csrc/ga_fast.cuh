@@ -724,8 +724,8 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 				uint4 ra;
 				ra.x = (uint32_t)VPn; ra.y = (uint32_t)(VPn >> 32); ra.z = (uint32_t)VNn; ra.w = (uint32_t)(VNn >> 32);
 				const size_t idx = (size_t)(slabOff + colIdx) * S;
-				ga_st_stream(&mem.colVV[idx], ra);
-				ga_st_stream(&mem.colS[idx], (uint32_t)sbsN | flags | ((flags && eq0) ? GA_CF_EQ0 : 0u));
+				mem.colVV[idx] = ra;
+				mem.colS[idx] = (uint32_t)sbsN | flags | ((flags && eq0) ? GA_CF_EQ0 : 0u);
 			}
 			fl.sh.tiny[tc][colIdx][fl.lane] = (uint16_t)(((uint32_t)endN << 3) | (sbE ? 4u : 0u) | (uint32_t)((VNn >> 62) & 2) | (uint32_t)(VPn >> 63));
 			nodeMin = endN < nodeMin ? endN : nodeMin;
