@@ -350,7 +350,9 @@ def main():
         checksum = 0
         aligned = 0
         summaries = []
+        arrivals = []
         for k, r in enumerate(pipe.align_all(batches * steps)):
+            arrivals.append(time.perf_counter() - t0)
             checksum += int(r.reads["score"][0])
             if k < len(batches):
                 ok = r.reads["failed"] == 0
@@ -366,7 +368,9 @@ def main():
         out["e2e"] = {"value": aligned_all * steps / e2e_s, "unit": "bp/s", "h2d_bytes_per_step": st["h2d_bytes"] // steps, "d2h_bytes_per_step": st["d2h_bytes"] // steps,
                       "ms_per_step": e2e_s / steps * 1e3, "mode": "ga_pipeline, depth %d (K passes over %d batch(es) streamed, results in order)" % (PIPELINE_DEPTH, len(batches)),
                       "device_ms_per_step": {"peq": st["peq_us"] / 1e3 / steps, "forward": st["forward_us"] / 1e3 / steps, "trace": st["trace_us"] / 1e3 / steps},
-                      "word_columns_per_step": st["word_columns"] // steps, "total_bp_per_step": total_bp}
+                      "word_columns_per_step": st["word_columns"] // steps, "total_bp_per_step": total_bp,
+                      # when each batch's results arrived (ms since the start of the timed region, this rank): fill, steady state, drain
+                      "batch_arrival_ms": [round(a * 1e3, 2) for a in arrivals[:32]]}
         out["e2e_launches"] = int(st["launches"])
         pipe.close()
         out["_summaries"] = summaries

@@ -263,8 +263,11 @@ static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, c
 #ifndef GA_HOSTSIM
 // Traceback (ga_trace.cuh): one warp per block walks T streams (lane per stream, all 32 lanes fetch the windows), the
 // windows and slice tables in the block's shared memory.  Runs after the forward kernel on the same stream.
+#ifndef GA_TRACE_MINBLOCKS
+#define GA_TRACE_MINBLOCKS 1   /* blocks per SM the traceback kernel's register budget must allow (tuning builds: -DGA_TRACE_MINBLOCKS=16) */
+#endif
 template <int T, int P>
-__global__ void __launch_bounds__(32) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
+__global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
 	uint32_t nStreams, uint32_t S, ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
 	extern __shared__ __align__(16) unsigned long long gaShared[];
