@@ -264,7 +264,7 @@ static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, c
 // Traceback (ga_trace.cuh): one warp per block walks T streams (lane per stream, all 32 lanes fetch the windows), the
 // windows and slice tables in the block's shared memory.  Runs after the forward kernel on the same stream.
 #ifndef GA_TRACE_MINBLOCKS
-#define GA_TRACE_MINBLOCKS 1   /* blocks per SM the traceback kernel's register budget must allow (tuning builds: -DGA_TRACE_MINBLOCKS=16) */
+#define GA_TRACE_MINBLOCKS 12   /* blocks per SM the traceback kernel's register budget must allow: 12 = 170 registers (it uses 168), one wave of 1667 six-stream warps on 148 SMs; measured: 16 blocks (128 registers) 6.1 ms, 14 (146) 6.2 ms, 12 (168) 5.3 ms at T = 6 */
 #endif
 template <int T, int P>
 __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
