@@ -134,12 +134,18 @@ class Graph:
 class PackedReads:
     """Reads + seeds marshalled into the flat arrays of ga_batch (kept alive with the struct)."""
 
-    def __init__(self, reads, b, B=0):
+    def __init__(self, reads, b, B=0, seq_alloc=None):
         # reads: [(name, sequence, [(node, pos, reverse)])]
+        # seq_alloc(nbytes) -> uint8 array: where the read bytes are put, e.g. page-locked host memory (a buffer the CUDA runtime
+        # knows as pinned is uploaded in place; anything else is first copied into the context's own pinned staging buffer)
         self.n = len(reads)
         self.total_bp = sum(len(r[1]) for r in reads)
         seq = "".join(r[1] for r in reads).encode()
-        self.seq = np.frombuffer(seq, dtype=np.uint8).copy() if seq else np.zeros(1, dtype=np.uint8)
+        if seq and seq_alloc is not None:
+            self.seq = seq_alloc(len(seq))
+            self.seq[:] = np.frombuffer(seq, dtype=np.uint8)
+        else:
+            self.seq = np.frombuffer(seq, dtype=np.uint8).copy() if seq else np.zeros(1, dtype=np.uint8)
         self.seq_off = np.zeros(self.n + 1, dtype=np.uint64)
         np.cumsum([len(r[1]) for r in reads], out=self.seq_off[1:])
         names = "".join(r[0] for r in reads).encode()

@@ -273,9 +273,13 @@ static ga_staged* stageOn(ga_ctx* ctx, ga::DeviceCtx* dev, const ga_batch* batch
 		st->dev = dev;
 		fillStaged(st, batch);
 		tm.lap("stage: marshal reads");
-		uint8_t* pinned = nullptr;
-		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads, [dev, &pinned](size_t bytes) { pinned = ga::AllocPinnedParts(dev, bytes); return pinned; },
-			[dev, &pinned](size_t off, size_t bytes) { ga::UploadPartsRange(dev, pinned, off, bytes); }));
+		// reads that already lie in page-locked memory (cudaHostAlloc / cudaHostRegister by the caller) are uploaded from there;
+		// otherwise they are copied into the context's pinned staging buffer first
+		const bool inPlace = !st->reads.empty() && ga::IsPinnedHost(st->reads[0].seq) && getenv("GA_NO_INPLACE_INPUT") == nullptr;
+		uint8_t* pinned = inPlace ? (uint8_t*)const_cast<char*>(st->reads[0].seq) : nullptr;
+		st->plan.reset(new ga::BatchPlan(ctx->graph->graph, st->reads,
+			[dev, &pinned, inPlace](size_t bytes) { if (inPlace) { ga::EnsureDeviceParts(dev, bytes); return pinned; } pinned = ga::AllocPinnedParts(dev, bytes); return pinned; },
+			[dev, &pinned](size_t off, size_t bytes) { ga::UploadPartsRange(dev, pinned, off, bytes); }, inPlace));
 		tm.lap("stage: plan + build parts");
 		st->device = ga::StageAndUpload(dev, st->plan->streams, st->plan->parts, st->plan->partsBytes, st->b, st->B, &ctx->stats, true);
 		ga::SetReadRanges(dev, st->device, st->plan->readOff);

@@ -37,6 +37,10 @@ void SetReadRanges(DeviceCtx* ctx, StagedBatch* batch, const std::vector<uint64_
 void UploadPartsRange(DeviceCtx* ctx, const uint8_t* parts, size_t offset, size_t bytes);
 // pinned host memory for a batch's padded parts (grow-only, owned by the context, reused by the next batch)
 uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes);
+// the device twin alone (the reads are uploaded from the caller's own page-locked buffer)
+void EnsureDeviceParts(DeviceCtx* ctx, size_t bytes);
+// true when `p` lies in page-locked host memory the CUDA runtime knows about (an asynchronous copy from it needs no staging)
+bool IsPinnedHost(const void* p);
 // sizing helpers for splitting a batch that would not fit the device in one launch
 size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth);
 size_t FreeDeviceBytes(DeviceCtx* ctx);

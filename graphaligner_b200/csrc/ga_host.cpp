@@ -289,7 +289,7 @@ static char complementOf(char c)
 }
 
 BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts,
-	const std::function<void(size_t, size_t)>& partsReady)
+	const std::function<void(size_t, size_t)>& partsReady, bool inPlace)
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
@@ -298,7 +298,19 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 	// aborts on is found out on the device as well (badChar is filled in when the results come back).
 	readOff.resize(n + 1);
 	size_t top = 0;
-	for (size_t ri = 0; ri < n; ri++) { readOff[ri] = top; top += reads[ri].seqLen; }
+	// in place: the caller's buffer is page-locked and the reads lie in it back to back (what ga_batch's offsets describe) - it
+	// is uploaded from where it is, nothing is copied on the host
+	if (inPlace && n > 0)
+	{
+		for (size_t ri = 0; ri + 1 < n && inPlace; ri++) inPlace = reads[ri + 1].seq == reads[ri].seq + reads[ri].seqLen;
+	}
+	else inPlace = false;
+	if (inPlace)
+	{
+		for (size_t ri = 0; ri < n; ri++) readOff[ri] = (size_t)(reads[ri].seq - reads[0].seq);
+		top = readOff[n - 1] + reads[n - 1].seqLen;
+	}
+	else for (size_t ri = 0; ri < n; ri++) { readOff[ri] = top; top += reads[ri].seqLen; }
 	readOff[n] = top;
 	partsBytes = top;
 	firstSeedOfRead.reserve(n + 1);
@@ -357,6 +369,18 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 		}
 	}
 	firstSeedOfRead.push_back((uint32_t)seeds.size());
+	if (inPlace)
+	{
+		parts = (uint8_t*)const_cast<char*>(reads[0].seq);
+		if (allocParts) allocParts(top + 64);   // the device twin only: the allocator knows that the plan is in place
+		if (partsReady)
+		{
+			// a few ranges, so that the first kernels' input is on its way while the rest is queued
+			const size_t pieces = std::min<size_t>(4, std::max<size_t>(1, top >> 22));
+			for (size_t k = 0; k < pieces; k++) partsReady(top * k / pieces, top * (k + 1) / pieces - top * k / pieces);
+		}
+		return;
+	}
 	if (allocParts) parts = allocParts(top + 64);
 	else
 	{

@@ -187,8 +187,10 @@ public:
 	// been uploaded); with no allocator the plan owns the storage
 	// allocParts: where the parts are built (pinned memory of a device context); partsReady(offset, bytes): called as soon as a
 	// contiguous range of them is complete, so that its upload overlaps the building of the rest
+	// inPlace: the reads' buffer is page-locked host memory - it becomes `parts` itself (allocParts(0) is still called once, partsReady
+	// for ranges of the caller's buffer)
 	BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& reads, const std::function<uint8_t*(size_t)>& allocParts = nullptr,
-		const std::function<void(size_t, size_t)>& partsReady = nullptr);
+		const std::function<void(size_t, size_t)>& partsReady = nullptr, bool inPlace = false);
 	std::vector<ga_stream_in> streams;
 	uint8_t* parts = nullptr;       // the reads' bytes, back to back (the streams' parts are ranges of them, ga_stream_in::seqOff / srcInfo)
 	size_t partsBytes = 0;

@@ -1397,6 +1397,25 @@ uint8_t* AllocPinnedParts(DeviceCtx* ctx, size_t bytes)
 	return (uint8_t*)ctx->pinParts.ensure(bytes);
 }
 
+void EnsureDeviceParts(DeviceCtx* ctx, size_t bytes)
+{
+	GA_CUDA(cudaSetDevice(ctx->device));
+	ctx->bParts.ensure(bytes + 64);
+}
+
+bool IsPinnedHost(const void* p)
+{
+#ifdef GA_HOSTSIM
+	(void)p;
+	return false;
+#else
+	cudaPointerAttributes attr;
+	memset(&attr, 0, sizeof(attr));
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return attr.type == cudaMemoryTypeHost;
+#endif
+}
+
 void UploadPartsRange(DeviceCtx* ctx, const uint8_t* parts, size_t offset, size_t bytes)
 {
 	if (bytes == 0) return;

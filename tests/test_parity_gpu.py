@@ -279,3 +279,40 @@ def test_gfa_edge_overlap(api, tmp_path, overlap):
     aligner = api.Aligner(api.Graph.from_case(case))
     assert_same(aligner.align(case.reads, case.b, case.B).as_dicts(), expected, "gfa overlap %d" % overlap)
     aligner.close()
+
+
+@pytest.mark.parametrize("name", ["bubbles_multiseed", "seed_pos1", "ragged_short"])
+def test_page_locked_input_is_used_in_place(api, golden_dir, name, monkeypatch):
+    # reads handed over in page-locked host memory are uploaded from the caller's buffer (no staging copy); the results must
+    # not depend on where the bytes lie: pinned, pinned through the pipeline, and the staged path forced by the environment
+    import torch
+    case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
+    expected = load_expected(os.path.join(golden_dir, name + ".expected"))
+    held = []
+
+    def pinned(nbytes):
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        held.append(t)
+        return t.numpy()
+
+    names = [r[0] for r in case.reads]
+    graph = api.Graph.from_case(case)
+    aligner = api.Aligner(graph)
+    packed = api.PackedReads(case.reads, case.b, case.B, seq_alloc=pinned)
+    res = aligner.align(packed)
+    res.names = names
+    assert_same(res.as_dicts(), expected, name + " (pinned input)")
+    res.free()
+    monkeypatch.setenv("GA_NO_INPLACE_INPUT", "1")
+    res = aligner.align(packed)
+    res.names = names
+    assert_same(res.as_dicts(), expected, name + " (pinned input, staged)")
+    res.free()
+    monkeypatch.delenv("GA_NO_INPLACE_INPUT")
+    aligner.close()
+    pipe = api.Pipeline(graph, depth=2)
+    for r in pipe.align_all([packed] * 3):
+        r.names = names
+        assert_same(r.as_dicts(), expected, name + " (pinned input, pipeline)")
+        r.free()
+    pipe.close()
