@@ -523,6 +523,7 @@ struct DeviceCtx
 	};
 	Pinned pinParts, pinOuts, pinArena, pinSmall, pinReadOff;
 	size_t budgetBytes = 0;    // device bytes a batch may use (FreeDeviceBytes), 0 = not queried yet
+	cudaEvent_t evWait = nullptr;      // blocking-sync event of waitStream
 	cudaEvent_t evKernel[4] = { nullptr, nullptr, nullptr, nullptr };   // around the three kernels of the last launch sequence
 	bool evRecorded = false;
 };
@@ -627,6 +628,9 @@ DeviceCtx* CreateDevice(int device)
 	}
 	GA_CUDA(cudaMemcpyToSymbol(c_sched, &ctx->sched, sizeof(GaUmapSchedule)));
 	for (auto& e : ctx->evKernel) GA_CUDA(cudaEventCreate(&e));
+#ifndef GA_HOSTSIM
+	if (getenv("GA_SPIN_WAIT") == nullptr) GA_CUDA(cudaEventCreateWithFlags(&ctx->evWait, cudaEventBlockingSync | cudaEventDisableTiming));
+#endif
 	return ctx;
 }
 
@@ -643,6 +647,7 @@ void DestroyDevice(DeviceCtx* ctx)
 	ctx->pinSmall.release();
 	ctx->pinReadOff.release();
 	for (auto& e : ctx->evKernel) if (e) cudaEventDestroy(e);
+	if (ctx->evWait) cudaEventDestroy(ctx->evWait);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -650,10 +655,24 @@ void DestroyDevice(DeviceCtx* ctx)
 const std::string& LastError(DeviceCtx* ctx) { return ctx->lastError; }
 void SetError(DeviceCtx* ctx, const std::string& msg) { ctx->lastError = msg; }
 void* DeviceStream(DeviceCtx* ctx) { return (void*)ctx->stream; }
+// Waits for the context's stream WITHOUT spinning: an event with cudaEventBlockingSync puts the thread to sleep.  The waits of
+// a batch last milliseconds (the kernels, the D2H), a box runs a lane or two per GPU, and the cores are needed by the other
+// lanes' host work - a spinning cudaStreamSynchronize per lane costs 16 of 32 cores on an 8-GPU box.
+static void waitStream(DeviceCtx* ctx)
+{
+#ifdef GA_HOSTSIM
+	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+#else
+	if (!ctx->evWait) { GA_CUDA(cudaStreamSynchronize(ctx->stream)); return; }
+	GA_CUDA(cudaEventRecord(ctx->evWait, ctx->stream));
+	GA_CUDA(cudaEventSynchronize(ctx->evWait));
+#endif
+}
+
 void SyncDevice(DeviceCtx* ctx)
 {
 	GA_CUDA(cudaSetDevice(ctx->device));
-	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	waitStream(ctx);
 }
 size_t GraphBytesOnDevice(DeviceCtx* ctx) { return ctx->graphBytes; }
 
@@ -1247,7 +1266,7 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	};
 	GA_CUDA(cudaMemcpyAsync(pinOuts, ctx->bOut.ptr, n * sizeof(ga_stream_out), cudaMemcpyDeviceToHost, ctx->stream));
 	GA_CUDA(cudaMemcpyAsync(pinTop, ctx->bArenaTop.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	waitStream(ctx);
 	lap("stream records");
 	if (stats && ctx->evRecorded)
 	{
@@ -1277,7 +1296,7 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		GA_CUDA(cudaMemcpyAsync(pin, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
-	GA_CUDA(cudaStreamSynchronize(ctx->stream));
+	waitStream(ctx);
 	lap("trace arena");
 #ifdef GA_PHASE_TIMING
 	{
