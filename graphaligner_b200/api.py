@@ -168,7 +168,9 @@ class Results:
         self.handle = handle
         n = lib.ga_results_count(handle)
         self.reads = self._view(lib.ga_results_reads(handle), READ_RESULT, n)
-        nm = int(self.reads["n_mappings"].sum())
+        # the reads' mapping ranges lie anywhere in the block (mapping_offset): the view covers up to the last one
+        ok = self.reads["failed"] == 0
+        nm = int((self.reads["mapping_offset"][ok] + self.reads["n_mappings"][ok]).max()) if n and ok.any() else 0
         self.mappings = self._view(lib.ga_results_mappings(handle), MAPPING, nm)
         self.names = names
         self.keepalive = keepalive   # the ga_batch buffers are referenced by the results (lazy trace items)

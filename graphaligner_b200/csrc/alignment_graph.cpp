@@ -232,5 +232,6 @@ ga_graph_view AlignmentGraph::View() const
 	v.outAdj = outAdj.data();
 	v.nodeRec = nullptr;
 	v.seqChunks = nullptr;
+	v.nodeIdRev = nullptr;
 	return v;
 }

@@ -39,7 +39,11 @@ struct ga_ctx
 struct ga_results
 {
 	ga::RawBuffer<ga_read_result> reads;
+	// The mapping records.  Results of one launch sequence: they lie in the chunk's trace arena (mapBase points into it) - the
+	// records the device wrote where it wrote them, the others in the room behind; ga_read_result::mapping_offset is relative to
+	// mapBase either way.  Results merged from several launch sequences: copied into `mappings`, read after read.
 	ga::RawBuffer<ga_mapping> mappings;
+	const ga_mapping* mapBase = nullptr;
 	// kept for the lazy trace items (ga_results_read_trace): what the device returned and what was decided per read.
 	// A batch too large for the device is aligned in several launches (chunks of reads); each keeps its own buffers.
 	const AlignmentGraph* graph = nullptr;
@@ -89,6 +93,15 @@ struct StageTimer
 		t = n;
 	}
 };
+
+// GA_TIMELINE=1: absolute time stamps (ms since the first one, with the context's address) of a batch's way through a lane
+static void timeline(const void* ctx, const char* what)
+{
+	static const bool on = getenv("GA_TIMELINE") != nullptr;
+	if (!on) return;
+	static const auto t0 = std::chrono::steady_clock::now();
+	fprintf(stderr, "[ga timeline] %9.2f ms  ctx %p  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ctx, what);
+}
 
 template <typename F>
 static int guarded(ga_ctx* ctx, F&& f)
@@ -234,15 +247,22 @@ static void fillStaged(ga_staged* st, const ga_batch* batch)
 }
 
 // the reads' records and, straight from the device's run records into their final place, the mappings
+static_assert(sizeof(ga_mapping) == sizeof(GaDeviceMapping) && sizeof(ga_mapping) == GA_MAP_WORDS * sizeof(uint32_t), "the device writes ga_mapping records");
+
+// mapTail: first word of the arena's room for host-written mapping records (ga::FinishStaged)
 static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as, const AlignmentGraph& graph, const std::vector<ga::ReadInput>& reads, const ga_stream_out* outs,
-	const uint32_t* arena)
+	uint32_t* arena, size_t arenaWords, size_t mapTail)
 {
 	const size_t n = as.size();
 	out->reads.resize(n);
 	out->lazy.resize(n);
+	// device-written records stay where they are; the others are written into the room behind the device's part
 	std::vector<uint64_t> mapOff(n + 1, 0);
-	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + (as[i].failed ? 0 : as[i].nMappings);
-	out->mappings.resize(mapOff[n]);
+	mapOff[0] = mapTail / GA_MAP_WORDS;
+	for (size_t i = 0; i < n; i++) mapOff[i + 1] = mapOff[i] + ((as[i].failed || as[i].deviceMapped) ? 0 : as[i].nMappings);
+	if (mapOff[n] * GA_MAP_WORDS > arenaWords) throw std::logic_error("packResults: the arena has no room for the mapping records");
+	ga_mapping* const base = (ga_mapping*)arena;
+	out->mapBase = base;
 	ga::ParallelFor(n, [&](size_t i) {
 		const ga::ReadAssembly& a = as[i];
 		ga_read_result& o = out->reads.data()[i];
@@ -251,7 +271,7 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 		o.score = a.failed ? std::numeric_limits<int32_t>::max() : a.score;
 		o.flags = a.flags;
 		o.word_columns = a.wordColumns;
-		o.mapping_offset = mapOff[i];
+		o.mapping_offset = a.deviceMapped ? a.deviceMapWord / GA_MAP_WORDS : mapOff[i];
 		out->lazy[i] = ga_results::Lazy { 0, a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
 		if (a.failed) return;
 		o.alignment_start = a.alignmentStart;
@@ -259,7 +279,8 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 		o.query_position = a.queryPosition;
 		o.n_mappings = a.nMappings;
 		o.n_trace = a.nTraceItems;
-		ga_mapping* dst = out->mappings.data() + mapOff[i];
+		if (a.deviceMapped) return;
+		ga_mapping* dst = base + mapOff[i];
 		ga::WriteMappings(graph, reads[i], a, outs, arena, dst);
 	});
 }
@@ -312,7 +333,8 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 		StageTimer tm;
 		res->chunks.emplace_back(new ga_results::Chunk());
 		ga_results::Chunk& ch = *res->chunks.back();
-		ga::FinishStaged(st->dev, st->device, ch.outs, ch.arena, &ctx->stats, &st->plan->badChar);
+		size_t mapTail = 0;
+		ga::FinishStaged(st->dev, st->device, ch.outs, ch.arena, &ctx->stats, &st->plan->badChar, &mapTail);
 		tm.lap("finish: wait kernel + D2H");
 		const AlignmentGraph& graph = ctx->graph->graph;
 		const size_t n = st->reads.size();
@@ -324,7 +346,7 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 		tm.lap("finish: assemble reads");
 		ctx->stats.streams += st->plan->streams.size();
 		for (size_t i = 0; i < ch.outs.size(); i++) ctx->stats.wordColumns += ch.outs.data()[i].wordColumns;
-		packResults(res, as, graph, st->reads, ch.outs.data(), ch.arena.data());
+		packResults(res, as, graph, st->reads, ch.outs.data(), ch.arena.data(), ch.arena.size(), mapTail);
 		res->graph = &graph;
 		res->inputs = st->reads;
 		ch.streams = st->plan->streams;
@@ -357,21 +379,25 @@ static ga_results* mergeParts(ga_ctx* ctx, std::vector<ga_results*>& parts, cons
 	all->lazy.resize(n);
 	all->inputs.resize(n);
 	all->graph = &ctx->graph->graph;
-	std::vector<uint64_t> mapBase(parts.size() + 1, 0);
-	for (size_t k = 0; k < parts.size(); k++) mapBase[k + 1] = mapBase[k] + parts[k]->mappings.size();
-	all->mappings.resize(mapBase.back());
-	// copy jobs of ~1 MiB so that the worker pool shares the work evenly
-	struct Job { size_t part; size_t begin, end; };
-	std::vector<Job> jobs;
-	const size_t step = ((size_t)1 << 20) / sizeof(ga_mapping);
+	// the parts' records lie in their own arenas: copied read after read into one array
+	std::vector<uint64_t> newOff(n + 1, 0);
 	for (size_t k = 0; k < parts.size(); k++)
 	{
-		for (size_t b0 = 0; b0 < parts[k]->mappings.size(); b0 += step) jobs.push_back(Job { k, b0, std::min(parts[k]->mappings.size(), b0 + step) });
+		for (size_t i = 0; i < parts[k]->lazy.size(); i++) newOff[cuts[k] + i + 1] = parts[k]->reads.data()[i].failed ? 0 : parts[k]->reads.data()[i].n_mappings;
 	}
-	ga::ParallelFor(jobs.size(), [&](size_t j) {
-		const Job& job = jobs[j];
-		memcpy(all->mappings.data() + mapBase[job.part] + job.begin, parts[job.part]->mappings.data() + job.begin, (job.end - job.begin) * sizeof(ga_mapping));
-	});
+	for (size_t i = 0; i < n; i++) newOff[i + 1] += newOff[i];
+	all->mappings.resize(newOff[n]);
+	all->mapBase = all->mappings.data();
+	for (size_t k = 0; k < parts.size(); k++)
+	{
+		const ga_results* part = parts[k];
+		const size_t first = cuts[k];
+		ga::ParallelFor(part->lazy.size(), [&](size_t i) {
+			const ga_read_result& r = part->reads.data()[i];
+			if (r.failed || r.n_mappings == 0) return;
+			memcpy(all->mappings.data() + newOff[first + i], part->mapBase + r.mapping_offset, (size_t)r.n_mappings * sizeof(ga_mapping));
+		});
+	}
 	for (size_t k = 0; k < parts.size(); k++)
 	{
 		ga_results* part = parts[k];
@@ -380,7 +406,7 @@ static ga_results* mergeParts(ga_ctx* ctx, std::vector<ga_results*>& parts, cons
 		for (size_t i = 0; i < part->lazy.size(); i++)
 		{
 			all->reads.data()[first + i] = part->reads.data()[i];
-			all->reads.data()[first + i].mapping_offset += mapBase[k];
+			all->reads.data()[first + i].mapping_offset = newOff[first + i];
 			all->lazy[first + i] = part->lazy[i];
 			all->lazy[first + i].chunk = chunkIndex;
 			all->inputs[first + i] = part->inputs[i];
@@ -409,10 +435,15 @@ static ga_results* runAndFinish(ga_ctx* ctx, ga_staged* st)
 {
 	if (!ctx->gpuTurn) return ga_run_staged(ctx, st) == 0 ? ga_finish_staged(ctx, st) : nullptr;
 	{
+		timeline(ctx, "staged, waiting for the GPU's turn");
 		std::lock_guard<std::mutex> turn(*ctx->gpuTurn);
+		timeline(ctx, "turn taken, kernels launched");
 		if (ga_run_staged(ctx, st) != 0 || ga_sync(ctx) != 0) return nullptr;
+		timeline(ctx, "kernels done, turn released");
 	}
-	return ga_finish_staged(ctx, st);
+	ga_results* r = ga_finish_staged(ctx, st);
+	timeline(ctx, "finished (D2H, assembly, packing)");
+	return r;
 }
 
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
@@ -491,7 +522,7 @@ ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
 
 size_t ga_results_count(const ga_results* r) { return r->reads.size(); }
 const ga_read_result* ga_results_reads(const ga_results* r) { return r->reads.data(); }
-const ga_mapping* ga_results_mappings(const ga_results* r) { return r->mappings.data(); }
+const ga_mapping* ga_results_mappings(const ga_results* r) { return r->mapBase ? r->mapBase : r->mappings.data(); }
 void ga_results_free(ga_results* r)
 {
 	StageTimer tm;
@@ -636,6 +667,7 @@ static void pipelineWorker(ga_pipeline* p, ga_pipeline::Lane* lane)
 		p->cv.wait(lock, [&]() { return p->stop || (lane->busy && !lane->done); });
 		if (p->stop) return;
 		lock.unlock();
+		timeline(lane->ctx, "batch picked up by the lane");
 		ga_results* r = ga_align_batch(lane->ctx, &lane->batch);
 		lock.lock();
 		lane->result = r;

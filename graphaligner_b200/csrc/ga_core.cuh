@@ -1716,7 +1716,7 @@ GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const 
 		out->wordColumns = st.wordColumns;
 		out->cyclicSlices = st.cyclicSlices;
 		out->rampRedos = st.rampRedos;
-		out->reserved = 0;
+		out->nMapped = 0;
 		out->nMoves = 0;
 		out->nPathNodes = 0;
 		out->nRuns = 0;
@@ -1812,9 +1812,9 @@ GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const 
 // upper-case letters the graph holds can be equal) of a complemented character is always that of an upper-case letter.
 GA_DEV void ga_part_char(const uint8_t* raw, const ga_stream_in& in, uint32_t i, uint32_t& mask, uint32_t& code)
 {
-	const uint32_t real = in.srcInfo & 0x7fffffffu;
+	const uint32_t real = GA_SRC_LEN(in.srcInfo);
 	if (i >= real) { mask = 15; code = 4; return; }
-	if (in.srcInfo & 0x80000000u)
+	if (in.srcInfo & GA_SRC_BACKWARD)
 	{
 		const uint8_t c = raw[in.seqOff - i];
 		const uint32_t m = ga_iupac_mask(c);

@@ -47,7 +47,11 @@ size_t FreeDeviceBytes(DeviceCtx* ctx);
 // launches the alignment kernel(s) on the context's stream (asynchronous); returns number of launches
 int RunStaged(DeviceCtx* ctx, StagedBatch* batch);
 // waits, copies results back, re-runs streams that overflowed their scratch with larger capacities
-void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar = nullptr);
+// mapTail (optional): the arena is allocated with room behind the device's records for one 32-byte mapping record per run of
+// every stream whose mappings the device did not write (ga_stream_out::nMapped == 0); *mapTail = first word of that room
+// (a multiple of 8), arena.size() covers it
+void FinishStaged(DeviceCtx* ctx, StagedBatch* batch, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar = nullptr,
+	size_t* mapTail = nullptr);
 void FreeStaged(DeviceCtx* ctx, StagedBatch* batch);
 void* DeviceStream(DeviceCtx* ctx);   // cudaStream_t
 void SyncDevice(DeviceCtx* ctx);

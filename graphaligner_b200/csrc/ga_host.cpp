@@ -293,6 +293,7 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 {
 	const size_t n = reads.size();
 	badChar.assign(n, 0);
+	static const bool deviceMappings = getenv("GA_NO_DEVICE_MAPPINGS") == nullptr;   // env: A/B measurements with the host writing every mapping
 	// the reads' bytes go to the device as they are, back to back; a stream names its source range in them and the
 	// device reads the (reverse-complemented, padded) part from there.  Which reads hold a character the reference
 	// aborts on is found out on the device as well (badChar is filled in when the results come back).
@@ -349,7 +350,7 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 				in.seqOff = readOff[ri] + partLen - 1;
 				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
 				in.trimRows = (uint32_t)pos;                       // GraphAligner.h:3086-3089
-				in.srcInfo = (uint32_t)partLen | 0x80000000u;
+				in.srcInfo = (uint32_t)partLen | GA_SRC_BACKWARD;
 				sp.bwStream = (int64_t)streams.size();
 				streams.push_back(in);
 			}
@@ -362,6 +363,8 @@ BatchPlan::BatchPlan(const AlignmentGraph& graph, const std::vector<ReadInput>& 
 				in.partLen = (uint32_t)((partLen + 63) / 64 * 64);
 				in.trimRows = (uint32_t)(len - pos - overlap);     // GraphAligner.h:3063-3066
 				in.srcInfo = (uint32_t)partLen;
+				// the read's only stream (one seed, at read position 0): its mappings can be written on the device
+				if (deviceMappings && reads[ri].nSeeds == 1 && pos == 0 && partLen < 0x40000000u) in.srcInfo |= GA_SRC_SOLO;
 				sp.fwStream = (int64_t)streams.size();
 				streams.push_back(in);
 			}
@@ -611,6 +614,37 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		as.flags |= FLAG_BAD_CHAR;
 		return as;
 	}
+	// A read whose single stream carries device-written mapping records (one valid seed at read position 0): everything the seed
+	// loop below would derive from its runs is already there - no backward part, rows not shifted, nothing to merge or prune.
+	if (last - first == 1 && !plan.seeds[first].invalid && plan.seeds[first].bwStream < 0 && plan.seeds[first].fwStream >= 0)
+	{
+		const ga_stream_out& o = outs[plan.seeds[first].fwStream];
+		if (o.status == GA_OK && o.nSlices > 0 && o.nMapped > 0)
+		{
+			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
+			const uint64_t recWord = o.traceOff + (o.nMoves + 15) / 16 + o.nPathNodes;
+			as.deviceMapped = true;
+			as.deviceMapWord = recWord + GA_MAP_PAD(recWord);
+			as.nMappings = o.nMapped;
+			as.score = o.score;
+			as.fwStream = o.nPositions > 0 ? plan.seeds[first].fwStream : -1;
+			as.mapFwStream = plan.seeds[first].fwStream;
+			as.splitIndex = std::get<1>(read.seeds[plan.seeds[first].seed]);   // 0
+			as.fwShifted = false;
+			as.queryPosition = (int32_t)as.splitIndex;
+			as.alignmentStart = as.splitIndex;
+			as.alignmentEnd = as.splitIndex + (size_t)o.nSlices * 64;
+			as.nTraceItems = o.nPositions > 0 ? o.nPositions - 1 : 0;
+			as.failed = false;
+			if (materialize)
+			{
+				as.mappings.resize(as.nMappings);
+				EmitMappings(graph, read, as, outs, arena, [&](size_t i, const FlatMapping& m) { as.mappings[i] = m; });
+			}
+			return as;
+		}
+	}
 	std::vector<std::tuple<size_t, size_t, size_t>> tried;
 	bool hasAlignment = false;
 	RunView bestFw, bestBw;
@@ -743,6 +777,24 @@ template <typename Sink>
 void emitMappingsTo(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, const Sink& sink)
 {
 	if (as.failed) return;
+	if (as.deviceMapped)
+	{
+		const GaDeviceMapping* rec = (const GaDeviceMapping*)(arena + as.deviceMapWord);
+		for (size_t i = 0; i < as.nMappings; i++)
+		{
+			FlatMapping m;
+			m.node_id = rec[i].node_id;
+			m.is_reverse = rec[i].is_reverse != 0;
+			m.offset = rec[i].offset;
+			m.rank = rec[i].rank;
+			m.from_length = rec[i].from_length;
+			m.to_length = rec[i].to_length;
+			m.read_start = rec[i].read_start;
+			if (m.read_start > read.seqLen) throw std::out_of_range("basic_string::substr");   // what sequence.substr would do
+			sink(i, m);
+		}
+		return;
+	}
 	size_t idx = 0;
 	if (as.mapBwCount)
 	{
@@ -774,6 +826,11 @@ void EmitMappings(const AlignmentGraph& graph, const ReadInput& read, const Read
 void WriteMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, ::ga_mapping* dst)
 {
 	if (as.failed) return;
+	if (as.deviceMapped)
+	{
+		memcpy(dst, arena + as.deviceMapWord, as.nMappings * sizeof(::ga_mapping));   // only when the records have to move (merged results)
+		return;
+	}
 	if (!as.mapBwCount && as.mapFwCount && !as.mapFwSkip)
 	{
 		// the common case (a seed at read position 0: forward part only) as one flat loop over the device's run records, last run

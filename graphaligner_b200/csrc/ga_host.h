@@ -240,6 +240,10 @@ struct ReadAssembly
 	int64_t mapFwStream = -1, mapBwStream = -1;
 	size_t mapBwFirst = 0, mapBwCount = 0, mapFwFirst = 0, mapFwCount = 0, mapFwSkip = 0;
 	size_t nMappings = 0;
+	// the device wrote the read's mapping records itself (GA_SRC_SOLO stream): they lie in the arena at word deviceMapWord
+	// (a multiple of 8), nMappings of them, as GaDeviceMapping = ::ga_mapping
+	bool deviceMapped = false;
+	uint64_t deviceMapWord = 0;
 	std::vector<FlatMapping> mappings;
 };
 

@@ -288,18 +288,23 @@ __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_gra
 	const GaTraceMem& tm = L.tm;
 	const uint32_t nMoves = L.t.nMoves, nPath = L.t.nPath, nRuns = L.t.nRuns;
 	const uint32_t moveWords = (nMoves + 15) / 16;
-	const uint32_t runWords = nRuns * GA_RUN_WORDS;
+	// a stream that is all its read has (GA_SRC_SOLO) leaves the read's final mapping records instead of its runs: the host then
+	// neither reads runs nor writes mappings for it (the records are D2H'd straight into the result block)
+	const bool mapped = have && doTrace && L.t.status == GA_OK && (L.in->srcInfo & GA_SRC_SOLO) != 0 && ga_tr_runs_mappable(tm, nRuns, g.nNodes);
+	const uint32_t runWords = mapped ? nRuns * GA_MAP_WORDS + 7u : nRuns * GA_RUN_WORDS;   // + 7: room to start on a 32-byte boundary
 	const uint32_t words = have ? moveWords + nPath + runWords : 0;
 	const unsigned long long off = words ? atomicAdd(arenaTop, (unsigned long long)words) : 0ull;
 	const bool fits = off + words <= arenaCap;
 	if (have)
 	{
 		out->traceOff = off;
+		out->nMapped = 0;
 		if (doTrace)
 		{
 			out->nMoves = nMoves;
 			out->nPathNodes = nPath;
 			out->nRuns = nRuns;
+			out->nMapped = mapped ? nRuns : 0;
 			out->nPositions = ga_trace_positions(L.t);
 			out->status = !fits && L.t.status == GA_OK ? GA_ERR_TRACE_OVERFLOW : L.t.status;
 		}
@@ -308,14 +313,21 @@ __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_gra
 	{
 		const uint32_t w = __shfl_sync(0xffffffffu, (fits && words) ? words : 0u, r);
 		if (w == 0) continue;
-		const uint32_t mw = __shfl_sync(0xffffffffu, moveWords, r), np = __shfl_sync(0xffffffffu, nPath, r), rw = __shfl_sync(0xffffffffu, runWords, r);
+		const uint32_t mw = __shfl_sync(0xffffffffu, moveWords, r), np = __shfl_sync(0xffffffffu, nPath, r), nr = __shfl_sync(0xffffffffu, nRuns, r);
+		const bool mp = __shfl_sync(0xffffffffu, mapped ? 1u : 0u, r) != 0;
 		const unsigned long long o = __shfl_sync(0xffffffffu, off, r);
 		const uint32_t* pm = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.moves, r);
 		const uint32_t* pp = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.pathNodes, r);
 		const uint32_t* pr = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.runs, r);
 		for (uint32_t i = lane; i < mw; i += 32) arena[o + i] = pm[(size_t)i * S];
 		for (uint32_t i = lane; i < np; i += 32) arena[o + mw + i] = pp[(size_t)i * S];
-		for (uint32_t i = lane; i < rw; i += 32) arena[o + mw + np + i] = pr[(size_t)i * S];
+		if (mp)
+		{
+			const unsigned long long mo = o + mw + np + GA_MAP_PAD(o + mw + np);
+			GaDeviceMapping* dst = (GaDeviceMapping*)(arena + mo);
+			for (uint32_t j = lane; j < nr; j += 32) dst[j] = ga_tr_mapping(g, pr, S, nr, j);
+		}
+		else for (uint32_t i = lane; i < nr * GA_RUN_WORDS; i += 32) arena[o + mw + np + i] = pr[(size_t)i * S];
 	}
 }
 #endif
@@ -429,23 +441,32 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 			const GaTraceMem& tm = lanes[l].tm;
 			const uint32_t nMoves = lanes[l].t.nMoves, nPath = lanes[l].t.nPath, nRuns = lanes[l].t.nRuns;
 			const uint32_t moveWords = (nMoves + 15) / 16;
-			const uint32_t runWords = nRuns * GA_RUN_WORDS;
+			const bool mapped = doTrace[l] && lanes[l].t.status == GA_OK && (lanes[l].in->srcInfo & GA_SRC_SOLO) != 0 && ga_tr_runs_mappable(tm, nRuns, g.nNodes);
+			const uint32_t runWords = mapped ? nRuns * GA_MAP_WORDS + 7u : nRuns * GA_RUN_WORDS;
 			const uint32_t words = moveWords + nPath + runWords;
 			const unsigned long long off = *arenaTop;
 			*arenaTop += words;
 			out->traceOff = off;
+			out->nMapped = 0;
 			if (doTrace[l])
 			{
 				out->nMoves = nMoves;
 				out->nPathNodes = nPath;
 				out->nRuns = nRuns;
+				out->nMapped = mapped ? nRuns : 0;
 				out->nPositions = ga_trace_positions(lanes[l].t);
 				out->status = off + words > arenaCap && lanes[l].t.status == GA_OK ? GA_ERR_TRACE_OVERFLOW : lanes[l].t.status;
 			}
 			if (off + words > arenaCap) continue;
 			for (uint32_t i = 0; i < moveWords; i++) arena[off + i] = tm.moves[(size_t)i * S];
 			for (uint32_t i = 0; i < nPath; i++) arena[off + moveWords + i] = tm.pathNodes[(size_t)i * S];
-			for (uint32_t i = 0; i < runWords; i++) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
+			if (mapped)
+			{
+				const unsigned long long mo = off + moveWords + nPath + GA_MAP_PAD(off + moveWords + nPath);
+				GaDeviceMapping* dst = (GaDeviceMapping*)(arena + mo);
+				for (uint32_t j = 0; j < nRuns; j++) dst[j] = ga_tr_mapping(g, tm.runs, S, nRuns, j);
+			}
+			else for (uint32_t i = 0; i < nRuns * GA_RUN_WORDS; i++) arena[off + moveWords + nPath + i] = tm.runs[(size_t)i * S];
 		}
 	}
 }
@@ -485,7 +506,7 @@ struct DeviceCtx
 	cudaStream_t stream = nullptr;
 	std::string lastError;
 	// graph
-	Buffer gNodeStart, gSeq, gInOff, gInAdj, gOutOff, gOutAdj, gNodeRec, gChunks;
+	Buffer gNodeStart, gSeq, gInOff, gInAdj, gOutOff, gOutAdj, gNodeRec, gChunks, gNodeIdRev;
 	ga_graph_view view;
 	size_t graphBytes = 0;
 	bool hasGraph = false;
@@ -638,7 +659,7 @@ void DestroyDevice(DeviceCtx* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->gNodeRec, &ctx->gChunks, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
+	Buffer* all[] = { &ctx->gNodeStart, &ctx->gSeq, &ctx->gInOff, &ctx->gInAdj, &ctx->gOutOff, &ctx->gOutAdj, &ctx->gNodeRec, &ctx->gChunks, &ctx->gNodeIdRev, &ctx->bParts, &ctx->bIn, &ctx->bOut, &ctx->bWd, &ctx->bTiny, &ctx->bHash,
 		&ctx->bHeap, &ctx->bNodeTmp, &ctx->bUbkt, &ctx->bHdr, &ctx->bHn, &ctx->bColVV, &ctx->bColS, &ctx->bPeq, &ctx->bPeqAux, &ctx->bPeqOff, &ctx->bMoves, &ctx->bPath, &ctx->bRuns, &ctx->bArena, &ctx->bArenaTop, &ctx->bColTop, &ctx->bReadOff, &ctx->bBad };
 	for (Buffer* b : all) b->release();
 	ctx->pinParts.release();
@@ -759,6 +780,12 @@ void UploadGraph(DeviceCtx* ctx, const AlignmentGraph& graph)
 				dst[k >> 4] |= base << ((uint32_t)(k & 15) * 2);
 			}
 		});
+		{
+			std::vector<long long> idRev(n);
+			for (size_t i = 0; i < n; i++) idRev[i] = ((long long)graph.NodeID(i) << 1) | (graph.Reverse(i) ? 1 : 0);
+			ctx->view.nodeIdRev = uploadVec(ctx, ctx->gNodeIdRev, idRev);
+			GA_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
 		// one allocation for both, so that one L2 access-policy window covers them
 		const size_t recBytes = (recs.size() * sizeof(ga_node_rec) + 255) / 256 * 256, chunkBytes = chunks.size() * sizeof(uint32_t);
 		ctx->gNodeRec.ensure(recBytes + chunkBytes);
@@ -922,7 +949,7 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		{
 			maxLen = std::max(maxLen, sb->sorted[i].partLen);
 			// moves (2 bits each, ~1.2 per row) + crossed nodes + runs; nodes are assumed >= 4 bp on average, the retry path covers the rest
-			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + ((uint64_t)(sb->sorted[i].partLen * 1.3 / avgNodeLen * 2.0 * scale) + 66) * (1 + GA_RUN_WORDS) + 8;
+			sb->arenaCap += (uint64_t)sb->sorted[i].partLen * 3 / 16 + ((uint64_t)(sb->sorted[i].partLen * 1.3 / avgNodeLen * 2.0 * scale) + 66) * (1 + GA_MAP_WORDS) + 16;
 			peqOff[i] = peqTop;
 			peqTop += (uint64_t)(sb->sorted[i].partLen / 64) * 2;
 		}
@@ -1240,8 +1267,9 @@ void pinnedRelease(void* p, size_t cap)
 }
 }
 
-void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar)
+void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& outs, RawBuffer<uint32_t>& arena, BatchStats* stats, std::vector<uint8_t>* badChar, size_t* mapTail)
 {
+	if (mapTail) *mapTail = 0;
 	GA_CUDA(cudaSetDevice(ctx->device));
 	const size_t n = sb->sorted.size();
 	outs.resize(n);
@@ -1287,13 +1315,21 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 	}
 	// the trace arena lands in a pinned block that the results then own (recycled through a process-wide pool): no
 	// second pass over ~100 MB, no fresh pages to fault in
-	if (top)
+	size_t tailWords = 0;
+	if (mapTail)
 	{
+		for (size_t i = 0; i < n; i++) if (pinOuts[i].nMapped == 0 && !isOverflow(pinOuts[i].status)) tailWords += (size_t)pinOuts[i].nRuns * GA_MAP_WORDS;
+	}
+	if (top || tailWords)
+	{
+		const size_t topAligned = ((size_t)top + 7) & ~(size_t)7;
+		const size_t total = mapTail ? topAligned + tailWords : (size_t)top;
 		size_t cap = 0;
-		uint32_t* pin = (uint32_t*)pinnedAcquire(top * sizeof(uint32_t) + 16, cap);
-		arena.adopt(pin, (size_t)top, cap, pinnedRelease);
+		uint32_t* pin = (uint32_t*)pinnedAcquire(total * sizeof(uint32_t) + 16, cap);
+		arena.adopt(pin, total, cap, pinnedRelease);
+		if (mapTail) *mapTail = topAligned;
 		lap("pinned block");
-		GA_CUDA(cudaMemcpyAsync(pin, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		if (top) GA_CUDA(cudaMemcpyAsync(pin, ctx->bArena.ptr, top * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	for (size_t i = 0; i < n; i++) outs.data()[sb->perm[i]] = pinOuts[i];
 	waitStream(ctx);
@@ -1332,11 +1368,12 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		retry->capScale = sb->capScale * 4;
 		RawBuffer<ga_stream_out> subOuts;
 		RawBuffer<uint32_t> subArena;
+		size_t subTail = 0;
 		try
 		{
 			layoutAndUpload(ctx, retry, stats);
 			RunStaged(ctx, retry);
-			FinishStaged(ctx, retry, subOuts, subArena, stats);
+			FinishStaged(ctx, retry, subOuts, subArena, stats, nullptr, mapTail ? &subTail : nullptr);
 		}
 		catch (...)
 		{
@@ -1346,10 +1383,23 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		delete retry;
 		if (stats) stats->retries += again.size();
 		RawBuffer<uint32_t> merged;
-		merged.resize(arena.size() + subArena.size());
-		if (arena.size()) memcpy(merged.data(), arena.data(), arena.size() * sizeof(uint32_t));
-		if (subArena.size()) memcpy(merged.data() + arena.size(), subArena.data(), subArena.size() * sizeof(uint32_t));
 		uint64_t base = arena.size();
+		if (mapTail)
+		{
+			// [records of the first launch | records of the re-run | room for both launches' host-written mappings]
+			const size_t recA = *mapTail, recB = subTail, roomA = arena.size() - recA, roomB = subArena.size() - recB;
+			merged.resize(recA + recB + roomA + roomB);
+			if (recA) memcpy(merged.data(), arena.data(), recA * sizeof(uint32_t));
+			if (recB) memcpy(merged.data() + recA, subArena.data(), recB * sizeof(uint32_t));
+			base = recA;
+			*mapTail = recA + recB;
+		}
+		else
+		{
+			merged.resize(arena.size() + subArena.size());
+			if (arena.size()) memcpy(merged.data(), arena.data(), arena.size() * sizeof(uint32_t));
+			if (subArena.size()) memcpy(merged.data() + arena.size(), subArena.data(), subArena.size() * sizeof(uint32_t));
+		}
 		arena.swap(merged);
 		for (size_t k = 0; k < again.size(); k++)
 		{
@@ -1373,7 +1423,7 @@ size_t EstimateStreamBytes(DeviceCtx* ctx, size_t partLen, int bandwidth)
 	const double scratch = 3.0 * caps.maxCols * sizeof(uint32_t) + 2.0 * caps.hashSize * sizeof(uint64_t) + (double)caps.maxQueue * sizeof(uint64_t) + 10.0 * caps.maxNodes * sizeof(uint32_t)
 		+ 2.0 * caps.maxNodes * sizeof(uint32_t);
 	const double history = slices * (colsGuess * (sizeof(uint4) + sizeof(uint32_t)) + nodesGuess * GA_HN_WORDS * sizeof(uint32_t) + GA_HDR_WORDS * sizeof(uint32_t) + 36.0);
-	const double trace = partLen * 1.5 + (partLen * 1.3 / avgNodeLen * 2.0 * scale + 66) * (1 + GA_RUN_WORDS) * sizeof(uint32_t) * 2.0 + 1024;
+	const double trace = partLen * 1.5 + (partLen * 1.3 / avgNodeLen * 2.0 * scale + 66) * (1 + GA_MAP_WORDS + GA_RUN_WORDS) * sizeof(uint32_t) + 1024;
 	return (size_t)((scratch + history + trace) * 1.15);
 }
 

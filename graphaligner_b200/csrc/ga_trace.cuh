@@ -777,6 +777,38 @@ GA_DEV void ga_trace_init(GaTraceLane& L, bool doTrace, int nSlices, uint32_t no
 	t.hintNode = 0;
 }
 
+// ---- mapping records on the device (GA_SRC_SOLO streams) ---------------------------------------------------------
+// traceToAlignment (GraphAligner.h:782-847) for a forward stream whose rows are not shifted: mapping j = run (nRuns-1-j) of the
+// backward-ordered run list; only the first mapping has an offset, every mapping but the last covers its last base too
+// (from_length = lastOff - firstOff + 1), to_length counts the read rows since the previous mapping's last row.
+// false = a run lies on one of the graph's two dummy nodes (the host's mappingRange handles that: keep the runs).
+GA_DEV bool ga_tr_runs_mappable(const GaTraceMem& tm, uint32_t nRuns, uint32_t nNodes)
+{
+	for (uint32_t k = 0; k < nRuns; k++)
+	{
+		const uint32_t node = tm.runs[(size_t)(k * GA_RUN_WORDS) * tm.S];
+		if (node == 0 || node + 1 == nNodes) return false;
+	}
+	return nRuns > 0;
+}
+
+GA_DEV GaDeviceMapping ga_tr_mapping(const ga_graph_view& g, const uint32_t* runs, size_t S, uint32_t nRuns, uint32_t j)
+{
+	const uint32_t* r = runs + (size_t)((nRuns - 1 - j) * GA_RUN_WORDS) * S;
+	const uint32_t node = r[0], firstOff = r[S], lastOff = r[2 * S], firstJ = r[3 * S], lastJ = r[4 * S];
+	const uint32_t beforeJ = j == 0 ? firstJ : runs[(size_t)((nRuns - j) * GA_RUN_WORDS + 4) * S];
+	const long long idRev = g.nodeIdRev[node];
+	GaDeviceMapping m;
+	m.node_id = idRev >> 1;
+	m.offset = j == 0 ? firstOff : 0;
+	m.rank = j;
+	m.from_length = (int32_t)(lastOff - firstOff) + (j + 1 == nRuns ? 0 : 1);
+	m.to_length = (int32_t)(lastJ - beforeJ);
+	m.read_start = firstJ;
+	m.is_reverse = (uint32_t)(idRev & 1);
+	return m;
+}
+
 // positions = the start cell plus one per move except the terminating one, minus the trimmed tail
 GA_DEV uint32_t ga_trace_positions(const GaTraceState& t) { return t.nMoves > t.skipped ? t.nMoves - t.skipped : 0; }
 

@@ -24,6 +24,7 @@ typedef struct ga_graph_view
 	 * on a chunk (one 128-bit load per 64 columns).  Built by the device layer at upload; NULL on the host side. */
 	const struct ga_node_rec* nodeRec;
 	const uint32_t* seqChunks;    /* 4 words per chunk */
+	const long long* nodeIdRev;   /* per node: digraph id << 1 | reverse flag (AlignmentGraph::NodeID / Reverse), for the mapping records */
 } ga_graph_view;
 
 /* len and degrees: len | min(inDeg, 15) << 24 | min(outDeg, 15) << 28.  in[] / out[]: the first two neighbours in the
@@ -49,8 +50,13 @@ typedef struct ga_stream_in
 	uint32_t partLen;    // padded length (multiple of 64) = reference sequence.size()
 	uint32_t startNode;  // graph node index whose columns are all 0 in the initial slice
 	uint32_t trimRows;   // trace positions with row >= trimRows are dropped (padding / DBG overlap, GraphAligner.h:3063-3066,3086-3089)
-	uint32_t srcInfo;    // real (unpadded) length of the part | backward << 31 (backward: reverse complement of the read's prefix)
+	uint32_t srcInfo;    // real (unpadded) length of the part | GA_SRC_SOLO | backward << 31 (backward: reverse complement of the read's prefix)
 } ga_stream_in;
+#define GA_SRC_LEN(x) ((x) & 0x3fffffffu)
+#define GA_SRC_BACKWARD 0x80000000u
+/* the stream is everything its read has (one seed at read position 0: forward part only, rows not shifted): the traceback
+ * kernel writes the read's final 32-byte mapping records instead of the run records (ga_stream_out::nMapped) */
+#define GA_SRC_SOLO 0x40000000u
 
 enum
 {
@@ -86,7 +92,7 @@ typedef struct ga_stream_out
 	uint32_t nTies;         // cells of the last retained slice tied at the minimum (incl. the chosen one)
 	uint32_t cyclicSlices;  // slices whose band held a cyclic component
 	uint32_t rampRedos;     // -B ramp: how often the stream went back and redid a stretch with the wide band (GraphAligner.h:2648-2719)
-	uint32_t reserved;
+	uint32_t nMapped;       // > 0: the stream's record holds nMapped (= nRuns) GaDeviceMapping records where the runs would be, 32-byte aligned in the arena
 	uint32_t tieNode[GA_MAX_TIES];
 	uint32_t tieOff[GA_MAX_TIES];
 #ifdef GA_PHASE_TIMING
@@ -95,6 +101,21 @@ typedef struct ga_stream_out
 } ga_stream_out;
 
 #define GA_RUN_WORDS 5   /* node, firstOff, lastOff, firstRow, lastRow (first = smallest row) */
+
+/* one vg::Mapping with its single Edit as the C ABI returns it (ga_mapping in include/graphaligner_b200.h, same layout) */
+typedef struct GaDeviceMapping
+{
+	long long node_id;
+	uint32_t offset;
+	uint32_t rank;
+	int32_t from_length;
+	int32_t to_length;
+	uint32_t read_start;
+	uint32_t is_reverse;
+} GaDeviceMapping;
+#define GA_MAP_WORDS 8
+/* words of padding in front of a stream's mapping records so that they start on a 32-byte boundary of the arena */
+#define GA_MAP_PAD(wordOff) ((8u - (uint32_t)((wordOff) & 7u)) & 7u)
 
 // moves (2 bits each, backward from the end cell)
 enum { GA_MOVE_H = 0, GA_MOVE_D = 1, GA_MOVE_V = 2, GA_MOVE_END = 3 };

@@ -76,7 +76,7 @@ typedef struct ga_read_result
 	uint64_t alignment_end;         /* AlignmentResult::alignmentEnd */
 	int32_t query_position;         /* alignment.query_position() */
 	uint32_t flags;                 /* GA_FLAG_* */
-	uint64_t mapping_offset;        /* first entry in ga_results_mappings() */
+	uint64_t mapping_offset;        /* first entry in ga_results_mappings(); the reads' ranges need not follow each other */
 	uint64_t n_mappings;            /* alignment.path().mapping_size() */
 	uint64_t reserved;
 	uint64_t n_trace;               /* AlignmentResult::trace.size(); the items come from ga_results_read_trace() */
