@@ -435,7 +435,9 @@ static ga_results* runAndFinish(ga_ctx* ctx, ga_staged* st)
 {
 	if (!ctx->gpuTurn) return ga_run_staged(ctx, st) == 0 ? ga_finish_staged(ctx, st) : nullptr;
 	{
-		timeline(ctx, "staged, waiting for the GPU's turn");
+		// the uploads of this batch finish under the other lanes' kernels, not inside this lane's turn
+		if (ga_sync(ctx) != 0) return nullptr;
+		timeline(ctx, "staged and uploaded, waiting for the GPU's turn");
 		std::lock_guard<std::mutex> turn(*ctx->gpuTurn);
 		timeline(ctx, "turn taken, kernels launched");
 		if (ga_run_staged(ctx, st) != 0 || ga_sync(ctx) != 0) return nullptr;

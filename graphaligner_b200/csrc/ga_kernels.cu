@@ -290,7 +290,23 @@ __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_gra
 	const uint32_t moveWords = (nMoves + 15) / 16;
 	// a stream that is all its read has (GA_SRC_SOLO) leaves the read's final mapping records instead of its runs: the host then
 	// neither reads runs nor writes mappings for it (the records are D2H'd straight into the result block)
-	const bool mapped = have && doTrace && L.t.status == GA_OK && (L.in->srcInfo & GA_SRC_SOLO) != 0 && ga_tr_runs_mappable(tm, nRuns, g.nNodes);
+	// (no run on one of the graph's two dummy nodes - ga_tr_runs_mappable, checked by the 32 lanes together, a stream at a time)
+	const bool candidate = have && doTrace && L.t.status == GA_OK && (L.in->srcInfo & GA_SRC_SOLO) != 0 && nRuns > 0;
+	uint32_t mappedMask = 0;
+	for (int r = 0; r < T; r++)
+	{
+		if (!__shfl_sync(0xffffffffu, candidate ? 1u : 0u, r)) continue;
+		const uint32_t nr = __shfl_sync(0xffffffffu, nRuns, r);
+		const uint32_t* pr = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)tm.runs, r);
+		bool dummy = false;
+		for (uint32_t j = lane; j < nr; j += 32)
+		{
+			const uint32_t node = pr[(size_t)(j * GA_RUN_WORDS) * S];
+			dummy = dummy || node == 0 || node + 1 == g.nNodes;
+		}
+		if (!__any_sync(0xffffffffu, dummy)) mappedMask |= 1u << r;
+	}
+	const bool mapped = candidate && ((mappedMask >> lane) & 1u) != 0;
 	const uint32_t runWords = mapped ? nRuns * GA_MAP_WORDS + 7u : nRuns * GA_RUN_WORDS;   // + 7: room to start on a 32-byte boundary
 	const uint32_t words = have ? moveWords + nPath + runWords : 0;
 	const unsigned long long off = words ? atomicAdd(arenaTop, (unsigned long long)words) : 0ull;
