@@ -33,7 +33,32 @@ struct ga_ctx
 	double budgetShare = 1.0;   // share of the device's free memory a batch of this context may plan with (ga_pipeline: 1 / depth)
 	// ga_pipeline: the contexts of one GPU take turns on the kernel.  Two alignment kernels in flight at once share the SMs and
 	// finish together, which puts the lanes in phase (both on the host, then both on the GPU) and loses the overlap.
-	std::mutex* gpuTurn = nullptr;
+	struct GpuTurn* gpuTurn = nullptr;
+	uint64_t ticket = 0;       // ga_pipeline: the batch's place in the submission order
+	bool ticketUsed = true;    // ... and whether its first launch has taken its place yet
+};
+
+// The lanes of a pipeline take the GPU one at a time, and for the first launch of every batch in the order the batches were
+// submitted: results are handed out in that order, so an older batch waiting behind a younger one's kernels is pure delay.
+struct GpuTurn
+{
+	std::mutex gpu;            // held while a lane's kernels run
+	std::mutex m;
+	std::condition_variable cv;
+	uint64_t serving = 0;      // ticket whose first launch may go next
+	void waitFor(uint64_t ticket)
+	{
+		std::unique_lock<std::mutex> lock(m);
+		cv.wait(lock, [&]() { return serving == ticket; });
+	}
+	void next()
+	{
+		{
+			std::lock_guard<std::mutex> lock(m);
+			serving++;
+		}
+		cv.notify_all();
+	}
 };
 
 struct ga_results
@@ -438,7 +463,13 @@ static ga_results* runAndFinish(ga_ctx* ctx, ga_staged* st)
 		// the uploads of this batch finish under the other lanes' kernels, not inside this lane's turn
 		if (ga_sync(ctx) != 0) return nullptr;
 		timeline(ctx, "staged and uploaded, waiting for the GPU's turn");
-		std::lock_guard<std::mutex> turn(*ctx->gpuTurn);
+		if (!ctx->ticketUsed) ctx->gpuTurn->waitFor(ctx->ticket);
+		std::lock_guard<std::mutex> turn(ctx->gpuTurn->gpu);
+		if (!ctx->ticketUsed)
+		{
+			ctx->ticketUsed = true;
+			ctx->gpuTurn->next();   // the next batch may queue up behind this lock
+		}
 		timeline(ctx, "turn taken, kernels launched");
 		if (ga_run_staged(ctx, st) != 0 || ga_sync(ctx) != 0) return nullptr;
 		timeline(ctx, "kernels done, turn released");
@@ -647,6 +678,7 @@ struct ga_pipeline
 		ga_ctx* ctx = nullptr;
 		std::thread worker;
 		ga_batch batch;
+		uint64_t ticket = 0;
 		ga_results* result = nullptr;
 		bool busy = false;    // a batch was submitted and its result not taken yet
 		bool done = false;    // ... and the worker has finished it
@@ -654,7 +686,7 @@ struct ga_pipeline
 	};
 	std::vector<std::unique_ptr<Lane>> lanes;
 	std::mutex m;
-	std::mutex gpuTurn;   // see ga_ctx::gpuTurn
+	GpuTurn gpuTurn;      // see ga_ctx::gpuTurn
 	std::condition_variable cv;
 	uint64_t submitted = 0, taken = 0;
 	bool stop = false;
@@ -670,7 +702,16 @@ static void pipelineWorker(ga_pipeline* p, ga_pipeline::Lane* lane)
 		if (p->stop) return;
 		lock.unlock();
 		timeline(lane->ctx, "batch picked up by the lane");
+		lane->ctx->ticket = lane->ticket;
+		lane->ctx->ticketUsed = lane->ctx->gpuTurn == nullptr;
 		ga_results* r = ga_align_batch(lane->ctx, &lane->batch);
+		if (!lane->ctx->ticketUsed)
+		{
+			// the batch never reached a launch (an error, no reads): its place in the order is given up, in order
+			lane->ctx->gpuTurn->waitFor(lane->ticket);
+			lane->ctx->gpuTurn->next();
+			lane->ctx->ticketUsed = true;
+		}
 		lock.lock();
 		lane->result = r;
 		if (!r) lane->error = lane->ctx->error;
@@ -755,6 +796,7 @@ int ga_pipeline_submit(ga_pipeline* p, const ga_batch* batch)
 		return -2;
 	}
 	lane.batch = *batch;
+	lane.ticket = p->submitted;
 	lane.result = nullptr;
 	lane.error.clear();
 	lane.done = false;
