@@ -924,7 +924,9 @@ static int pickFastStreamsPerWarp(DeviceCtx* ctx, size_t nStreams)
 {
 	if (ctx->forceS > 0) return ctx->forceS;
 	const size_t slots = (size_t)ctx->smCount * 4;
-	static const int candidates[] = { 16, 17, 18, 20, 24, 28, 32 };
+	// (a small batch runs with few streams per warp: the chain of a warp is the longest of its lanes' chains plus what their
+	// divergent parts serialise, so fewer lanes per warp make a shorter launch as long as every warp still has a sub-partition)
+	static const int candidates[] = { 4, 6, 8, 12, 16, 17, 18, 20, 24, 28, 32 };
 	for (int S : candidates)
 	{
 		if ((nStreams + S - 1) / S <= slots) return S;
@@ -1113,9 +1115,17 @@ static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
 	// 13.2 ms at T = 8, 14.8 at 6, 18.1 at 16, 28.3 at 32.
 	const size_t n = sb->sorted.size();
 	int T = ctx->traceT;
-	if (T == 0) T = n <= (size_t)ctx->smCount * 12 * 6 ? 6 : 8;
+	if (T == 0)
+	{
+		// one wave (12 warps per SM) with as few streams per warp as that allows, 8 once the batch runs in waves anyway
+		const size_t slots = (size_t)ctx->smCount * 12;
+		T = 8;
+		for (int t : { 2, 3, 4, 5, 6 }) { if ((n + t - 1) / t <= slots) { T = t; break; } }
+	}
 	const int P = ctx->traceP;
-	if (T == 6) launchTraceTP<6, 1>(ctx, sb);
+	if (T == 2) launchTraceTP<2, 1>(ctx, sb);
+	else if (T == 3) launchTraceTP<3, 1>(ctx, sb);
+	else if (T == 6) launchTraceTP<6, 1>(ctx, sb);
 	else if (T == 5) launchTraceTP<5, 1>(ctx, sb);
 	else if (T == 7) launchTraceTP<7, 1>(ctx, sb);
 	else if (T == 4 && P == 1) launchTraceTP<4, 1>(ctx, sb);
@@ -1173,7 +1183,9 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 			case 18: launchFast<18>(ctx, sb); break;
 			case 17: launchFast<17>(ctx, sb); break;
 			case 16: launchFast<16>(ctx, sb); break;
+			case 12: launchFast<12>(ctx, sb); break;
 			case 8: launchFast<8>(ctx, sb); break;
+			case 6: launchFast<6>(ctx, sb); break;
 			case 4: launchFast<4>(ctx, sb); break;
 			default: throw std::logic_error("unsupported streams-per-warp (small-band kernel)");
 		}
