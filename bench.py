@@ -328,7 +328,9 @@ def main():
                "word_columns_per_step": wc_all, "failed_reads": failed_all, "resident_reads": n_res, "stream_errors": res_streams_err,
                "streams": int(stats["streams"]), "streams_rerun_with_general_layout": int(stats["retries"]),
                "kernel_split_ms": {"peq": stats["peq_us"] / 1e3, "forward": stats["forward_us"] / 1e3, "trace": stats["trace_us"] / 1e3},
-               "mean_kernel_ms": sum(kernel_ms) / len(kernel_ms), "word_columns_rank0": res_wc, "kernel_launches": int(stats["launches"]),
+               "mean_kernel_ms": sum(kernel_ms) / len(kernel_ms), "word_columns_rank0": res_wc,
+               # the staged batch's launch counter is read out when it is finished: it also holds the warm-up runs
+               "kernel_launches": int(stats["launches"]) * steps // max(1, steps + warmup),
                "clocks": clocks.summary(), "wall_s_resident": wall}
         # ---- end to end through the C ABI with host buffers ----------------------------------------------------
         if with_single_call:
@@ -454,7 +456,7 @@ def main():
                 "gpu_launches": head["kernel_launches"],
                 "kernel_split_ms": head["kernel_split_ms"],
                 "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "T lane-op/s", "frac": (achieved / int_peak) if int_peak else None,
-                             "kernel": "forward DP kernel (ga_fast_kernel<16> on this workload)", "kernel_ms": fwd_s * 1e3,
+                             "kernel": "forward DP kernel (ga_fast_kernel<S> for small bands - config 2: S = 17 - else ga_forward_kernel<S>)", "kernel_ms": fwd_s * 1e3,
                              "note": "50 INT32 lane-ops per forward word update (SURVEY 8d) x word updates of one launch / the kernel's own launch duration; "
                                      "peak = dependency-free LOP3/IADD3 probe measured in this run (the contract's hbm|tensor bounds do not bind an integer kernel)",
                              "traffic": traffic, "traffic_source": traffic_file, "traffic_kernel": traffic_kernel,
