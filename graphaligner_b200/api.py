@@ -243,7 +243,7 @@ class Aligner:
         if not h:
             raise RuntimeError("ga_align_batch failed: " + self.last_error())
         names = None if isinstance(reads, PackedReads) else [r[0] for r in reads]
-        return Results(self._lib, h, names, keepalive=packed)
+        return Results(self._lib, h, names, keepalive=(packed, self.graph))   # the results refer to the batch buffers and to the graph
 
     def stage(self, packed):
         h = self._lib.ga_stage_batch(self.ctx, C.byref(packed.struct))
@@ -263,7 +263,7 @@ class Aligner:
         h = self._lib.ga_finish_staged(self.ctx, staged)
         if not h:
             raise RuntimeError("ga_finish_staged failed: " + self.last_error())
-        return Results(self._lib, h, names, keepalive=keepalive)
+        return Results(self._lib, h, names, keepalive=(keepalive, self.graph))
 
     def free_staged(self, staged):
         self._lib.ga_staged_free(self.ctx, staged)
@@ -326,7 +326,7 @@ class Pipeline:
         packed, names = self._pending.pop(0)
         if not h:
             raise RuntimeError("ga_pipeline_next failed: " + self.last_error())
-        return Results(self._lib, h, names, keepalive=packed)
+        return Results(self._lib, h, names, keepalive=(packed, self.graph))
 
     def align_all(self, batches, b=10, B=0):
         """Generator: aligns an iterable of batches, at most `depth` in flight, yielding their Results in order."""

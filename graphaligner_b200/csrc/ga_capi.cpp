@@ -374,6 +374,8 @@ ga_results* ga_finish_staged(ga_ctx* ctx, ga_staged* st)
 		packResults(res, as, graph, st->reads, ch.outs.data(), ch.arena.data(), ch.arena.size(), mapTail);
 		res->graph = &graph;
 		res->inputs = st->reads;
+		// the seed lists live in the staged batch, which does not outlive this call; nothing reads them from the results
+		for (ga::ReadInput& in : res->inputs) { in.seeds = nullptr; in.nSeeds = 0; }
 		ch.streams = st->plan->streams;
 		tm.lap("finish: pack results");
 	});
@@ -831,6 +833,15 @@ int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out)
 {
 	std::lock_guard<std::mutex> lock(p->m);
 	memset(out, 0, sizeof(*out));
+	// the lanes' workers update their contexts' counters while a batch is in flight: a snapshot is only taken of idle lanes
+	for (auto& l : p->lanes)
+	{
+		if (l->busy && !l->done)
+		{
+			p->error = "ga_pipeline_get_stats: batches in flight (take their results first)";
+			return -1;
+		}
+	}
 	for (auto& l : p->lanes)
 	{
 		ga_stats s;

@@ -172,7 +172,7 @@ int ga_pipeline_graph_upload(ga_pipeline* p, const ga_graph* g); /* one replica 
 int ga_pipeline_submit(ga_pipeline* p, const ga_batch* batch);   /* asynchronous; 0, -2 = full */
 ga_results* ga_pipeline_next(ga_pipeline* p);                    /* oldest submitted batch's results (blocks); NULL on error */
 int ga_pipeline_in_flight(const ga_pipeline* p);
-int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out);        /* summed over the lanes */
+int ga_pipeline_get_stats(ga_pipeline* p, ga_stats* out);        /* summed over the lanes; -1 while a lane is still working on a batch */
 int ga_pipeline_reset_stats(ga_pipeline* p);
 
 #ifdef __cplusplus
