@@ -296,6 +296,7 @@ static void packResults(ga_results* out, const std::vector<ga::ReadAssembly>& as
 		o.score = a.failed ? std::numeric_limits<int32_t>::max() : a.score;
 		o.flags = a.flags;
 		o.word_columns = a.wordColumns;
+		o.reserved = a.estimated;   // EstimatedCorrectlyAligned of the chosen seed (kept for the two-round seed loop, also for failed reads)
 		o.mapping_offset = a.deviceMapped ? a.deviceMapWord / GA_MAP_WORDS : mapOff[i];
 		out->lazy[i] = ga_results::Lazy { 0, a.fwStream, a.bwStream, a.splitIndex, a.fwShifted, a.failed, a.nTraceItems };
 		if (a.failed) return;
@@ -481,7 +482,128 @@ static ga_results* runAndFinish(ga_ctx* ctx, ga_staged* st)
 	return r;
 }
 
+static ga_results* alignAllSeeds(ga_ctx* ctx, const ga_batch* batch);
+
+// ---- seeds in two rounds -------------------------------------------------------------------------------------------
+// The reference takes a read's seeds one after the other and skips a seed whose (node, read position) lies on the trace of an
+// earlier seed's alignment (GraphAligner.h:420-450).  With seeds from one true locus - the usual output of a seeder - every
+// seed after the first is skipped.  Aligning all seeds at once (and replaying the rule afterwards) therefore does several
+// times the reference's DP work.  Two rounds: the first seed of every read; then, for the reads that have more, the seeds the
+// first alignment does not cover (all of them at once, the rule replayed among them).  The outcome is the reference's: a seed
+// is run unless the first seed's trace covers it, the replay inside round two applies the traces of round two, and the first
+// seed keeps the read unless a later one has a strictly larger EstimatedCorrectlyAligned (GraphAligner.h:434-449).
+static ga_results* combineRounds(ga_ctx* ctx, ga_results* r1, ga_results* r2, size_t n)
+{
+	ga_results* all = new ga_results();
+	all->reads.resize(n);
+	all->lazy.resize(n);
+	all->inputs = r1->inputs;
+	all->graph = r1->graph;
+	const uint32_t chunks1 = (uint32_t)r1->chunks.size();
+	// which round decides a read: round two when it ran seeds of the read and either hit a stream error there (the loop ends with
+	// a failure, as it would have with all seeds at once) or found a strictly larger estimate
+	std::vector<uint8_t> fromTwo(n, 0);
+	std::vector<uint64_t> newOff(n + 1, 0);
+	for (size_t i = 0; i < n; i++)
+	{
+		const ga_read_result& a = r1->reads.data()[i];
+		const ga_read_result& b = r2->reads.data()[i];
+		const bool ranTwo = b.word_columns > 0 || b.flags != 0 || !b.failed;
+		fromTwo[i] = ranTwo && ((b.flags & GA_FLAG_STREAM_ERROR) || b.reserved > a.reserved) ? 1 : 0;
+		const ga_read_result& pick = fromTwo[i] ? b : a;
+		newOff[i + 1] = newOff[i] + (pick.failed ? 0 : pick.n_mappings);
+	}
+	all->mappings.resize(newOff[n]);
+	all->mapBase = all->mappings.data();
+	ga::ParallelFor(n, [&](size_t i) {
+		const ga_results* part = fromTwo[i] ? r2 : r1;
+		ga_read_result o = part->reads.data()[i];
+		if (!o.failed && o.n_mappings) memcpy(all->mappings.data() + newOff[i], part->mapBase + o.mapping_offset, (size_t)o.n_mappings * sizeof(ga_mapping));
+		o.mapping_offset = newOff[i];
+		o.flags = r1->reads.data()[i].flags | r2->reads.data()[i].flags;
+		o.word_columns = r1->reads.data()[i].word_columns + r2->reads.data()[i].word_columns;
+		all->reads.data()[i] = o;
+		all->lazy[i] = part->lazy[i];
+		if (fromTwo[i]) all->lazy[i].chunk += chunks1;
+	});
+	for (auto& c : r1->chunks) all->chunks.push_back(std::move(c));
+	for (auto& c : r2->chunks) all->chunks.push_back(std::move(c));
+	delete r1;
+	delete r2;
+	(void)ctx;
+	return all;
+}
+
 ga_results* ga_align_batch(ga_ctx* ctx, const ga_batch* batch)
+{
+	const size_t n = batch->n_reads;
+	static const bool oneRound = getenv("GA_ALL_SEEDS_AT_ONCE") != nullptr;   // A/B measurements
+	bool several = false;
+	for (size_t i = 0; i < n && !several && !oneRound; i++) several = batch->seed_offsets[i + 1] - batch->seed_offsets[i] > 1;
+	if (!several || !ctx->graph) return alignAllSeeds(ctx, batch);
+	const AlignmentGraph& graph = ctx->graph->graph;
+	// round one: the first seed of every read; a read with a seed the reference would throw on keeps all its seeds here (the
+	// failure is then reported exactly as before)
+	std::vector<uint64_t> off1(n + 1, 0), off2(n + 1, 0);
+	std::vector<int32_t> node1, node2;
+	std::vector<uint64_t> pos1, pos2;
+	std::vector<uint8_t> rev1, rev2;
+	std::vector<uint8_t> twoRounds(n, 0);
+	auto push = [&](std::vector<int32_t>& nd, std::vector<uint64_t>& ps, std::vector<uint8_t>& rv, uint64_t k) {
+		nd.push_back(batch->seed_node[k]); ps.push_back(batch->seed_pos[k]); rv.push_back(batch->seed_reverse[k]);
+	};
+	for (size_t i = 0; i < n; i++)
+	{
+		const uint64_t first = batch->seed_offsets[i], last = batch->seed_offsets[i + 1];
+		bool valid = true;
+		if (last - first > 1)
+		{
+			ga::ReadInput r;
+			r.name = ""; r.nameLen = 0; r.seeds = nullptr; r.nSeeds = 0;
+			r.seq = batch->sequences + batch->seq_offsets[i];
+			r.seqLen = (size_t)(batch->seq_offsets[i + 1] - batch->seq_offsets[i]);
+			for (uint64_t k = first; k < last && valid; k++) valid = ga::SeedIsValid(graph, r, ga::SeedHit((int)batch->seed_node[k], (size_t)batch->seed_pos[k], batch->seed_reverse[k] != 0));
+		}
+		twoRounds[i] = last - first > 1 && valid ? 1 : 0;
+		for (uint64_t k = first; k < (twoRounds[i] ? first + 1 : last); k++) push(node1, pos1, rev1, k);
+		off1[i + 1] = node1.size();
+	}
+	if (node1.empty()) { node1.push_back(0); pos1.push_back(0); rev1.push_back(0); }
+	ga_batch b1 = *batch;
+	b1.seed_offsets = off1.data(); b1.seed_node = node1.data(); b1.seed_pos = pos1.data(); b1.seed_reverse = rev1.data();
+	ga_results* r1 = alignAllSeeds(ctx, &b1);
+	if (!r1) return nullptr;
+	// round two: the other seeds of those reads, unless the first alignment covers them or ended the read with a stream error
+	int rc = guarded(ctx, [&]() {
+		std::vector<std::tuple<size_t, size_t, size_t>> tried;
+		for (size_t i = 0; i < n; i++)
+		{
+			if (twoRounds[i] && !(r1->reads.data()[i].flags & (GA_FLAG_STREAM_ERROR | GA_FLAG_BAD_CHAR)))
+			{
+				const ga_results::Lazy& lz = r1->lazy[i];
+				const ga_results::Chunk& ch = *r1->chunks[lz.chunk];
+				tried.clear();
+				ga::CollectTried(graph, ch.outs.data(), ch.arena.data(), lz.fwStream, lz.bwStream, lz.splitIndex, lz.fwShifted, tried);
+				for (uint64_t k = batch->seed_offsets[i] + 1; k < batch->seed_offsets[i + 1]; k++)
+				{
+					if (!ga::SeedCovered(graph, tried, ga::SeedHit((int)batch->seed_node[k], (size_t)batch->seed_pos[k], batch->seed_reverse[k] != 0))) push(node2, pos2, rev2, k);
+				}
+			}
+			off2[i + 1] = node2.size();
+		}
+	});
+	if (rc != 0) { delete r1; return nullptr; }
+	if (node2.empty()) return r1;
+	ga_batch b2 = *batch;
+	b2.seed_offsets = off2.data(); b2.seed_node = node2.data(); b2.seed_pos = pos2.data(); b2.seed_reverse = rev2.data();
+	ga_results* r2 = alignAllSeeds(ctx, &b2);
+	if (!r2) { delete r1; return nullptr; }
+	ga_results* all = nullptr;
+	rc = guarded(ctx, [&]() { all = combineRounds(ctx, r1, r2, n); });
+	return rc == 0 ? all : nullptr;
+}
+
+static ga_results* alignAllSeeds(ga_ctx* ctx, const ga_batch* batch)
 {
 	// split the batch when its DP history would not fit the device (the history is ~64 B per band column and slice)
 	std::vector<size_t> cuts;   // chunk boundaries in reads

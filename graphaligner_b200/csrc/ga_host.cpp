@@ -635,6 +635,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			as.queryPosition = (int32_t)as.splitIndex;
 			as.alignmentStart = as.splitIndex;
 			as.alignmentEnd = as.splitIndex + (size_t)o.nSlices * 64;
+			as.estimated = (size_t)o.nSlices * 64;
 			as.nTraceItems = o.nPositions > 0 ? o.nPositions - 1 : 0;
 			as.failed = false;
 			if (materialize)
@@ -737,6 +738,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		}
 	}
 	if (!hasAlignment) return as;
+	as.estimated = bestEstimated;
 	size_t fk = 0, fl = 0, bk = 0, bl = 0;
 	const bool fwOk = mappingRange(graph, bestFw, fk, fl);
 	const bool bwOk = mappingRange(graph, bestBw, bk, bl);
@@ -769,6 +771,59 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		EmitMappings(graph, read, as, outs, arena, [&](size_t i, const FlatMapping& m) { as.mappings[i] = m; });
 	}
 	return as;
+}
+
+// ---- seeds in two rounds (ga_align_batch): what a later seed of a read needs to know about an earlier seed's alignment ----
+bool SeedIsValid(const AlignmentGraph& graph, const ReadInput& read, const SeedHit& hit)
+{
+	// the checks of BatchPlan (reference: nodeLookup.at / substr throw std::out_of_range, GraphAligner.h:423,2977-2998)
+	const int nodeId = std::get<0>(hit);
+	const size_t pos = std::get<1>(hit);
+	return graph.HasNode(nodeId * 2) && graph.HasNode(nodeId * 2 + 1) && pos < read.seqLen && pos + (size_t)graph.DBGOverlap <= read.seqLen;
+}
+
+void CollectTried(const AlignmentGraph& graph, const ga_stream_out* outs, const uint32_t* arena, int64_t fwStream, int64_t bwStream, size_t splitIndex, bool fwShifted,
+	std::vector<std::tuple<size_t, size_t, size_t>>& tried)
+{
+	// addAlignmentNodes, GraphAligner.h:594-634: (first row, last row, node) of every run of the seed's forward and backward trace
+	if (fwStream >= 0)
+	{
+		const ga_stream_out& o = outs[fwStream];
+		if (o.status == GA_OK && o.nSlices > 0 && o.nMapped > 0)
+		{
+			// the device wrote mapping records instead of runs (rows not shifted): the rows follow from read_start / to_length
+			const uint64_t recWord = o.traceOff + (o.nMoves + 15) / 16 + o.nPathNodes;
+			const GaDeviceMapping* rec = (const GaDeviceMapping*)(arena + recWord + GA_MAP_PAD(recWord));
+			size_t lastJ = rec[0].read_start;
+			for (uint32_t i = 0; i < o.nMapped; i++)
+			{
+				lastJ += (size_t)rec[i].to_length;
+				tried.emplace_back((size_t)rec[i].read_start, lastJ, graph.Lookup((int)rec[i].node_id));
+			}
+		}
+		else
+		{
+			const RunView fw = viewOf(graph, o, arena, false, 0, fwShifted ? splitIndex : 0);
+			for (size_t i = 0; i < fw.n; i++) { const TraceRun r = fw.get(i); tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node); }
+		}
+	}
+	if (bwStream >= 0)
+	{
+		const RunView bw = viewOf(graph, outs[bwStream], arena, true, splitIndex - 1, 0);
+		for (size_t i = 0; i < bw.n; i++) { const TraceRun r = bw.get(i); tried.emplace_back(r.firstJ, r.lastJ, (size_t)r.node); }
+	}
+}
+
+bool SeedCovered(const AlignmentGraph& graph, const std::vector<std::tuple<size_t, size_t, size_t>>& tried, const SeedHit& hit)
+{
+	// "seed i already aligned", GraphAligner.h:425-429
+	const size_t nodeIndex = graph.Lookup(std::get<0>(hit) * 2);
+	const size_t pos = std::get<1>(hit);
+	for (const auto& t : tried)
+	{
+		if (std::get<0>(t) <= pos && std::get<1>(t) >= pos && std::get<2>(t) == nodeIndex) return true;
+	}
+	return false;
 }
 
 namespace

@@ -240,6 +240,7 @@ struct ReadAssembly
 	int64_t mapFwStream = -1, mapBwStream = -1;
 	size_t mapBwFirst = 0, mapBwCount = 0, mapFwFirst = 0, mapFwCount = 0, mapFwSkip = 0;
 	size_t nMappings = 0;
+	size_t estimated = 0;                   // EstimatedCorrectlyAligned of the chosen seed (64 x retained slices), also when the read failed
 	// the device wrote the read's mapping records itself (GA_SRC_SOLO stream): they lie in the arena at word deviceMapWord
 	// (a multiple of 8), nMappings of them, as GaDeviceMapping = ::ga_mapping
 	bool deviceMapped = false;
@@ -256,6 +257,12 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 	const ga_stream_out* outs, const uint32_t* arena, bool materialize = true);
 void EmitMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena,
 	const std::function<void(size_t, const FlatMapping&)>& sink);
+// Seeds in two rounds (ga_align_batch): validity of a seed (BatchPlan's checks), the (first row, last row, node) triples of an
+// aligned seed's traces (addAlignmentNodes, GraphAligner.h:594-634) and the reference's "seed already aligned" test against them
+bool SeedIsValid(const AlignmentGraph& graph, const ReadInput& read, const SeedHit& hit);
+void CollectTried(const AlignmentGraph& graph, const ga_stream_out* outs, const uint32_t* arena, int64_t fwStream, int64_t bwStream, size_t splitIndex, bool fwShifted,
+	std::vector<std::tuple<size_t, size_t, size_t>>& tried);
+bool SeedCovered(const AlignmentGraph& graph, const std::vector<std::tuple<size_t, size_t, size_t>>& tried, const SeedHit& hit);
 // the same, as the C ABI's records (include/graphaligner_b200.h), into dst[0 .. nMappings)
 void WriteMappings(const AlignmentGraph& graph, const ReadInput& read, const ReadAssembly& as, const ga_stream_out* outs, const uint32_t* arena, ::ga_mapping* dst);
 

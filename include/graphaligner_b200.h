@@ -78,7 +78,7 @@ typedef struct ga_read_result
 	uint32_t flags;                 /* GA_FLAG_* */
 	uint64_t mapping_offset;        /* first entry in ga_results_mappings(); the reads' ranges need not follow each other */
 	uint64_t n_mappings;            /* alignment.path().mapping_size() */
-	uint64_t reserved;
+	uint64_t reserved;              /* EstimatedCorrectlyAligned of the chosen seed = 64 x retained slices (GraphAligner.h:371-374), also for a failed read */
 	uint64_t n_trace;               /* AlignmentResult::trace.size(); the items come from ga_results_read_trace() */
 	uint64_t word_columns;          /* forward-pass word updates spent on this read (all seeds, both directions) */
 } ga_read_result;
