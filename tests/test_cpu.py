@@ -80,3 +80,18 @@ def test_parallel_generators_make_valid_cases(tmp_path):
     expected, _ = run_reference(path, threads=4)
     assert sum(1 for e in expected if not e["failed"]) >= 22
     assert all(e["score"] < 0.3 * 3000 for e in expected if not e["failed"])
+
+
+def test_word_level_primitives_against_reference_wordslice():
+    # the column primitives of the product (ga_merge_cols, ga_col_value, ga_vertical_merge: ga_core.cuh compiled
+    # for the host) against the reference's own WordSlice::mergeWith / getValue (WordSlice.h:202,223,361-421) on random columns
+    import os
+    import subprocess
+    import pytest
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "word_harness")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/word_harness not built")
+    for seed in (1, 2):
+        r = subprocess.run([exe, "100000", str(seed)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-600:]
+        assert "100000 merges" in r.stdout and "identical" in r.stdout
