@@ -204,8 +204,10 @@ __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_
 
 #ifndef GA_HOSTSIM
 // Small-band forward kernel (ga_fast.cuh): one warp per block, S streams per warp, the warp's state in its block's shared memory
+// (32, 1): shared memory admits four of these blocks per SM at most, so ptxas may take the registers it wants (119, no spills;
+// with its default budget 96 and 24 bytes of spills - 8.19 vs 8.10 ms, within the noise)
 template <int S>
-__global__ void __launch_bounds__(32) ga_fast_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
+__global__ void __launch_bounds__(32, 1) ga_fast_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
 	const ga_stream_in* __restrict__ streams, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* __restrict__ outs)
 {
 	extern __shared__ __align__(16) unsigned long long gaShared[];
