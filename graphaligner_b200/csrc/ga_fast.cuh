@@ -23,6 +23,9 @@
 #define GAF_HEAP 32u
 #define GAF_NONE 0xffu
 #define GAF_NOPCS 0xfffu
+#ifndef GAF_STEPS
+#define GAF_STEPS 2         /* columns of a node a lane takes per pass of the column loop (measured: 1 -> 8.10 ms, 2 -> 7.55 ms, 3 -> 7.77 ms, 4 -> 7.61 ms) */
+#endif
 #define GAF_ORD_CHAIN 0x100u
 #define GAF_ORD_NOUP 0x200u
 
@@ -537,7 +540,10 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 		if (!run) oi = (uint32_t)nc;
 		for (uint32_t it = 0; it < maxc; it++)
 		{
-			if (kLeft == 0 && oi >= (uint32_t)nc) continue;
+			// (a lane takes up to two columns per pass: the warp is done when no lane has a column left)
+			const bool work = kLeft > 0 || oi < (uint32_t)nc;
+			if (!GA_WARP_ANY(work)) break;
+			if (!work) continue;
 			uint32_t isFirst = 0;
 			if (kLeft == 0)
 			{
@@ -675,70 +681,77 @@ GA_DEV void ga_fast_stream(const ga_graph_view& g, const ga_caps& caps, const Ga
 				}
 			}
 			// ---- one column by the word step: columns 1.. of a node (GraphAligner.h:1349-1399,1532-1570) or the first column of a chain ----
-			// the next 32 bases of a node longer than that: 8 bytes of its chunks
-			if ((k & 31u) == 0 && k > 0) seqBits = *((const uint64_t*)g.seqChunks + (size_t)chunkIdx * 2 + (k >> 5));
-			const uint32_t base = (uint32_t)seqBits & 3u;
-			seqBits >>= 2;
-			uint64_t Eq = eqTab[(size_t)base * S];
-			const uint32_t previousEq = (prevMask >> base) & 1u;
-			// this column in the previous slice
-			const uint32_t topRaw = fl.sh.tiny[tp][topIdx][fl.lane];
-			const uint32_t topDec = (uint32_t)tinyRef + (((topRaw >> 3) - (uint32_t)tinyRef) & 0x1fffu);
-			const int32_t topScore = inPrev ? (int32_t)topDec : INF;
-			const int32_t topRow62 = (int32_t)topDec - (int32_t)(topRaw & 1u) + (int32_t)((topRaw >> 1) & 1u);
-			const bool upPresent = upScore != INF;
-			// row -1 score = min(left + 1, up-left + 1, previous slice's end score); the flag says the latter attains it
-			const int32_t s1 = sbsL + 1;
-			const int32_t sbs0 = upScore + 1 < s1 ? upScore + 1 : s1;
-			const bool sbE = topScore <= sbs0;
-			// ga_next_col, straight-line
-			if (!(LsbE && upPresent)) Eq &= ~(uint64_t)1;
-			const int32_t dgn = upRow62 + 1 - (int32_t)previousEq;
-			int32_t sbsN = (sbE && upPresent && dgn < s1) ? dgn : s1;
-			const bool lower = topScore < sbsN;
-			const bool legal = topScore >= sbsL - 1;
-			sbsN = (lower && legal) ? topScore : sbsN;
-			const bool needMerge = lower && !legal;
-			const int32_t hin = sbsN - sbsL;
-			const uint64_t Xv = Eq | VN;
-			if (hin < 0) Eq |= 1;
-			const uint32_t eq0 = (uint32_t)Eq & 1u;
-			const uint64_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
-			uint64_t Ph = VN | ~(Xh | VP);
-			uint64_t Mh = VP & Xh;
-			int32_t endN = endL + (int32_t)(Ph >> 63) - (int32_t)(Mh >> 63);
-			Ph = (Ph << 1) | (hin > 0 ? 1u : 0u);
-			Mh = (Mh << 1) | (hin < 0 ? 1u : 0u);
-			uint64_t VPn = Mh | ~(Xv | Ph);
-			uint64_t VNn = Ph & Xv;
-			uint32_t flags = isFirst ? GA_CF_LINK : GA_CF_PLAIN;
-			if (needMerge)
-			{
-				GaCol c;
-				c.VP = VPn; c.VN = VNn; c.sbs = sbsN; c.scoreEnd = endN;
-				ga_vertical_merge(c, topScore);
-				VPn = c.VP; VNn = c.VN; sbsN = c.sbs; endN = c.scoreEnd;
-				flags = 0;
-			}
-			{
-				uint4 ra;
-				ra.x = (uint32_t)VPn; ra.y = (uint32_t)(VPn >> 32); ra.z = (uint32_t)VNn; ra.w = (uint32_t)(VNn >> 32);
-				const size_t idx = (size_t)(slabOff + colIdx) * S;
-				mem.colVV[idx] = ra;
-				mem.colS[idx] = (uint32_t)sbsN | flags | ((flags && eq0) ? GA_CF_EQ0 : 0u);
-			}
-			fl.sh.tiny[tc][colIdx][fl.lane] = (uint16_t)(((uint32_t)endN << 3) | (sbE ? 4u : 0u) | (uint32_t)((VNn >> 62) & 2) | (uint32_t)(VPn >> 63));
-			nodeMin = endN < nodeMin ? endN : nodeMin;
-			scoreMax = endN > scoreMax ? endN : scoreMax;
-			VP = VPn; VN = VNn; sbsL = sbsN; endL = endN;
-			LsbE = sbE ? 1u : 0u;
-			upScore = topScore;
-			upRow62 = topRow62;
-			lastSlot = slot;
-			k++;
-			kLeft--;
-			colIdx++;
-			topIdx += inPrev ? 1u : 0u;
+			// (a lambda so that a lane can take two columns of a node in one pass of the loop: the second step's shared-memory reads
+			// and address arithmetic then overlap the first step's stores - one warp per sub-partition has no other warp to fill its stalls)
+			auto wordStep = [&](const uint32_t first) {
+				// the next 32 bases of a node longer than that: 8 bytes of its chunks
+				if ((k & 31u) == 0 && k > 0) seqBits = *((const uint64_t*)g.seqChunks + (size_t)chunkIdx * 2 + (k >> 5));
+				const uint32_t base = (uint32_t)seqBits & 3u;
+				seqBits >>= 2;
+				uint64_t Eq = eqTab[(size_t)base * S];
+				const uint32_t previousEq = (prevMask >> base) & 1u;
+				// this column in the previous slice
+				const uint32_t topRaw = fl.sh.tiny[tp][topIdx][fl.lane];
+				const uint32_t topDec = (uint32_t)tinyRef + (((topRaw >> 3) - (uint32_t)tinyRef) & 0x1fffu);
+				const int32_t topScore = inPrev ? (int32_t)topDec : INF;
+				const int32_t topRow62 = (int32_t)topDec - (int32_t)(topRaw & 1u) + (int32_t)((topRaw >> 1) & 1u);
+				const bool upPresent = upScore != INF;
+				// row -1 score = min(left + 1, up-left + 1, previous slice's end score); the flag says the latter attains it
+				const int32_t s1 = sbsL + 1;
+				const int32_t sbs0 = upScore + 1 < s1 ? upScore + 1 : s1;
+				const bool sbE = topScore <= sbs0;
+				// ga_next_col, straight-line
+				if (!(LsbE && upPresent)) Eq &= ~(uint64_t)1;
+				const int32_t dgn = upRow62 + 1 - (int32_t)previousEq;
+				int32_t sbsN = (sbE && upPresent && dgn < s1) ? dgn : s1;
+				const bool lower = topScore < sbsN;
+				const bool legal = topScore >= sbsL - 1;
+				sbsN = (lower && legal) ? topScore : sbsN;
+				const bool needMerge = lower && !legal;
+				const int32_t hin = sbsN - sbsL;
+				const uint64_t Xv = Eq | VN;
+				if (hin < 0) Eq |= 1;
+				const uint32_t eq0 = (uint32_t)Eq & 1u;
+				const uint64_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+				uint64_t Ph = VN | ~(Xh | VP);
+				uint64_t Mh = VP & Xh;
+				int32_t endN = endL + (int32_t)(Ph >> 63) - (int32_t)(Mh >> 63);
+				Ph = (Ph << 1) | (hin > 0 ? 1u : 0u);
+				Mh = (Mh << 1) | (hin < 0 ? 1u : 0u);
+				uint64_t VPn = Mh | ~(Xv | Ph);
+				uint64_t VNn = Ph & Xv;
+				uint32_t flags = first ? GA_CF_LINK : GA_CF_PLAIN;
+				if (needMerge)
+				{
+					GaCol c;
+					c.VP = VPn; c.VN = VNn; c.sbs = sbsN; c.scoreEnd = endN;
+					ga_vertical_merge(c, topScore);
+					VPn = c.VP; VNn = c.VN; sbsN = c.sbs; endN = c.scoreEnd;
+					flags = 0;
+				}
+				{
+					uint4 ra;
+					ra.x = (uint32_t)VPn; ra.y = (uint32_t)(VPn >> 32); ra.z = (uint32_t)VNn; ra.w = (uint32_t)(VNn >> 32);
+					const size_t idx = (size_t)(slabOff + colIdx) * S;
+					mem.colVV[idx] = ra;
+					mem.colS[idx] = (uint32_t)sbsN | flags | ((flags && eq0) ? GA_CF_EQ0 : 0u);
+				}
+				fl.sh.tiny[tc][colIdx][fl.lane] = (uint16_t)(((uint32_t)endN << 3) | (sbE ? 4u : 0u) | (uint32_t)((VNn >> 62) & 2) | (uint32_t)(VPn >> 63));
+				nodeMin = endN < nodeMin ? endN : nodeMin;
+				scoreMax = endN > scoreMax ? endN : scoreMax;
+				VP = VPn; VN = VNn; sbsL = sbsN; endL = endN;
+				LsbE = sbE ? 1u : 0u;
+				upScore = topScore;
+				upRow62 = topRow62;
+				lastSlot = slot;
+				k++;
+				kLeft--;
+				colIdx++;
+				topIdx += inPrev ? 1u : 0u;
+			};
+			wordStep(isFirst);
+#pragma unroll
+			for (int u = 1; u < GAF_STEPS; u++) { if (kLeft > 0) wordStep(0); }
 		}
 		const bool failed = st.status != GA_OK;
 		GA_TLAP(st, 3);
