@@ -316,3 +316,42 @@ def test_page_locked_input_is_used_in_place(api, golden_dir, name, monkeypatch):
         assert_same(r.as_dicts(), expected, name + " (pinned input, pipeline)")
         r.free()
     pipe.close()
+
+
+@pytest.mark.parametrize("budget", ["1", "3"])
+def test_seed_rounds_with_split_launches(api, golden_dir, budget, monkeypatch):
+    # reads with several seeds run in two rounds (first seed, then the seeds its alignment does not cover); with a tiny device
+    # budget each round is cut into several launches and the rounds' results are merged read by read - blocking call and pipeline
+    monkeypatch.setenv("GA_MEM_BUDGET_MB", budget)
+    for name in ("bubbles_multiseed", "seed_pos1"):
+        case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
+        expected = load_expected(os.path.join(golden_dir, name + ".expected"))
+        graph = api.Graph.from_case(case)
+        aligner = api.Aligner(graph)
+        res = aligner.align(case.reads, case.b, case.B)
+        assert_same(res.as_dicts(), expected, name)
+        assert aligner.stats()["launches"] > 8
+        res.free()
+        aligner.close()
+        pipe = api.Pipeline(graph, depth=2)
+        for r in pipe.align_all([api.PackedReads(case.reads, case.b, case.B)] * 2):
+            r.names = [x[0] for x in case.reads]
+            assert_same(r.as_dicts(), expected, name + " (pipeline)")
+            r.free()
+        pipe.close()
+
+
+def test_all_seeds_at_once_gives_the_same_results(api, golden_dir, tmp_path):
+    # the two-round seed loop against the one-round form (every seed aligned speculatively, the pruning replayed afterwards), in a
+    # fresh process because the switch is read once
+    import subprocess
+    import sys
+    script = ("import os, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+              "from graphaligner_b200 import api\nfrom graphaligner_b200.tools import gacase\nfrom helpers import assert_same, load_expected\n"
+              "case = gacase.read_case(%r); exp = load_expected(%r)\n"
+              "al = api.Aligner(api.Graph.from_case(case)); res = al.align(case.reads, case.b, case.B)\n"
+              "assert_same(res.as_dicts(), exp, 'one round'); print('streams', al.stats()['streams'])\n"
+              % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+                 os.path.join(golden_dir, "bubbles_multiseed.gacase"), os.path.join(golden_dir, "bubbles_multiseed.expected")))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=dict(os.environ, GA_ALL_SEEDS_AT_ONCE="1"))
+    assert r.returncode == 0, r.stderr[-800:]
