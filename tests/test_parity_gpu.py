@@ -330,7 +330,7 @@ def test_seed_rounds_with_split_launches(api, golden_dir, budget, monkeypatch):
         aligner = api.Aligner(graph)
         res = aligner.align(case.reads, case.b, case.B)
         assert_same(res.as_dicts(), expected, name)
-        assert aligner.stats()["launches"] > 8
+        assert aligner.stats()["launches"] >= 4   # more than one launch sequence (two rounds, each possibly split)
         res.free()
         aligner.close()
         pipe = api.Pipeline(graph, depth=2)
