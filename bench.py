@@ -180,7 +180,8 @@ def main():
     ap.add_argument("--parity-sample", type=int, default=None)
     ap.add_argument("--bands", type=str, default=None, help="comma-separated band widths instead of the config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stock-cpu", action="store_true", help="also time the stock-flags (asserts on) flavour of the reference on the cpu sample")
+    ap.add_argument("--no-stock-cpu", action="store_true", help="skip the stock-flags (asserts on, reference makefile:3) flavour of the reference on the cpu sample")
+    ap.add_argument("--stock-cpu", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--replicate", type=int, default=1, help="align R copies of the read set per step (batch-size study only; not the BASELINE config)")
     args = ap.parse_args()
 
@@ -481,7 +482,7 @@ def main():
                 else:
                     cpu_line = {"value": None, "unit": "bp/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/ref_align unavailable"}
             line["cpu_baseline"] = cpu_line
-            if args.stock_cpu:
+            if not args.no_stock_cpu and args.config == 2:
                 sample = min(len(reads), cfg["cpu"])
                 _, t = run_reference(case, reads[:sample], band0, cores, tmpdir, flavour="ref_align_stock")
                 line["cpu_baseline_stock"] = ({"value": t["aligned_bp"] / (t["wall_ms"] * 1e-3), "unit": "bp/s", "cores": cores, "kind": "reference",
