@@ -66,35 +66,93 @@ __constant__ GaHmmTables c_hmm;
 __constant__ GaUmapSchedule c_sched;
 
 #ifndef GA_HOSTSIM
-// Match masks for every 64-row slice of every stream: one block per stream, one thread per slice, 64 bytes in, 32 bytes out.
-__global__ void ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq,
-	uint32_t* __restrict__ peqAux)
+// Character table of the two pre-pass kernels in shared memory: IUPAC match mask (4 bits, 0 = a character the reference
+// aborts on) | exact code << 4, from the same two functions the rest of the code uses (ga_iupac_mask, ga_exact_code)
+__device__ __forceinline__ void ga_fill_char_table(uint8_t* tab)
 {
-	const uint32_t stream = blockIdx.x;
-	if (stream >= nStreams) return;
-	const ga_stream_in in = streams[stream];
-	const uint32_t nslices = in.partLen / 64;
-	for (uint32_t sl = threadIdx.x; sl < nslices; sl += blockDim.x)
+	for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) tab[c] = (uint8_t)(ga_iupac_mask((uint8_t)c) | (ga_exact_code((uint8_t)c) << 4));
+	__syncthreads();
+}
+
+// character i of a stream's part as ga_part_char gives it (mask, exact code), through the table
+__device__ __forceinline__ void ga_part_char_tab(const uint8_t* __restrict__ raw, const uint8_t* tab, const ga_stream_in& in, uint32_t real, uint32_t i, uint32_t& mask, uint32_t& code)
+{
+	if (i >= real) { mask = 15; code = 4; return; }
+	if (in.srcInfo & GA_SRC_BACKWARD)
 	{
-		uint64_t A, C, G, T;
-		ga_peq_words(parts, in, sl, A, C, G, T);
-		uint4* dst = peq + peqOff[stream] + (size_t)sl * 2;
-		dst[0] = make_uint4((uint32_t)A, (uint32_t)(A >> 32), (uint32_t)C, (uint32_t)(C >> 32));
-		dst[1] = make_uint4((uint32_t)G, (uint32_t)(G >> 32), (uint32_t)T, (uint32_t)(T >> 32));
-		peqAux[peqOff[stream] / 2 + sl] = ga_peq_aux(parts, in, sl);
+		const uint32_t m = tab[raw[in.seqOff - i]] & 15u;
+		mask = ((m & 1u) << 3) | ((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 8u) >> 3);
+		code = mask == 1 ? 0u : (mask == 2 ? 1u : (mask == 4 ? 2u : (mask == 8 ? 3u : 4u)));
+	}
+	else
+	{
+		const uint32_t t = tab[raw[in.seqOff + i]];
+		mask = t & 15u;
+		code = t >> 4;
 	}
 }
 
-// Reads the reference aborts on (a character outside its IUPAC switch, GraphAligner.h:2039-2110): one block per read
-__global__ void ga_validate_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ readOff, uint32_t nReads, uint32_t* __restrict__ bad)
+// Match masks for every 64-row slice of every stream (ga_peq_words / ga_peq_aux): one block per stream, one WARP per slice -
+// lane l reads characters l and l + 32 of the slice (two coalesced 32-byte rows of the read), the four match words are the
+// ballots of the characters' mask bits.  64 bytes in, 36 bytes out per slice.
+__global__ void __launch_bounds__(128) ga_peq_kernel(const ga_stream_in* __restrict__ streams, const uint64_t* __restrict__ peqOff, const uint8_t* __restrict__ parts, uint32_t nStreams, uint4* __restrict__ peq,
+	uint32_t* __restrict__ peqAux)
 {
+	__shared__ uint8_t tab[256];
+	ga_fill_char_table(tab);
+	const uint32_t stream = blockIdx.x;
+	if (stream >= nStreams) return;
+	const ga_stream_in in = streams[stream];
+	const uint32_t real = GA_SRC_LEN(in.srcInfo);
+	const uint32_t nslices = in.partLen / 64;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const uint64_t off = peqOff[stream];
+	uint32_t m0, c0;
+	ga_part_char_tab(parts, tab, in, real, 0, m0, c0);
+	for (uint32_t sl = warp; sl < nslices; sl += nwarps)
+	{
+		uint32_t ma, ca, mb, cb;
+		ga_part_char_tab(parts, tab, in, real, sl * 64 + lane, ma, ca);
+		ga_part_char_tab(parts, tab, in, real, sl * 64 + 32 + lane, mb, cb);
+		uint32_t w[8];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			w[2 * k] = __ballot_sync(0xffffffffu, (ma >> k) & 1u);
+			w[2 * k + 1] = __ballot_sync(0xffffffffu, (mb >> k) & 1u);
+		}
+		// the exact code of the character above the slice = the last character of the slice before (lane 31's second character)
+		const uint32_t prevCode = __shfl_sync(0xffffffffu, cb, 31);
+		if (lane == 0)
+		{
+			uint4* dst = peq + off + (size_t)sl * 2;
+			dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+			dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+			if (sl + 1 < nslices) peqAux[off / 2 + sl + 1] = prevCode | (m0 << 4);
+			if (sl == 0) peqAux[off / 2] = 4u | (m0 << 4);
+		}
+	}
+}
+
+// Reads the reference aborts on (a character outside its IUPAC switch, GraphAligner.h:2039-2110): one block per read, four
+// characters per thread and pass
+__global__ void __launch_bounds__(128) ga_validate_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ readOff, uint32_t nReads, uint32_t* __restrict__ bad)
+{
+	__shared__ uint8_t tab[256];
+	ga_fill_char_table(tab);
 	const uint32_t read = blockIdx.x;
 	if (read >= nReads) return;
 	const uint8_t* p = raw + readOff[read];
 	const uint64_t len = readOff[read + 1] - readOff[read];
-	uint32_t any = 0;
-	for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) any |= ga_iupac_mask(p[i]) == 0 ? 1u : 0u;
-	any = __syncthreads_or((int)any);
+	uint32_t ok = 15u;
+	uint64_t i = threadIdx.x;
+	for (; i + 3 * blockDim.x < len; i += 4 * blockDim.x)
+	{
+		const uint8_t a = p[i], b = p[i + blockDim.x], c = p[i + 2 * blockDim.x], d = p[i + 3 * blockDim.x];
+		ok = (tab[a] & 15u) && (tab[b] & 15u) && (tab[c] & 15u) && (tab[d] & 15u) ? ok : 0u;
+	}
+	for (; i < len; i += blockDim.x) ok = (tab[p[i]] & 15u) ? ok : 0u;
+	const int any = __syncthreads_or(ok == 0u ? 1 : 0);
 	if (threadIdx.x == 0) bad[read] = any ? 1u : 0u;
 }
 #endif
