@@ -59,6 +59,16 @@
 #define GA_ALT_CUTOFF 200000u   // GraphAlignerCommon.h:10
 #define GA_HDR_WORDS 12u        // slabOff, ncols, nodeOff, nNodes, minScore, flags, HMM state after the slice (2 doubles), last minimum cell (slot, column)
 #define GA_HN_WORDS 5u          // node, colStart, nodeMin, len, first sequence chunk (ga_node_rec::seqChunk)
+// flags word of a slice header (word 5): bit 0 CurrentlyCorrect, bit 1 FalseFromCorrect, and for -B ramp runs (ga_run_stream<.., RAMP>):
+#define GA_HF_ALT 4u            // the reference kept a sqrt checkpoint of this slice that is another instance of it than the one the
+                                // history holds: word 1 = header index of that instance (what the slice looks like from the slice below)
+#define GA_HF_RAMPBW 8u         // the slice ran with rampBandwidth (DPTable::bandwidthPerSlice)
+#define GA_HF_STALE 16u         // (checkpoint entries) the entry is not the instance the forward pass ended with
+// -B ramp runs keep the reference's sqrt checkpoints (DPTable::slices, GraphAligner.h:2772-2786) as copies of slice headers behind the
+// maxSlices headers of a stream: GA_CP_SLOTS stack entries, then the pending one (storeSlice); word 1 of an entry = slice index + 1
+#define GA_CP_EXTRA 8u
+#define GA_CP_SLOTS(maxSlices) ((maxSlices) + GA_CP_EXTRA)
+#define GA_HDR_SLOTS_RAMP(maxSlices) (2u * (maxSlices) + GA_CP_EXTRA + 1u)
 
 #ifdef GA_HOST_DEBUG
 static unsigned long long g_dbgFast = 0, g_dbgOuter = 0, g_dbgGeneral = 0, g_dbgNodeStart = 0, g_dbgRow0 = 0, g_dbgMerged = 0, g_dbgReload = 0, g_dbgLink = 0;
@@ -1703,7 +1713,7 @@ GA_DEV int ga_first_emitted_min_node(const ga_graph_view& g, const ga_caps& caps
 // slice and the cell the traceback starts from.  Reads the slice headers, node lists and columns from the history in
 // global memory; scratch: indeg, order, uorder, unext, ubkt (one entry per band node of a slice).
 // ------------------------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, bool RAMP = false>
 GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const GaLaneMem& mem, GaStreamState& st, bool active, uint32_t slicesRun, uint32_t debugFlags, ga_stream_out* out)
 {
 	// ---- end trimming, trace start, traceback.  No early returns: the traceback is a warp-wide loop --------------------
@@ -1749,7 +1759,8 @@ GA_DEV void ga_finish_stream(const ga_graph_view& g, const ga_caps& caps, const 
 			// trace start = minScoreIndex.back() of the last retained slice (GraphAligner.h:918-932): the highest tied column
 			// of the LAST evaluated node that attains the slice minimum.  Evaluation order = reverse of Tarjan's component
 			// emission order over the band (GraphAligner.h:1836-1856,2360), so the wanted node is the first one emitted.
-			const int sl = n - 1;
+			// (-B ramp: where the reference's last sqrt checkpoint is this very slice it starts from the checkpoint's instance of it)
+			const int sl = (RAMP && (GA_HDR(n - 1, 5) & GA_HF_ALT)) ? (int)GA_HDR(n - 1, 1) : n - 1;
 			const int32_t minScore = (int32_t)GA_HDR(sl, 4);
 			const uint32_t nodeOff = GA_HDR(sl, 2), nNodes = GA_HDR(sl, 3), slabOff = GA_HDR(sl, 0);
 			uint32_t nTies = 0;
@@ -1858,7 +1869,15 @@ GA_DEV uint32_t ga_peq_aux(const uint8_t* raw, const ga_stream_in& in, uint32_t 
 // Whole stream, forward part: slices (lock step across the warp), end trimming, tie list, trace start.
 // `active` = this lane holds a stream.  warpColTop is the warp-uniform bump pointer into the column slab.
 // ------------------------------------------------------------------------------------------------------------
-template <int LANES, bool SMALL>
+// RAMP (-B > -b, general layout only): the stream also keeps the reference's sqrt checkpoints.  The reference traces back
+// through slices it RE-COMPUTES from those checkpoints (getSlicesFromTable, GraphAligner.h:2858-2943), and after a ramp redo
+// its pending checkpoint (storeSlice) can be a slice of the abandoned narrow-band pass: the stretch behind such a checkpoint
+// is then re-computed from the abandoned slice's end state and differs from what the forward pass found.  To return what the
+// reference returns, the checkpoint stack is replayed here (same pushes and pops), and after the forward pass the stretch
+// behind every checkpoint that is not the final instance of its slice is computed again from that checkpoint (second phase of
+// the slice loop); the traceback (ga_trace.cuh, ALT) then sees each slice as the reference does: its re-computed instance
+// when it walks through it, the checkpoint's instance when it looks up from the slice below.
+template <int LANES, bool SMALL, bool RAMP = false>
 GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaHmmTables& hmm, const GaUmapSchedule& sch, const GaLaneMem& mem, bool active,
 	const ga_stream_in* in, const uint32_t* peqAux, int initialBandwidth, int rampBandwidth, uint32_t debugFlags, ga_stream_out* out)
 {
@@ -1907,16 +1926,125 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		}
 	}
 	// per-lane slice cursor and ramp state (GraphAligner.h:2602-2719); the warp iterates until every lane is done
+	static_assert(!(RAMP && SMALL), "the checkpoint replay uses the general layout");
 	int ls = 0;
 	int rampUntil = 0, rampRedoIndex = -1;
 	uint32_t gen = 1;          // stamp generator for the node -> slot tables (stamp 1 = the initial slice in table 0)
 	int tp = 0;                // table holding the previous slice
 	uint32_t stampPrev = 1;
 	uint32_t maskPrev = ga_hash_window(1, caps.hashSize);
+	// RAMP: the reference's checkpoint stack (DPTable::slices) and pending checkpoint (storeSlice), GraphAligner.h:2597,2772-2786
+	const uint32_t cpBase = caps.maxSlices, cpPending = caps.maxSlices + GA_CP_SLOTS(caps.maxSlices);
+	uint32_t cpN = 0;
+	int storeS = -1;                 // slice of the pending checkpoint (-1: the initial slice)
+	uint32_t storeMem = 28;          // its EstimatedMemoryUsage (GraphAligner.h:136-139): 4 B per column + 28 B per node; initial slice: no cells counted
+	uint32_t sampF = 1;              // getSamplingFrequency, GraphAligner.h:2962-2967
+	if (RAMP) while ((sampF + 1) * (sampF + 1) <= st.nslices) sampF++;
+	int phase = 0;                   // 0 = forward pass, 1 = stretches behind stale checkpoints
+	int nKept = 0;                   // slices left by removeWronglyAlignedEnd
+	uint32_t rk = 0;                 // phase 1: checkpoint whose stretch [ls, segEnd) is being computed
+	int segStart = 0, segEnd = 0;
+#define GA_CP_S(k) ((int)GA_HDR(cpBase + (k), 1) - 1)
+	// the previous slice becomes the instance with header h again: state from the header, tables rebuilt from its columns
+	auto loadPrevState = [&](uint32_t h)
+	{
+		st.prevMin = (int32_t)GA_HDR(h, 4);
+		uint64_t c = (uint64_t)GA_HDR(h, 6) | ((uint64_t)GA_HDR(h, 7) << 32);
+		uint64_t f = (uint64_t)GA_HDR(h, 8) | ((uint64_t)GA_HDR(h, 9) << 32);
+		st.hmmC = ga_bits_to_double(c);
+		st.hmmF = ga_bits_to_double(f);
+		pNodeOff = GA_HDR(h, 2);
+		pNodes = GA_HDR(h, 3);
+	};
+	auto rebuildPrevTables = [&](uint32_t h)
+	{
+		stampPrev = ++gen;
+		maskPrev = ga_hash_window(pNodes, caps.hashSize);
+		const uint32_t tSlab = GA_HDR(h, 0);
+		for (uint32_t i = 0; i < pNodes; i++)
+		{
+			ga_hash_insert<LANES>(mem.hash[tp], maskPrev, stampPrev, GA_HN(pNodeOff + i, 0), i);
+			const uint32_t cs = GA_HN(pNodeOff + i, 1), len = GA_HN(pNodeOff + i, 3);
+			for (uint32_t k = 0; k < len; k++)
+			{
+				GaCol c = ga_col_load<LANES>(mem, tSlab + cs + k);
+				ga_tiny_st<LANES, SMALL>(mem.tiny[tp], cs + k, ga_tiny_pack(c, false));
+			}
+		}
+	};
+	// phase 1: the next checkpoint from k on that is stale and has slices behind it; false = none left (then every slice whose
+	// checkpoint is another instance than the history's gets its GA_HF_ALT reference)
+	auto nextStretch = [&](uint32_t k) -> bool
+	{
+		for (; k < cpN; k++)
+		{
+			if (!(GA_HDR(cpBase + k, 5) & GA_HF_STALE)) continue;
+			const int from = GA_CP_S(k) + 1, to = (k + 1 == cpN) ? nKept : GA_CP_S(k + 1) + 1;
+			if (to <= from) continue;
+			rk = k; segStart = from; segEnd = to; ls = from;
+			loadPrevState(cpBase + k);
+			rebuildPrevTables(cpBase + k);
+			return true;
+		}
+		for (k = 1; k < cpN; k++)
+		{
+			const int cs = GA_CP_S(k);
+			if (GA_HDR(cpBase + k, 0) != GA_HDR(cs, 0)) { GA_HDR(cs, 5) |= GA_HF_ALT; GA_HDR(cs, 1) = cpBase + k; }
+		}
+		return false;
+	};
 	while (true)
 	{
 		GA_TLAP(st, 5);
-		bool run = !st.done && (uint32_t)ls < st.nslices;
+		if (RAMP)
+		{
+			if (phase == 0 && (st.done || (uint32_t)ls >= st.nslices))
+			{
+				// the forward pass of this lane is over: removeWronglyAlignedEnd on the checkpoints (GraphAligner.h:2554-2569), then
+				// the reference's walk over them (getTraceFromTable, GraphAligner.h:918-941)
+				phase = 1;
+				st.done = true;
+				if (active && st.status == GA_OK && st.rampRedos > 0 && cpN > 0)
+				{
+					nKept = (int)st.slicesPushed;
+					if (nKept > 0)
+					{
+						bool currentlyCorrect = (GA_HDR(nKept - 1, 5) & 1u) != 0;
+						while (!currentlyCorrect)
+						{
+							nKept--;
+							if (nKept == 0) break;
+							currentlyCorrect = (GA_HDR(nKept - 1, 5) & 2u) != 0;
+						}
+					}
+					if (nKept > 0)
+					{
+						while (cpN > 1 && GA_CP_S(cpN - 1) >= nKept) cpN--;
+						// checkpoints out of order: the reference re-computes an empty stretch and reads its first slice (it crashes)
+						bool ordered = true, anyStale = false;
+						for (uint32_t k = 1; k < cpN; k++)
+						{
+							if (GA_CP_S(k) <= GA_CP_S(k - 1)) ordered = false;
+						}
+						if (!ordered) st.status = GA_ERR_TRACE;
+						else
+						{
+							for (uint32_t k = 1; k < cpN; k++)
+							{
+								const bool stale = GA_HDR(cpBase + k, 0) != GA_HDR(GA_CP_S(k), 0);
+								if (stale) { GA_HDR(cpBase + k, 5) |= GA_HF_STALE; anyStale = true; }
+							}
+							if (anyStale && nextStretch(1)) st.done = false;
+						}
+					}
+				}
+			}
+			else if (phase == 1 && !st.done && ls >= segEnd)
+			{
+				if (!nextStretch(rk + 1)) st.done = true;
+			}
+		}
+		bool run = !st.done && ((RAMP && phase == 1) || (uint32_t)ls < st.nslices);
 		if (!GA_WARP_ANY(run)) break;
 		const int s = ls;
 		const int tc = tp ^ 1;
@@ -1925,6 +2053,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		uint32_t ncols = 0;
 		int nc = 0;
 		uint32_t nodeOff = st.histNodeTop;
+		int bandwidth = initialBandwidth;
 		if (run)
 		{
 			if (gen >= 0xfffeu) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; run = false; }
@@ -1932,7 +2061,9 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			{
 				stampCur = ++gen;
 				// slices up to rampUntil run with rampBandwidth; rampUntil starts at 0, so slice 0 always does (GraphAligner.h:2612)
-				int bandwidth = (rampUntil >= s) ? rampBandwidth : initialBandwidth;
+				bandwidth = (rampUntil >= s) ? rampBandwidth : initialBandwidth;
+				// a re-computed slice runs with the bandwidth its final instance ran with (bandwidthPerSlice, GraphAligner.h:2896)
+				if (RAMP && phase == 1) bandwidth = (GA_HDR(s, 5) & GA_HF_RAMPBW) ? rampBandwidth : initialBandwidth;
 				nc = ga_select_band<LANES, SMALL>(g, caps, sch, mem, st, bandwidth, pNodeOff, pNodes, mem.tiny[tp], mem.hash[tp], maskPrev, stampPrev, mem.hash[tc], maskCur, stampCur, gen, nodeOff, ncols);
 				if (nc <= 0) { if (st.status == GA_OK) st.status = GA_ERR_INTERNAL; st.done = true; run = false; ncols = 0; }
 			}
@@ -1957,7 +2088,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		cx.pNodes = pNodes;
 		cx.slabOff = (uint32_t)slabOff;
 		cx.hasPrevSlab = s > 0;
-		cx.pSlabOff = s > 0 ? GA_HDR(s - 1, 0) : 0;
+		cx.pSlabOff = s > 0 ? GA_HDR((RAMP && phase == 1 && s == segStart) ? cpBase + rk : (uint32_t)(s - 1), 0) : 0;
 		cx.tinyCur = mem.tiny[tc];
 		cx.tinyPrev = mem.tiny[tp];
 		cx.tinyRef = st.prevMin;
@@ -1973,6 +2104,22 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		GA_HDR(s, 3) = (uint32_t)nc;
 		GaSliceResult res;
 		if (!ga_fill_slice<LANES, SMALL>(g, caps, hmm, mem, st, cx, ncols, res)) { st.done = true; continue; }
+		if (RAMP && phase == 1)
+		{
+			// a re-computed slice replaces the history's instance; the stop and ramp rules do not apply (GraphAligner.h:2893-2935)
+			st.hmmC = res.hmmC;
+			st.hmmF = res.hmmF;
+			st.prevMin = res.minScore;
+			GA_HDR(s, 4) = (uint32_t)res.minScore;
+			pNodeOff = nodeOff;
+			pNodes = (uint32_t)nc;
+			st.histNodeTop = nodeOff + (uint32_t)nc;
+			tp = tc;
+			stampPrev = stampCur;
+			maskPrev = maskCur;
+			ls = s + 1;
+			continue;
+		}
 		// remember where a ramp would restart from (GraphAligner.h:2630-2634)
 		if (rampUntil == s - 1 || (rampUntil < s && res.currentlyCorrect && res.falseFromCorrect)) rampRedoIndex = s - 1;
 		if (!res.correctFromCorrect) { st.done = true; continue; }   // GraphAligner.h:2640-2647: stop, slice not recorded
@@ -1985,15 +2132,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 			st.rampRedos++;
 			if (target < 0) { st.status = GA_ERR_INTERNAL; st.done = true; continue; }
 			// the previous slice becomes slice `target` again: state from its header, tables rebuilt from the history
-			st.prevMin = (int32_t)GA_HDR(target, 4);
-			{
-				uint64_t c = (uint64_t)GA_HDR(target, 6) | ((uint64_t)GA_HDR(target, 7) << 32);
-				uint64_t f = (uint64_t)GA_HDR(target, 8) | ((uint64_t)GA_HDR(target, 9) << 32);
-				st.hmmC = ga_bits_to_double(c);
-				st.hmmF = ga_bits_to_double(f);
-			}
-			pNodeOff = GA_HDR(target, 2);
-			pNodes = GA_HDR(target, 3);
+			loadPrevState((uint32_t)target);
 			st.histNodeTop = nodeOff + (uint32_t)nc;   // abandoned entries are simply left behind
 			if (SMALL)
 			{
@@ -2002,21 +2141,9 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 				st.histNodeTop += (pNodeOff + pNodes - st.histNodeTop) & (GA_HN_RING - 1u);
 			}
 			st.slicesPushed = (uint32_t)target + 1;
-			stampPrev = ++gen;
-			maskPrev = ga_hash_window(pNodes, caps.hashSize);
-			{
-				const uint32_t tSlab = GA_HDR(target, 0);
-				for (uint32_t i = 0; i < pNodes; i++)
-				{
-					ga_hash_insert<LANES>(mem.hash[tp], maskPrev, stampPrev, GA_HN(pNodeOff + i, 0), i);
-					const uint32_t cs = GA_HN(pNodeOff + i, 1), len = GA_HN(pNodeOff + i, 3);
-					for (uint32_t k = 0; k < len; k++)
-					{
-						GaCol c = ga_col_load<LANES>(mem, tSlab + cs + k);
-						ga_tiny_st<LANES, SMALL>(mem.tiny[tp], cs + k, ga_tiny_pack(c, false));
-					}
-				}
-			}
+			rebuildPrevTables((uint32_t)target);
+			// the checkpoints behind the restart point go, the pending one stays (GraphAligner.h:2667)
+			if (RAMP) while (cpN > 1 && GA_CP_S(cpN - 1) > target) cpN--;
 			ls = target + 1;
 			continue;
 		}
@@ -2029,13 +2156,36 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		st.hmmF = res.hmmF;
 		st.prevMin = res.minScore;
 		GA_HDR(s, 4) = (uint32_t)res.minScore;
-		GA_HDR(s, 5) = (res.currentlyCorrect ? 1u : 0u) | (res.falseFromCorrect ? 2u : 0u);
+		GA_HDR(s, 5) = (res.currentlyCorrect ? 1u : 0u) | (res.falseFromCorrect ? 2u : 0u) | ((RAMP && bandwidth == rampBandwidth) ? GA_HF_RAMPBW : 0u);
 		{
 			uint64_t c = ga_double_to_bits(res.hmmC), f = ga_double_to_bits(res.hmmF);
 			GA_HDR(s, 6) = (uint32_t)c; GA_HDR(s, 7) = (uint32_t)(c >> 32);
 			GA_HDR(s, 8) = (uint32_t)f; GA_HDR(s, 9) = (uint32_t)(f >> 32);
 		}
 		st.slicesPushed = (uint32_t)s + 1;
+		if (RAMP)
+		{
+			// checkpoints (GraphAligner.h:2772-2786): at a sampling point the pending one is pushed unless it is the slice on top of the
+			// stack, and this slice becomes pending; any slice cheaper to keep than the pending one replaces it
+			const uint32_t memUse = 4u * ncols + 28u * (uint32_t)nc;
+			bool capture = false;
+			if ((uint32_t)s % sampF == 0 && (cpN == 0 || storeS != GA_CP_S(cpN - 1)))
+			{
+				if (cpN >= GA_CP_SLOTS(caps.maxSlices)) { st.status = GA_ERR_HIST_OVERFLOW; st.done = true; continue; }
+				if (storeS >= 0) for (uint32_t f = 0; f < GA_HDR_WORDS; f++) GA_HDR(cpBase + cpN, f) = GA_HDR(cpPending, f);
+				else for (uint32_t f = 0; f < GA_HDR_WORDS; f++) GA_HDR(cpBase + cpN, f) = 0;
+				cpN++;
+				capture = true;
+			}
+			if (capture || memUse < storeMem)
+			{
+				for (uint32_t f = 0; f < GA_HDR_WORDS; f++) GA_HDR(cpPending, f) = GA_HDR(s, f);
+				GA_HDR(cpPending, 1) = (uint32_t)s + 1;
+				GA_HDR(cpPending, 5) &= ~(GA_HF_STALE | GA_HF_ALT);
+				storeS = s;
+				storeMem = memUse;
+			}
+		}
 		pNodeOff = nodeOff;
 		pNodes = (uint32_t)nc;
 		st.histNodeTop = nodeOff + (uint32_t)nc;
@@ -2044,7 +2194,8 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		maskPrev = maskCur;
 		ls = s + 1;
 	}
-	ga_finish_stream<LANES>(g, caps, mem, st, active, slicesRun, debugFlags, out);
+#undef GA_CP_S
+	ga_finish_stream<LANES, RAMP>(g, caps, mem, st, active, slicesRun, debugFlags, out);
 }
 
 #endif

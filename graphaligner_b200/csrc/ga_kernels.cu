@@ -226,7 +226,7 @@ static __host__ __device__ inline void setupLaneMem(GaLaneMem& mem, const Scratc
 // S = streams per warp (lanes S..31 idle).  Small batches run with small S: more warps to hide latency and
 // less divergence; big batches run with S = 32 for full lane utilisation.
 #ifndef GA_HOSTSIM
-template <int S, bool SMALL>
+template <int S, bool SMALL, bool RAMP = false>
 __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs,
 	const ga_stream_in* __restrict__ streams, uint32_t nStreams, int initialBandwidth, int rampBandwidth, uint32_t debugFlags,
 	ga_stream_out* __restrict__ outs)
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(64, 10) ga_forward_kernel(ga_graph_view g, ga_
 	setupLaneMem(mem, sp, wd, caps, warp, ml, S, SMALL, ws, eqTab);
 	mem.peq = active ? sp.peq + sp.peqOff[stream] : nullptr;
 	ga_stream_out* out = active ? outs + stream : nullptr;
-	ga_run_stream<S, SMALL>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, active ? sp.peqAux + sp.peqOff[stream] / 2 : nullptr, initialBandwidth, rampBandwidth, debugFlags, out);
+	ga_run_stream<S, SMALL, RAMP>(g, wc, c_hmm, c_sched, mem, active, active ? streams + stream : nullptr, active ? sp.peqAux + sp.peqOff[stream] / 2 : nullptr, initialBandwidth, rampBandwidth, debugFlags, out);
 }
 #endif
 
@@ -326,7 +326,7 @@ static __host__ __device__ inline GaTraceMem traceMemOf(const ScratchPtrs& sp, c
 #ifndef GA_TRACE_MINBLOCKS
 #define GA_TRACE_MINBLOCKS 12   /* blocks per SM the traceback kernel's register budget must allow: 12 = 170 registers (it uses 168), one wave of 1667 six-stream warps on 148 SMs; measured: 16 blocks (128 registers) 6.1 ms, 14 (146) 6.2 ms, 12 (168) 5.3 ms at T = 6 */
 #endif
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_graph_view g, ScratchPtrs sp, const WarpDesc* __restrict__ warpDescs, const ga_stream_in* __restrict__ streams,
 	uint32_t nStreams, uint32_t S, ga_stream_out* __restrict__ outs, uint32_t* __restrict__ arena, unsigned long long* arenaTop, unsigned long long arenaCap)
 {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(32, GA_TRACE_MINBLOCKS) ga_trace_kernel(ga_gra
 	L.in = have ? streams + stream : streams;
 	if (have) L.tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
 	ga_trace_init(L, doTrace, doTrace ? out->nSlices : 0, doTrace ? out->endNode : 0, doTrace ? out->endOff : 0, doTrace ? out->score : 0);
-	ga_trace_warp<T, P>(g, sh, lane, &L, S);
+	ga_trace_warp<T, P, ALT>(g, sh, lane, &L, S);
 	// compact the streams' trace records into the arena: the warp copies one stream's record at a time, 32 words per step
 	const GaTraceMem& tm = L.tm;
 	const uint32_t nMoves = L.t.nMoves, nPath = L.t.nPath, nRuns = L.t.nRuns;
@@ -487,7 +487,8 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 		std::fill(ws.begin(), ws.end(), 0ull);
 		setupLaneMem(mem, sp, wd, caps, w, 0, S, false, ws.data(), eqTab.data());
 		mem.peq = sp.peq + sp.peqOff[stream];
-		ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, sp.peqAux + sp.peqOff[stream] / 2, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+		if (rampBandwidth > initialBandwidth) ga_run_stream<1, false, true>(g, wc, c_hmm, c_sched, mem, true, streams + stream, sp.peqAux + sp.peqOff[stream] / 2, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
+		else ga_run_stream<1, false>(g, wc, c_hmm, c_sched, mem, true, streams + stream, sp.peqAux + sp.peqOff[stream] / 2, initialBandwidth, rampBandwidth, debugFlags, outs + stream);
 	}
 	// the traceback "launch": the same warp code with its lanes as loops, HT streams per "warp"
 	const int HT = 4, HP = 1;
@@ -508,7 +509,8 @@ static void hostsim_align(ga_graph_view g, ga_caps caps, ScratchPtrs sp, const W
 			if (have) lanes[l].tm = traceMemOf(sp, warpDescs[stream / S], stream, S);
 			ga_trace_init(lanes[l], doTrace[l], doTrace[l] ? out->nSlices : 0, doTrace[l] ? out->endNode : 0, doTrace[l] ? out->endOff : 0, doTrace[l] ? out->score : 0);
 		}
-		ga_trace_warp<HT, HP>(g, sh, 0, lanes, S);
+		if (rampBandwidth > initialBandwidth) ga_trace_warp<HT, HP, true>(g, sh, 0, lanes, S);
+		else ga_trace_warp<HT, HP>(g, sh, 0, lanes, S);
 		for (int l = 0; l < HT; l++)
 		{
 			const uint32_t stream = first + l;
@@ -1041,7 +1043,8 @@ static void layoutAndUpload(DeviceCtx* ctx, StagedBatch* sb, BatchStats* stats)
 		d.maxPathNodes = (uint32_t)std::min<uint64_t>(0x7fffffffu, (uint64_t)(maxLen * 1.3 / avgNodeLen * 2.0 * scale) + 64);
 		d.maxRuns = d.maxPathNodes + 2;
 		d.hdrBase = hdrTop;
-		hdrTop += (uint64_t)d.maxSlices * GA_HDR_WORDS * S;
+		// (-B ramp: the checkpoint copies behind the slice headers, ga_core.cuh GA_CP_SLOTS)
+		hdrTop += (uint64_t)(sb->B > sb->b ? GA_HDR_SLOTS_RAMP(d.maxSlices) : d.maxSlices) * GA_HDR_WORDS * S;
 		d.hnBase = hnTop;
 		hnTop += (uint64_t)d.histNodes * GA_HN_WORDS * S;
 		d.movesBase = movesTop;
@@ -1149,11 +1152,14 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 	const int threads = 64;
 	const unsigned blocks = (unsigned)((sb->nWarps * 32 + threads - 1) / threads);
 	const size_t smemBytes = (size_t)(threads / 32) * 4 * S * sizeof(unsigned long long);
-	ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+	// -B ramp: the instantiation that also replays the reference's sqrt checkpoints (ga_run_stream<.., RAMP>)
+	if (sb->B > sb->b) ga_forward_kernel<S, false, true><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+	else ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
 		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
 }
 
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 static void launchTraceTP(DeviceCtx* ctx, StagedBatch* sb)
 {
 	const size_t n = sb->sorted.size();
@@ -1161,10 +1167,10 @@ static void launchTraceTP(DeviceCtx* ctx, StagedBatch* sb)
 	const uint64_t bit = 1ull << (ctx->device & 63);
 	if (!(attrDone.load() & bit))
 	{
-		GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<T, P>)));
+		GA_CUDA(cudaFuncSetAttribute(ga_trace_kernel<T, P, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaTraceShared<T, P>)));
 		attrDone.fetch_or(bit);
 	}
-	ga_trace_kernel<T, P><<<(unsigned)((n + T - 1) / T), 32, sizeof(GaTraceShared<T, P>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n,
+	ga_trace_kernel<T, P, ALT><<<(unsigned)((n + T - 1) / T), 32, sizeof(GaTraceShared<T, P>), ctx->stream>>>(ctx->view, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (uint32_t)n,
 		(uint32_t)sb->S, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 }
 
@@ -1174,6 +1180,8 @@ static void launchTrace(DeviceCtx* ctx, StagedBatch* sb)
 	// 12 warps per SM): 10 000 streams 5.3 ms at T = 6 (one wave), 7.0 at 8, 8.9 at 5 (two waves); 28 000 streams in waves
 	// 13.2 ms at T = 8, 14.8 at 6, 18.1 at 16, 28.3 at 32.
 	const size_t n = sb->sorted.size();
+	// -B ramp: the walk that tells a slice's checkpoint instance from its re-computed one (ga_trace.cuh, ALT)
+	if (sb->B > sb->b) { launchTraceTP<8, 1, true>(ctx, sb); return; }
 	int T = ctx->traceT;
 	if (T == 0)
 	{

@@ -147,9 +147,13 @@ GA_DEV int ga_tr_find(const GaTraceMem& tm, uint32_t nodeOff, uint32_t nNodes, u
 
 // value of (node, off) at `row` of slice s, or `maxv` when the node is not in that slice's band
 // (getValueOrMax, GraphAligner.h:2008-2017).  s == -1 is the initial slice: seed node = 0, else maxv.
+// ALT (-B ramp runs, ga_run_stream<.., RAMP>): seen from the slice below, a slice is the instance the reference kept as a sqrt
+// checkpoint (GA_HF_ALT: header index in word 1), which after a ramp redo need not be the instance the walk goes through.
+template <bool ALT = false>
 GA_DEV int32_t ga_tr_value(const GaTraceMem& tm, uint32_t startNode, int s, uint32_t node, uint32_t off, int row, int32_t maxv)
 {
 	if (s < 0) return node == startNode ? 0 : maxv;
+	if (ALT && (GA_TR_HDR(s, 5) & GA_HF_ALT)) s = (int)GA_TR_HDR(s, 1);
 	const uint32_t nodeOff = GA_TR_HDR(s, 2), nNodes = GA_TR_HDR(s, 3);
 	const int slot = ga_tr_find(tm, nodeOff, nNodes, node);
 	if (slot < 0) return maxv;
@@ -174,6 +178,7 @@ struct GaTraceState
 	int upSlice;                 // slice whose band the up table holds (-1: none)
 	uint32_t upNodeOff, upNodes, upSlab;
 	bool upCached;
+	bool upAlt;                  // ALT: the up table holds the checkpoint instance of the slice above, not the one to walk through
 	int hintSlice, hintSlot;     // band slot (or -1) of node hintNode in slice hintSlice, as found in that slice's cached table
 	uint32_t hintNode;
 	bool locate;                 // node changed without a link: look it up in the slice's band again
@@ -208,18 +213,20 @@ GA_DEV uint32_t ga_tr_node_base(const ga_graph_view& g, GaTraceState& t, uint32_
 
 // end score (row 63) of column `off` of `node` in the slice above the lane's, or maxv when the node is not in that band
 // (getValueOrMax on the previous slice, GraphAligner.h:2008-2017); the band comes from the up table in shared memory
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 GA_DEV int32_t ga_tr_up_end(const GaTraceMem& tm, GaTraceShared<T, P>& sh, uint32_t lane, GaTraceState& t, uint32_t startNode, uint32_t node, uint32_t off, int32_t maxv)
 {
 	if (t.s <= 0) return node == startNode ? 0 : maxv;
-	if (!t.upCached || t.upSlice != t.s - 1) return ga_tr_value(tm, startNode, t.s - 1, node, off, 63, maxv);
+	if (!t.upCached || t.upSlice != t.s - 1) return ga_tr_value<ALT>(tm, startNode, t.s - 1, node, off, 63, maxv);
 	int slot = t.hintSlot;
 	if (t.hintSlice != t.s - 1 || t.hintNode != node)
 	{
 		// (slice, node) -> slot is remembered: the walk asks for two columns of a node, then usually moves up into it
 		slot = -1;
 		for (uint32_t i = 0; i < t.upNodes; i++) if (sh.upId[i][lane] == node) slot = (int)i;
-		t.hintSlice = t.s - 1;
+		// (a slot of the checkpoint instance's band says nothing about the instance to walk through: the hint is kept under a
+		// slice number no walk is ever in)
+		t.hintSlice = (ALT && t.upAlt) ? -3 : t.s - 1;
 		t.hintNode = node;
 		t.hintSlot = slot;
 	}
@@ -407,7 +414,7 @@ GA_DEV void ga_tr_walk(GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLane& L, i
 
 // GENERAL step of one stream lane (node starts, slice borders, merged columns): the reference's candidates from the stored
 // columns' cell values.  Leaves t.s decremented when the walk went up a slice.
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 GA_DEV void ga_tr_general(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLane& L)
 {
 	const GaTraceMem& tm = L.tm;
@@ -450,8 +457,8 @@ GA_DEV void ga_tr_general(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint3
 			else
 			{
 				// row 63 of the slice above; a node's columns are contiguous there too
-				ds = ga_tr_up_end<T, P>(tm, sh, lane, t, startNode, node, off - 1, maxv);
-				us = ga_tr_up_end<T, P>(tm, sh, lane, t, startNode, node, off, maxv);
+				ds = ga_tr_up_end<T, P, ALT>(tm, sh, lane, t, startNode, node, off - 1, maxv);
+				us = ga_tr_up_end<T, P, ALT>(tm, sh, lane, t, startNode, node, off, maxv);
 			}
 			if (hs == here - 1) { move = GA_MOVE_H; noff = off - 1; }
 			else if (ds == diagWant) { move = GA_MOVE_D; noff = off - 1; }
@@ -482,7 +489,7 @@ GA_DEV void ga_tr_general(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint3
 				const int32_t hs = uslot >= 0 ? ga_col_value(uc.VP, uc.VN, uc.sbs, row) : maxv;
 				if (hs == here - 1) { move = GA_MOVE_H; nnode = u; noff = uoff; break; }
 				int32_t ds;
-				if (row == 0) ds = ga_tr_up_end<T, P>(tm, sh, lane, t, startNode, u, uoff, maxv);
+				if (row == 0) ds = ga_tr_up_end<T, P, ALT>(tm, sh, lane, t, startNode, u, uoff, maxv);
 				else ds = uslot >= 0 ? ga_col_value(uc.VP, uc.VN, uc.sbs, row - 1) : maxv;
 				if (ds == diagWant) { move = GA_MOVE_D; nnode = u; noff = uoff; break; }
 			}
@@ -490,7 +497,7 @@ GA_DEV void ga_tr_general(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint3
 			{
 				int32_t us;
 				if (row > 0) us = here - (int32_t)((cur.VP >> row) & 1) + (int32_t)((cur.VN >> row) & 1);
-				else us = ga_tr_up_end<T, P>(tm, sh, lane, t, startNode, node, off, maxv);
+				else us = ga_tr_up_end<T, P, ALT>(tm, sh, lane, t, startNode, node, off, maxv);
 				if (us == here - 1) { move = GA_MOVE_V; }
 			}
 		}
@@ -598,7 +605,7 @@ GA_DEV void ga_tr_fill_masks(GaTraceShared<T, P>& sh, uint32_t j, uint32_t e)
 
 // Entering slice sw (one stream lane): its header, match words and node list (already here when the lane came down from
 // the slice below: it was that slice's up table), then the tables of the slice above.
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 GA_DEV void ga_tr_enter_slice(GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLane& L, int sw)
 {
 	const GaTraceMem& tm = L.tm;
@@ -609,7 +616,7 @@ GA_DEV void ga_tr_enter_slice(GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLan
 		sh.peq[k * 2][lane] = (uint64_t)q.x | ((uint64_t)q.y << 32);
 		sh.peq[k * 2 + 1][lane] = (uint64_t)q.z | ((uint64_t)q.w << 32);
 	}
-	const bool fromUp = t.upSlice == sw;
+	const bool fromUp = t.upSlice == sw && !(ALT && t.upAlt);
 	if (fromUp) { t.sSlab = t.upSlab; t.sNodeOff = t.upNodeOff; t.sNodes = t.upNodes; t.sCached = t.upCached; }
 	else
 	{
@@ -619,7 +626,16 @@ GA_DEV void ga_tr_enter_slice(GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLan
 		t.sCached = t.sNodes <= GA_TR_NODES;
 	}
 	uint32_t upSlab = 0, upNodeOff = 0, upNodes = 0;
-	if (sw > 0) { upSlab = GA_TR_HDR(sw - 1, 0); upNodeOff = GA_TR_HDR(sw - 1, 2); upNodes = GA_TR_HDR(sw - 1, 3); }
+	if (sw > 0)
+	{
+		uint32_t uh = (uint32_t)(sw - 1);
+		if (ALT)
+		{
+			t.upAlt = (GA_TR_HDR(uh, 5) & GA_HF_ALT) != 0;
+			if (t.upAlt) uh = GA_TR_HDR(uh, 1);
+		}
+		upSlab = GA_TR_HDR(uh, 0); upNodeOff = GA_TR_HDR(uh, 2); upNodes = GA_TR_HDR(uh, 3);
+	}
 	if (t.sCached)
 	{
 		for (uint32_t i = 0; i < t.sNodes; i++)
@@ -675,7 +691,7 @@ GA_DEV void ga_tr_enter_slice(GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLan
 
 // Walks the T streams of a warp.  Device: called by all 32 lanes, lanes[0] is the calling lane's stream (lanes >= T have
 // none and only help with the windows).  Host: lanes[0..T).
-template <int T, int P>
+template <int T, int P, bool ALT = false>
 GA_DEV void ga_trace_warp(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint32_t lane, GaTraceLane* lanes, size_t S)
 {
 	(void)lane;
@@ -699,7 +715,7 @@ GA_DEV void ga_trace_warp(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint3
 		GA_TR_EACH(l)
 		{
 			GaTraceLane& L = GA_TR_LANE(l);
-			if (L.t.walking && L.t.s == sw) ga_tr_enter_slice<T, P>(sh, l, L, sw);
+			if (L.t.walking && L.t.s == sw) ga_tr_enter_slice<T, P, ALT>(sh, l, L, sw);
 		}
 		GA_SYNCWARP();
 		GA_TR_COUNT(slices);
@@ -734,7 +750,7 @@ GA_DEV void ga_trace_warp(const ga_graph_view& g, GaTraceShared<T, P>& sh, uint3
 				GA_TR_EACH(l)
 				{
 					GaTraceLane& L = GA_TR_LANE(l);
-					if (L.t.needGen) ga_tr_general<T, P>(g, sh, l, L);
+					if (L.t.needGen) ga_tr_general<T, P, ALT>(g, sh, l, L);
 				}
 			}
 			GA_SYNCWARP();
@@ -772,6 +788,7 @@ GA_DEV void ga_trace_init(GaTraceLane& L, bool doTrace, int nSlices, uint32_t no
 	t.upSlice = -1;
 	t.upNodeOff = t.upNodes = t.upSlab = 0;
 	t.upCached = false;
+	t.upAlt = false;
 	t.hintSlice = -2;
 	t.hintSlot = -1;
 	t.hintNode = 0;
