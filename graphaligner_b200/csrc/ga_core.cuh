@@ -1989,7 +1989,7 @@ GA_DEV void ga_run_stream(const ga_graph_view& g, const ga_caps& caps, const GaH
 		for (k = 1; k < cpN; k++)
 		{
 			const int cs = GA_CP_S(k);
-			if (GA_HDR(cpBase + k, 0) != GA_HDR(cs, 0)) { GA_HDR(cs, 5) |= GA_HF_ALT; GA_HDR(cs, 1) = cpBase + k; }
+			if (GA_HDR(cpBase + k, 0) != GA_HDR(cs, 0)) { GA_HDR(cs, 5) |= GA_HF_ALT; GA_HDR(cs, 1) = cpBase + k; st.rampRedos |= GA_RAMP_STALE_BIT; }
 		}
 		return false;
 	};

@@ -18,6 +18,7 @@ static const uint32_t FLAG_BAD_SEED = 2;       // seed node not in graph / posit
 static const uint32_t FLAG_BAD_CHAR = 4;       // read holds a character the reference aborts on
 static const uint32_t FLAG_CYCLIC = 8;         // some band held a cyclic component
 static const uint32_t FLAG_RAMP_REDO = 16;     // -B: a stream went back and redid a stretch with the wide band
+static const uint32_t FLAG_RAMP_STALE = 32;    // -B: ... and the reference's stale sqrt checkpoint decided part of the trace (GA_RAMP_STALE_BIT of rampRedos)
 
 std::string ReverseComplement(const std::string& str)
 {
@@ -622,7 +623,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 		if (o.status == GA_OK && o.nSlices > 0 && o.nMapped > 0)
 		{
 			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
-			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO | ((o.rampRedos & GA_RAMP_STALE_BIT) ? FLAG_RAMP_STALE : 0u);
 			const uint64_t recWord = o.traceOff + (o.nMoves + 15) / 16 + o.nPathNodes;
 			as.deviceMapped = true;
 			as.deviceMapWord = recWord + GA_MAP_PAD(recWord);
@@ -680,7 +681,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			const ga_stream_out& o = outs[sp.bwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
 			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
-			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO | ((o.rampRedos & GA_RAMP_STALE_BIT) ? FLAG_RAMP_STALE : 0u);
 			if (o.status == GA_OK && o.nSlices > 0)
 			{
 				bwSlices = (size_t)o.nSlices;
@@ -696,7 +697,7 @@ ReadAssembly AssembleRead(const AlignmentGraph& graph, const ReadInput& read, co
 			const ga_stream_out& o = outs[sp.fwStream];
 			if (o.status != GA_OK && o.status != GA_EMPTY) streamError = true;
 			if (o.cyclicSlices) as.flags |= FLAG_CYCLIC;
-			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO;
+			if (o.rampRedos) as.flags |= FLAG_RAMP_REDO | ((o.rampRedos & GA_RAMP_STALE_BIT) ? FLAG_RAMP_STALE : 0u);
 			if (o.status == GA_OK && o.nSlices > 0)
 			{
 				fwSlices = (size_t)o.nSlices;

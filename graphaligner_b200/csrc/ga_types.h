@@ -91,7 +91,7 @@ typedef struct ga_stream_out
 	uint64_t traceOff;      // offset (in 32-bit words) of this stream's record in the trace arena
 	uint32_t nTies;         // cells of the last retained slice tied at the minimum (incl. the chosen one)
 	uint32_t cyclicSlices;  // slices whose band held a cyclic component
-	uint32_t rampRedos;     // -B ramp: how often the stream went back and redid a stretch with the wide band (GraphAligner.h:2648-2719)
+	uint32_t rampRedos;     // -B ramp: how often the stream went back and redid a stretch with the wide band (GraphAligner.h:2648-2719); GA_RAMP_STALE_BIT: a checkpoint of the abandoned pass was used
 	uint32_t nMapped;       // > 0: the stream's record holds nMapped (= nRuns) GaDeviceMapping records where the runs would be, 32-byte aligned in the arena
 	uint32_t tieNode[GA_MAX_TIES];
 	uint32_t tieOff[GA_MAX_TIES];
@@ -100,6 +100,7 @@ typedef struct ga_stream_out
 #endif
 } ga_stream_out;
 
+#define GA_RAMP_STALE_BIT 0x80000000u
 #define GA_RUN_WORDS 5   /* node, firstOff, lastOff, firstRow, lastRow (first = smallest row) */
 
 /* one vg::Mapping with its single Edit as the C ABI returns it (ga_mapping in include/graphaligner_b200.h, same layout) */

@@ -88,6 +88,8 @@ typedef struct ga_read_result
 #define GA_FLAG_BAD_CHAR 4u         /* read character the reference aborts on */
 #define GA_FLAG_CYCLIC 8u           /* a band held a cyclic component */
 #define GA_FLAG_RAMP_REDO 16u       /* -B: a stream went back and redid a stretch with the ramp bandwidth (GraphAligner.h:2648-2719) */
+#define GA_FLAG_RAMP_STALE 32u      /* -B: after a redo the reference traced through a stretch re-computed from a sqrt checkpoint of the abandoned pass
+                                       (GraphAligner.h:2667,2772-2786,2858-2943); the result is that one, as the reference reports it */
 
 typedef struct ga_mapping            /* 32 bytes: a batch of 10 000 x 10 kbp reads on 32-bp nodes returns 3.3 million of them */
 {

@@ -72,6 +72,12 @@ def cases():
     from graphaligner_b200.tools import fuzz
     fuzz.RAMP = True
     yield "ramp_redo", fuzz.make_case(8)[0]
+    # -B where the redo leaves a STALE sqrt checkpoint behind (the reference does not rewind its pending checkpoint, GraphAligner.h:2667,
+    # 2772-2786) and the reference survives it: the stretch behind that checkpoint is re-computed from a slice of the abandoned
+    # narrow-band pass when the trace is taken (getSlicesFromTable, GraphAligner.h:2858-2943), so score and trace are not the ones of
+    # the redone forward pass (profiles/r02_ramp_fuzz.txt: read_6 of the first, read_6 and read_10 of the second)
+    yield "ramp_stale", fuzz.make_case(30078)[0]
+    yield "ramp_stale_long", fuzz.make_case(30025)[0]
     fuzz.RAMP = False
 
 

@@ -5,10 +5,12 @@ from graphaligner_b200.tools import gacase
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_ALIGN = os.path.join(ROOT, "oracle", "_ref", "ref_align")
-GOLDEN = ["smallexample", "dag_snp", "bubbles_multiseed", "tangle_cycles", "seed_pos1", "gfa", "ragged_short", "wide_band", "ramp", "ramp_redo", "cyclic_partial_confirm", "cyclic_last_call_min"]
+GOLDEN = ["smallexample", "dag_snp", "bubbles_multiseed", "tangle_cycles", "seed_pos1", "gfa", "ragged_short", "wide_band", "ramp", "ramp_redo", "ramp_stale", "ramp_stale_long", "cyclic_partial_confirm", "cyclic_last_call_min"]
 # fixtures whose expected output depends on the reference's work-list schedule inside cyclic components; the cell-by-cell
 # restatement (oracle/ga_oracle.cpp) evaluates the fix point and says so in its header
 SCHEDULE_DEPENDENT = ["cyclic_partial_confirm", "cyclic_last_call_min"]
+# fixtures whose expected output comes from a stale sqrt checkpoint after a -B ramp redo (the restatement keeps the whole table)
+STALE_CHECKPOINT = ["ramp_stale", "ramp_stale_long"]
 KEYS = ("failed", "score", "start", "end", "qpos", "nmap", "ntrace", "th")
 
 

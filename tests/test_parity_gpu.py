@@ -102,22 +102,46 @@ def test_ramp_redo_fixture_fires_the_ramp(api, golden_dir):
     aligner.close()
 
 
-def test_ramp_bandwidth_runs(api):
-    # -B: slice 0 and every redone stretch use the wide band (GraphAligner.h:2612,2648-2719).  The reference's own ramp
-    # path keeps a stale sqrt checkpoint across a redo and then crashes or traces through recomputed slices that differ from
-    # its forward pass (measured: profiles/r02_ramp_fuzz.txt), so beyond the goldens (ramp, ramp_redo) this checks invariants:
-    # every read aligns, and a wide-band rescue can only help the coverage
-    g = synth.make_graph(301, 40000, chop=32, bubble_every=120, indel_frac=0.5)
-    narrow = synth.make_case(301, g, 48, 3000, b=3, B=0, errors=(0.08, 0.08, 0.08))
-    ramped = synth.make_case(301, g, 48, 3000, b=3, B=40, errors=(0.08, 0.08, 0.08))
-    aligner = api.Aligner(api.Graph.from_case(narrow))
-    a = aligner.align(narrow.reads, 3, 0).as_dicts()
-    b = aligner.align(ramped.reads, 3, 40).as_dicts()
-    assert all(x["flags"] & 1 == 0 for x in a + b)
-    cover_a = sum(x["end"] - x["start"] for x in a if not x["failed"])
-    cover_b = sum(x["end"] - x["start"] for x in b if not x["failed"])
-    assert cover_b >= cover_a
+@pytest.mark.parametrize("name,reads", [("ramp_stale", ["read_6"]), ("ramp_stale_long", ["read_6", "read_10"])])
+def test_ramp_stale_fixtures_take_the_stale_checkpoint_path(api, golden_dir, name, reads):
+    # the ramp_stale goldens (bit-exact in test_golden above) pin the reference's stale-checkpoint behaviour only if those reads
+    # really go through it here: GA_FLAG_RAMP_STALE (32) = a stretch was re-computed from a checkpoint of the abandoned pass
+    case = gacase.read_case(os.path.join(golden_dir, name + ".gacase"))
+    aligner = api.Aligner(api.Graph.from_case(case))
+    d = aligner.align(case.reads, case.b, case.B).as_dicts()
+    stale = [x["name"] for x in d if x["flags"] & 32]
+    assert set(reads) <= set(stale), stale
+    assert all(x["flags"] & 16 for x in d if x["flags"] & 32)
     aligner.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
+def test_ramp_against_reference_run_here(api, tmp_path):
+    # -B differential: narrow bands that lose noisy reads, a wide backup band (GraphAligner.h:2612-2719).  The reference itself
+    # crashes on about a third of the inputs where a redo fires (it reads slices its stale checkpoint's band does not hold:
+    # profiles/r02_ramp_fuzz.txt); every case it survives must be identical, redo or not, stale checkpoint or not.
+    from graphaligner_b200.tools import fuzz
+    fuzz.RAMP = True
+    try:
+        cases = [fuzz.make_case(seed)[0] for seed in range(30300, 30340)]
+    finally:
+        fuzz.RAMP = False
+    compared = redo = stale = 0
+    for i, case in enumerate(cases):
+        path = str(tmp_path / ("ramp%d.gacase" % i))
+        gacase.write_case(case, path)
+        try:
+            expected, _ = run_reference(path)
+        except RuntimeError:
+            continue   # the reference crashed
+        aligner = api.Aligner(api.Graph.from_case(case))
+        d = aligner.align(case.reads, case.b, case.B).as_dicts()
+        aligner.close()
+        assert_same(d, expected, "ramp fuzz %d" % (30300 + i))
+        compared += 1
+        redo += sum(1 for x in d if x["flags"] & 16)
+        stale += sum(1 for x in d if x["flags"] & 32)
+    assert compared >= 20 and redo >= 50 and stale >= 1, (compared, redo, stale)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
