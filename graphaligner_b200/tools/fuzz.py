@@ -70,7 +70,7 @@ def main():
     global LONG_NODES, RAMP
     LONG_NODES = "--long-nodes" in sys.argv
     RAMP = "--ramp" in sys.argv
-    redo_same = redo_differ = redo_crashed = reads_redo = reads_redo_differ = 0
+    redo_same = redo_differ = redo_crashed = reads_redo = reads_redo_differ = reads_stale = cases_stale = stream_errors = 0
     first, count = int(sys.argv[1]), int(sys.argv[2])
     keep = sys.argv[sys.argv.index("--keep") + 1] if "--keep" in sys.argv else None
     from graphaligner_b200 import api
@@ -87,7 +87,9 @@ def main():
             if RAMP:
                 aligner = api.Aligner(api.Graph.from_case(case))
                 res = aligner.align(case.reads, case.b, case.B)
-                redo_crashed += 1 if any(m["flags"] & 16 for m in res.as_dicts()) else 0
+                d = res.as_dicts()
+                redo_crashed += 1 if any(m["flags"] & 16 for m in d) else 0
+                stream_errors += 1 if any(m["flags"] & 1 for m in d) else 0   # e.g. checkpoints out of order: the reference reads an empty stretch
                 res.free()
                 aligner.close()
             if not keep:
@@ -104,6 +106,9 @@ def main():
         if RAMP:
             redo = [m["name"] if "name" in m else i for i, m in enumerate(mine) if m["flags"] & 16]
             reads_redo += len(redo)
+            nstale = sum(1 for m in mine if m["flags"] & 32)   # GA_FLAG_RAMP_STALE: the reference's stale checkpoint decided part of the trace
+            reads_stale += nstale
+            cases_stale += 1 if nstale else 0
             reads_redo_differ += sum(1 for i, (m, e) in enumerate(zip(mine, expected)) if (m["flags"] & 16) and e["name"] in bad)
             if redo:
                 if bad:
@@ -123,6 +128,8 @@ def main():
     if RAMP:
         print("ramp: cases where a redo fired: identical %d, different %d, reference crashed %d; reads with a redo %d, of them different %d"
               % (redo_same, redo_differ, redo_crashed, reads_redo, reads_redo_differ), flush=True)
+        print("ramp: reference finished: %d reads in %d cases went through a stale checkpoint (GA_FLAG_RAMP_STALE); reference crashed: %d of those cases report a stream error here"
+              % (reads_stale, cases_stale, stream_errors), flush=True)
     return 1 if differ else 0
 
 
