@@ -643,6 +643,7 @@ struct StagedBatch
 	int capScale = 1;
 	int S = 32;            // streams per warp
 	bool smemScratch = false;   // small-band mode: per-slice scratch in shared memory
+	bool noReplay = false;      // -B ramp: forward pass without the replay of the reference's stale sqrt checkpoints (second try of a stream, see FinishStaged)
 	size_t peqWords = 0;
 	uint64_t colPoolCap = 0;
 	size_t nReads = 0;     // reads whose characters the run validates (SetReadRanges), 0 = none
@@ -1142,7 +1143,7 @@ static void launchFast(DeviceCtx* ctx, StagedBatch* sb)
 		attrDone.fetch_or(bit);
 	}
 	ga_fast_kernel<S><<<(unsigned)sb->nWarps, 32, sizeof(GaFastShared<S>), ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags | (sb->noReplay ? 2u : 0u), (ga_stream_out*)ctx->bOut.ptr);
 }
 
 template <int S>
@@ -1154,9 +1155,9 @@ static void launchAlign(DeviceCtx* ctx, StagedBatch* sb)
 	const size_t smemBytes = (size_t)(threads / 32) * 4 * S * sizeof(unsigned long long);
 	// -B ramp: the instantiation that also replays the reference's sqrt checkpoints (ga_run_stream<.., RAMP>)
 	if (sb->B > sb->b) ga_forward_kernel<S, false, true><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags | (sb->noReplay ? 2u : 0u), (ga_stream_out*)ctx->bOut.ptr);
 	else ga_forward_kernel<S, false><<<blocks, threads, smemBytes, ctx->stream>>>(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr,
-		(uint32_t)n, sb->b, sb->B, ctx->debugFlags, (ga_stream_out*)ctx->bOut.ptr);
+		(uint32_t)n, sb->b, sb->B, ctx->debugFlags | (sb->noReplay ? 2u : 0u), (ga_stream_out*)ctx->bOut.ptr);
 }
 
 template <int T, int P, bool ALT = false>
@@ -1227,7 +1228,7 @@ int RunStaged(DeviceCtx* ctx, StagedBatch* sb)
 		for (uint64_t i = ro[r]; i < ro[r + 1]; i++) any |= ga_iupac_mask(((const uint8_t*)ctx->bParts.ptr)[i]) == 0 ? 1u : 0u;
 		((uint32_t*)ctx->bBad.ptr)[r] = any;
 	}
-	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags,
+	hostsim_align(ctx->view, sb->caps, sb->sp, (const WarpDesc*)ctx->bWd.ptr, (const ga_stream_in*)ctx->bIn.ptr, (const uint8_t*)ctx->bParts.ptr, (uint32_t)n, sb->b, sb->B, ctx->debugFlags | (sb->noReplay ? 2u : 0u),
 		sb->smemScratch, (ga_stream_out*)ctx->bOut.ptr, (uint32_t*)ctx->bArena.ptr, (unsigned long long*)ctx->bArenaTop.ptr, (unsigned long long)sb->arenaCap);
 #else
 	// device time of each kernel of the launch sequence: events on the stream (read in FinishStaged; GA_KERNEL_TIMING prints them)
@@ -1447,13 +1448,21 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		stats->launches += sb->launches;
 		sb->launches = 0;
 	}
-	// streams that ran out of scratch are re-run with larger capacities (never on the CPU)
+	// streams that ran out of scratch are re-run with larger capacities (never on the CPU); then (-B ramp) streams whose walk through
+	// a stretch re-computed from a stale checkpoint failed - a band without the node the walk stands on, where the reference
+	// reads a slice that is not there and crashes - are re-run without the replay: they report the alignment of their own
+	// forward pass instead of a failure
 	std::vector<uint32_t> again;
+	for (int pass = 0; pass < 2; pass++)
+	{
+	again.clear();
 	for (size_t i = 0; i < n; i++)
 	{
-		if (isOverflow(outs.data()[i].status)) again.push_back((uint32_t)i);
+		const ga_stream_out& o = outs.data()[i];
+		const bool staleFailure = (o.rampRedos & GA_RAMP_STALE_BIT) != 0 && o.status != GA_OK && o.status != GA_EMPTY && !isOverflow(o.status);
+		if (pass == 0 ? isOverflow(o.status) : staleFailure) again.push_back((uint32_t)i);
 	}
-	if (!again.empty() && sb->capScale < 1024)   // 1024: capacities beyond the 200 000-column switch to the alternate method
+	if (!again.empty() && (pass == 0 ? sb->capScale < 1024 : !sb->noReplay))   // 1024: capacities beyond the 200 000-column switch to the alternate method
 	{
 		std::vector<uint32_t> inv(n);
 		for (size_t i = 0; i < n; i++) inv[sb->perm[i]] = (uint32_t)i;
@@ -1461,7 +1470,8 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 		for (size_t k = 0; k < again.size(); k++) sub[k] = sb->sorted[inv[again[k]]];
 		// NOTE: the retry reuses the context's device buffers, so the staged batch cannot be run again afterwards
 		StagedBatch* retry = StageStreams(ctx, sub, sb->hostParts, sb->hostPartsBytes, sb->b, sb->B, stats);
-		retry->capScale = sb->capScale * 4;
+		retry->capScale = pass == 0 ? sb->capScale * 4 : sb->capScale;
+		retry->noReplay = sb->noReplay || pass == 1;
 		RawBuffer<ga_stream_out> subOuts;
 		RawBuffer<uint32_t> subArena;
 		size_t subTail = 0;
@@ -1502,6 +1512,7 @@ void FinishStaged(DeviceCtx* ctx, StagedBatch* sb, RawBuffer<ga_stream_out>& out
 			outs.data()[again[k]] = subOuts.data()[k];
 			outs.data()[again[k]].traceOff += base;
 		}
+	}
 	}
 }
 
