@@ -1,10 +1,9 @@
 // bin/Aligner: the reference's command line (AlignerMain.cpp:8-101) and driver (Aligner.cpp:231-322) over the GPU hot path.
 //   -g graph (.vg / .gfa)   -f reads (.fastq/.fq/.fasta/.fa)   -s seeds (GAM)   -a output GAM   -t threads
 //   -b initial bandwidth    -B ramp bandwidth   -d dynamic row start (multiple of 64, unused like upstream)   -i (dead upstream)
-//   -G cuda device (extra)
+//   -A augmented graph (.vg input only, as upstream)   -G cuda devices (extra: "0", "0-7", "0,2")
 // Same validation messages and exit(0) paths; same per-read log lines, alignment_<t>_<read>.gam and trace_<t>_<read>.trace files.
-// Differences: all reads are aligned in one GPU batch, reported as "thread 0"; -t only sizes the host worker pool;
-// -A (augmented graph) is not built.
+// Differences: all reads are aligned in GPU batches, reported as "thread 0"; -t only sizes the host worker pool.
 #include <unistd.h>
 #include <algorithm>
 #include <cstdlib>
