@@ -144,6 +144,34 @@ def test_ramp_against_reference_run_here(api, tmp_path):
     assert compared >= 20 and redo >= 50 and stale >= 1, (compared, redo, stale)
 
 
+HOSTSIM = os.path.join(os.path.dirname(REF_ALIGN), "libga_hostsim.so")
+
+
+@pytest.mark.skipif(not os.path.exists(HOSTSIM), reason="oracle/_ref/libga_hostsim.so not built")
+def test_ramp_big_batch_matches_cpu_emulation(api, tmp_path):
+    # 3 000 noisy reads with -b 2 -B 22: about 900 streams redo a stretch and 300 go through a stale checkpoint.  The reference
+    # cannot check a batch like this (one read it crashes on ends its process), so the device - 32 streams per warp in lock
+    # step, lanes in different phases of the slice loop - is compared with the CPU emulation of the same code (one stream at a
+    # time), which the reference pins case by case (test_ramp_against_reference_run_here, profiles/r02_ramp_fuzz.txt).
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "profiles", "tools", "ramp_big_batch_probe.py")
+    outs = []
+    for lib in (None, HOSTSIM):
+        env = dict(os.environ)
+        env.pop("GA_LIB", None)
+        if lib:
+            env["GA_LIB"] = lib
+        out = str(tmp_path / ("ramp_%s.txt" % ("emu" if lib else "gpu")))
+        r = subprocess.run([sys.executable, probe, out, "3000"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
+    lines = outs[0].split("\n")
+    assert sum(1 for l in lines if " flags=" in l and int(l.split(" flags=")[1].split()[0]) & 32) >= 100
+
+
 @pytest.mark.skipif(not os.path.exists(REF_ALIGN), reason="oracle/_ref not built")
 def test_small_band_overflow_reruns_with_general_layout(api, tmp_path, monkeypatch):
     # 32-bp nodes and band 10 select the small-band layout (16 nodes per band in shared memory); tangles hold far more
