@@ -10,8 +10,9 @@
 // Reads the same .gacase files and prints the same lines as oracle/ref_driver.cpp.
 //
 // Known limits (stated, not hidden): bands >= 200 000 bp (the reference's calculateSliceAlternate /
-// BacktraceOverride, GraphAligner.h:2148-2329,167-354) and the -B ramp redo (GraphAligner.h:2648-2719) are
-// not restated; inside a cyclic band component the reference's per-node minimum and tie order depend on
+// BacktraceOverride, GraphAligner.h:2148-2329,167-354) are not restated.  The -B ramp redo (GraphAligner.h:2648-2719) IS, with
+// the sqrt checkpoints and the traceback through re-computed slices (getSlicesFromTable, :2858-2943) as the reference has
+// them - including the pending checkpoint a redo does not rewind (fixtures ramp_redo, ramp_stale, ramp_stale_long).  Inside a cyclic band component the reference's per-node minimum and tie order depend on
 // its work-list schedule (confirmedRows, GraphAligner.h:1355-1416,2364-2420), here the fix point is used - the two
 // fixtures that pin that schedule (tests/golden/cyclic_*) are checked against oracle/_ref/ref_align only.
 #include <algorithm>
@@ -121,17 +122,6 @@ struct Column
 	int scoreEnd() const { return v[63]; }
 };
 
-struct Slice
-{
-	long j = -64;                                   // first row
-	std::vector<size_t> nodes;                      // band, in the reference's band order
-	std::map<size_t, std::vector<Column>> cols;     // node -> its columns
-	std::map<size_t, int> nodeMin;
-	int minScore = 0;
-	std::vector<size_t> minScoreIndex;              // tied minimum columns, in evaluation order
-	bool has(size_t n) const { return cols.count(n) != 0; }
-};
-
 // AlignmentCorrectnessEstimation.cpp:6-30,71-89 - same constants, same association of the sums
 struct Hmm
 {
@@ -156,6 +146,18 @@ struct Hmm
 		r.wrong = nf;
 		return r;
 	}
+};
+
+struct Slice
+{
+	long j = -64;                                   // first row
+	std::vector<size_t> nodes;                      // band, in the reference's band order
+	std::map<size_t, std::vector<Column>> cols;     // node -> its columns
+	std::map<size_t, int> nodeMin;
+	int minScore = 0;
+	std::vector<size_t> minScoreIndex;              // tied minimum columns, in evaluation order
+	Hmm hmm;                                        // DPSlice::correctness after this slice
+	bool has(size_t n) const { return cols.count(n) != 0; }
 };
 
 struct Aligner
@@ -448,14 +450,39 @@ struct Aligner
 		}
 	}
 
+	// DPTable, GraphAligner.h:356-368.  `slices` are the sqrt checkpoints (slices[0] = the initial slice, j = -64); the reference keeps
+	// only their end scores (getFrozenSqrtEndScores), here a checkpoint is the whole slice - fillSlice reads its last row only.
 	struct Table
 	{
-		std::vector<Slice> slices;      // slices[0] = initial slice (j = -64), slices[s + 1] = slice s
+		std::vector<Slice> slices;
+		std::vector<int> bandwidthPerSlice;
 		std::vector<Hmm> correctness;   // one per retained slice
+		size_t samplingFrequency = 1;
 	};
 
-	// getSqrtSlices + removeWronglyAlignedEnd, GraphAligner.h:2554-2856 (every slice kept: the sqrt checkpoints only
-	// save memory in the reference, getSlicesFromTable recomputes identical slices)
+	// DPSlice::EstimatedMemoryUsage, GraphAligner.h:136-139: sizeof(TinySlice) = 4 per cell of the band, 28 per node; the initial
+	// slice never has its cells counted (getInitialSliceOnlyOneNode leaves numCells 0)
+	size_t memoryUse(const Slice& sl) const
+	{
+		size_t cells = 0;
+		if (sl.j >= 0) for (size_t n : sl.nodes) cells += g.len(n);
+		return cells * 4 + sl.nodes.size() * 28;
+	}
+
+	// pickMethodAndExtendFill, GraphAligner.h:2473-2521 (bit-vector branch) with the HMM step of fillDPSlice
+	Slice nextSlice(const Slice& prev, const std::string& part, int bandwidth) const
+	{
+		Slice cur;
+		cur.j = prev.j + 64;
+		cur.nodes = selectBand(prev, bandwidth);
+		fillSlice(cur, prev, part);
+		cur.hmm = prev.hmm.next(cur.minScore - prev.minScore);
+		return cur;
+	}
+
+	// getSqrtSlices + removeWronglyAlignedEnd, GraphAligner.h:2554-2856, as written: the -B ramp redo (:2648-2719) swaps back to the
+	// remembered slice and pops table.slices, but the pending checkpoint `storeSlice` is NOT rewound - a slice of the abandoned
+	// pass can be pushed at the next sampling point (:2772-2786)
 	Table forward(const std::string& part, size_t startNode) const
 	{
 		Table t;
@@ -465,22 +492,43 @@ struct Aligner
 		for (auto& col : init.cols[startNode]) { col.sbs = 0; for (int r = 0; r < 64; r++) col.v[r] = 0; }
 		init.nodeMin[startNode] = 0;
 		init.minScore = 0;
-		t.slices.push_back(init);
-		Hmm hmm;
-		size_t numSlices = part.size() / 64;
-		for (size_t s = 0; s < numSlices; s++)
+		init.minScoreIndex.push_back(g.end(startNode) - 1);
+		const size_t numSlices = part.size() / 64;
+		t.samplingFrequency = (size_t)(int)sqrt((double)numSlices);   // getSamplingFrequency, GraphAligner.h:2962-2967
+		Slice lastSlice = init, storeSlice = init, rampSlice = init;
+		size_t rampRedoIndex = (size_t)-1, rampUntil = 0;
+		for (size_t slice = 0; slice < numSlices; slice++)
 		{
-			int bandwidth = (s == 0) ? B : b;   // rampUntil = 0: slice 0 runs with rampBandwidth, GraphAligner.h:2612
-			const Slice& prev = t.slices.back();
-			Slice cur;
-			cur.j = (long)s * 64;
-			cur.nodes = selectBand(prev, bandwidth);
-			fillSlice(cur, prev, part);
-			Hmm next = hmm.next(cur.minScore - prev.minScore);
-			if (!next.correctFromCorrect) break;   // GraphAligner.h:2640-2647
-			hmm = next;
-			t.correctness.push_back(next);
-			t.slices.push_back(std::move(cur));
+			const int bandwidth = (rampUntil >= slice) ? B : b;   // GraphAligner.h:2612
+			Slice newSlice = nextSlice(lastSlice, part, bandwidth);
+			if (rampUntil == slice - 1 || (rampUntil < slice && newSlice.hmm.currentlyCorrect() && newSlice.hmm.falseFromCorrect))   // :2630-2634
+			{
+				rampSlice = lastSlice;
+				rampRedoIndex = slice - 1;
+			}
+			if (!newSlice.hmm.correctFromCorrect) break;   // :2640-2647
+			if (!newSlice.hmm.currentlyCorrect() && rampUntil < slice && B > b)   // :2648-2719
+			{
+				rampUntil = slice;
+				std::swap(slice, rampRedoIndex);
+				std::swap(lastSlice, rampSlice);
+				while (t.bandwidthPerSlice.size() > slice + 1) t.bandwidthPerSlice.pop_back();
+				while (t.correctness.size() > slice + 1) t.correctness.pop_back();
+				while (t.slices.size() > 1 && t.slices.back().j > (long)(slice * 64)) t.slices.pop_back();
+				continue;
+			}
+			t.bandwidthPerSlice.push_back(bandwidth);
+			t.correctness.push_back(newSlice.hmm);
+			if (slice % t.samplingFrequency == 0)   // :2772-2782
+			{
+				if (t.slices.empty() || storeSlice.j != t.slices.back().j)
+				{
+					t.slices.push_back(storeSlice);
+					storeSlice = newSlice;
+				}
+			}
+			if (memoryUse(newSlice) < memoryUse(storeSlice)) storeSlice = newSlice;   // :2783-2786
+			lastSlice = std::move(newSlice);
 		}
 		// removeWronglyAlignedEnd, GraphAligner.h:2554-2569
 		if (!t.correctness.empty())
@@ -489,12 +537,35 @@ struct Aligner
 			while (!currentlyCorrect)
 			{
 				t.correctness.pop_back();
+				t.bandwidthPerSlice.pop_back();
 				if (t.correctness.empty()) break;
 				currentlyCorrect = t.correctness.back().falseFromCorrect;
 			}
+			if (t.correctness.empty()) t.slices.clear();
+			while (t.slices.size() > 1 && t.slices.back().j >= (long)(t.correctness.size() * 64)) t.slices.pop_back();
 		}
-		t.slices.resize(t.correctness.size() + 1);
 		return t;
+	}
+
+	// getSlicesFromTable, GraphAligner.h:2858-2943: the slices behind checkpoint startIndex, up to the next checkpoint (or the end),
+	// computed again from the checkpoint with the bandwidths the forward pass recorded
+	std::vector<Slice> slicesFromTable(const Table& t, const std::string& part, size_t startIndex) const
+	{
+		const size_t startSlice = (size_t)((t.slices[startIndex].j + 64) / 64);
+		size_t endSlice = startIndex == t.slices.size() - 1 ? t.bandwidthPerSlice.size() : (size_t)((t.slices[startIndex + 1].j + 64) / 64);
+		if (endSlice <= startSlice || endSlice > t.bandwidthPerSlice.size())
+		{
+			fprintf(stderr, "ga_oracle: sqrt checkpoints out of order after a ramp redo (the reference reads an empty stretch here)\n");
+			exit(8);
+		}
+		std::vector<Slice> result;
+		Slice lastSlice = t.slices[startIndex];
+		for (size_t slice = startSlice; slice < endSlice; slice++)
+		{
+			result.push_back(nextSlice(lastSlice, part, t.bandwidthPerSlice[slice]));
+			lastSlice = result.back();
+		}
+		return result;
 	}
 
 	int valueOrMax(const Slice& s, size_t w, int row, int maxv) const   // getValueOrMax, GraphAligner.h:2008-2017
@@ -507,14 +578,16 @@ struct Aligner
 	typedef std::pair<size_t, long> Pos;   // (graph position, read row)
 
 	// pickBacktracePredecessor, GraphAligner.h:493-591
-	Pos predecessor(const Table& t, const std::string& part, Pos pos) const
+	Pos predecessor(const Slice& slice, const Slice& previous, const std::string& part, Pos pos) const
 	{
-		size_t si = (size_t)(pos.second / 64) + 1;
-		const Slice& slice = t.slices[si];
-		const Slice& previous = t.slices[si - 1];
 		int row = (int)(pos.second - slice.j);
 		int maxv = (int)part.size();
 		size_t node = g.indexToNode(pos.first);
+		if (!slice.has(node))
+		{
+			fprintf(stderr, "ga_oracle: the trace stands on a node the slice does not hold (the reference reads a missing slice here)\n");
+			exit(8);
+		}
 		int here = slice.cols.at(node)[pos.first - g.start(node)].v[row];
 		if (pos.second == 0 && previous.has(node) && (here == 0 || here == 1)) return { pos.first, -1 };
 		bool match = characterMatch(part[pos.second], g.seq[pos.first]);
@@ -533,17 +606,40 @@ struct Aligner
 		exit(7);
 	}
 
-	// getTraceFromTable, GraphAligner.h:894-957: start at minScoreIndex.back() of the last slice, walk to row -1
+	// getTraceFromTable, GraphAligner.h:894-957, with getTraceFromTableInner / getTraceFromSlice / getSliceBoundaryTrace (:960-1021):
+	// from the last checkpoint to the first, the stretch behind each one is computed again and walked; the step across a
+	// checkpoint looks at the checkpoint's own slice
 	std::pair<int, std::vector<Pos>> trace(const Table& t, const std::string& part) const
 	{
-		if (t.correctness.empty()) return { std::numeric_limits<int>::max(), {} };
-		const Slice& last = t.slices.back();
+		if (t.slices.empty() || t.bandwidthPerSlice.empty()) return { std::numeric_limits<int>::max(), {} };
+		int score = 0;
 		std::vector<Pos> result;
-		result.emplace_back(last.minScoreIndex.back(), last.j + 63);
-		while (result.back().second != -1) result.push_back(predecessor(t, part, result.back()));
-		result.pop_back();
+		for (size_t i = t.slices.size() - 1; i < t.slices.size(); i--)
+		{
+			if ((size_t)((t.slices[i].j + 64) / 64) == t.bandwidthPerSlice.size())
+			{
+				score = t.slices.back().minScore;
+				result.emplace_back(t.slices.back().minScoreIndex.back(), t.slices.back().j + 63);
+				continue;
+			}
+			const std::vector<Slice> partTable = slicesFromTable(t, part, i);
+			if (i == t.slices.size() - 1)
+			{
+				score = partTable.back().minScore;
+				result.emplace_back(partTable.back().minScoreIndex.back(), partTable.back().j + 63);
+			}
+			for (size_t k = partTable.size() - 1; k < partTable.size(); k--)
+			{
+				// getTraceFromSlice: down to the slice's first row
+				while (result.back().second != partTable[k].j) result.push_back(predecessor(partTable[k], partTable[k], part, result.back()));
+				// getSliceBoundaryTrace: along the first row and over the border, into the slice before (the checkpoint for k = 0)
+				const Slice& before = k > 0 ? partTable[k - 1] : t.slices[i];
+				while (result.back().second == partTable[k].j) result.push_back(predecessor(partTable[k], before, part, result.back()));
+			}
+		}
+		result.pop_back();   // the position in row -1
 		std::reverse(result.begin(), result.end());
-		return { last.minScore, result };
+		return { score, result };
 	}
 };
 

@@ -9,7 +9,7 @@ GOLDEN = ["smallexample", "dag_snp", "bubbles_multiseed", "tangle_cycles", "seed
 # fixtures whose expected output depends on the reference's work-list schedule inside cyclic components; the cell-by-cell
 # restatement (oracle/ga_oracle.cpp) evaluates the fix point and says so in its header
 SCHEDULE_DEPENDENT = ["cyclic_partial_confirm", "cyclic_last_call_min"]
-# fixtures whose expected output comes from a stale sqrt checkpoint after a -B ramp redo (the restatement keeps the whole table)
+# fixtures whose expected output comes from a stale sqrt checkpoint after a -B ramp redo (GraphAligner.h:2667,2772-2786,2858-2943)
 STALE_CHECKPOINT = ["ramp_stale", "ramp_stale_long"]
 KEYS = ("failed", "score", "start", "end", "qpos", "nmap", "ntrace", "th")
 

@@ -50,13 +50,44 @@ RESTATEMENT = os.path.join(ROOT, "oracle", "_ref", "ga_oracle")
 
 
 @pytest.mark.skipif(not os.path.exists(RESTATEMENT), reason="oracle restatement not built (python __graft_entry__.py)")
-@pytest.mark.parametrize("name", [n for n in GOLDEN if n not in SCHEDULE_DEPENDENT + STALE_CHECKPOINT])
+@pytest.mark.parametrize("name", [n for n in GOLDEN if n not in SCHEDULE_DEPENDENT])
 def test_restatement_oracle_reproduces_golden(golden_dir, name):
     # oracle/ga_oracle.cpp (cell-by-cell restatement) pinned against outputs of the unmodified reference
     import subprocess
     res = subprocess.run([RESTATEMENT, os.path.join(golden_dir, name + ".gacase")], capture_output=True, text=True, check=True)
     got, _ = gacase.parse_ref_output(res.stdout)
     assert_same(got, load_expected(os.path.join(golden_dir, name + ".expected")), name)
+
+
+@pytest.mark.skipif(not (os.path.exists(RESTATEMENT) and os.path.exists(REF_ALIGN)), reason="oracle not built")
+def test_restatement_oracle_ramp_redo_against_reference_run_here(tmp_path):
+    # -B ramp redo with the reference's sqrt checkpoints (GraphAligner.h:2648-2719,2772-2786,2858-2943) in the cell-by-cell restatement:
+    # ramp fuzz cases on acyclic graph kinds, every case the reference survives must be identical (the restatement stops with
+    # exit code 8 where the reference reads a slice that is not there)
+    import subprocess
+    from graphaligner_b200.tools import fuzz
+    assert set(STALE_CHECKPOINT) <= set(GOLDEN)
+    fuzz.RAMP = True
+    try:
+        cases = [(seed, fuzz.make_case(seed)) for seed in range(30000, 30060) if seed % 6 in (0, 1, 2)]
+    finally:
+        fuzz.RAMP = False
+    compared = 0
+    for seed, (case, desc) in cases:
+        if desc["rl"] > 1000:
+            continue
+        path = str(tmp_path / ("r%d.gacase" % seed))
+        gacase.write_case(case, path)
+        try:
+            expected, _ = run_reference(path)
+        except RuntimeError:
+            continue
+        res = subprocess.run([RESTATEMENT, path], capture_output=True, text=True)
+        assert res.returncode == 0, "seed %d: %s" % (seed, res.stderr[-300:])
+        got, _ = gacase.parse_ref_output(res.stdout)
+        assert_same(got, expected, "restatement, ramp fuzz %d" % seed)
+        compared += 1
+    assert compared >= 8
 
 
 def test_parallel_generators_make_valid_cases(tmp_path):
